@@ -1,0 +1,152 @@
+/* mbb_b200 -- C ABI of the B200 (sm_100a) modified-blackbody likelihood library.
+ *
+ * This is the drop-in boundary for the hot path of aconley/mbb_emcee:
+ * everything the reference does per walker inside `likelihood.__call__`
+ * (mbb_emcee/likelihood.py:790-834), and per chain sample inside
+ * `mbb_results.compute_*` (mbb_emcee/results.py:570-801), runs in CUDA kernels
+ * behind these entry points.  Plain C, plain pointers and sizes, no torch
+ * types.  The shared library is libmbb_b200.so (mbb_emcee_b200/csrc).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message
+ *     of the last failure on the calling thread is `mbb_last_error()`.
+ *   - parameter vectors are (T, beta, lambda0, alpha, fnorm), the order of
+ *     likelihood.py:20-22.  `layout` MBB_AOS is emcee's [n][5] row-major
+ *     block, MBB_SOA is [5][n].
+ *   - `mem` says where `pars`/outputs live: MBB_HOST pointers are staged
+ *     through the context's pinned buffers (H2D, kernel, D2H, synchronous on
+ *     return); MBB_DEVICE pointers (e.g. torch.Tensor.data_ptr()) are used in
+ *     place and the call returns after the launch -- call mbb_sync() before
+ *     reading results on the host.
+ *   - the caller owns every buffer it passes; set_* calls copy into
+ *     library-owned device memory; nothing library-allocated is returned.
+ *   - a context is bound to one device and one stream; calls on one context
+ *     must be serialised by the caller; different contexts (one per GPU) may
+ *     be driven from different threads.
+ *   - there is NO CPU fallback: without a usable CUDA device
+ *     mbb_ctx_create fails.
+ */
+#ifndef MBB_B200_H
+#define MBB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mbb_ctx mbb_ctx;
+
+enum { MBB_AOS = 0, MBB_SOA = 1 };
+enum { MBB_HOST = 0, MBB_DEVICE = 1 };
+enum { MBB_MATH_FAITHFUL = 0, MBB_MATH_FAST = 1 };
+
+/* per-evaluation status codes written to `status[]`; 0/1 are normal outcomes,
+ * the others correspond to exceptions the reference raises. */
+enum {
+  MBB_ST_OK = 0,
+  MBB_ST_BELOW_LOWLIM = 1,  /* likelihood.py:806-807, lnlike = -inf            */
+  MBB_ST_BAD_ALPHA = 2,     /* modified_blackbody.py:219-221, ValueError       */
+  MBB_ST_BAD_BETA = 3,      /* modified_blackbody.py:222-224, ValueError       */
+  MBB_ST_BRACKET_LOW = 4,   /* modified_blackbody.py:294-300, ValueError       */
+  MBB_ST_BRACKET_HIGH = 5,  /* modified_blackbody.py:310-316, ValueError       */
+  MBB_ST_NO_CONVERGE = 6,   /* scipy brentq RuntimeError (:321, :633)          */
+  MBB_ST_OVERFLOW = 7,      /* modified_blackbody.py:326-328, OverflowError    */
+  MBB_ST_PEAK_BRACKET = 8,  /* modified_blackbody.py:612-630, Exception        */
+  MBB_ST_NONFINITE = 9      /* NaN/inf parameters                              */
+};
+
+int mbb_version(void);
+const char *mbb_last_error(void);
+/* number of CUDA devices visible; <0 if the runtime cannot initialise */
+int mbb_device_count(void);
+
+/* ---- context ------------------------------------------------------------ */
+int mbb_ctx_create(int device_ordinal, mbb_ctx **out);
+int mbb_ctx_destroy(mbb_ctx *ctx);
+int mbb_sync(mbb_ctx *ctx);
+/* total kernel launches issued by this context so far (bench "gpu_launches") */
+int64_t mbb_launch_count(const mbb_ctx *ctx);
+/* the cudaStream_t (as an integer) kernels are launched on, for event timing */
+uint64_t mbb_stream_handle(const mbb_ctx *ctx);
+/* milliseconds the kernels of the most recent compute call took on the device
+ * (CUDA events on the context's stream around the launch); call after mbb_sync
+ * for MBB_DEVICE calls. */
+int mbb_last_kernel_ms(mbb_ctx *ctx, float *ms);
+
+/* ---- model: replaces the constructor arguments the reference threads through
+ *      likelihood._set_sed (likelihood.py:765-768) ------------------------- */
+int mbb_set_model(mbb_ctx *ctx, double wavenorm, int opthin, int noalpha);
+int mbb_set_math_mode(mbb_ctx *ctx, int mode);
+
+/* ---- passbands: replaces response.__call__ (response.py:544-576).
+ * Band b owns nodes [band_off[b], band_off[b+1]).  node_wave_um are the
+ * wavelengths the SED is evaluated at (response._wave, or _normwave for a
+ * delta band); node_weight = response._sedmult * response._normfac (1 for a
+ * delta band), so band flux = sum_i f_nu(wave_i) * weight_i.
+ * scalar_path[b] != 0 marks bands the reference evaluates through its numpy
+ * twin (x = (h/kT)*1e9*nu, modified_blackbody.py:461-464: delta passbands
+ * inside a response set) instead of the Cython loop (x = (1e9*h/kT)*nu,
+ * fnu.pyx:16) -- only observable in MBB_MATH_FAITHFUL. */
+int mbb_set_bands(mbb_ctx *ctx, int nbands, const int32_t *band_off,
+                  const double *node_wave_um, const double *node_weight,
+                  const uint8_t *scalar_path);
+
+/* ---- data: replaces likelihood.set_phot / set_cov (likelihood.py:158-232,
+ * 330-357).  flux[nsrc][nbands]; exactly one of ivar[nsrc][nbands]
+ * (= 1/unc^2, :222) or cinv[nsrc][nbands][nbands] (= inv(C), :356) non-NULL. */
+int mbb_set_data(mbb_ctx *ctx, int nsrc, int nbands, const double *flux,
+                 const double *ivar, const double *cinv);
+
+/* ---- limits and priors: likelihood.py:73, 83-92, 462-483, 541-570.
+ * Index 5 of the 6-slot arrays is the ghost parameter lambda_peak. */
+int mbb_set_priors(mbb_ctx *ctx, const double lowlim[5],
+                   const uint8_t has_uplim[6], const double uplim[6],
+                   const uint8_t has_gprior[6], const double gmean[6],
+                   const double givar[6]);
+
+/* ---- THE hot entry: likelihood.__call__ for n parameter vectors
+ * (likelihood.py:790-834).  Evaluation i uses source src_index[i] if
+ * src_index != NULL, else i / walkers_per_source (pass n for a single
+ * source).  out_status may be NULL. */
+int mbb_loglike(mbb_ctx *ctx, int64_t n, const double *pars, int layout,
+                const int32_t *src_index, int64_t walkers_per_source,
+                double *out_lnlike, int32_t *out_status, int mem);
+
+/* ---- SED evaluation: modified_blackbody.__call__ / f_nu
+ * (modified_blackbody.py:441-554) for n parameter vectors on a common
+ * frequency grid: out[n][nfreq] in mJy.  scalar_path selects the numpy-twin
+ * rounding of x (see mbb_set_bands).  Always MBB_MATH_FAITHFUL. */
+int mbb_fnu(mbb_ctx *ctx, int64_t n, const double *pars, int layout,
+            int nfreq, const double *freq_ghz, int scalar_path, double *out,
+            int32_t *out_status, int mem);
+
+/* ---- per-walker constants: modified_blackbody.__init__ + max_wave
+ * (modified_blackbody.py:200-337, 581-637).  out_consts[n][6] =
+ * (normfac, xmerge, kappa, x0, xnorm, max_wave_um); max_wave is computed only
+ * if want_peak != 0 (else 0). */
+int mbb_sed_consts(mbb_ctx *ctx, int64_t n, const double *pars, int layout,
+                   int want_peak, double *out_consts, int32_t *out_status,
+                   int mem);
+
+/* ---- chain post-processing: mbb_results.compute_peaklambda / compute_lir /
+ * compute_dustmass over chain[nwalkers][nsteps][5] (results.py:534-801,
+ * 1267-1326), including the sequential allclose-dedupe of _map_chain
+ * (results.py:553-566).  which: bit0 peak lambda, bit1 L_IR, bit2 dust mass;
+ * outputs [nwalkers][nsteps], NULL where not requested.
+ * L_IR: integral of f_nu over [lir_min, lir_max]*(1+z) um in the observer
+ * frame times 3.11749657e4*dl_mpc^2*1e-17 (results.py:665-673).  */
+int mbb_chain_post(mbb_ctx *ctx, int64_t nwalkers, int64_t nsteps,
+                   const double *chain, int which, double z, double dl_mpc,
+                   double lir_min_um, double lir_max_um, double kappa,
+                   double kappa_wave_um, double *out_peak, double *out_lir,
+                   double *out_dustmass, int32_t *out_status, int mem);
+
+/* ---- measurement aid: sustained DFMA rate of this device in TFLOP/s
+ * (2 flops per DFMA), the FP64 roofline denominator bench.py reports. */
+int mbb_fp64_peak(mbb_ctx *ctx, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBB_B200_H */

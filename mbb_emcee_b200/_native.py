@@ -1,0 +1,298 @@
+"""ctypes binding of libmbb_b200.so (the C ABI in include/mbb_b200.h).
+
+There is no CPU fallback anywhere in this package: if the shared library has
+not been built, or no CUDA device is usable, the first call that needs the
+device raises ``MBBNativeError`` -- loudly, never silently.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+__all__ = ["MBBNativeError", "Context", "library_path", "load_library",
+           "default_context", "raise_for_status", "STATUS_NAMES"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBNAME = os.path.join(_HERE, "csrc", "libmbb_b200.so")
+
+AOS, SOA = 0, 1
+HOST, DEVICE = 0, 1
+MATH_FAITHFUL, MATH_FAST = 0, 1
+
+STATUS_NAMES = {0: "ok", 1: "below lower limit", 2: "bad alpha", 3: "bad beta",
+                4: "bracket low", 5: "bracket high", 6: "no convergence",
+                7: "overflow", 8: "peak bracket", 9: "non-finite"}
+
+
+class MBBNativeError(RuntimeError):
+    """The CUDA library is missing, failed to load, or reported an error."""
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int32_p = ctypes.POINTER(ctypes.c_int32)
+_c_uint8_p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def library_path():
+    return _LIBNAME
+
+
+def load_library():
+    """Load libmbb_b200.so (once) and declare every entry point of the header."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIBNAME):
+            raise MBBNativeError(
+                "CUDA extension not built: %s is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                "`make -C mbb_emcee_b200/csrc` (needs nvcc, sm_100a). "
+                "This package has no CPU fallback." % _LIBNAME)
+        try:
+            lib = ctypes.CDLL(_LIBNAME)
+        except OSError as exc:
+            raise MBBNativeError("could not load %s: %s" % (_LIBNAME, exc))
+        vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+        sig = {
+            "mbb_version": (i32, []),
+            "mbb_last_error": (ctypes.c_char_p, []),
+            "mbb_device_count": (i32, []),
+            "mbb_ctx_create": (i32, [i32, ctypes.POINTER(vp)]),
+            "mbb_ctx_destroy": (i32, [vp]),
+            "mbb_sync": (i32, [vp]),
+            "mbb_launch_count": (i64, [vp]),
+            "mbb_stream_handle": (ctypes.c_uint64, [vp]),
+            "mbb_last_kernel_ms": (i32, [vp, ctypes.POINTER(ctypes.c_float)]),
+            "mbb_set_model": (i32, [vp, dbl, i32, i32]),
+            "mbb_set_math_mode": (i32, [vp, i32]),
+            "mbb_set_bands": (i32, [vp, i32, vp, vp, vp, vp]),
+            "mbb_set_data": (i32, [vp, i32, i32, vp, vp, vp]),
+            "mbb_set_priors": (i32, [vp, vp, vp, vp, vp, vp, vp]),
+            "mbb_loglike": (i32, [vp, i64, vp, i32, vp, i64, vp, vp, i32]),
+            "mbb_fnu": (i32, [vp, i64, vp, i32, i32, vp, i32, vp, vp, i32]),
+            "mbb_sed_consts": (i32, [vp, i64, vp, i32, i32, vp, vp, i32]),
+            "mbb_chain_post": (i32, [vp, i64, i64, vp, i32, dbl, dbl, dbl, dbl, dbl, dbl,
+                                     vp, vp, vp, vp, i32]),
+            "mbb_fp64_peak": (i32, [vp, i32, ctypes.POINTER(dbl)]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(lib, name)      # AttributeError here = header/library drift
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ctx_create",
+                    "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
+                    "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_bands",
+                    "mbb_set_data", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
+                    "mbb_chain_post", "mbb_fp64_peak"]
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def raise_for_status(status, pars=None):
+    """Map device status codes to the exceptions the reference raises
+    (SURVEY.md 8b): ValueError for bad alpha/beta and bracket failures
+    (modified_blackbody.py:219-224, 294-317), RuntimeError for a non-converged
+    root solve, OverflowError for kappa (:326-328), Exception for the
+    lambda_peak bracket (:612-630)."""
+    status = np.asarray(status)
+    bad = np.nonzero(status > 1)[0]
+    if bad.size == 0:
+        return
+    i = int(bad[0])
+    code = int(status.flat[i])
+    where = "" if pars is None else " for parameters %s" % (np.asarray(pars).reshape(-1, 5)[i],)
+    msg = {2: "alpha must be positive", 3: "beta must be non-negative",
+           4: "Couldn't bracket low alpha merge point",
+           5: "Couldn't bracket high alpha merge point",
+           6: "root solve failed to converge",
+           7: "overflow computing the merge constant",
+           8: "Couldn't bracket maximum", 9: "non-finite parameters or result"}[code] + where
+    if code in (2, 3, 4, 5, 9):
+        raise ValueError(msg)
+    if code == 6:
+        raise RuntimeError(msg)
+    if code == 7:
+        raise OverflowError(msg)
+    raise Exception(msg)
+
+
+class Context(object):
+    """One device + one stream + the staged tables (``mbb_ctx``)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        handle = ctypes.c_void_p()
+        rc = self._lib.mbb_ctx_create(int(device), ctypes.byref(handle))
+        if rc != 0:
+            raise MBBNativeError(self._lib.mbb_last_error().decode())
+        self._h = handle
+        self.device = int(device)
+        self.model = (500.0, False, False)
+        self.math_mode = MATH_FAST
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MBBNativeError(self._lib.mbb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mbb_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration -----------------------------------------------------
+    def set_model(self, wavenorm, opthin, noalpha):
+        self._ck(self._lib.mbb_set_model(self._h, float(wavenorm), int(bool(opthin)),
+                                         int(bool(noalpha))))
+        self.model = (float(wavenorm), bool(opthin), bool(noalpha))
+
+    def set_math_mode(self, mode):
+        self._ck(self._lib.mbb_set_math_mode(self._h, int(mode)))
+        self.math_mode = int(mode)
+
+    def set_bands(self, band_off, node_wave, node_weight, scalar_path=None):
+        off = np.ascontiguousarray(band_off, dtype=np.int32)
+        wv, wt = _f64(node_wave), _f64(node_weight)
+        nb = off.size - 1
+        if wv.size != off[-1] or wt.size != off[-1]:
+            raise ValueError("node arrays do not match band_off")
+        sp = None if scalar_path is None else np.ascontiguousarray(scalar_path, dtype=np.uint8)
+        self._ck(self._lib.mbb_set_bands(self._h, nb, _ptr(off), _ptr(wv), _ptr(wt), _ptr(sp)))
+        self.nbands = nb
+
+    def set_data(self, flux, ivar=None, cinv=None):
+        flux = np.atleast_2d(_f64(flux))
+        nsrc, nb = flux.shape
+        iv = None if ivar is None else np.atleast_2d(_f64(ivar))
+        ci = None if cinv is None else _f64(cinv).reshape(nsrc, nb, nb)
+        self._ck(self._lib.mbb_set_data(self._h, nsrc, nb, _ptr(flux), _ptr(iv), _ptr(ci)))
+        self.nsrc = nsrc
+
+    def set_priors(self, lowlim, has_uplim, uplim, has_gprior, gmean, givar):
+        lo = _f64(lowlim)
+        hu = np.ascontiguousarray(has_uplim, dtype=np.uint8)
+        up = _f64(uplim)
+        hg = np.ascontiguousarray(has_gprior, dtype=np.uint8)
+        gm, gi = _f64(gmean), _f64(givar)
+        if lo.size != 5 or any(a.size != 6 for a in (hu, up, hg, gm, gi)):
+            raise ValueError("limits/priors arrays have the wrong length")
+        self._ck(self._lib.mbb_set_priors(self._h, _ptr(lo), _ptr(hu), _ptr(up), _ptr(hg),
+                                          _ptr(gm), _ptr(gi)))
+
+    # -- compute -----------------------------------------------------------
+    def loglike(self, pars, src_index=None, walkers_per_source=None, layout=AOS):
+        """Host arrays in, host arrays out: (lnlike[n], status[n])."""
+        P = _f64(pars)
+        n = P.size // 5
+        out = np.empty(n, dtype=np.float64)
+        st = np.empty(n, dtype=np.int32)
+        si = None if src_index is None else np.ascontiguousarray(src_index, dtype=np.int32)
+        wps = n if walkers_per_source is None else int(walkers_per_source)
+        self._ck(self._lib.mbb_loglike(self._h, n, _ptr(P), layout, _ptr(si), max(wps, 1),
+                                       _ptr(out), _ptr(st), HOST))
+        return out, st
+
+    def loglike_device(self, n, pars_ptr, out_ptr, status_ptr=0, src_index_ptr=0,
+                       walkers_per_source=None, layout=AOS):
+        """Raw device pointers (e.g. torch.Tensor.data_ptr()); asynchronous."""
+        wps = n if walkers_per_source is None else int(walkers_per_source)
+        self._ck(self._lib.mbb_loglike(self._h, int(n), ctypes.c_void_p(pars_ptr), layout,
+                                       ctypes.c_void_p(src_index_ptr) if src_index_ptr else None,
+                                       max(wps, 1), ctypes.c_void_p(out_ptr),
+                                       ctypes.c_void_p(status_ptr) if status_ptr else None, DEVICE))
+
+    def fnu(self, pars, freq_ghz, scalar_path=False):
+        P = _f64(pars).reshape(-1, 5)
+        f = _f64(freq_ghz).ravel()
+        out = np.empty((P.shape[0], f.size), dtype=np.float64)
+        st = np.empty(P.shape[0], dtype=np.int32)
+        self._ck(self._lib.mbb_fnu(self._h, P.shape[0], _ptr(P), AOS, f.size, _ptr(f),
+                                   int(bool(scalar_path)), _ptr(out), _ptr(st), HOST))
+        return out, st
+
+    def sed_consts(self, pars, want_peak=False):
+        P = _f64(pars).reshape(-1, 5)
+        out = np.empty((P.shape[0], 6), dtype=np.float64)
+        st = np.empty(P.shape[0], dtype=np.int32)
+        self._ck(self._lib.mbb_sed_consts(self._h, P.shape[0], _ptr(P), AOS, int(bool(want_peak)),
+                                          _ptr(out), _ptr(st), HOST))
+        return out, st
+
+    def chain_post(self, chain, which, z=0.0, dl_mpc=1.0, lir_min=8.0, lir_max=1000.0,
+                   kappa=2.64, kappa_wave=125.0):
+        chain = _f64(chain)
+        nw, ns = chain.shape[0], chain.shape[1]
+        pk = np.empty((nw, ns)) if which & 1 else None
+        lir = np.empty((nw, ns)) if which & 2 else None
+        dm = np.empty((nw, ns)) if which & 4 else None
+        st = np.empty((nw, ns), dtype=np.int32)
+        self._ck(self._lib.mbb_chain_post(self._h, nw, ns, _ptr(chain), int(which), float(z),
+                                          float(dl_mpc), float(lir_min), float(lir_max),
+                                          float(kappa), float(kappa_wave), _ptr(pk), _ptr(lir),
+                                          _ptr(dm), _ptr(st), HOST))
+        return pk, lir, dm, st
+
+    def sync(self):
+        self._ck(self._lib.mbb_sync(self._h))
+
+    def launch_count(self):
+        return int(self._lib.mbb_launch_count(self._h))
+
+    def stream_handle(self):
+        return int(self._lib.mbb_stream_handle(self._h))
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float()
+        self._ck(self._lib.mbb_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def fp64_peak(self, iters=20000):
+        t = ctypes.c_double()
+        self._ck(self._lib.mbb_fp64_peak(self._h, int(iters), ctypes.byref(t)))
+        return float(t.value)
+
+
+_default_ctx = {}
+_default_lock = threading.Lock()
+
+
+def default_device():
+    """CUDA ordinal used when none is given: MBB_B200_DEVICE, else LOCAL_RANK
+    (one process per GPU under torchrun), else 0."""
+    device = int(os.environ.get("MBB_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    n = load_library().mbb_device_count()
+    if n > 0:
+        device %= n
+    return device
+
+
+def default_context(device=None):
+    """Shared context for single-SED conveniences (modified_blackbody objects)."""
+    if device is None:
+        device = default_device()
+    with _default_lock:
+        ctx = _default_ctx.get(device)
+        if ctx is None:
+            ctx = Context(device)
+            _default_ctx[device] = ctx
+        return ctx

@@ -1,0 +1,804 @@
+// C ABI of libmbb_b200.so -- see include/mbb_b200.h for the contract.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mbb_b200.h"
+#include "mbb_kernels.cuh"
+
+using namespace mbb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(_e));                 \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <class T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct mbb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int64_t launches = 0;
+
+  // model
+  double wavenorm = 500.0;
+  int opthin = 0, noalpha = 0;
+  int math_mode = MBB_MATH_FAST;
+
+  // passbands
+  int nb = 0, nn = 0, nn_pad = 0;
+  std::vector<int> h_off;
+  std::vector<unsigned char> h_scalar;
+  std::vector<double> h_packed;   // [freq|w|lhi|llo|rcube] x nn_pad
+  DevBuf<double> d_packed;
+  DevBuf<int> d_off;
+  DevBuf<unsigned char> d_scalar;
+  SmallTab small;
+  bool bands_set = false;
+
+  // data
+  int nsrc = 0, data_nb = 0;
+  DevBuf<double> d_flux, d_ivar, d_cinv;
+  bool has_ivar = false, has_cinv = false;
+
+  Priors pri;
+
+  // pipelined staging for MBB_HOST mbb_loglike calls (see mbb_loglike)
+  struct Slot {
+    cudaStream_t s = nullptr;
+    cudaEvent_t done = nullptr;
+    PinBuf<double> hin, hout;
+    PinBuf<int> hst, hsrc;
+    DevBuf<double> din, dout;
+    DevBuf<int> dst, dsrc;
+    int64_t pend_e0 = -1, pend_n = 0;   // chunk whose outputs still sit in hout/hst
+  };
+  Slot slots[3];
+  bool slots_ready = false;
+
+  // staging for the other MBB_HOST calls
+  PinBuf<double> h_in, h_out;
+  PinBuf<int> h_st, h_src;
+  DevBuf<double> d_in, d_out, d_aux0, d_aux1;
+  DevBuf<int> d_st, d_src, d_owner, d_work;
+  DevBuf<unsigned> d_count;
+};
+
+namespace {
+
+void default_priors(Priors& p) {
+  // likelihood.py:73, 83-92
+  const double low[5] = {1, 0.1, 1, 0.1, 1e-3};
+  for (int i = 0; i < 5; ++i) p.lowlim[i] = low[i];
+  for (int i = 0; i < 6; ++i) {
+    p.uplim[i] = kInf;
+    p.has_uplim[i] = 0;
+    p.has_gprior[i] = 0;
+    p.gmean[i] = 0.0;
+    p.givar[i] = 1.0;
+  }
+  p.has_uplim[1] = p.has_uplim[3] = 1;
+  p.uplim[1] = p.uplim[3] = 20.0;
+  p.any_gprior = 0;
+}
+
+struct Use {
+  mbb_ctx* c;
+  int prev = -1;
+  explicit Use(mbb_ctx* ctx) : c(ctx) {
+    cudaGetDevice(&prev);
+    if (prev != c->device) cudaSetDevice(c->device);
+  }
+  ~Use() {
+    if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
+  }
+};
+
+void begin_timing(mbb_ctx* c) { cudaEventRecord(c->ev0, c->stream); }
+void end_timing(mbb_ctx* c) {
+  cudaEventRecord(c->ev1, c->stream);
+  c->timed = true;
+}
+
+template <template <bool, bool, bool> class L, class... A>
+void dispatch3(bool thin, bool alpha, bool fast, A&&... args) {
+  if (thin) {
+    if (alpha) {
+      if (fast) L<true, true, true>::run(args...); else L<true, true, false>::run(args...);
+    } else {
+      if (fast) L<true, false, true>::run(args...); else L<true, false, false>::run(args...);
+    }
+  } else {
+    if (alpha) {
+      if (fast) L<false, true, true>::run(args...); else L<false, true, false>::run(args...);
+    } else {
+      if (fast) L<false, false, true>::run(args...); else L<false, false, false>::run(args...);
+    }
+  }
+}
+
+template <bool THIN, bool ALPHA, bool FAST>
+struct LaunchThread {
+  static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
+    const unsigned grid = (unsigned)((a.n + 255) / 256);
+    ModelP m{c->wavenorm};
+    loglike_thread_kernel<THIN, ALPHA, FAST><<<grid, 256, 0, st>>>(a, m, c->pri, d, c->small);
+    *err = cudaSuccess;
+  }
+};
+
+template <bool THIN, bool ALPHA, bool FAST>
+struct LaunchWarp {
+  static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
+    NodeTab t;
+    t.packed = c->d_packed.p;
+    t.band_off = c->d_off.p;
+    t.scalar_path = c->d_scalar.p;
+    t.nb = c->nb;
+    t.nn = c->nn;
+    t.nn_pad = c->nn_pad;
+    size_t smem = warp_kernel_smem(c->nn_pad, c->nb, true);
+    t.in_smem = smem <= c->smem_optin ? 1 : 0;
+    if (!t.in_smem) smem = warp_kernel_smem(c->nn_pad, c->nb, false);
+    auto kern = loglike_warp_kernel<THIN, ALPHA, FAST>;
+    *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (*err != cudaSuccess) return;
+    const long long ntiles = (a.n + kWarpTile - 1) / kWarpTile;
+    unsigned grid = (unsigned)(ntiles < c->sm_count ? ntiles : c->sm_count);
+    ModelP m{c->wavenorm};
+    kern<<<grid, kWarpTile, smem, st>>>(a, m, c->pri, d, t);
+  }
+};
+
+template <bool THIN, bool ALPHA, bool UNUSED>
+struct LaunchFnu {
+  static void run(mbb_ctx* c, const EvalArgs& a, const double* freq, int nfreq, int scalar_path) {
+    dim3 grid((unsigned)((nfreq + 255) / 256), (unsigned)a.n);
+    ModelP m{c->wavenorm};
+    fnu_kernel<THIN, ALPHA><<<grid, 256, 0, c->stream>>>(a, m, freq, nfreq, scalar_path);
+  }
+};
+
+template <bool THIN, bool ALPHA, bool UNUSED>
+struct LaunchConsts {
+  static void run(mbb_ctx* c, const EvalArgs& a, int want_peak) {
+    const unsigned grid = (unsigned)((a.n + 127) / 128);
+    ModelP m{c->wavenorm};
+    sed_consts_kernel<THIN, ALPHA><<<grid, 128, 0, c->stream>>>(a, m, want_peak);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int mbb_version(void) { return 100; }
+
+const char* mbb_last_error(void) { return g_err.c_str(); }
+
+int mbb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+    return -1;
+  }
+  return n;
+}
+
+int mbb_ctx_create(int device_ordinal, mbb_ctx** out) {
+  if (!out) return fail("mbb_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(std::string("no usable CUDA device (there is no CPU fallback): ") +
+                (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device_ordinal < 0 || device_ordinal >= n) return fail("mbb_ctx_create: bad device ordinal");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major < 10)
+    return fail("mbb_ctx_create: kernels are built for sm_100a only; device is sm_" +
+                std::to_string(prop.major) + std::to_string(prop.minor));
+  mbb_ctx* c = new mbb_ctx();
+  c->device = device_ordinal;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  default_priors(c->pri);
+  Use u(c);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    delete c;
+    return fail("mbb_ctx_create: stream/event creation failed");
+  }
+  *out = c;
+  return 0;
+}
+
+int mbb_ctx_destroy(mbb_ctx* c) {
+  if (!c) return 0;
+  Use u(c);
+  cudaStreamSynchronize(c->stream);
+  c->d_packed.release(); c->d_off.release(); c->d_scalar.release();
+  c->d_flux.release(); c->d_ivar.release(); c->d_cinv.release();
+  c->h_in.release(); c->h_out.release(); c->h_st.release(); c->h_src.release();
+  c->d_in.release(); c->d_out.release(); c->d_aux0.release(); c->d_aux1.release();
+  c->d_st.release(); c->d_src.release(); c->d_owner.release(); c->d_work.release();
+  c->d_count.release();
+  for (auto& sl : c->slots) {
+    sl.hin.release(); sl.hout.release(); sl.hst.release(); sl.hsrc.release();
+    sl.din.release(); sl.dout.release(); sl.dst.release(); sl.dsrc.release();
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.s) cudaStreamDestroy(sl.s);
+  }
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int mbb_sync(mbb_ctx* c) {
+  if (!c) return fail("null context");
+  Use u(c);
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int64_t mbb_launch_count(const mbb_ctx* c) { return c ? c->launches : 0; }
+
+uint64_t mbb_stream_handle(const mbb_ctx* c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+
+int mbb_last_kernel_ms(mbb_ctx* c, float* ms) {
+  if (!c || !ms) return fail("null argument");
+  if (!c->timed) return fail("no timed call yet");
+  Use u(c);
+  CK(cudaEventSynchronize(c->ev1));
+  CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+
+int mbb_set_model(mbb_ctx* c, double wavenorm, int opthin, int noalpha) {
+  if (!c) return fail("null context");
+  if (!(wavenorm > 0.0)) return fail("wavenorm must be positive");
+  const bool changed = wavenorm != c->wavenorm;
+  c->wavenorm = wavenorm;
+  c->opthin = opthin ? 1 : 0;
+  c->noalpha = noalpha ? 1 : 0;
+  if (changed && c->bands_set) return fail("set the model before the bands (tables depend on wavenorm)");
+  return 0;
+}
+
+int mbb_set_math_mode(mbb_ctx* c, int mode) {
+  if (!c) return fail("null context");
+  if (mode != MBB_MATH_FAITHFUL && mode != MBB_MATH_FAST) return fail("unknown math mode");
+  c->math_mode = mode;
+  return 0;
+}
+
+int mbb_set_bands(mbb_ctx* c, int nbands, const int32_t* band_off, const double* node_wave_um,
+                  const double* node_weight, const uint8_t* scalar_path) {
+  if (!c) return fail("null context");
+  if (nbands <= 0 || nbands > kMaxBands) return fail("nbands must be in 1.." + std::to_string(kMaxBands));
+  if (!band_off || !node_wave_um || !node_weight) return fail("null table pointer");
+  if (band_off[0] != 0) return fail("band_off[0] must be 0");
+  for (int b = 0; b < nbands; ++b)
+    if (band_off[b + 1] <= band_off[b]) return fail("band_off must be strictly increasing");
+  const int nn = band_off[nbands];
+  for (int i = 0; i < nn; ++i)
+    if (!(node_wave_um[i] > 0.0)) return fail("node wavelengths must be positive");
+  Use u(c);
+  CK(cudaStreamSynchronize(c->stream));
+  c->nb = nbands;
+  c->nn = nn;
+  c->nn_pad = (nn + 1) & ~1;
+  c->h_off.assign(band_off, band_off + nbands + 1);
+  c->h_scalar.assign(nbands, 0);
+  if (scalar_path)
+    for (int b = 0; b < nbands; ++b) c->h_scalar[b] = scalar_path[b] ? 1 : 0;
+  const int np = c->nn_pad;
+  c->h_packed.assign((size_t)5 * np, 0.0);
+  for (int i = 0; i < nn; ++i) {
+    const double wv = node_wave_um[i];
+    // frequency exactly as the reference forms it: um_to_GHz / wave
+    // (modified_blackbody.py:551-554)
+    c->h_packed[i] = kUmToGHz / wv;
+    c->h_packed[np + i] = node_weight[i];
+    // L = log(wave / wavenorm) as hi + lo, from the x87 80-bit logl (64-bit mantissa)
+    long double l = logl((long double)wv) - logl((long double)c->wavenorm);
+    const double hi = (double)l;
+    c->h_packed[2 * np + i] = hi;
+    c->h_packed[3 * np + i] = (double)(l - (long double)hi);
+    long double r = (long double)c->wavenorm / (long double)wv;
+    c->h_packed[4 * np + i] = (double)(r * r * r);
+  }
+  for (int i = nn; i < np; ++i) c->h_packed[i] = 1.0;   // harmless padding node, weight 0
+  CK(c->d_packed.reserve(c->h_packed.size()));
+  CK(c->d_off.reserve(nbands + 1));
+  CK(c->d_scalar.reserve(nbands));
+  CK(cudaMemcpyAsync(c->d_packed.p, c->h_packed.data(), c->h_packed.size() * sizeof(double),
+                     cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_off.p, c->h_off.data(), (nbands + 1) * sizeof(int), cudaMemcpyHostToDevice,
+                     c->stream));
+  CK(cudaMemcpyAsync(c->d_scalar.p, c->h_scalar.data(), nbands, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (nn <= kSmallMaxNodes) {
+    SmallTab& s = c->small;
+    memset(&s, 0, sizeof(s));
+    s.nb = nbands;
+    for (int i = 0; i < nn; ++i) {
+      s.freq[i] = c->h_packed[i];
+      s.w[i] = c->h_packed[np + i];
+      s.lhi[i] = c->h_packed[2 * np + i];
+      s.llo[i] = c->h_packed[3 * np + i];
+      s.rcube[i] = c->h_packed[4 * np + i];
+    }
+    for (int b = 0; b <= nbands; ++b) s.band_off[b] = band_off[b];
+    for (int b = 0; b < nbands; ++b) s.scalar_path[b] = c->h_scalar[b];
+  }
+  c->bands_set = true;
+  return 0;
+}
+
+int mbb_set_data(mbb_ctx* c, int nsrc, int nbands, const double* flux, const double* ivar,
+                 const double* cinv) {
+  if (!c) return fail("null context");
+  if (nsrc <= 0 || nbands <= 0) return fail("nsrc and nbands must be positive");
+  if (!flux) return fail("flux is NULL");
+  if ((ivar == nullptr) == (cinv == nullptr)) return fail("give exactly one of ivar / cinv");
+  Use u(c);
+  CK(cudaStreamSynchronize(c->stream));
+  const size_t n1 = (size_t)nsrc * nbands;
+  CK(c->d_flux.reserve(n1));
+  CK(cudaMemcpy(c->d_flux.p, flux, n1 * sizeof(double), cudaMemcpyHostToDevice));
+  c->has_ivar = c->has_cinv = false;
+  if (ivar) {
+    CK(c->d_ivar.reserve(n1));
+    CK(cudaMemcpy(c->d_ivar.p, ivar, n1 * sizeof(double), cudaMemcpyHostToDevice));
+    c->has_ivar = true;
+  } else {
+    const size_t n2 = n1 * nbands;
+    CK(c->d_cinv.reserve(n2));
+    CK(cudaMemcpy(c->d_cinv.p, cinv, n2 * sizeof(double), cudaMemcpyHostToDevice));
+    c->has_cinv = true;
+  }
+  c->nsrc = nsrc;
+  c->data_nb = nbands;
+  return 0;
+}
+
+int mbb_set_priors(mbb_ctx* c, const double lowlim[5], const uint8_t has_uplim[6],
+                   const double uplim[6], const uint8_t has_gprior[6], const double gmean[6],
+                   const double givar[6]) {
+  if (!c) return fail("null context");
+  if (!lowlim || !has_uplim || !uplim || !has_gprior || !gmean || !givar) return fail("null argument");
+  Priors& p = c->pri;
+  for (int i = 0; i < 5; ++i) p.lowlim[i] = lowlim[i];
+  p.any_gprior = 0;
+  for (int i = 0; i < 6; ++i) {
+    p.has_uplim[i] = has_uplim[i] ? 1 : 0;
+    p.uplim[i] = uplim[i];
+    p.has_gprior[i] = has_gprior[i] ? 1 : 0;
+    p.gmean[i] = gmean[i];
+    p.givar[i] = givar[i];
+    if (has_gprior[i]) p.any_gprior = 1;
+  }
+  return 0;
+}
+
+namespace {
+
+bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a) {
+  DataRef d;
+  d.flux = c->d_flux.p;
+  d.ivar = c->has_ivar ? c->d_ivar.p : nullptr;
+  d.cinv = c->has_cinv ? c->d_cinv.p : nullptr;
+  d.nsrc = c->nsrc;
+  d.nb = c->nb;
+  const bool thin = c->opthin != 0, alpha = c->noalpha == 0, fast = c->math_mode == MBB_MATH_FAST;
+  cudaError_t err = cudaSuccess;
+  if (c->nn <= kSmallMaxNodes) dispatch3<LaunchThread>(thin, alpha, fast, c, st, a, d, &err);
+  else dispatch3<LaunchWarp>(thin, alpha, fast, c, st, a, d, &err);
+  CK(err);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Evaluations per pipeline chunk of the host path (env MBB_B200_CHUNK overrides).
+int64_t host_chunk() {
+  static int64_t v = 0;
+  if (v == 0) {
+    const char* e = getenv("MBB_B200_CHUNK");
+    v = e ? atoll(e) : (int64_t)1 << 21;
+    if (v < 1024) v = 1024;
+  }
+  return v;
+}
+
+}  // namespace
+
+// Host path: the batch is cut into chunks that flow through three slots, each
+// with its own stream: H2D copy, kernel and D2H copy of consecutive chunks
+// overlap (two copy engines + SMs).  Caller memory that is already pinned
+// (cudaHostAlloc / cudaHostRegister / torch pin_memory) is copied from and to
+// directly; pageable memory is staged through the slot's pinned buffers.
+int mbb_loglike(mbb_ctx* c, int64_t n, const double* pars, int layout, const int32_t* src_index,
+                int64_t walkers_per_source, double* out_lnlike, int32_t* out_status, int mem) {
+  if (!c) return fail("null context");
+  if (n < 0) return fail("n is negative");
+  if (n == 0) return 0;
+  if (!pars || !out_lnlike) return fail("null pars/out pointer");
+  if (!c->bands_set) return fail("mbb_set_bands has not been called");
+  if (!c->has_ivar && !c->has_cinv) return fail("mbb_set_data has not been called");
+  if (c->data_nb != c->nb) return fail("data has a different number of bands than the band table");
+  if (layout != MBB_AOS && layout != MBB_SOA) return fail("bad layout");
+  if (!src_index) {
+    if (walkers_per_source <= 0) return fail("walkers_per_source must be positive");
+    if ((n + walkers_per_source - 1) / walkers_per_source > c->nsrc)
+      return fail("n / walkers_per_source exceeds the number of sources set");
+  }
+  Use u(c);
+  const long long wps = walkers_per_source > 0 ? walkers_per_source : 1;
+  if (mem == MBB_DEVICE) {
+    EvalArgs a{};
+    a.n = n; a.e0 = 0; a.wps = wps; a.layout = layout;
+    a.pars = pars; a.src_index = src_index; a.out = out_lnlike; a.status = out_status;
+    begin_timing(c);
+    int rc = launch_loglike(c, c->stream, a);
+    end_timing(c);
+    return rc;
+  }
+  if (src_index)
+    for (int64_t i = 0; i < n; ++i)
+      if (src_index[i] < 0 || src_index[i] >= c->nsrc) return fail("src_index out of range");
+  if (!c->slots_ready) {
+    for (auto& sl : c->slots) {
+      CK(cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    c->slots_ready = true;
+  }
+  const bool pin_in = is_pinned(pars) && is_pinned(src_index);
+  const bool pin_out = is_pinned(out_lnlike) && is_pinned(out_status);
+  const int64_t CH = n < host_chunk() ? n : host_chunk();
+  const int64_t nchunks = (n + CH - 1) / CH;
+  for (auto& sl : c->slots) sl.pend_e0 = -1;
+  auto drain = [&](mbb_ctx::Slot& sl) -> int {
+    CK(cudaStreamSynchronize(sl.s));
+    if (sl.pend_e0 >= 0 && !pin_out) {
+      memcpy(out_lnlike + sl.pend_e0, sl.hout.p, (size_t)sl.pend_n * sizeof(double));
+      if (out_status) memcpy(out_status + sl.pend_e0, sl.hst.p, (size_t)sl.pend_n * sizeof(int));
+    }
+    sl.pend_e0 = -1;
+    return 0;
+  };
+  begin_timing(c);
+  for (int64_t k = 0; k < nchunks; ++k) {
+    mbb_ctx::Slot& sl = c->slots[k % 3];
+    if (drain(sl)) return 1;
+    const int64_t e0 = k * CH;
+    const int64_t m = (n - e0) < CH ? (n - e0) : CH;
+    CK(sl.din.reserve((size_t)CH * 5));
+    CK(sl.dout.reserve((size_t)CH));
+    CK(sl.dst.reserve((size_t)CH));
+    if (k == 0) CK(cudaStreamWaitEvent(sl.s, c->ev0, 0));
+    // ---- inputs
+    if (layout == MBB_AOS) {
+      const double* src = pars + e0 * 5;
+      if (!pin_in) {
+        CK(sl.hin.reserve((size_t)CH * 5));
+        memcpy(sl.hin.p, src, (size_t)m * 5 * sizeof(double));
+        src = sl.hin.p;
+      }
+      CK(cudaMemcpyAsync(sl.din.p, src, (size_t)m * 5 * sizeof(double), cudaMemcpyHostToDevice, sl.s));
+    } else {
+      if (!pin_in) CK(sl.hin.reserve((size_t)CH * 5));
+      for (int i = 0; i < 5; ++i) {
+        const double* src = pars + (size_t)i * n + e0;
+        if (!pin_in) {
+          memcpy(sl.hin.p + (size_t)i * m, src, (size_t)m * sizeof(double));
+          src = sl.hin.p + (size_t)i * m;
+        }
+        CK(cudaMemcpyAsync(sl.din.p + (size_t)i * m, src, (size_t)m * sizeof(double),
+                           cudaMemcpyHostToDevice, sl.s));
+      }
+    }
+    EvalArgs a{};
+    a.n = m; a.e0 = e0; a.wps = wps; a.layout = layout;
+    a.pars = sl.din.p; a.src_index = nullptr; a.out = sl.dout.p; a.status = sl.dst.p;
+    if (src_index) {
+      CK(sl.dsrc.reserve((size_t)CH));
+      const int* src = src_index + e0;
+      if (!pin_in) {
+        CK(sl.hsrc.reserve((size_t)CH));
+        memcpy(sl.hsrc.p, src, (size_t)m * sizeof(int));
+        src = sl.hsrc.p;
+      }
+      CK(cudaMemcpyAsync(sl.dsrc.p, src, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, sl.s));
+      a.src_index = sl.dsrc.p;
+    }
+    // ---- kernel
+    if (launch_loglike(c, sl.s, a)) return 1;
+    // ---- outputs
+    double* dsto = out_lnlike + e0;
+    int* dsts = out_status ? out_status + e0 : nullptr;
+    if (!pin_out) {
+      CK(sl.hout.reserve((size_t)CH));
+      CK(sl.hst.reserve((size_t)CH));
+      dsto = sl.hout.p;
+      dsts = out_status ? sl.hst.p : nullptr;
+      sl.pend_e0 = e0;
+      sl.pend_n = m;
+    }
+    CK(cudaMemcpyAsync(dsto, sl.dout.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, sl.s));
+    if (dsts) CK(cudaMemcpyAsync(dsts, sl.dst.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, sl.s));
+    CK(cudaEventRecord(sl.done, sl.s));
+  }
+  for (auto& sl : c->slots) {
+    if (drain(sl)) return 1;
+  }
+  end_timing(c);
+  return 0;
+}
+
+int mbb_fnu(mbb_ctx* c, int64_t n, const double* pars, int layout, int nfreq, const double* freq_ghz,
+            int scalar_path, double* out, int32_t* out_status, int mem) {
+  if (!c) return fail("null context");
+  if (n <= 0 || nfreq <= 0) return fail("n and nfreq must be positive");
+  if (n > 65535) return fail("mbb_fnu: at most 65535 parameter vectors per call");
+  if (!pars || !freq_ghz || !out) return fail("null pointer");
+  Use u(c);
+  EvalArgs a{};
+  a.n = n;
+  a.wps = 1;
+  a.layout = layout;
+  a.src_index = nullptr;
+  const double* dfreq = freq_ghz;
+  const size_t no = (size_t)n * nfreq;
+  if (mem == MBB_DEVICE) {
+    a.pars = pars;
+    a.out = out;
+    a.status = out_status;
+  } else {
+    CK(c->h_in.reserve((size_t)n * 5 + nfreq));
+    CK(c->d_in.reserve((size_t)n * 5 + nfreq));
+    CK(c->h_out.reserve(no));
+    CK(c->d_out.reserve(no));
+    CK(c->h_st.reserve((size_t)n));
+    CK(c->d_st.reserve((size_t)n));
+    memcpy(c->h_in.p, pars, (size_t)n * 5 * sizeof(double));
+    memcpy(c->h_in.p + n * 5, freq_ghz, (size_t)nfreq * sizeof(double));
+    CK(cudaMemcpyAsync(c->d_in.p, c->h_in.p, ((size_t)n * 5 + nfreq) * sizeof(double),
+                       cudaMemcpyHostToDevice, c->stream));
+    a.pars = c->d_in.p;
+    dfreq = c->d_in.p + n * 5;
+    a.out = c->d_out.p;
+    a.status = c->d_st.p;
+  }
+  begin_timing(c);
+  dispatch3<LaunchFnu>(c->opthin != 0, c->noalpha == 0, false, c, a, dfreq, nfreq, scalar_path);
+  end_timing(c);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  if (mem != MBB_DEVICE) {
+    CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, no * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_st.p, c->d_st.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_out.p, no * sizeof(double));
+    if (out_status) memcpy(out_status, c->h_st.p, (size_t)n * sizeof(int));
+  }
+  return 0;
+}
+
+int mbb_sed_consts(mbb_ctx* c, int64_t n, const double* pars, int layout, int want_peak,
+                   double* out_consts, int32_t* out_status, int mem) {
+  if (!c) return fail("null context");
+  if (n <= 0) return fail("n must be positive");
+  if (!pars || !out_consts) return fail("null pointer");
+  Use u(c);
+  EvalArgs a{};
+  a.n = n;
+  a.wps = 1;
+  a.layout = layout;
+  a.src_index = nullptr;
+  if (mem == MBB_DEVICE) {
+    a.pars = pars;
+    a.out = out_consts;
+    a.status = out_status;
+  } else {
+    CK(c->h_in.reserve((size_t)n * 5));
+    CK(c->d_in.reserve((size_t)n * 5));
+    CK(c->h_out.reserve((size_t)n * 6));
+    CK(c->d_out.reserve((size_t)n * 6));
+    CK(c->h_st.reserve((size_t)n));
+    CK(c->d_st.reserve((size_t)n));
+    memcpy(c->h_in.p, pars, (size_t)n * 5 * sizeof(double));
+    CK(cudaMemcpyAsync(c->d_in.p, c->h_in.p, (size_t)n * 5 * sizeof(double), cudaMemcpyHostToDevice,
+                       c->stream));
+    a.pars = c->d_in.p;
+    a.out = c->d_out.p;
+    a.status = c->d_st.p;
+  }
+  begin_timing(c);
+  dispatch3<LaunchConsts>(c->opthin != 0, c->noalpha == 0, false, c, a, want_peak);
+  end_timing(c);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  if (mem != MBB_DEVICE) {
+    CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaMemcpyAsync(c->h_st.p, c->d_st.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(out_consts, c->h_out.p, (size_t)n * 6 * sizeof(double));
+    if (out_status) memcpy(out_status, c->h_st.p, (size_t)n * sizeof(int));
+  }
+  return 0;
+}
+
+int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* chain, int which,
+                   double z, double dl_mpc, double lir_min_um, double lir_max_um, double kappa,
+                   double kappa_wave_um, double* out_peak, double* out_lir, double* out_dustmass,
+                   int32_t* out_status, int mem) {
+  if (!c) return fail("null context");
+  if (nwalkers <= 0 || nsteps <= 0) return fail("empty chain");
+  if (!chain) return fail("chain is NULL");
+  const int64_t ns = nwalkers * nsteps;
+  if (ns >= (int64_t)1 << 31) return fail("chain too long for one call (>= 2^31 samples); shard it");
+  if ((which & 1) && !out_peak) return fail("out_peak is NULL");
+  if ((which & 2) && !out_lir) return fail("out_lir is NULL");
+  if ((which & 4) && !out_dustmass) return fail("out_dustmass is NULL");
+  if (which & 2) return fail("L_IR integration is not built into this revision of the library");
+  (void)lir_min_um; (void)lir_max_um;
+  Use u(c);
+  const double* dchain = chain;
+  double *dpk = out_peak, *ddm = out_dustmass;
+  int* dst = out_status;
+  if (mem != MBB_DEVICE) {
+    CK(c->d_in.reserve((size_t)ns * 5));
+    CK(cudaMemcpyAsync(c->d_in.p, chain, (size_t)ns * 5 * sizeof(double), cudaMemcpyHostToDevice,
+                       c->stream));
+    dchain = c->d_in.p;
+    if (which & 1) { CK(c->d_aux0.reserve((size_t)ns)); dpk = c->d_aux0.p; }
+    if (which & 4) { CK(c->d_aux1.reserve((size_t)ns)); ddm = c->d_aux1.p; }
+    CK(c->d_st.reserve((size_t)ns));
+    dst = c->d_st.p;
+  }
+  CK(c->d_owner.reserve((size_t)ns));
+  CK(c->d_work.reserve((size_t)ns));
+  CK(c->d_count.reserve(1));
+  CK(cudaMemsetAsync(c->d_count.p, 0, sizeof(unsigned), c->stream));
+  // results.compute_dustmass precomputation (results.py:778-793)
+  DustConsts dc;
+  {
+    const double dl = dl_mpc * 3.0856775814913673e24;
+    dc.dl2 = dl * dl;
+    dc.opz = 1.0 + z;
+    const double wavenorm_rest = c->wavenorm / dc.opz;
+    const double nunorm_rest = 299792458e6 / wavenorm_rest;
+    dc.temp_fac = 6.6260693e-27 * nunorm_rest / 1.38065e-16;
+    dc.bnu_fac = 2 * 6.6260693e-27 * pow(nunorm_rest, 3) / pow(299792458e2, 2);
+    dc.knu_fac = wavenorm_rest / kappa_wave_um;
+    dc.kappa = kappa;
+    dc.wavenorm = c->wavenorm;
+    dc.opthin = c->opthin;
+  }
+  begin_timing(c);
+  chain_dedupe_kernel<<<(unsigned)((nwalkers + 63) / 64), 64, 0, c->stream>>>(
+      dchain, nwalkers, nsteps, c->d_owner.p, c->d_work.p, c->d_count.p);
+  chain_unique_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(
+      dchain, c->d_work.p, c->d_count.p, which, dc, dpk, ddm, dst);
+  chain_fill_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(
+      c->d_owner.p, nwalkers, nsteps, (which & 1) ? dpk : nullptr, nullptr, (which & 4) ? ddm : nullptr,
+      dst);
+  end_timing(c);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  if (mem != MBB_DEVICE) {
+    if (which & 1)
+      CK(cudaMemcpyAsync(out_peak, dpk, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (which & 4)
+      CK(cudaMemcpyAsync(out_dustmass, ddm, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost,
+                         c->stream));
+    if (out_status)
+      CK(cudaMemcpyAsync(out_status, dst, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int mbb_fp64_peak(mbb_ctx* c, int iters, double* tflops) {
+  if (!c || !tflops) return fail("null argument");
+  if (iters <= 0) iters = 20000;
+  Use u(c);
+  CK(c->d_out.reserve(16));
+  const int blocks = c->sm_count * 8, threads = 256;
+  fp64_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->d_out.p, 1000, 1.0);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    begin_timing(c);
+    fp64_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->d_out.p, iters, 1.0 + rep);
+    end_timing(c);
+    c->launches += 1;
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return 0;
+}
+
+}  // extern "C"

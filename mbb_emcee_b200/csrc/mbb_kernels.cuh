@@ -1,0 +1,480 @@
+// sm_100a kernels of the modified-blackbody likelihood hot path.
+//
+//   loglike_thread_kernel  one thread per evaluation; node tables (<= 32 nodes:
+//                          delta / few-node configs such as BASELINE cfg1/cfg5)
+//                          travel in the kernel parameter block, i.e. the
+//                          constant bank -- uniform across the warp, no loads.
+//   loglike_warp_kernel    persistent, one CTA per SM.  The passband node
+//                          tables (up to ~5.6k nodes) are staged ONCE per CTA
+//                          into shared memory by a TMA bulk copy
+//                          (cp.async.bulk + mbarrier).  Each tile of 512
+//                          evaluations runs in two phases: (1) thread-per-
+//                          evaluation setup (limits, per-walker constants incl.
+//                          the merge-point root solve, prior terms incl. the
+//                          lambda_peak solve) -> shared memory; (2) warp-per-
+//                          evaluation node loop, lanes striding the nodes of a
+//                          band, warp-shuffle reduction per band, then the
+//                          chi-square (diagonal or full inverse covariance).
+//   fnu_kernel, sed_consts_kernel, chain_* kernels: the API's other entries.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mbb_model.cuh"
+
+namespace mbb {
+
+constexpr int kSmallMaxNodes = 32;
+constexpr int kMaxBands = kMaxBandsPerThread;
+constexpr int kWarpTile = 512;     // evaluations per tile == threads per CTA
+constexpr int kSedcStride = 12;    // doubles per evaluation kept in smem
+
+struct EvalArgs {
+  const double* pars;
+  const int* src_index;
+  double* out;
+  int* status;
+  long long n;
+  long long e0;       // global index of evaluation 0 (chunked host path)
+  long long wps;      // walkers per source (when src_index == nullptr)
+  int layout;         // 0 = [n][5], 1 = [5][n]
+};
+
+struct ModelP {
+  double wavenorm;
+};
+
+struct DataRef {
+  const double* flux;   // [nsrc][nb]
+  const double* ivar;   // [nsrc][nb] or null
+  const double* cinv;   // [nsrc][nb][nb] or null
+  int nsrc;
+  int nb;
+};
+
+struct SmallTab {
+  double freq[kSmallMaxNodes];
+  double w[kSmallMaxNodes];
+  double lhi[kSmallMaxNodes];
+  double llo[kSmallMaxNodes];
+  double rcube[kSmallMaxNodes];
+  int band_off[kSmallMaxNodes + 1];
+  unsigned char scalar_path[kSmallMaxNodes];
+  int nb;
+};
+
+struct NodeTab {
+  const double* packed;   // [freq | w | lhi | llo | rcube], each nn_pad doubles
+  const int* band_off;    // nb + 1
+  const unsigned char* scalar_path;
+  int nb;
+  int nn;
+  int nn_pad;             // even, so every sub-array is 16-byte aligned
+  int in_smem;            // stage the packed table into shared memory
+};
+
+__device__ __forceinline__ void load_pars(const EvalArgs& a, long long e, double p[5]) {
+  if (a.layout == 0) {
+    const double* q = a.pars + e * 5;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) p[i] = __ldg(q + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) p[i] = __ldg(a.pars + (long long)i * a.n + e);
+  }
+}
+
+__device__ __forceinline__ long long source_of(const EvalArgs& a, long long e) {
+  return a.src_index ? (long long)__ldg(a.src_index + e) : (a.e0 + e) / a.wps;
+}
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ---------------------------------------------------------------------------
+// thread-per-evaluation kernel
+// ---------------------------------------------------------------------------
+template <bool THIN, bool ALPHA, bool FAST>
+__global__ void __launch_bounds__(256)
+loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
+                      const SmallTab t) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  double p[5];
+  load_pars(a, e, p);
+  const long long src = source_of(a, e);
+  int st;
+  const double lnl = loglike_one<THIN, ALPHA, FAST>(
+      p, m.wavenorm, pr, t, d.flux + src * d.nb, d.ivar ? d.ivar + src * d.nb : nullptr,
+      d.cinv ? d.cinv + src * (long long)d.nb * d.nb : nullptr, st);
+  a.out[e] = lnl;
+  if (a.status) a.status[e] = st;
+}
+
+// ---------------------------------------------------------------------------
+// TMA bulk copy + mbarrier helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Shared-memory footprint of the warp kernel (bytes); host and device agree.
+__host__ __device__ inline size_t warp_kernel_smem(int nn_pad, int nb, bool tables_in_smem) {
+  size_t doubles = (tables_in_smem ? (size_t)5 * nn_pad : 0)    // node tables
+                   + (size_t)kWarpTile * kSedcStride              // per-eval constants
+                   + (size_t)kWarpTile * 2                        // pen, gp
+                   + (size_t)(kWarpTile / 32) * kMaxBands         // per-warp diff scratch
+                   + 2;                                           // mbarrier (+pad)
+  size_t ints = (size_t)kWarpTile                                 // status
+                + (size_t)(kMaxBands + 1);                        // band offsets
+  return doubles * 8 + ints * 4 + kMaxBands;                      // + scalar_path bytes
+}
+
+// ---------------------------------------------------------------------------
+// warp-per-evaluation persistent kernel
+// ---------------------------------------------------------------------------
+template <bool THIN, bool ALPHA, bool FAST>
+__global__ void __launch_bounds__(kWarpTile, 1)
+loglike_warp_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
+                    const NodeTab t) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  const int nn_pad = t.nn_pad;
+  double* tab = sm;                                   // 5 * nn_pad (if in_smem)
+  double* sedc = tab + (t.in_smem ? 5 * nn_pad : 0);  // kWarpTile * kSedcStride
+  double* s_pen = sedc + kWarpTile * kSedcStride;
+  double* s_gp = s_pen + kWarpTile;
+  double* s_diff = s_gp + kWarpTile;                  // (kWarpTile/32) * kMaxBands
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_diff + (kWarpTile / 32) * kMaxBands);
+  int* s_status = reinterpret_cast<int*>(bar + 2);
+  int* s_off = s_status + kWarpTile;
+  unsigned char* s_scalar = reinterpret_cast<unsigned char*>(s_off + kMaxBands + 1);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nb = t.nb;
+
+  // ---- stage the passband tables once per CTA (TMA bulk copy) -------------
+  if (t.in_smem) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)(5 * nn_pad * sizeof(double));
+      mbar_expect_tx(bar, bytes);
+      // <= 64 KiB per copy keeps each request comfortably inside the engine's limits
+      unsigned done = 0;
+      while (done < bytes) {
+        unsigned chunk = bytes - done;
+        if (chunk > 65536u) chunk = 65536u;
+        bulk_g2s(reinterpret_cast<unsigned char*>(tab) + done,
+                 reinterpret_cast<const unsigned char*>(t.packed) + done, chunk, bar);
+        done += chunk;
+      }
+    }
+  }
+  for (int i = tid; i <= nb; i += blockDim.x) s_off[i] = t.band_off[i];
+  for (int i = tid; i < nb; i += blockDim.x) s_scalar[i] = t.scalar_path[i];
+  if (t.in_smem) mbar_wait(bar, 0);
+  __syncthreads();
+
+  const double* g_tab = t.in_smem ? tab : t.packed;
+  const double* n_freq = g_tab;
+  const double* n_w = g_tab + nn_pad;
+  const double* n_lhi = g_tab + 2 * nn_pad;
+  const double* n_llo = g_tab + 3 * nn_pad;
+  const double* n_rc = g_tab + 4 * nn_pad;
+
+  const long long ntiles = (a.n + kWarpTile - 1) / kWarpTile;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // ---- phase 1: one thread per evaluation ------------------------------
+    {
+      const long long e = tile * kWarpTile + tid;
+      int st = ST_OK;
+      double pen = 0.0, gp = 0.0;
+      double* c = sedc + tid * kSedcStride;
+      if (e < a.n) {
+        double p[5];
+        load_pars(a, e, p);
+        if (below_lowlim(pr, p)) {
+          st = ST_BELOW_LOWLIM;
+        } else {
+          Sed s;
+          sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
+          if (FAST) sed_setup_fast<THIN, ALPHA>(s, m.wavenorm);
+          st = s.status;
+          if (st == ST_OK) prior_terms<THIN>(pr, p, s, pen, gp, st);
+          c[0] = s.hokt9; c[1] = s.hokt_e9; c[2] = s.beta; c[3] = s.alpha;
+          c[4] = s.x0; c[5] = s.normfac; c[6] = s.xmerge; c[7] = s.kappa;
+          c[8] = s.amp_grey; c[9] = s.amp_pow; c[10] = s.q_hi; c[11] = s.q_lo;
+        }
+      } else {
+        st = -1;   // beyond the end
+      }
+      s_pen[tid] = pen;
+      s_gp[tid] = gp;
+      s_status[tid] = st;
+    }
+    __syncthreads();
+
+    // ---- phase 2: one warp per evaluation, lanes stride the nodes --------
+    for (int k = 0; k < 32; ++k) {
+      const int slot = warp * 32 + k;
+      const int st = s_status[slot];
+      if (st < 0) break;
+      const long long e = tile * kWarpTile + slot;
+      if (st != ST_OK) {
+        if (lane == 0) {
+          a.out[e] = (st == ST_BELOW_LOWLIM) ? -kInf : qnan();
+          if (a.status) a.status[e] = st;
+        }
+        continue;
+      }
+      const double* c = sedc + slot * kSedcStride;
+      Sed s;
+      s.hokt9 = c[0]; s.hokt_e9 = c[1]; s.beta = c[2]; s.alpha = c[3];
+      s.x0 = c[4]; s.normfac = c[5]; s.xmerge = c[6]; s.kappa = c[7];
+      s.amp_grey = c[8]; s.amp_pow = c[9]; s.q_hi = c[10]; s.q_lo = c[11];
+      const long long src = source_of(a, e);
+      const double* fl = d.flux + src * d.nb;
+      double* wdiff = s_diff + warp * kMaxBands;
+      double chi = 0.0;
+      for (int b = 0; b < nb; ++b) {
+        const double hk = s_scalar[b] ? s.hokt_e9 : s.hokt9;
+        const int i1 = s_off[b + 1];
+        double acc = 0.0;
+        for (int i = s_off[b] + lane; i < i1; i += 32) {
+          const double cx = hk * n_freq[i];
+          double f;
+          if (FAST) f = node_fnu_fast<THIN, ALPHA>(s, cx, n_lhi[i], n_llo[i], n_rc[i]);
+          else f = node_fnu<THIN, ALPHA>(s, cx);
+          acc = fma(f, n_w[i], acc);
+        }
+        acc = warp_sum(acc);
+        const double df = __ldg(fl + b) - acc;
+        if (d.cinv) {
+          if (lane == 0) wdiff[b] = df;
+        } else {
+          chi = fma(df * df, __ldg(d.ivar + src * d.nb + b), chi);
+        }
+      }
+      if (d.cinv) {
+        __syncwarp();
+        const double* ci = d.cinv + src * (long long)nb * nb;
+        double part = 0.0;
+        for (int r = lane; r < nb; r += 32) {
+          double row = 0.0;
+          for (int cc = 0; cc < nb; ++cc) row = fma(__ldg(ci + r * nb + cc), wdiff[cc], row);
+          part = fma(wdiff[r], row, part);
+        }
+        chi = warp_sum(part);
+        __syncwarp();
+      }
+      if (lane == 0) {
+        double lnl = -0.5 * chi;
+        lnl += s_pen[slot];
+        if (pr.any_gprior) lnl += s_gp[slot];
+        int so = ST_OK;
+        if (lnl != lnl) so = ST_NONFINITE;
+        a.out[e] = lnl;
+        if (a.status) a.status[e] = so;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// f_nu on a common frequency grid: out[n][nfreq]  (modified_blackbody.__call__)
+// grid = (ceil(nfreq/256), n); the per-walker constants are computed once per
+// block by thread 0 and broadcast through shared memory.
+// ---------------------------------------------------------------------------
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(256)
+fnu_kernel(const EvalArgs a, const ModelP m, const double* __restrict__ freq, int nfreq,
+           int scalar_path) {
+  __shared__ Sed s;
+  const long long e = blockIdx.y;
+  if (threadIdx.x == 0) {
+    double p[5];
+    load_pars(a, e, p);
+    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
+    if (a.status && blockIdx.x == 0) a.status[e] = s.status;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nfreq) return;
+  double v;
+  if (s.status != ST_OK) {
+    v = qnan();
+  } else {
+    const double cx = (scalar_path ? s.hokt_e9 : s.hokt9) * __ldg(freq + i);
+    v = node_fnu<THIN, ALPHA>(s, cx);
+  }
+  a.out[e * nfreq + i] = v;
+}
+
+// per-walker constants (+ optional peak wavelength): out[n][6]
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(128)
+sed_consts_kernel(const EvalArgs a, const ModelP m, int want_peak) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  double p[5];
+  load_pars(a, e, p);
+  Sed s;
+  sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
+  int st = s.status;
+  double peak = 0.0;
+  if (want_peak && st == ST_OK) peak = max_wave<THIN>(s.T, s.beta, s.x0, st);
+  double* o = a.out + e * 6;
+  o[0] = s.normfac; o[1] = s.xmerge; o[2] = s.kappa; o[3] = s.x0; o[4] = s.xnorm; o[5] = peak;
+  if (a.status) a.status[e] = st;
+}
+
+// ---------------------------------------------------------------------------
+// chain post-processing (results.py:534-801)
+// ---------------------------------------------------------------------------
+// Pass 1, one thread per walker: the sequential allclose-dedupe of _map_chain
+// (results.py:553-566).  owner[w][t] = step index whose value step t reuses
+// (t itself when it must be computed).  np.allclose(prev, cur): every
+// |prev_i - cur_i| <= 1e-8 + 1e-5*|cur_i|.
+__global__ void chain_dedupe_kernel(const double* __restrict__ chain, long long nwalkers,
+                                    long long nsteps, int* __restrict__ owner,
+                                    int* __restrict__ work, unsigned* __restrict__ nwork) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwalkers) return;
+  const double* base = chain + w * nsteps * 5;
+  double prev[5];
+  long long prev_t = 0;
+  for (long long tt = 0; tt < nsteps; ++tt) {
+    double cur[5];
+    bool same = tt > 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      cur[i] = base[tt * 5 + i];
+      if (tt > 0) same = same && (fabs(prev[i] - cur[i]) <= 1e-8 + 1e-5 * fabs(cur[i]));
+    }
+    if (same) {
+      owner[w * nsteps + tt] = (int)prev_t;
+    } else {
+      owner[w * nsteps + tt] = (int)tt;
+      prev_t = tt;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) prev[i] = cur[i];
+      unsigned slot = atomicAdd(nwork, 1u);
+      work[slot] = (int)(w * nsteps + tt);   // flat sample index (fits: checked on host)
+    }
+  }
+}
+
+struct DustConsts {   // results.compute_dustmass precomputation (results.py:778-793)
+  double opz, bnu_fac, temp_fac, knu_fac, dl2, kappa, wavenorm;
+  int opthin;
+};
+
+// Pass 2: one thread per unique sample.  Peak wavelength reproduces the
+// reference's compute_peaklambda, which always builds the SED optically thick
+// with alpha (results.py:574-580 never forwards opthin/noalpha) -- max_wave
+// itself does not depend on alpha.
+__global__ void __launch_bounds__(128)
+chain_unique_kernel(const double* __restrict__ chain, const int* __restrict__ work,
+                    const unsigned* __restrict__ nwork, int which, DustConsts dc,
+                    double* __restrict__ out_peak, double* __restrict__ out_dust,
+                    int* __restrict__ status) {
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *nwork) return;
+  const long long idx = work[j];
+  const double* p = chain + idx * 5;
+  const double T = p[0], beta = p[1], lambda0 = p[2], fnorm = p[4];
+  int st = ST_OK;
+  if (which & 1) {
+    const double hcokt = kH * kCum / (kK * T);
+    const double x0 = hcokt / lambda0;
+    double pk = qnan();
+    if (!(p[3] > 0.0)) st = ST_BAD_ALPHA;           // the thick+alpha ctor would raise
+    else if (!(beta >= 0.0)) st = ST_BAD_BETA;
+    else pk = max_wave<false>(T, beta, x0, st);
+    out_peak[idx] = pk;
+  }
+  if (which & 4) {
+    // results._dmass_calc (results.py:726-744)
+    const double msolar8 = 1.97792e41;
+    const double Tr = T * dc.opz;
+    const double S_nu = fnorm * 1e-26;
+    const double B_nu = dc.bnu_fac / expm1(dc.temp_fac / Tr);
+    const double K_nu = 10.0 * dc.kappa * pow(dc.knu_fac, -beta);
+    double dm = dc.dl2 * S_nu / (dc.opz * K_nu * B_nu * msolar8);
+    if (!dc.opthin) {
+      const double tau = pow(lambda0 / dc.wavenorm, beta);
+      dm *= -tau / expm1(-tau);
+    }
+    out_dust[idx] = dm;
+  }
+  if (status) status[idx] = st;
+}
+
+// Pass 3: repeated steps copy their owner's value.
+__global__ void chain_fill_kernel(const int* __restrict__ owner, long long nwalkers,
+                                  long long nsteps, double* __restrict__ a0,
+                                  double* __restrict__ a1, double* __restrict__ a2,
+                                  int* __restrict__ status) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nwalkers * nsteps) return;
+  const long long w = i / nsteps;
+  const long long o = w * nsteps + owner[i];
+  if (o == i) return;
+  if (a0) a0[i] = a0[o];
+  if (a1) a1[i] = a1[o];
+  if (a2) a2[i] = a2[o];
+  if (status) status[i] = status[o];
+}
+
+// ---------------------------------------------------------------------------
+// FP64 roofline denominator: 8 independent DFMA chains per thread.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3;
+  double a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 0.999999, c = 1e-9 * threadIdx.x;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 12345.678) out[0] = r;   // keep the chains alive
+}
+
+}  // namespace mbb

@@ -1,0 +1,133 @@
+// TEST INFRASTRUCTURE -- host emulation of the device model code.
+//
+// Compiles mbb_emcee_b200/csrc/mbb_model.cuh (the exact source the CUDA
+// kernels are built from) with g++ and runs it in plain host loops, so the CPU
+// test-suite can check the *logic* of the device code (setup, node formulas in
+// both arithmetic modes, root solves, limits/priors, chi-square) against the
+// oracle without a GPU.  libm replaces libdevice, so agreement with the GPU is
+// to rounding, not bit for bit.  Built into tests/_hostemu/ (git-ignored);
+// NEVER loaded by the product package -- the product has no CPU path.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "../../mbb_emcee_b200/csrc/mbb_model.cuh"
+
+using namespace mbb;
+
+namespace {
+template <bool THIN, bool ALPHA, bool FAST>
+void run_loglike(long long n, const double* pars, double wavenorm, const Priors& pr, const TabView& t,
+                 const double* flux, const double* ivar, const double* cinv, long long wps, double* out,
+                 int* status) {
+  const int nb = t.nb;
+  for (long long e = 0; e < n; ++e) {
+    const long long src = e / wps;
+    int st;
+    out[e] = loglike_one<THIN, ALPHA, FAST>(pars + 5 * e, wavenorm, pr, t, flux + src * nb,
+                                             ivar ? ivar + src * nb : nullptr,
+                                             cinv ? cinv + src * nb * nb : nullptr, st);
+    status[e] = st;
+  }
+}
+
+template <bool THIN, bool ALPHA>
+void run_consts(long long n, const double* pars, double wavenorm, int want_peak, double* out, int* status) {
+  for (long long e = 0; e < n; ++e) {
+    const double* p = pars + 5 * e;
+    Sed s;
+    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+    int st = s.status;
+    double peak = 0.0;
+    if (want_peak && st == ST_OK) peak = max_wave<THIN>(s.T, s.beta, s.x0, st);
+    double* o = out + 6 * e;
+    o[0] = s.normfac; o[1] = s.xmerge; o[2] = s.kappa; o[3] = s.x0; o[4] = s.xnorm; o[5] = peak;
+    status[e] = st;
+  }
+}
+
+template <bool THIN, bool ALPHA>
+void run_fnu(long long n, const double* pars, double wavenorm, int nfreq, const double* freq, int scalar_path,
+             int fast, double* out) {
+  for (long long e = 0; e < n; ++e) {
+    const double* p = pars + 5 * e;
+    Sed s;
+    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+    if (fast) sed_setup_fast<THIN, ALPHA>(s, wavenorm);
+    for (int i = 0; i < nfreq; ++i) {
+      const double cx = (scalar_path ? s.hokt_e9 : s.hokt9) * freq[i];
+      double v;
+      if (s.status != ST_OK) {
+        v = kInf - kInf;
+      } else if (fast) {
+        const double wave = kUmToGHz / freq[i];
+        long double l = logl((long double)wave) - logl((long double)wavenorm);
+        const double hi = (double)l, lo = (double)(l - (long double)hi);
+        long double r = (long double)wavenorm / (long double)wave;
+        v = node_fnu_fast<THIN, ALPHA>(s, cx, hi, lo, (double)(r * r * r));
+      } else {
+        v = node_fnu<THIN, ALPHA>(s, cx);
+      }
+      out[e * nfreq + i] = v;
+    }
+  }
+}
+}  // namespace
+
+#define DISPATCH2(fn, thin, alpha, ...)                         \
+  do {                                                          \
+    if (thin) { if (alpha) fn<true, true>(__VA_ARGS__); else fn<true, false>(__VA_ARGS__); } \
+    else { if (alpha) fn<false, true>(__VA_ARGS__); else fn<false, false>(__VA_ARGS__); }    \
+  } while (0)
+
+extern "C" {
+
+struct EmuPriors {
+  double lowlim[5], uplim[6], gmean[6], givar[6];
+  unsigned char has_uplim[6], has_gprior[6];
+};
+
+void emu_loglike(int thin, int alpha, int fast, long long n, const double* pars, double wavenorm,
+                 const EmuPriors* ep, int nb, const int* band_off, const double* wave, const double* weight,
+                 const unsigned char* scalar_path, const double* flux, const double* ivar, const double* cinv,
+                 long long wps, double* out, int* status) {
+  Priors pr;
+  pr.any_gprior = 0;
+  for (int i = 0; i < 5; ++i) pr.lowlim[i] = ep->lowlim[i];
+  for (int i = 0; i < 6; ++i) {
+    pr.uplim[i] = ep->uplim[i]; pr.gmean[i] = ep->gmean[i]; pr.givar[i] = ep->givar[i];
+    pr.has_uplim[i] = ep->has_uplim[i]; pr.has_gprior[i] = ep->has_gprior[i];
+    if (ep->has_gprior[i]) pr.any_gprior = 1;
+  }
+  const int nn = band_off[nb];
+  std::vector<double> freq(nn), lhi(nn), llo(nn), rc(nn);
+  for (int i = 0; i < nn; ++i) {       // same table construction as mbb_set_bands (mbb_capi.cu)
+    freq[i] = kUmToGHz / wave[i];
+    long double l = logl((long double)wave[i]) - logl((long double)wavenorm);
+    lhi[i] = (double)l;
+    llo[i] = (double)(l - (long double)lhi[i]);
+    long double r = (long double)wavenorm / (long double)wave[i];
+    rc[i] = (double)(r * r * r);
+  }
+  TabView t{freq.data(), weight, lhi.data(), llo.data(), rc.data(), band_off, scalar_path, nb};
+#define GO(T, A, F) run_loglike<T, A, F>(n, pars, wavenorm, pr, t, flux, ivar, cinv, wps, out, status)
+  if (thin) {
+    if (alpha) { if (fast) GO(true, true, true); else GO(true, true, false); }
+    else { if (fast) GO(true, false, true); else GO(true, false, false); }
+  } else {
+    if (alpha) { if (fast) GO(false, true, true); else GO(false, true, false); }
+    else { if (fast) GO(false, false, true); else GO(false, false, false); }
+  }
+#undef GO
+}
+
+void emu_consts(int thin, int alpha, long long n, const double* pars, double wavenorm, int want_peak,
+                double* out, int* status) {
+  DISPATCH2(run_consts, thin, alpha, n, pars, wavenorm, want_peak, out, status);
+}
+
+void emu_fnu(int thin, int alpha, long long n, const double* pars, double wavenorm, int nfreq,
+             const double* freq, int scalar_path, int fast, double* out) {
+  DISPATCH2(run_fnu, thin, alpha, n, pars, wavenorm, nfreq, freq, scalar_path, fast, out);
+}
+}

@@ -1,0 +1,82 @@
+"""TEST INFRASTRUCTURE: ctypes wrapper of the host-emulation build of the
+device model code (tests/hostemu/emu.cpp).  Never used by the product."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(HERE, "_hostemu", "libmbb_hostemu.so")
+_lib = None
+
+
+class EmuPriors(ctypes.Structure):
+    _fields_ = [("lowlim", ctypes.c_double * 5), ("uplim", ctypes.c_double * 6),
+                ("gmean", ctypes.c_double * 6), ("givar", ctypes.c_double * 6),
+                ("has_uplim", ctypes.c_ubyte * 6), ("has_gprior", ctypes.c_ubyte * 6)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s"])
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _c(a, dt=np.float64):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def priors_struct(lowlim, has_uplim, uplim, has_gprior, gmean, givar):
+    ep = EmuPriors()
+    for i in range(5):
+        ep.lowlim[i] = float(lowlim[i])
+    for i in range(6):
+        ep.uplim[i] = float(uplim[i])
+        ep.gmean[i] = float(gmean[i])
+        ep.givar[i] = float(givar[i])
+        ep.has_uplim[i] = 1 if has_uplim[i] else 0
+        ep.has_gprior[i] = 1 if has_gprior[i] else 0
+    return ep
+
+
+def loglike(opthin, noalpha, fast, pars, wavenorm, ep, band_off, wave, weight, scalar_path,
+            flux, ivar=None, cinv=None, wps=None):
+    P = _c(pars).reshape(-1, 5)
+    n = P.shape[0]
+    out = np.empty(n)
+    st = np.empty(n, dtype=np.int32)
+    off = _c(band_off, np.int32)
+    wv, wt = _c(wave), _c(weight)
+    sp = _c(scalar_path, np.uint8)
+    fl, iv, ci = _c(flux), _c(ivar), _c(cinv)
+    lib().emu_loglike(int(opthin), int(not noalpha), int(fast), ctypes.c_longlong(n), _p(P),
+                      ctypes.c_double(wavenorm), ctypes.byref(ep), int(off.size - 1), _p(off), _p(wv),
+                      _p(wt), _p(sp), _p(fl), _p(iv), _p(ci),
+                      ctypes.c_longlong(n if wps is None else wps), _p(out), _p(st))
+    return out, st
+
+
+def consts(opthin, noalpha, pars, wavenorm, want_peak=True):
+    P = _c(pars).reshape(-1, 5)
+    n = P.shape[0]
+    out = np.empty((n, 6))
+    st = np.empty(n, dtype=np.int32)
+    lib().emu_consts(int(opthin), int(not noalpha), ctypes.c_longlong(n), _p(P),
+                     ctypes.c_double(wavenorm), int(want_peak), _p(out), _p(st))
+    return out, st
+
+
+def fnu(opthin, noalpha, pars, wavenorm, freq, scalar_path=False, fast=False):
+    P = _c(pars).reshape(-1, 5)
+    f = _c(freq)
+    out = np.empty((P.shape[0], f.size))
+    lib().emu_fnu(int(opthin), int(not noalpha), ctypes.c_longlong(P.shape[0]), _p(P),
+                  ctypes.c_double(wavenorm), int(f.size), _p(f), int(scalar_path), int(fast), _p(out))
+    return out

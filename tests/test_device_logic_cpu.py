@@ -1,0 +1,118 @@
+"""CPU: the device model source (csrc/mbb_model.cuh), compiled for the host,
+against the golden vectors of the executed reference.
+
+This checks the LOGIC the kernels are built from -- per-walker setup incl. the
+Newton (thin) and Brent (thick) merge-point solves, the four f_nu variants in
+both arithmetic modes, max_wave, limits, priors, chi-square with and without
+covariance -- before any GPU time is spent.  Tolerance: 1e-12 relative, the
+north-star bar (observed: ~1e-15)."""
+import numpy as np
+import pytest
+
+import hostemu_lib as emu
+from conftest import VARIANTS, relerr
+
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
+@pytest.mark.parametrize("wavenorm", [500.0, 250.0])
+def test_setup_constants(golden, name, opthin, noalpha, wavenorm):
+    g = golden.sed
+    tag = "%s_wn%d" % (name, int(wavenorm))
+    out, st = emu.consts(opthin, noalpha, g[tag + "_P"], wavenorm)
+    assert (st == 0).all()
+    assert relerr(out[:, 0], g[tag + "_normfac"]).max() < TOL
+    if not noalpha:
+        assert relerr(out[:, 1], g[tag + "_xmerge"]).max() < TOL
+        assert relerr(out[:, 2], g[tag + "_kappa"]).max() < TOL
+    if not opthin:
+        assert relerr(out[:, 3], g[tag + "_x0"]).max() == 0.0
+
+
+@pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
+def test_max_wave(golden, name, opthin, noalpha):
+    g = golden.sed
+    tag = name + "_wn500"
+    out, st = emu.consts(opthin, noalpha, g[tag + "_P"], 500.0, want_peak=True)
+    assert (st == 0).all()
+    assert relerr(out[:, 5], g[tag + "_maxwave"]).max() < TOL
+
+
+@pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
+@pytest.mark.parametrize("wavenorm", [500.0, 250.0])
+@pytest.mark.parametrize("fast", [False, True])
+def test_fnu(golden, name, opthin, noalpha, wavenorm, fast):
+    g = golden.sed
+    tag = "%s_wn%d" % (name, int(wavenorm))
+    freq = 299792458e-3 / g["waves"]
+    arr = emu.fnu(opthin, noalpha, g[tag + "_P"], wavenorm, freq, scalar_path=False, fast=fast)
+    assert relerr(arr, g[tag + "_fnu_array"]).max() < TOL
+    sc = emu.fnu(opthin, noalpha, g[tag + "_P"], wavenorm, freq, scalar_path=True, fast=fast)
+    assert relerr(sc, g[tag + "_fnu_scalar"]).max() < TOL
+
+
+def _setup(golden, cfgname):
+    from mbb_emcee_b200 import likelihood, synthetic
+    cfg = synthetic.CONFIGS[cfgname]
+    g = golden.like
+    like = likelihood(wavenorm=cfg["wavenorm"], noalpha=cfg["noalpha"], opthin=cfg["opthin"],
+                      response=cfg["response"])
+    like.set_phot(cfg["bands"], g[cfgname + "_flux"], g[cfgname + "_unc"])
+    if cfgname + "_cov" in g:
+        like.set_cov(g[cfgname + "_cov"])
+    for nm, v in cfg.get("uplims", []):
+        like.set_uplim(nm, v)
+    for nm, m, s in cfg.get("gpriors", []):
+        like.set_gaussian_prior(nm, m, s)
+    return cfg, like
+
+
+def _emu_like(like, P, fast):
+    off, wave, weight, scalar = like.band_tables()
+    ep = emu.priors_struct(like.lowlims, like.has_uplims, like.uplims, like.has_gpriors,
+                           like.gprior_means, like.gprior_ivars)
+    return emu.loglike(like.opthin, like.noalpha, fast, P, like.wavenorm, ep, off, wave, weight, scalar,
+                       like.data_flux, ivar=None if like.has_data_covmatrix else like._ivar,
+                       cinv=like.data_invcovmatrix)
+
+
+@pytest.mark.parametrize("cfgname", ["cfg1", "cfg2", "cfg3"])
+@pytest.mark.parametrize("fast", [False, True])
+def test_loglike(golden, cfgname, fast):
+    cfg, like = _setup(golden, cfgname)
+    g = golden.like
+    assert np.array_equal(like.uplims, g[cfgname + "_uplim"])
+    P, ref = g[cfgname + "_P"], g[cfgname + "_lnlike"]
+    ll, st = _emu_like(like, P, fast)
+    assert np.array_equal(st == 1, np.isneginf(ref))
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+    assert (st <= 1).all()
+    fin = np.isfinite(ref)
+    assert relerr(ll[fin], ref[fin]).max() < TOL
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_loglike_extra(golden, fast):
+    from mbb_emcee_b200 import likelihood
+    g = golden.like
+    like = likelihood(wavenorm=500.0)
+    like.set_phot(g["extra_wave"], g["extra_flux"], g["extra_unc"])
+    like.set_cov(g["extra_cov"])
+    like.set_gaussian_prior('beta', 1.8, 0.3)
+    like.set_uplim('lambda_peak', 300.0)
+    like.set_gaussian_prior('lambda_peak', 250.0, 40.0)
+    ll, st = _emu_like(like, g["extra_P"], fast)
+    assert (st == 0).all()
+    assert relerr(ll, g["extra_lnlike"]).max() < TOL
+
+
+def test_status_codes():
+    ep = emu.priors_struct([0, -1, 0, -1, 0], [0] * 6, [np.inf] * 6, [0] * 6, [0] * 6, [1] * 6)
+    P = np.array([[10.0, 2.0, 100.0, -1.0, 5.0],      # alpha <= 0  -> ValueError
+                  [10.0, -0.5, 100.0, 2.0, 5.0],      # beta < 0    -> ValueError
+                  [np.nan, 2.0, 100.0, 2.0, 5.0]])    # NaN
+    off = np.array([0, 1], dtype=np.int32)
+    ll, st = emu.loglike(False, False, False, P, 500.0, ep, off, [250.0], [1.0], [0], [3.0], ivar=[1.0])
+    assert list(st) == [2, 3, 9]
+    assert np.isnan(ll).all()

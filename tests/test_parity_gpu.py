@@ -1,0 +1,388 @@
+"""GPU: parity of the CUDA path with the reference, through the C ABI.
+
+Checks (all calls go product API -> ctypes -> libmbb_b200.so -> sm_100a kernels):
+  * golden vectors recorded from the executed reference (tests/golden);
+  * the CPU oracle on seeded random inputs;
+  * at BASELINE's full size (1e5 sources x 512 walkers) size-independent
+    properties plus an oracle-checked random sample;
+  * chain bit-identity under the emcee 2.2 stretch move for a fixed RNG seed.
+
+Tolerance (north star): 1e-12 relative on f_nu and log-likelihood.
+"""
+import numpy as np
+import pytest
+
+from conftest import VARIANTS, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mbb_emcee_b200 import _native
+    return _native.Context(0)
+
+
+# --------------------------------------------------------------------------- SED
+@pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
+@pytest.mark.parametrize("wavenorm", [500.0, 250.0])
+def test_fnu_and_constants_golden(ctx, golden, name, opthin, noalpha, wavenorm):
+    g = golden.sed
+    tag = "%s_wn%d" % (name, int(wavenorm))
+    P = g[tag + "_P"]
+    ctx.set_model(wavenorm, opthin, noalpha)
+    freq = 299792458e-3 / g["waves"]
+    arr, st = ctx.fnu(P, freq, scalar_path=False)
+    assert (st == 0).all()
+    assert relerr(arr, g[tag + "_fnu_array"]).max() < TOL
+    sc, st = ctx.fnu(P, freq, scalar_path=True)
+    assert relerr(sc, g[tag + "_fnu_scalar"]).max() < TOL
+    c, st = ctx.sed_consts(P, want_peak=True)
+    assert (st == 0).all()
+    assert relerr(c[:, 0], g[tag + "_normfac"]).max() < TOL
+    if not noalpha:
+        assert relerr(c[:, 1], g[tag + "_xmerge"]).max() < TOL
+        assert relerr(c[:, 2], g[tag + "_kappa"]).max() < TOL
+    assert relerr(c[:, 5], g[tag + "_maxwave"]).max() < TOL
+
+
+def test_reference_known_answers():
+    """The reference's own tests (mbb_emcee/tests/test_modified_blackbody.py),
+    run against the product classes."""
+    from numpy.testing import assert_allclose
+    from mbb_emcee_b200 import modified_blackbody
+    mbb = modified_blackbody(10.0, 2.0, 800.0, 2.0, 45.0)
+    assert mbb.has_alpha and not mbb.optically_thin
+    assert_allclose(mbb(500), 45.0, atol=1e-4)
+    wave = np.array([250.0, 350.0, 500.0, 850.0])
+    assert_allclose(mbb(wave), [21.96268738, 39.53249977, 45.0, 22.06274444], rtol=1e-4)
+    mbb = modified_blackbody(15.0, 1.8, 200.0, 3.0, 50.0, opthin=True)
+    assert mbb.has_alpha and mbb.optically_thin and mbb.lambda0 is None
+    assert_allclose(mbb(wave), [178.34976, 111.03026, 50.0, 10.880588], rtol=1e-4)
+    thin = modified_blackbody(15.0, 1.8, 5.0, 3.0, 50.0, opthin=True)
+    thick = modified_blackbody(15.0, 1.8, 5.0, 3.0, 50.0, opthin=False)
+    w2 = np.array([500.0, 850.0, 1100.0, 2500.0])
+    assert_allclose(thin(w2), thick(w2), rtol=1e-3)
+    assert modified_blackbody(20.0, 1.9, None, 3.5, 50.0, noalpha=True, opthin=True).wavemerge is None
+    assert_allclose(modified_blackbody(20.0, 1.9, None, 3.5, 50.0, opthin=True).wavemerge, 85.66065, rtol=1e-3)
+    assert_allclose(modified_blackbody(35.0, 2.2, None, 2.8, 50.0, opthin=True).wavemerge, 51.40211, rtol=1e-3)
+    assert modified_blackbody(20.0, 1.9, 250.0, 3.5, 50.0, noalpha=True).wavemerge is None
+    assert_allclose(modified_blackbody(20.0, 1.9, 250.0, 3.5, 50.0).wavemerge, 109.5506829, rtol=1e-3)
+    assert_allclose(modified_blackbody(40.0, 1.5, 600.0, 3.0, 50.0).wavemerge, 60.10021595, rtol=1e-3)
+    with pytest.raises(ValueError):
+        modified_blackbody(10.0, 2.0, 800.0, -1.0, 45.0)
+    with pytest.raises(ValueError):
+        modified_blackbody(10.0, -2.0, 800.0, 2.0, 45.0)
+
+
+# -------------------------------------------------------------------- likelihood
+def _make_like(golden, cfgname, mode):
+    from mbb_emcee_b200 import likelihood, synthetic
+    cfg = synthetic.CONFIGS[cfgname]
+    g = golden.like
+    like = likelihood(wavenorm=cfg["wavenorm"], noalpha=cfg["noalpha"], opthin=cfg["opthin"],
+                      response=cfg["response"], device=0)
+    like.math_mode = mode
+    like.set_phot(cfg["bands"], g[cfgname + "_flux"], g[cfgname + "_unc"])
+    if cfgname + "_cov" in g:
+        like.set_cov(g[cfgname + "_cov"])
+    for nm, v in cfg.get("uplims", []):
+        like.set_uplim(nm, v)
+    for nm, m, s in cfg.get("gpriors", []):
+        like.set_gaussian_prior(nm, m, s)
+    return cfg, like
+
+
+def _oracle_spec(oracle, like):
+    spec = oracle.LikeSpec(like.wavenorm, like.noalpha, like.opthin)
+    if like.response_integrate:
+        spec.set_phot([oracle.band_from_response(r) for r in like._responses],
+                      like.data_flux, like._flux_unc)
+    else:
+        spec.set_phot(like.data_wave, like.data_flux, like._flux_unc)
+    spec.lowlim = np.array(like.lowlims, dtype=np.float64)
+    spec.has_uplim = list(like.has_uplims)
+    spec.uplim = np.array(like.uplims, dtype=np.float64)
+    spec.has_gprior = list(like.has_gpriors)
+    spec.gprior_mean = np.array(like.gprior_means)
+    spec.gprior_ivar = np.array(like.gprior_ivars)
+    if like.has_data_covmatrix:
+        spec.set_cov(like.data_covmatrix)
+    return spec
+
+
+@pytest.mark.parametrize("cfgname", ["cfg1", "cfg2", "cfg3"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_loglike_golden(golden, cfgname, mode):
+    cfg, like = _make_like(golden, cfgname, mode)
+    g = golden.like
+    P, ref = g[cfgname + "_P"], g[cfgname + "_lnlike"]
+    ll, st = like.evaluate(P)
+    assert np.array_equal(st == 1, np.isneginf(ref))
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+    assert (st <= 1).all()
+    fin = np.isfinite(ref)
+    assert relerr(ll[fin], ref[fin]).max() < TOL
+    # emcee's calling convention: one row -> python float
+    one = like(P[6])
+    assert isinstance(one, float) and abs(one - ref[6]) <= TOL * abs(ref[6])
+    assert like(P[0]) == float("-inf")
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_loglike_extra_golden(golden, mode):
+    from mbb_emcee_b200 import likelihood
+    g = golden.like
+    like = likelihood(wavenorm=500.0, device=0)
+    like.math_mode = mode
+    like.set_phot(g["extra_wave"], g["extra_flux"], g["extra_unc"])
+    like.set_cov(g["extra_cov"])
+    like.set_gaussian_prior('beta', 1.8, 0.3)
+    like.set_uplim('lambda_peak', 300.0)
+    like.set_gaussian_prior('lambda_peak', 250.0, 40.0)
+    ll = like(g["extra_P"])
+    assert relerr(ll, g["extra_lnlike"]).max() < TOL
+    assert abs(ll[0] - (-30.13025033346131)) < 1e-11
+
+
+@pytest.mark.parametrize("cfgname,n", [("cfg1", 4000), ("cfg2", 1500), ("cfg3", 700)])
+def test_loglike_vs_oracle_random(golden, oracle, cfgname, n):
+    """Seeded random walkers around the truth (and well away from it)."""
+    from mbb_emcee_b200 import synthetic
+    cfg, like = _make_like(golden, cfgname, 1)
+    rng = np.random.RandomState(9000 + n)
+    up = np.where(like.has_uplims[:5], like.uplims[:5], np.inf)
+    P = synthetic.walker_cloud(cfg["truth"], n, rng, like.lowlims, up,
+                               sigma=3.0 * synthetic.P0_SIGMA)
+    want = oracle.loglike_batch(_oracle_spec(oracle, like), P)
+    for mode in (0, 1):
+        like.math_mode = mode
+        got = like(P)
+        assert relerr(got, want).max() < TOL, mode
+    # ragged tail: a batch that is not a multiple of the tile / block size
+    got = like(P[:n - 37])
+    assert relerr(got, want[:n - 37]).max() < TOL
+    # SoA layout gives the same numbers as AoS
+    from mbb_emcee_b200 import _native
+    soa, st = like.context.loglike(np.ascontiguousarray(P.T), layout=_native.SOA)
+    assert np.array_equal(soa, like(P))
+
+
+def test_all_variants_tabulated_vs_oracle(oracle):
+    """Every (thin|thick)x(alpha|noalpha) variant through the warp kernel."""
+    from mbb_emcee_b200 import likelihood, synthetic
+    rng = np.random.RandomState(77)
+    bands = ["PACS_70um", "PACS_160um", "SPIRE_350um", "ALMA_alma_230", "Y_delta_500um"]
+    for name, opthin, noalpha in VARIANTS:
+        like = likelihood(wavenorm=350.0, opthin=opthin, noalpha=noalpha, response=True, device=0)
+        like.set_phot(bands, [40.0, 90.0, 50.0, 3.0, 28.0], [4.0, 9.0, 5.0, 1.0, 3.0])
+        P = synthetic.walker_cloud((14.0, 1.8, 300.0, 3.0, 30.0), 300, rng, like.lowlims)
+        want = oracle.loglike_batch(_oracle_spec(oracle, like), P)
+        for mode in (0, 1):
+            like.math_mode = mode
+            assert relerr(like(P), want).max() < TOL, (name, mode)
+
+
+def test_whole_wheel_global_table_path(oracle):
+    """All 18 shipped filters (4677 nodes): the node table no longer fits the
+    shared-memory budget, so the kernel reads it from global memory."""
+    from mbb_emcee_b200 import likelihood, response_set, synthetic
+    names = list(response_set().keys())
+    like = likelihood(response=True, device=0)
+    rng = np.random.RandomState(5)
+    like.set_phot(names, rng.uniform(5, 50, len(names)), rng.uniform(1, 5, len(names)))
+    P = synthetic.walker_cloud((20.0, 1.6, 200.0, 2.5, 30.0), 96, rng, like.lowlims)
+    want = oracle.loglike_batch(_oracle_spec(oracle, like), P)
+    assert relerr(like(P), want).max() < TOL
+
+
+def test_multi_source_batch(oracle):
+    """Several sources in one call: walkers_per_source and explicit src_index."""
+    from mbb_emcee_b200 import _native, synthetic
+    rng = np.random.RandomState(11)
+    nsrc, nw = 7, 40
+    waves = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0]
+    flux = rng.uniform(5, 80, (nsrc, 6))
+    unc = rng.uniform(1, 6, (nsrc, 6))
+    ctx = _native.Context(0)
+    ctx.set_model(500.0, True, True)
+    off = np.arange(7, dtype=np.int32)
+    ctx.set_bands(off, waves, np.ones(6))
+    ctx.set_data(flux, ivar=1.0 / unc**2)
+    low = np.array([1, 0.1, 1, 0.1, 1e-3])
+    P = synthetic.walker_cloud((12.0, 1.8, 1300.0, 4.0, 30.0), nsrc * nw, rng, low)
+    got, st = ctx.loglike(P, walkers_per_source=nw)
+    want = np.empty(nsrc * nw)
+    for s in range(nsrc):
+        spec = oracle.LikeSpec(500.0, True, True)
+        spec.set_phot(waves, flux[s], unc[s])
+        want[s * nw:(s + 1) * nw] = oracle.loglike_batch(spec, P[s * nw:(s + 1) * nw])
+    assert relerr(got, want).max() < TOL
+    idx = rng.randint(0, nsrc, nsrc * nw).astype(np.int32)
+    got2, st = ctx.loglike(P, src_index=idx)
+    for i in range(0, nsrc * nw, 13):
+        spec = oracle.LikeSpec(500.0, True, True)
+        spec.set_phot(waves, flux[idx[i]], unc[idx[i]])
+        assert abs(got2[i] - oracle.loglike(spec, P[i])) <= TOL * abs(got2[i])
+
+
+def test_error_statuses():
+    """Failures that make the reference raise surface as the same exception types."""
+    from mbb_emcee_b200 import likelihood
+    like = likelihood(device=0)
+    like.set_phot([250.0, 350.0, 500.0], [30.0, 40.0, 30.0], [3.0, 4.0, 3.0])
+    like.set_lowlim('alpha', -5.0)
+    with pytest.raises(ValueError):
+        like([10.0, 2.0, 100.0, -1.0, 30.0])          # alpha <= 0
+    like.set_lowlim('beta', -5.0)
+    with pytest.raises(ValueError):
+        like([10.0, -1.0, 100.0, 2.0, 30.0])          # beta < 0
+    ll, st = like.evaluate(np.array([[10.0, 2.0, 100.0, 2.0, 30.0], [np.nan, 2.0, 100.0, 2.0, 30.0]]))
+    assert st[0] == 0 and np.isfinite(ll[0]) and st[1] == 9 and np.isnan(ll[1])
+    with pytest.raises(ValueError):
+        like(np.zeros((3, 4)))
+
+
+# ------------------------------------------------------------ full-size properties
+def test_full_size_properties(oracle):
+    """BASELINE configs[4]: 1e5 sources x 512 walkers in one device-resident
+    launch.  Properties that do not need the oracle at full size, plus an
+    oracle check of a random sample of the 5.12e7 results."""
+    import torch
+    from mbb_emcee_b200 import _native, synthetic
+    cfg = synthetic.CONFIGS["cfg5"]
+    nsrc, nw = cfg["nsources"], cfg["nwalkers"]
+    n = nsrc * nw
+    rng = np.random.RandomState(cfg["seed"])
+    waves = np.array(cfg["bands"])
+    flux = rng.uniform(5.0, 80.0, (nsrc, 6))
+    unc = np.maximum(0.1 * flux, 1.0)
+    ctx = _native.Context(0)
+    ctx.set_model(cfg["wavenorm"], cfg["opthin"], cfg["noalpha"])
+    ctx.set_bands(np.arange(7, dtype=np.int32), waves, np.ones(6))
+    ctx.set_data(flux, ivar=1.0 / unc**2)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    truth = torch.tensor([12.0, 1.8, 1300.0, 4.0, 30.0], dtype=torch.float64, device=dev)
+    sig = torch.tensor(synthetic.P0_SIGMA, dtype=torch.float64, device=dev)
+    P = truth + sig * torch.randn((n, 5), dtype=torch.float64, device=dev, generator=g)
+    P[:, 0].clamp_(min=2.0)
+    P[:, 1].clamp_(min=0.2)
+    P[:, 4].clamp_(min=0.5)
+    P[::1000, 0] = 0.5                                   # sprinkle -inf gates
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.loglike_device(n, P.data_ptr(), out.data_ptr(), st.data_ptr(), walkers_per_source=nw)
+    ctx.sync()
+    # (1) gate: exactly the sprinkled rows are -inf, nothing is NaN
+    assert bool(torch.isneginf(out[::1000]).all())
+    assert int(torch.isneginf(out).sum()) == (n + 999) // 1000
+    assert not bool(torch.isnan(out).any())
+    assert int((st > 1).sum()) == 0
+    # (2) determinism: a second launch is bit-identical
+    out2 = torch.empty_like(out)
+    ctx.loglike_device(n, P.data_ptr(), out2.data_ptr(), 0, walkers_per_source=nw)
+    ctx.sync()
+    assert bool(torch.equal(out, out2))
+    # (3) layout invariance: SoA input gives bit-identical results
+    Pt = P.t().contiguous()
+    out3 = torch.empty_like(out)
+    ctx.loglike_device(n, Pt.data_ptr(), out3.data_ptr(), 0, walkers_per_source=nw, layout=_native.SOA)
+    ctx.sync()
+    assert bool(torch.equal(out, out3))
+    # (4) explicit source indices reproduce the implicit i // nw mapping
+    src = (torch.arange(n, device=dev) // nw).to(torch.int32)
+    out4 = torch.empty_like(out)
+    ctx.loglike_device(n, P.data_ptr(), out4.data_ptr(), 0, src_index_ptr=src.data_ptr())
+    ctx.sync()
+    assert bool(torch.equal(out, out4))
+    # (5) the pipelined host path (pageable numpy in/out) gives the same bits
+    sl = slice(0, 5_000_000)
+    host, hst = ctx.loglike(P[sl].cpu().numpy(), walkers_per_source=nw)
+    assert np.array_equal(host, out[sl].cpu().numpy())
+    # (6) a random sample of the full-size results against the oracle
+    pick = rng.randint(0, n, 400)
+    Ph = P[torch.as_tensor(pick, device=dev)].cpu().numpy()
+    got = out[torch.as_tensor(pick, device=dev)].cpu().numpy()
+    for j, i in enumerate(pick):
+        spec = oracle.LikeSpec(cfg["wavenorm"], cfg["noalpha"], cfg["opthin"])
+        spec.set_phot(waves, flux[i // nw], unc[i // nw])
+        want = oracle.loglike(spec, Ph[j])
+        assert (np.isneginf(want) and np.isneginf(got[j])) or abs(got[j] - want) <= TOL * abs(want)
+
+
+# ------------------------------------------------------------------ chain identity
+@pytest.mark.parametrize("cfgname,nwalk,nsteps", [("cfg1", 250, 120), ("cfg2", 60, 40), ("cfg3", 40, 25)])
+def test_chain_bit_identity(golden, oracle, cfgname, nwalk, nsteps):
+    """Same RNG seed, same emcee-2.2 move sequence: the chain driven by the
+    device log-probability is bit-identical to the one driven by the CPU
+    oracle, and the stored log-probabilities agree to 1e-12."""
+    from mbb_emcee_b200 import mbb_fitter, synthetic
+    cfg, like = _make_like(golden, cfgname, 1)
+    fit = mbb_fitter(nwalkers=nwalk, wavenorm=cfg["wavenorm"], noalpha=cfg["noalpha"],
+                     opthin=cfg["opthin"], response=cfg["response"], device=0)
+    g = golden.like
+    fit.set_data(cfg["bands"], g[cfgname + "_flux"], g[cfgname + "_unc"],
+                 covmatrix=g[cfgname + "_cov"] if cfgname + "_cov" in g else None)
+    for nm, v in cfg.get("uplims", []):
+        fit.set_uplim(nm, v)
+    for nm, m, s in cfg.get("gpriors", []):
+        fit.set_gaussian_prior(nm, m, s)
+    if cfg["noalpha"]:
+        fit.fix_param('alpha')
+    np.random.seed(cfg["seed"])
+    p0 = fit.generate_initial_values(list(cfg["truth"]), [2, 0.2, 100, 0.3, 5.0])
+    fit.sampler.random_state = np.random.RandomState(2024).get_state()
+    fit.sampler.reset()
+    fit.sampler.run_mcmc(p0, nsteps)
+    spec = _oracle_spec(oracle, fit.like)
+    chain, lnp, nacc = oracle.stretch_chain(lambda P: oracle.loglike_batch(spec, P), p0, nsteps,
+                                            np.random.RandomState(2024))
+    assert np.array_equal(fit.sampler.chain, chain)
+    assert np.array_equal(fit.sampler.naccepted, nacc)
+    assert relerr(fit.sampler.lnprobability, lnp).max() < TOL
+    assert 0.05 < np.mean(fit.sampler.acceptance_fraction) < 0.95
+    if cfg["noalpha"]:
+        assert (fit.sampler.chain[:, :, 3] == cfg["truth"][3]).all()     # fixed stays fixed
+
+
+def test_fitter_run_end_to_end(golden):
+    """mbb_fitter.run (burn-in, reset, main chain) and mbb_results statistics."""
+    from mbb_emcee_b200 import mbb_fitter, mbb_results, synthetic
+    cfg = synthetic.CONFIGS["cfg1"]
+    g = golden.like
+    fit = mbb_fitter(nwalkers=100, opthin=True, noalpha=True, device=0)
+    fit.set_data(cfg["bands"], g["cfg1_flux"], g["cfg1_unc"])
+    fit.fix_param('alpha')
+    np.random.seed(1)
+    p0 = fit.generate_initial_values([12.0, 1.8, 2500.0, 4.0, 30.0], [2, 0.2, 100, 0.3, 5.0])
+    fit.run(30, 150, p0)
+    assert fit.sampled and fit.sampler.chain.shape == (100, 150, 5)
+    res = mbb_results(fit=fit, redshift=2.0, lumdist=1.6e4)
+    cen = res.par_cen('T')
+    assert abs(cen[0] - 12.0) < 3.0
+    res.compute_dustmass()
+    res.compute_peaklambda()
+    assert np.isfinite(res.dustmass).all() and np.isfinite(res.peaklambda).all()
+    assert "ChiSquare" in str(res)
+
+
+# ------------------------------------------------------------- chain post-processing
+@pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
+def test_chain_post_golden(golden, name, opthin, noalpha):
+    from mbb_emcee_b200 import mbb_results, synthetic
+    cfg = synthetic.CONFIGS["cfg4"]
+    g = golden.results
+    chain = g[name + "_chain"]
+    res = mbb_results.from_chain(chain, wavenorm=cfg["wavenorm"], noalpha=noalpha, opthin=opthin,
+                                 redshift=cfg["z"], lumdist=cfg["lumdist"], device=0)
+    res.compute_peaklambda()
+    assert relerr(res.peaklambda, g[name + "_peaklambda"]).max() < TOL
+    res.compute_dustmass(kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
+    assert relerr(res.dustmass, g[name + "_dustmass"]).max() < TOL
+    # the allclose-dedupe: step 5 of walker 0 is within 3e-6 of step 4
+    assert res.peaklambda[0, 5] == res.peaklambda[0, 4]
+    assert res.dustmass[0, 5] == res.dustmass[0, 4]
