@@ -292,6 +292,7 @@ def run_b200(args):
     name = args.workload
     W = build_workload(name, rank, args.nsrc)
     ctx, n, nw, P = W["ctx"], W["n"], W["nw"], W["P"]
+    ctx.set_math_mode(0 if args.math == "faithful" else 1)
     out = torch.empty(n, dtype=torch.float64, device=dev)
     st = torch.empty(n, dtype=torch.int32, device=dev)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev) if name != "cfg5" else None
@@ -344,35 +345,45 @@ def run_b200(args):
     nneg = int(torch.isneginf(out).sum().item())
 
     # ---- end-to-end through the host-buffer C-ABI call ------------------------
-    P_host = torch.empty((n, 5), dtype=torch.float64).pin_memory()
-    out_host = torch.empty(n, dtype=torch.float64).pin_memory()
-    P_host.copy_(P)
-    torch.cuda.synchronize()
-    Pn, on = P_host.numpy(), out_host.numpy()
-    import ctypes
-    lib = ctx._lib
+    e2e = None
+    if not args.no_e2e:
+        P_host = torch.empty((n, 5), dtype=torch.float64).pin_memory()
+        out_host = torch.empty(n, dtype=torch.float64).pin_memory()
+        P_host.copy_(P)
+        torch.cuda.synchronize()
+        Pn, on = P_host.numpy(), out_host.numpy()
+        import ctypes
+        lib = ctx._lib
 
-    def step_host():
-        rc = lib.mbb_loglike(ctx._h, n, ctypes.c_void_p(Pn.ctypes.data), 0, None, nw,
-                             ctypes.c_void_p(on.ctypes.data), None, 0)
-        if rc != 0:
-            raise RuntimeError(lib.mbb_last_error().decode())
+        def step_host():
+            rc = lib.mbb_loglike(ctx._h, n, ctypes.c_void_p(Pn.ctypes.data), 0, None, nw,
+                                 ctypes.c_void_p(on.ctypes.data), None, 0)
+            if rc != 0:
+                raise RuntimeError(lib.mbb_last_error().decode())
 
-    e2e_steps = max(1, min(args.steps, 5))
-    step_host()
-    barrier()
-    e2e_ms = []
-    for _ in range(e2e_steps):
-        t1 = time.perf_counter()
-        step_host()                      # synchronous: returns with results in host memory
-        e2e_ms.append(1e3 * (time.perf_counter() - t1))
-    barrier()
+        e2e_steps = max(1, min(args.steps, 5))
+        l0 = ctx.launch_count()
+        step_host()
+        e2e_launches = ctx.launch_count() - l0
+        barrier()
+        e2e_ms = []
+        for _ in range(e2e_steps):
+            t1 = time.perf_counter()
+            step_host()                      # synchronous: returns with results in host memory
+            e2e_ms.append(1e3 * (time.perf_counter() - t1))
+        barrier()
+        same = bool(np.array_equal(on[:100000], out[:100000].cpu().numpy()))
+        te = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms_max = float(te.item())
+        e2e = {"value": n * world / (e2e_ms_max * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(n * 8),
+               "ms_per_step": e2e_ms_max, "steps": e2e_steps,
+               "gpu_launches_per_step": int(e2e_launches),
+               "api": "mbb_loglike(MBB_HOST) with pinned host arrays; pipelined H2D/kernel/D2H",
+               "matches_device_path": same}
     clocks = sampler.stop()
-    same = bool(np.array_equal(on[:100000], out[:100000].cpu().numpy()))
-    te = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(te.item())
 
     if rank == 0:
         total = n * world
@@ -387,6 +398,8 @@ def run_b200(args):
         achieved_gbs = n * BYTES_PER_EVAL / (step_ms * 1e-3) / 1e9
         cb = None
         try:
+            if args.no_cpu_baseline:
+                raise RuntimeError("skipped (--no-cpu-baseline)")
             per_worker = 20000 if name == "cfg5" else 1500
             cores = len(os.sched_getaffinity(0))
             Pc = P[:cores * per_worker].cpu().numpy()
@@ -400,7 +413,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(main_config(name, W["nsrc"]), parallelism="sources sharded, "
                            "%d rank(s), no data-path collective" % world,
-                           math_mode="fast (exp-only node arithmetic, csrc/mbb_model.cuh)"),
+                           math_mode=args.math),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None,
                          "note": "achieved = %d algorithmic FP64 flop/eval (reference formulation, "
@@ -412,11 +425,7 @@ def run_b200(args):
                                  if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json"))
                                  else "fallback"}},
             "cpu_baseline": cb,
-            "e2e": {"value": total / (e2e_ms_max * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(n * 8),
-                    "ms_per_step": e2e_ms_max, "steps": e2e_steps,
-                    "api": "mbb_loglike(MBB_HOST) with pinned host arrays; pipelined H2D/kernel/D2H",
-                    "matches_device_path": same},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"status_errors": nbad, "neg_inf": nneg, "wall_s_timed_region": wall,
@@ -436,6 +445,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2"])
     ap.add_argument("--nsrc", type=int, default=None, help="sources per GPU (default: workload's)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg")
+    ap.add_argument("--math", default="fast", choices=["fast", "faithful"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -181,7 +181,7 @@ template <bool THIN, bool ALPHA, bool FAST>
 struct LaunchThread {
   static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
     const unsigned grid = (unsigned)((a.n + 255) / 256);
-    ModelP m{c->wavenorm};
+    ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
     loglike_thread_kernel<THIN, ALPHA, FAST><<<grid, 256, 0, st>>>(a, m, c->pri, d, c->small);
     *err = cudaSuccess;
   }
@@ -205,7 +205,7 @@ struct LaunchWarp {
     if (*err != cudaSuccess) return;
     const long long ntiles = (a.n + kWarpTile - 1) / kWarpTile;
     unsigned grid = (unsigned)(ntiles < c->sm_count ? ntiles : c->sm_count);
-    ModelP m{c->wavenorm};
+    ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
     kern<<<grid, kWarpTile, smem, st>>>(a, m, c->pri, d, t);
   }
 };
@@ -214,7 +214,7 @@ template <bool THIN, bool ALPHA, bool UNUSED>
 struct LaunchFnu {
   static void run(mbb_ctx* c, const EvalArgs& a, const double* freq, int nfreq, int scalar_path) {
     dim3 grid((unsigned)((nfreq + 255) / 256), (unsigned)a.n);
-    ModelP m{c->wavenorm};
+    ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
     fnu_kernel<THIN, ALPHA><<<grid, 256, 0, c->stream>>>(a, m, freq, nfreq, scalar_path);
   }
 };
@@ -223,7 +223,7 @@ template <bool THIN, bool ALPHA, bool UNUSED>
 struct LaunchConsts {
   static void run(mbb_ctx* c, const EvalArgs& a, int want_peak) {
     const unsigned grid = (unsigned)((a.n + 127) / 128);
-    ModelP m{c->wavenorm};
+    ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
     sed_consts_kernel<THIN, ALPHA><<<grid, 128, 0, c->stream>>>(a, m, want_peak);
   }
 };
@@ -718,11 +718,10 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
   if ((which & 1) && !out_peak) return fail("out_peak is NULL");
   if ((which & 2) && !out_lir) return fail("out_lir is NULL");
   if ((which & 4) && !out_dustmass) return fail("out_dustmass is NULL");
-  if (which & 2) return fail("L_IR integration is not built into this revision of the library");
-  (void)lir_min_um; (void)lir_max_um;
+  if ((which & 2) && (!(lir_min_um > 0.0) || !(lir_max_um > 0.0))) return fail("L_IR limits must be positive");
   Use u(c);
   const double* dchain = chain;
-  double *dpk = out_peak, *ddm = out_dustmass;
+  double *dpk = out_peak, *ddm = out_dustmass, *dlir = out_lir;
   int* dst = out_status;
   if (mem != MBB_DEVICE) {
     CK(c->d_in.reserve((size_t)ns * 5));
@@ -731,6 +730,7 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
     dchain = c->d_in.p;
     if (which & 1) { CK(c->d_aux0.reserve((size_t)ns)); dpk = c->d_aux0.p; }
     if (which & 4) { CK(c->d_aux1.reserve((size_t)ns)); ddm = c->d_aux1.p; }
+    if (which & 2) { CK(c->d_out.reserve((size_t)ns)); dlir = c->d_out.p; }
     CK(c->d_st.reserve((size_t)ns));
     dst = c->d_st.p;
   }
@@ -758,15 +758,33 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
       dchain, nwalkers, nsteps, c->d_owner.p, c->d_work.p, c->d_count.p);
   chain_unique_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(
       dchain, c->d_work.p, c->d_count.p, which, dc, dpk, ddm, dst);
+  if (which & 2) {
+    // mbb_freqint (results.py:1310-1326) and freq_integrate (modified_blackbody.py:658-674)
+    double lo = lir_min_um, hi = lir_max_um;
+    if (lo > hi) { double t = lo; lo = hi; hi = t; }
+    const double opz = 1.0 + z;
+    const double fmin = kUmToGHz / (hi * opz), fmax = kUmToGHz / (lo * opz);
+    const double prefac = dl_mpc > 0.0 ? 3.11749657e4 * (dl_mpc * dl_mpc) : 1.0;
+    const unsigned grid = (unsigned)((ns + 127) / 128);
+    const bool thin = c->opthin != 0, alpha = c->noalpha == 0;
+#define LIR(T, A) chain_lir_kernel<T, A><<<grid, 128, 0, c->stream>>>(dchain, c->d_work.p, c->d_count.p, \
+                                   c->wavenorm, fmin, fmax, prefac, dlir, dst)
+    if (thin) { if (alpha) LIR(true, true); else LIR(true, false); }
+    else { if (alpha) LIR(false, true); else LIR(false, false); }
+#undef LIR
+    c->launches += 1;
+  }
   chain_fill_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(
-      c->d_owner.p, nwalkers, nsteps, (which & 1) ? dpk : nullptr, nullptr, (which & 4) ? ddm : nullptr,
-      dst);
+      c->d_owner.p, nwalkers, nsteps, (which & 1) ? dpk : nullptr, (which & 2) ? dlir : nullptr,
+      (which & 4) ? ddm : nullptr, dst);
   end_timing(c);
   c->launches += 3;
   CK(cudaGetLastError());
   if (mem != MBB_DEVICE) {
     if (which & 1)
       CK(cudaMemcpyAsync(out_peak, dpk, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (which & 2)
+      CK(cudaMemcpyAsync(out_lir, dlir, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (which & 4)
       CK(cudaMemcpyAsync(out_dustmass, ddm, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost,
                          c->stream));

@@ -41,6 +41,7 @@ struct EvalArgs {
 
 struct ModelP {
   double wavenorm;
+  double nu_norm;     // 299792.458 / wavenorm [GHz]
 };
 
 struct DataRef {
@@ -84,7 +85,11 @@ __device__ __forceinline__ void load_pars(const EvalArgs& a, long long e, double
 }
 
 __device__ __forceinline__ long long source_of(const EvalArgs& a, long long e) {
-  return a.src_index ? (long long)__ldg(a.src_index + e) : (a.e0 + e) / a.wps;
+  if (a.src_index) return (long long)__ldg(a.src_index + e);
+  const unsigned long long g = (unsigned long long)(a.e0 + e);
+  // 32-bit division whenever it is exact (64-bit integer division costs ~100 instructions)
+  if (((g | (unsigned long long)a.wps) >> 32) == 0) return (long long)((unsigned)g / (unsigned)a.wps);
+  return (long long)(g / (unsigned long long)a.wps);
 }
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -103,7 +108,7 @@ loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const D
   const long long src = source_of(a, e);
   int st;
   const double lnl = loglike_one<THIN, ALPHA, FAST>(
-      p, m.wavenorm, pr, t, d.flux + src * d.nb, d.ivar ? d.ivar + src * d.nb : nullptr,
+      p, m.wavenorm, m.nu_norm, pr, t, d.flux + src * d.nb, d.ivar ? d.ivar + src * d.nb : nullptr,
       d.cinv ? d.cinv + src * (long long)d.nb * d.nb : nullptr, st);
   a.out[e] = lnl;
   if (a.status) a.status[e] = st;
@@ -231,14 +236,21 @@ loglike_warp_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Dat
         if (below_lowlim(pr, p)) {
           st = ST_BELOW_LOWLIM;
         } else {
-          Sed s;
-          sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
-          if (FAST) sed_setup_fast<THIN, ALPHA>(s, m.wavenorm);
-          st = s.status;
-          if (st == ST_OK) prior_terms<THIN>(pr, p, s, pen, gp, st);
-          c[0] = s.hokt9; c[1] = s.hokt_e9; c[2] = s.beta; c[3] = s.alpha;
-          c[4] = s.x0; c[5] = s.normfac; c[6] = s.xmerge; c[7] = s.kappa;
-          c[8] = s.amp_grey; c[9] = s.amp_pow; c[10] = s.q_hi; c[11] = s.q_lo;
+          if (FAST) {
+            FastSed s;
+            fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm, m.nu_norm);
+            st = s.status;
+            if (st == ST_OK) prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+            c[0] = s.hokt9; c[2] = s.beta; c[3] = s.alpha; c[6] = s.xmerge;
+            c[8] = s.amp_grey; c[9] = s.amp_pow; c[10] = s.q_hi; c[11] = s.q_lo;
+          } else {
+            Sed s;
+            sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
+            st = s.status;
+            if (st == ST_OK) prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+            c[0] = s.hokt9; c[1] = s.hokt_e9; c[2] = s.beta; c[3] = s.alpha;
+            c[4] = s.x0; c[5] = s.normfac; c[6] = s.xmerge; c[7] = s.kappa;
+          }
         }
       } else {
         st = -1;   // beyond the end
@@ -264,21 +276,26 @@ loglike_warp_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Dat
       }
       const double* c = sedc + slot * kSedcStride;
       Sed s;
-      s.hokt9 = c[0]; s.hokt_e9 = c[1]; s.beta = c[2]; s.alpha = c[3];
-      s.x0 = c[4]; s.normfac = c[5]; s.xmerge = c[6]; s.kappa = c[7];
-      s.amp_grey = c[8]; s.amp_pow = c[9]; s.q_hi = c[10]; s.q_lo = c[11];
+      FastSed fs;
+      if (FAST) {
+        fs.hokt9 = c[0]; fs.beta = c[2]; fs.alpha = c[3]; fs.xmerge = c[6];
+        fs.amp_grey = c[8]; fs.amp_pow = c[9]; fs.q_hi = c[10]; fs.q_lo = c[11];
+      } else {
+        s.hokt9 = c[0]; s.hokt_e9 = c[1]; s.beta = c[2]; s.alpha = c[3];
+        s.x0 = c[4]; s.normfac = c[5]; s.xmerge = c[6]; s.kappa = c[7];
+      }
       const long long src = source_of(a, e);
       const double* fl = d.flux + src * d.nb;
       double* wdiff = s_diff + warp * kMaxBands;
       double chi = 0.0;
       for (int b = 0; b < nb; ++b) {
-        const double hk = s_scalar[b] ? s.hokt_e9 : s.hokt9;
+        const double hk = FAST ? fs.hokt9 : (s_scalar[b] ? s.hokt_e9 : s.hokt9);
         const int i1 = s_off[b + 1];
         double acc = 0.0;
         for (int i = s_off[b] + lane; i < i1; i += 32) {
           const double cx = hk * n_freq[i];
           double f;
-          if (FAST) f = node_fnu_fast<THIN, ALPHA>(s, cx, n_lhi[i], n_llo[i], n_rc[i]);
+          if (FAST) f = node_fnu_fast<THIN, ALPHA>(fs, cx, n_lhi[i], n_llo[i], n_rc[i]);
           else f = node_fnu<THIN, ALPHA>(s, cx);
           acc = fma(f, n_w[i], acc);
         }
@@ -444,6 +461,63 @@ chain_unique_kernel(const double* __restrict__ chain, const int* __restrict__ wo
     out_dust[idx] = dm;
   }
   if (status) status[idx] = st;
+}
+
+// L_IR / freq_integrate: tiles of 128 unique samples; phase 1 thread-per-sample
+// setup (incl. the merge-point solve), phase 2 warp-per-sample quadrature with
+// the 128 nodes spread over the lanes (see lir_span / lir_node).
+// out = prefac * 1e-17 * integral f_nu dnu [mJy GHz]  (results.py:665-673,
+// modified_blackbody.py:671-674).
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(128)
+chain_lir_kernel(const double* __restrict__ chain, const int* __restrict__ work,
+                 const unsigned* __restrict__ nwork, double wavenorm, double fmin_ghz,
+                 double fmax_ghz, double prefac, double* __restrict__ out_lir,
+                 int* __restrict__ status) {
+  __shared__ double c[128][8];
+  __shared__ int s_st[128];
+  const unsigned total = *nwork;
+  const unsigned tile0 = blockIdx.x * 128u;
+  if (tile0 >= total) return;
+  const int tid = threadIdx.x;
+  {
+    const unsigned j = tile0 + tid;
+    int st = -1;
+    if (j < total) {
+      const double* p = chain + (long long)work[j] * 5;
+      Sed s;
+      sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+      st = s.status;
+      c[tid][0] = s.hokt_e9; c[tid][1] = s.normfac; c[tid][2] = s.xmerge; c[tid][3] = s.kappa;
+      c[tid][4] = s.x0; c[tid][5] = s.beta; c[tid][6] = s.alpha;
+    }
+    s_st[tid] = st;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int k = 0; k < 32; ++k) {
+    const int slot = warp * 32 + k;
+    const int st = s_st[slot];
+    if (st < 0) break;
+    const long long idx = work[tile0 + slot];
+    if (st != ST_OK) {
+      if (lane == 0) { out_lir[idx] = qnan(); if (status) status[idx] = st; }
+      continue;
+    }
+    const double hk = c[slot][0], beta = c[slot][5], x0 = c[slot][4];
+    const LirSpan sp = lir_span<ALPHA>(hk * fmin_ghz, hk * fmax_ghz, beta, c[slot][6], c[slot][2],
+                                       c[slot][3]);
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < kLirNodes / 32; ++q) acc += lir_node<THIN>(sp, lane + 32 * q, beta, x0);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const double fint = c[slot][1] * (acc + sp.pow_part) / hk;
+      const double v = prefac * (1e-17 * fint);
+      out_lir[idx] = v;
+      if (status) status[idx] = (v == v) ? ST_OK : ST_NONFINITE;
+    }
+  }
 }
 
 // Pass 3: repeated steps copy their owner's value.

@@ -16,48 +16,26 @@
 //               (f/fnorm near 1).  ~2.5x fewer FP64 instructions per node;
 //               agrees with FAITHFUL to a few 1e-16 (tests/test_parity_gpu.py).
 #pragma once
-#include <cmath>
-#include <cstdint>
-
-#if defined(__CUDACC__)
-#define MBB_HD __host__ __device__ __forceinline__
-#define MBB_HD_NOINLINE __host__ __device__ __noinline__
-#else
-#define MBB_HD inline
-#define MBB_HD_NOINLINE inline
-#endif
+#include "mbb_model_defs.cuh"
+#include "mbb_fastmath.cuh"
 
 namespace mbb {
-
-// Physical constants exactly as the reference hardwires them
-// (modified_blackbody.py:15-18, fnu.pyx:14-15).
-constexpr double kH = 6.6260693e-34;      // J s
-constexpr double kK = 1.3806505e-23;      // J / K
-constexpr double kCum = 299792458e6;      // um / s
-constexpr double kUmToGHz = 299792458e-3; // um * GHz
-constexpr double kInf = __builtin_huge_val();
-
-// Per-evaluation status.  0 and 1 are normal outcomes; the rest map to the
-// exceptions the reference raises (SURVEY.md 8b "Errors").
-enum Status : int {
-  ST_OK = 0,
-  ST_BELOW_LOWLIM = 1,   // likelihood.py:806-807 -> -inf
-  ST_BAD_ALPHA = 2,      // modified_blackbody.py:219-221 ValueError
-  ST_BAD_BETA = 3,       // :222-224 ValueError
-  ST_BRACKET_LOW = 4,    // :294-300 ValueError
-  ST_BRACKET_HIGH = 5,   // :310-316 ValueError
-  ST_NO_CONVERGE = 6,    // brentq RuntimeError
-  ST_OVERFLOW = 7,       // :326-328 OverflowError
-  ST_PEAK_BRACKET = 8,   // :612-630 Exception
-  ST_NONFINITE = 9       // NaN/inf parameters or result
-};
 
 struct Sed {
   double T, beta, lambda0, alpha, fnorm;
   double hokt9;    // 1e9*h/(k*T): array (Cython) path, fnu.pyx:16
   double hokt_e9;  // (h/(k*T))*1e9: scalar (numpy) path, modified_blackbody.py:461-464
   double hcokt, xnorm, x0, normfac, xmerge, kappa;
-  // FAST-mode amplitudes (see header comment)
+  int status;
+};
+
+// FAST-mode per-walker state: lives in registers, never in local memory.
+//   grey side : f = amp_grey * G_i            (see node_fnu_fast)
+//   power side: f = amp_pow  * exp(alpha * L_i),  L_i = log(wave_i / wavenorm)
+struct FastSed {
+  double T, beta, alpha;
+  double hokt9;                 // 1e9*h/(k*T)
+  double x0, xmerge;
   double amp_grey, amp_pow, q_hi, q_lo;
   int status;
 };
@@ -65,16 +43,6 @@ struct Sed {
 // ---------------------------------------------------------------------------
 // small math helpers
 // ---------------------------------------------------------------------------
-MBB_HD bool finite_d(double x) { return x - x == 0.0; }
-
-// exp(b * (l_hi + l_lo)) with the product carried in double-double.
-MBB_HD double exp_prod(double b, double l_hi, double l_lo) {
-  double y = b * l_hi;
-  double e = fma(b, l_hi, -y) + b * l_lo;
-  double r = exp(y);
-  return fma(r, e, r);
-}
-
 // Python's float ** float raises OverflowError when a finite base overflows;
 // callers test the result with finite_d().
 MBB_HD double ppow(double x, double y) { return pow(x, y); }
@@ -173,7 +141,6 @@ MBB_HD_NOINLINE void sed_setup(Sed& s, double T, double beta, double lambda0, do
   s.T = T; s.beta = beta; s.lambda0 = lambda0; s.alpha = alpha; s.fnorm = fnorm;
   s.status = ST_OK;
   s.x0 = 0.0; s.xmerge = kInf; s.kappa = 0.0;
-  s.amp_grey = s.amp_pow = s.q_hi = s.q_lo = 0.0;
   if (ALPHA && !(alpha > 0.0)) { s.status = ST_BAD_ALPHA; }
   if (!(beta >= 0.0)) { s.status = ST_BAD_BETA; }
   if (!finite_d(T) || !finite_d(fnorm) || (!THIN && !finite_d(lambda0))) s.status = ST_NONFINITE;
@@ -241,46 +208,114 @@ MBB_HD_NOINLINE void sed_setup(Sed& s, double T, double beta, double lambda0, do
   if (!finite_d(s.normfac)) s.status = ST_OVERFLOW;
 }
 
-// FAST-mode amplitudes, derived from the same per-walker constants:
-//   grey side : f = amp_grey * G_i            G_i see node_fnu_fast
-//   power side: f = amp_pow  * exp(alpha * L_i)
-// where L_i = log(wave_i / wavenorm)  (so cx_i / xnorm = exp(-L_i)).
-template <bool THIN, bool ALPHA>
-MBB_HD void sed_setup_fast(Sed& s, double wavenorm) {
-  if (s.status != ST_OK) return;
-  const double xn = s.xnorm;
-  double tn_fac = 1.0;   // -expm1(-t_n), t_n = (xnorm/x0)^beta  (thick only)
-  if (!THIN) {
-    // q = log(xnorm / x0) = log(lambda0 / wavenorm), carried as hi + lo
-    double r = s.lambda0 / wavenorm;
-    double q = log(r);
-    // one Newton correction: log(r) = q + (r*exp(-q) - 1) + O(eps^2)
-    s.q_hi = q;
-    s.q_lo = fma(r, exp(-q), -1.0);
-    tn_fac = -expm1(-exp_prod(s.beta, s.q_hi, s.q_lo));
+// ---------------------------------------------------------------------------
+// FAST-mode per-walker setup.  Same quantities as sed_setup, but
+//   * only what the FAST node formulas need (no normfac / kappa: the
+//     normalisation is carried as ratios, so nothing over/underflows);
+//   * one IEEE division (hokt9, formed exactly as fnu.pyx:16 does) -- every
+//     other quotient goes through div_fast, every exp/expm1 through
+//     mbb_fastmath.cuh;
+//   * xnorm = hokt9 * (c/wavenorm) instead of (h c / k T) / wavenorm: the same
+//     number to 1-2 ulp.
+// `nu_norm` = 299792.458 / wavenorm [GHz], precomputed on the host.
+// ---------------------------------------------------------------------------
+MBB_HD double merge_residual_fast(double x, double alpha, double beta, double inv_x0) {
+  const double t = exp_fast(beta * log(x * inv_x0));
+  // t/expm1(t): -> 1 as t -> 0, -> 0 as t -> inf (saturating expm1_fast)
+  const double bterm = t < 1e-280 ? 1.0 : t * rcp_fast(expm1_fast(t));
+  return x + expm1_fast(-x) * (3.0 + alpha + beta * bterm);
+}
+
+MBB_HD double thin_merge_root_fast(double a) {
+  double x = a;
+  for (int it = 0; it < 12; ++it) {
+    const double e = a * exp_fast(-x);
+    const double dx = div_fast((x - a) + e, 1.0 - e);
+    x -= dx;
+    if (fabs(dx) <= 1.2e-16 * x) break;
   }
-  // amplitude of the grey-body side if the normalisation wavelength is on it
-  const double grey_at_norm = THIN ? s.fnorm * expm1(xn) : s.fnorm * expm1(xn) / tn_fac;
-  if (!ALPHA) { s.amp_grey = grey_at_norm; return; }
-  // R = grey(xmerge) * xmerge^alpha / (grey(xnorm) * xnorm^alpha) * [expm1(xnorm) / tn_fac]^-1 ...
-  // written as ratios so nothing over/underflows:
-  const double xm = s.xmerge;
-  const double lmn = log(xm / xn);
+  return x;
+}
+
+template <bool THIN, bool ALPHA>
+MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double alpha, double fnorm,
+                       double wavenorm, double nu_norm) {
+  f.T = T; f.beta = beta; f.alpha = alpha;
+  f.status = ST_OK;
+  f.x0 = 0.0; f.xmerge = kInf; f.amp_grey = f.amp_pow = f.q_hi = f.q_lo = 0.0;
+  if (ALPHA && !(alpha > 0.0)) f.status = ST_BAD_ALPHA;
+  if (!(beta >= 0.0)) f.status = ST_BAD_BETA;
+  if (!finite_d(T) || !finite_d(fnorm) || (!THIN && !finite_d(lambda0)) || (ALPHA && !finite_d(alpha)) ||
+      !finite_d(beta))
+    f.status = ST_NONFINITE;
+  f.hokt9 = 1e9 * kH / (kK * T);
+  if (f.status != ST_OK) return;
+  const double xn = f.hokt9 * nu_norm;
+  double inv_x0 = 0.0, tn_fac = 1.0;
+  if (!THIN) {
+    // q = log(xnorm/x0) = log(lambda0/wavenorm)
+    const double r = lambda0 / wavenorm;
+    f.x0 = div_fast(xn, r);
+    inv_x0 = rcp_fast(f.x0);
+    f.q_hi = log(r);
+    f.q_lo = 0.0;
+    tn_fac = -expm1_fast(-exp_prod_fast(beta, f.q_hi, f.q_lo));     // 1 - exp(-(xn/x0)^beta)
+  }
+  const double em_n = expm1_fast(xn);
+  const double grey_at_norm = THIN ? fnorm * em_n : div_fast(fnorm * em_n, tn_fac);
+  if (!ALPHA) {
+    f.amp_grey = grey_at_norm;
+    if (!finite_d(f.amp_grey)) f.status = ST_OVERFLOW;
+    return;
+  }
+  if (THIN) {
+    f.xmerge = thin_merge_root_fast(3.0 + alpha + beta);               // modified_blackbody.py:253-254
+  } else {
+    // bracket + Brent exactly as sed_setup (modified_blackbody.py:286-321)
+    double a = 0.1, av = merge_residual_fast(a, alpha, beta, inv_x0);
+    int it = 0;
+    while (av >= 0.0) {
+      a /= 2.0;
+      av = merge_residual_fast(a, alpha, beta, inv_x0);
+      if (it > 100) { f.status = ST_BRACKET_LOW; break; }
+      ++it;
+    }
+    double b = 15.0, bv = merge_residual_fast(b, alpha, beta, inv_x0);
+    it = 0;
+    while (f.status == ST_OK && bv <= 0.0) {
+      b *= 2.0;
+      bv = merge_residual_fast(b, alpha, beta, inv_x0);
+      if (it > 100) { f.status = ST_BRACKET_HIGH; break; }
+      ++it;
+    }
+    if (f.status == ST_OK && (!(av < 0.0) || !(bv > 0.0))) f.status = ST_NONFINITE;
+    if (f.status != ST_OK) return;
+    int st = ST_OK;
+    f.xmerge = brent_root([=](double x) { return merge_residual_fast(x, alpha, beta, inv_x0); }, a, b,
+                          av, bv, st);
+    if (st != ST_OK) { f.status = st; return; }
+  }
+  // R = grey(xmerge) xmerge^alpha / (grey(xnorm) xnorm^alpha), built from ratios
+  const double xm = f.xmerge;
+  const double lmn = log(div_fast(xm, xn));
+  const double inv_em_m = rcp_fast(expm1_fast(xm));
   double R;
   if (THIN) {
-    R = exp((3.0 + s.beta + s.alpha) * lmn) / expm1(xm);
+    R = exp_fast((3.0 + beta + alpha) * lmn) * inv_em_m * em_n;        // times grey_at_norm/fnorm
+    // (amp_grey = fnorm*em_n when xn <= xm) -> amp_pow = fnorm * R
   } else {
-    double tm = exp(s.beta * (lmn + s.q_hi));
-    R = -expm1(-tm) * exp((3.0 + s.alpha) * lmn) / expm1(xm);
+    const double tm = exp_fast(beta * (lmn + f.q_hi));
+    R = -expm1_fast(-tm) * exp_fast((3.0 + alpha) * lmn) * inv_em_m * div_fast(em_n, tn_fac);
   }
-  // R = kappa * xnorm^-(3+b+alpha) [thin] or kappa * xnorm^-(3+alpha) [thick]
+  // here R = amp_pow / fnorm when the normalisation wavelength sits on the grey side
   if (xn > xm) {
-    s.amp_pow = s.fnorm;
-    s.amp_grey = s.fnorm / R;
+    f.amp_pow = fnorm;
+    f.amp_grey = div_fast(fnorm * grey_at_norm, fnorm * R);
   } else {
-    s.amp_grey = grey_at_norm;
-    s.amp_pow = grey_at_norm * R;
+    f.amp_grey = grey_at_norm;
+    f.amp_pow = fnorm * R;
   }
+  if (!finite_d(f.amp_grey) || !finite_d(f.amp_pow)) f.status = ST_OVERFLOW;
 }
 
 // ---------------------------------------------------------------------------
@@ -311,17 +346,15 @@ MBB_HD double node_fnu(const Sed& s, double cx) {
 }
 
 // One node, FAST arithmetic.  l_hi/l_lo = log(wave_i/wavenorm) (double-double),
-// rcube = (wavenorm/wave_i)^3, cx as above.
+// rcube = (wavenorm/wave_i)^3, cx = hokt9 * freq_i.
 template <bool THIN, bool ALPHA>
-MBB_HD double node_fnu_fast(const Sed& s, double cx, double l_hi, double l_lo, double rcube) {
-  if (ALPHA && cx > s.xmerge) return s.amp_pow * exp_prod(s.alpha, l_hi, l_lo);
-  const double em = expm1(cx);
-  if (THIN) return s.amp_grey * exp_prod(-(s.beta + 3.0), l_hi, l_lo) / em;
+MBB_HD double node_fnu_fast(const FastSed& s, double cx, double l_hi, double l_lo, double rcube) {
+  if (ALPHA && cx > s.xmerge) return s.amp_pow * exp_prod_fast(s.alpha, l_hi, l_lo);
+  const double em = expm1_fast(cx);
+  if (THIN) return div_fast(s.amp_grey * exp_prod_fast(-(s.beta + 3.0), l_hi, l_lo), em);
   // t = (cx/x0)^beta = exp(beta * (q - L_i))
-  double d_hi = s.q_hi - l_hi;
-  double d_lo = s.q_lo - l_lo;
-  double t = exp_prod(s.beta, d_hi, d_lo);
-  return s.amp_grey * (-expm1(-t)) * rcube / em;
+  const double t = exp_prod_fast(s.beta, s.q_hi - l_hi, s.q_lo - l_lo);
+  return div_fast(s.amp_grey * (-expm1_fast(-t)) * rcube, em);
 }
 
 // ---------------------------------------------------------------------------
@@ -371,6 +404,84 @@ MBB_HD_NOINLINE double max_wave(double T, double beta, double x0, int& status) {
 }
 
 // ---------------------------------------------------------------------------
+// Frequency integral of f_nu: modified_blackbody.freq_integrate
+// (modified_blackbody.py:639-674), the integrand of L_IR (results.py:669-673).
+//
+// The reference hands f_nu to scipy.integrate.quad (adaptive QUADPACK,
+// ~150-360 integrand calls).  Here the integral is done in closed form where
+// one exists and by a fixed rule elsewhere:
+//   * above the merge point f_nu is a pure power law, kappa x^-alpha:
+//     integrated analytically;
+//   * the grey-body part is integrated in u = ln x (x = h nu / k T), where the
+//     integrand x * grey(x) is analytic and bell-shaped, with 8 equal panels
+//     of 16-point Gauss-Legendre over [x1, min(x_end, xcut)]; beyond
+//     xcut = 50 + 3 (4 + beta) the integrand is < 1e-17 of its peak.
+// Against a 40-digit mpmath integral this is accurate to ~1e-15; the
+// reference's own quad() result is only good to ~1e-9 when alpha is on (kink
+// at the merge inside the interval), so parity with it is checked at 5e-9 and
+// parity with the truth at 1e-13 (tests).
+// ---------------------------------------------------------------------------
+constexpr int kLirPanels = 8;
+constexpr int kLirNodes = 16 * kLirPanels;
+
+MBB_HD void gl16(int j, double& t, double& w) {
+  const double T[8] = {0.095012509837637441, 0.28160355077925892, 0.45801677765722737,
+                       0.61787624440264377,  0.755404408355003,   0.86563120238783176,
+                       0.9445750230732326,   0.98940093499164994};
+  const double W[8] = {0.18945061045506864, 0.18260341504492364, 0.16915651939500265,
+                       0.14959598881657671, 0.12462897125553407, 0.095158511682492605,
+                       0.062253523938647456, 0.027152459411754176};
+  const int k = j < 8 ? 7 - j : j - 8;
+  t = j < 8 ? -T[k] : T[k];
+  w = W[k];
+}
+
+// grey-body shape (before normfac) at x, numpy formulation (modified_blackbody.py:468-490)
+template <bool THIN>
+MBB_HD double grey_shape(double x, double beta, double x0) {
+  if (THIN) return ppow(x, 3.0 + beta) / expm1(x);
+  return -expm1(-ppow(x / x0, beta)) * (x * x * x) / expm1(x);
+}
+
+struct LirSpan {
+  double u1, du;     // grey-body part: u in [u1, u1 + kLirPanels*du], 0 panels if du <= 0
+  double pow_part;   // analytic integral of kappa x^-alpha over the power-law part
+};
+
+template <bool ALPHA>
+MBB_HD LirSpan lir_span(double x1, double x2, double beta, double alpha, double xmerge, double kappa) {
+  LirSpan sp;
+  sp.pow_part = 0.0;
+  double xg2 = x2;
+  if (ALPHA) {
+    if (x2 > xmerge) {
+      const double xa = x1 > xmerge ? x1 : xmerge;
+      const double om = 1.0 - alpha;
+      if (fabs(om) > 1e-9) sp.pow_part = kappa * (ppow(x2, om) - ppow(xa, om)) / om;
+      else sp.pow_part = kappa * log(x2 / xa);
+      xg2 = xmerge;
+    }
+  }
+  const double xcut = fmax(50.0 + 3.0 * (4.0 + beta), x1 + 40.0);
+  const double xe = fmin(xg2, xcut);
+  sp.u1 = log(x1);
+  sp.du = xe > x1 ? (log(xe) - sp.u1) / kLirPanels : 0.0;
+  return sp;
+}
+
+// contribution of quadrature node `node` (0..kLirNodes-1) to the u-integral
+template <bool THIN>
+MBB_HD double lir_node(const LirSpan& sp, int node, double beta, double x0) {
+  if (!(sp.du > 0.0)) return 0.0;
+  double t, w;
+  gl16(node & 15, t, w);
+  const double a = sp.u1 + sp.du * (node >> 4);
+  const double u = a + 0.5 * sp.du * (t + 1.0);
+  const double x = exp(u);
+  return 0.5 * sp.du * w * grey_shape<THIN>(x, beta, x0) * x;
+}
+
+// ---------------------------------------------------------------------------
 // Limits and priors: likelihood._check_lowlim / _uplim_prior / _gprior
 // (likelihood.py:643-752).  Index 5 is the ghost parameter lambda_peak.
 // ---------------------------------------------------------------------------
@@ -394,8 +505,8 @@ MBB_HD bool below_lowlim(const Priors& pr, const double p[5]) {
 // Returns the soft-upper-limit penalty in `pen` and the Gaussian-prior term in
 // `gp`; the caller adds them in the reference's order (likelihood.py:828-832).
 template <bool THIN>
-MBB_HD void prior_terms(const Priors& pr, const double p[5], const Sed& s, double& pen,
-                        double& gp, int& status) {
+MBB_HD void prior_terms(const Priors& pr, const double p[5], double T, double beta, double x0,
+                        double& pen, double& gp, int& status) {
   pen = 0.0;
   gp = 0.0;
 #pragma unroll
@@ -411,7 +522,7 @@ MBB_HD void prior_terms(const Priors& pr, const double p[5], const Sed& s, doubl
   }
   double peak = 0.0;
   const bool need_peak = pr.has_uplim[5] || (pr.any_gprior && pr.has_gprior[5]);
-  if (need_peak) peak = max_wave<THIN>(s.T, s.beta, s.x0, status);
+  if (need_peak) peak = max_wave<THIN>(T, beta, x0, status);
   if (pr.has_uplim[5]) {
     double lim = pr.uplim[5];
     if (peak > lim) {
@@ -456,46 +567,65 @@ struct TabView {
 
 constexpr int kMaxBandsPerThread = 64;
 
+// chi-square of one evaluation given a callable returning f_nu at node i
+template <class Tab, class NodeFn>
+MBB_HD double chi_square(const Tab& t, const double* flux, const double* ivar, const double* cinv,
+                         NodeFn node) {
+  const int nb = t.nb;
+  double chi = 0.0;
+  if (!cinv) {
+    for (int b = 0; b < nb; ++b) {
+      double acc = 0.0;
+      for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i) acc = fma(node(b, i), t.w[i], acc);
+      const double df = flux[b] - acc;
+      chi = fma(df * df, ivar[b], chi);
+    }
+    return chi;
+  }
+  double diff[kMaxBandsPerThread];
+  for (int b = 0; b < nb; ++b) {
+    double acc = 0.0;
+    for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i) acc = fma(node(b, i), t.w[i], acc);
+    diff[b] = flux[b] - acc;
+  }
+  for (int r = 0; r < nb; ++r) {
+    double row = 0.0;
+    for (int c = 0; c < nb; ++c) row = fma(cinv[r * nb + c], diff[c], row);
+    chi = fma(diff[r], row, chi);
+  }
+  return chi;
+}
+
 template <bool THIN, bool ALPHA, bool FAST, class Tab>
-MBB_HD double loglike_one(const double p[5], double wavenorm, const Priors& pr, const Tab& t,
-                          const double* flux, const double* ivar, const double* cinv, int& st) {
+MBB_HD double loglike_one(const double p[5], double wavenorm, double nu_norm, const Priors& pr,
+                          const Tab& t, const double* flux, const double* ivar, const double* cinv,
+                          int& st) {
   st = ST_OK;
   if (below_lowlim(pr, p)) {
     st = ST_BELOW_LOWLIM;
     return -kInf;
   }
-  Sed s;
-  sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
-  if (FAST) sed_setup_fast<THIN, ALPHA>(s, wavenorm);
-  st = s.status;
   const double nan = kInf - kInf;
-  if (st != ST_OK) return nan;
-  const int nb = t.nb;
-  double chi = 0.0;
-  double diff[kMaxBandsPerThread];
-  for (int b = 0; b < nb; ++b) {
-    const double hk = t.scalar_path[b] ? s.hokt_e9 : s.hokt9;
-    double acc = 0.0;
-    for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i) {
-      const double cx = hk * t.freq[i];
-      double f;
-      if (FAST) f = node_fnu_fast<THIN, ALPHA>(s, cx, t.lhi[i], t.llo[i], t.rcube[i]);
-      else f = node_fnu<THIN, ALPHA>(s, cx);
-      acc = fma(f, t.w[i], acc);
-    }
-    const double df = flux[b] - acc;
-    if (cinv) diff[b] = df;
-    else chi = fma(df * df, ivar[b], chi);
+  double chi, pen, gp;
+  if (FAST) {
+    FastSed s;
+    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm, nu_norm);
+    st = s.status;
+    if (st != ST_OK) return nan;
+    chi = chi_square(t, flux, ivar, cinv, [&](int, int i) {
+      return node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[i], t.lhi[i], t.llo[i], t.rcube[i]);
+    });
+    prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+  } else {
+    Sed s;
+    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+    st = s.status;
+    if (st != ST_OK) return nan;
+    chi = chi_square(t, flux, ivar, cinv, [&](int b, int i) {
+      return node_fnu<THIN, ALPHA>(s, (t.scalar_path[b] ? s.hokt_e9 : s.hokt9) * t.freq[i]);
+    });
+    prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
   }
-  if (cinv) {
-    for (int r = 0; r < nb; ++r) {
-      double row = 0.0;
-      for (int c = 0; c < nb; ++c) row = fma(cinv[r * nb + c], diff[c], row);
-      chi = fma(diff[r], row, chi);
-    }
-  }
-  double pen, gp;
-  prior_terms<THIN>(pr, p, s, pen, gp, st);
   double lnl = -0.5 * chi;
   lnl += pen;
   if (pr.any_gprior) lnl += gp;

@@ -24,7 +24,7 @@ void run_loglike(long long n, const double* pars, double wavenorm, const Priors&
   for (long long e = 0; e < n; ++e) {
     const long long src = e / wps;
     int st;
-    out[e] = loglike_one<THIN, ALPHA, FAST>(pars + 5 * e, wavenorm, pr, t, flux + src * nb,
+    out[e] = loglike_one<THIN, ALPHA, FAST>(pars + 5 * e, wavenorm, kUmToGHz / wavenorm, pr, t, flux + src * nb,
                                              ivar ? ivar + src * nb : nullptr,
                                              cinv ? cinv + src * nb * nb : nullptr, st);
     status[e] = st;
@@ -52,24 +52,46 @@ void run_fnu(long long n, const double* pars, double wavenorm, int nfreq, const 
   for (long long e = 0; e < n; ++e) {
     const double* p = pars + 5 * e;
     Sed s;
-    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
-    if (fast) sed_setup_fast<THIN, ALPHA>(s, wavenorm);
+    FastSed fs;
+    int status;
+    if (fast) {
+      fast_setup<THIN, ALPHA>(fs, p[0], p[1], p[2], p[3], p[4], wavenorm, kUmToGHz / wavenorm);
+      status = fs.status;
+    } else {
+      sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+      status = s.status;
+    }
     for (int i = 0; i < nfreq; ++i) {
-      const double cx = (scalar_path ? s.hokt_e9 : s.hokt9) * freq[i];
       double v;
-      if (s.status != ST_OK) {
+      if (status != ST_OK) {
         v = kInf - kInf;
       } else if (fast) {
         const double wave = kUmToGHz / freq[i];
         long double l = logl((long double)wave) - logl((long double)wavenorm);
         const double hi = (double)l, lo = (double)(l - (long double)hi);
         long double r = (long double)wavenorm / (long double)wave;
-        v = node_fnu_fast<THIN, ALPHA>(s, cx, hi, lo, (double)(r * r * r));
+        v = node_fnu_fast<THIN, ALPHA>(fs, fs.hokt9 * freq[i], hi, lo, (double)(r * r * r));
       } else {
-        v = node_fnu<THIN, ALPHA>(s, cx);
+        v = node_fnu<THIN, ALPHA>(s, (scalar_path ? s.hokt_e9 : s.hokt9) * freq[i]);
       }
       out[e * nfreq + i] = v;
     }
+  }
+}
+
+template <bool THIN, bool ALPHA>
+void run_lir(long long n, const double* pars, double wavenorm, double fmin, double fmax, double prefac,
+             double* out, int* status) {
+  for (long long e = 0; e < n; ++e) {
+    const double* p = pars + 5 * e;
+    Sed s;
+    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+    status[e] = s.status;
+    if (s.status != ST_OK) { out[e] = kInf - kInf; continue; }
+    const LirSpan sp = lir_span<ALPHA>(s.hokt_e9 * fmin, s.hokt_e9 * fmax, s.beta, s.alpha, s.xmerge, s.kappa);
+    double acc = 0.0;
+    for (int node = 0; node < kLirNodes; ++node) acc += lir_node<THIN>(sp, node, s.beta, s.x0);
+    out[e] = prefac * (1e-17 * (s.normfac * (acc + sp.pow_part) / s.hokt_e9));
   }
 }
 }  // namespace
@@ -124,6 +146,21 @@ void emu_loglike(int thin, int alpha, int fast, long long n, const double* pars,
 void emu_consts(int thin, int alpha, long long n, const double* pars, double wavenorm, int want_peak,
                 double* out, int* status) {
   DISPATCH2(run_consts, thin, alpha, n, pars, wavenorm, want_peak, out, status);
+}
+
+void emu_lir(int thin, int alpha, long long n, const double* pars, double wavenorm, double fmin, double fmax,
+             double prefac, double* out, int* status) {
+  DISPATCH2(run_lir, thin, alpha, n, pars, wavenorm, fmin, fmax, prefac, out, status);
+}
+
+// element-wise checks of the lean math (mode 0 exp, 1 expm1, 2 reciprocal, 3 a/b with b = x+1)
+void emu_fastmath(int mode, long long n, const double* x, double* out) {
+  for (long long i = 0; i < n; ++i) {
+    if (mode == 0) out[i] = exp_fast(x[i]);
+    else if (mode == 1) out[i] = expm1_fast(x[i]);
+    else if (mode == 2) out[i] = rcp_fast(x[i]);
+    else out[i] = div_fast(x[i], x[i] + 1.0);
+  }
 }
 
 void emu_fnu(int thin, int alpha, long long n, const double* pars, double wavenorm, int nfreq,

@@ -80,3 +80,22 @@ def fnu(opthin, noalpha, pars, wavenorm, freq, scalar_path=False, fast=False):
     lib().emu_fnu(int(opthin), int(not noalpha), ctypes.c_longlong(P.shape[0]), _p(P),
                   ctypes.c_double(wavenorm), int(f.size), _p(f), int(scalar_path), int(fast), _p(out))
     return out
+
+
+def lir(opthin, noalpha, pars, wavenorm, minwave, maxwave, prefac=1.0):
+    """freq_integrate over [minwave, maxwave] um (observer frame), times prefac."""
+    P = _c(pars).reshape(-1, 5)
+    n = P.shape[0]
+    out = np.empty(n)
+    st = np.empty(n, dtype=np.int32)
+    fmin, fmax = 299792458e-3 / maxwave, 299792458e-3 / minwave
+    lib().emu_lir(int(opthin), int(not noalpha), ctypes.c_longlong(n), _p(P), ctypes.c_double(wavenorm),
+                  ctypes.c_double(fmin), ctypes.c_double(fmax), ctypes.c_double(prefac), _p(out), _p(st))
+    return out, st
+
+
+def fastmath(mode, x):
+    x = _c(x)
+    out = np.empty_like(x)
+    lib().emu_fastmath(int(mode), ctypes.c_longlong(x.size), _p(x), _p(out))
+    return out

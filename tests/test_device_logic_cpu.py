@@ -116,3 +116,78 @@ def test_status_codes():
     ll, st = emu.loglike(False, False, False, P, 500.0, ep, off, [250.0], [1.0], [0], [3.0], ivar=[1.0])
     assert list(st) == [2, 3, 9]
     assert np.isnan(ll).all()
+
+
+def _mp_truth(oracle, s, minwave, maxwave):
+    """40-digit integral of the reference's f_nu, split at the merge point."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    hok = mp.mpf(oracle.H) / (mp.mpf(oracle.K) * mp.mpf(s.T)) * mp.mpf(1e9)
+    nf = mp.mpf(s.normfac)
+
+    def grey(x):
+        if s.opthin:
+            return x**(3 + mp.mpf(s.beta)) / mp.expm1(x)
+        return -mp.expm1(-(x / mp.mpf(s.x0))**mp.mpf(s.beta)) * x**3 / mp.expm1(x)
+
+    def f(nu):
+        x = hok * nu
+        if (not s.noalpha) and x > mp.mpf(s.xmerge):
+            return nf * mp.mpf(s.kappa) * x**(-mp.mpf(s.alpha))
+        return nf * grey(x)
+
+    f1, f2 = mp.mpf(oracle.UM_TO_GHZ) / maxwave, mp.mpf(oracle.UM_TO_GHZ) / minwave
+    pts = [f1, f2]
+    if not s.noalpha:
+        fm = mp.mpf(s.xmerge) / hok
+        if f1 < fm < f2:
+            pts = [f1, fm, f2]
+    grid = []
+    for a, b in zip(pts[:-1], pts[1:]):
+        grid += [a + (b - a) * mp.mpf(i) / 8 for i in range(8)]
+    grid.append(pts[-1])
+    return mp.quad(f, grid) * mp.mpf(10)**-17
+
+
+@pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
+def test_freq_integrate(golden, oracle, name, opthin, noalpha):
+    """Fixed-rule quadrature vs the reference's adaptive quad (2e-8: the
+    reference itself is only that good with the merge kink inside the range)
+    and vs a 40-digit truth (1e-13)."""
+    g = golden.sed
+    tag = name + "_wn500"
+    ref = g[tag + "_freqint"]
+    m = np.isfinite(ref)
+    P = g[tag + "_P"][m]
+    got, st = emu.lir(opthin, noalpha, P, 500.0, 24.0, 3000.0)
+    assert (st == 0).all()
+    assert relerr(got, ref[m]).max() < 2e-8      # quad epsrel = 1.49e-8
+    for i in range(0, len(P), 5):
+        s = oracle.make_sed(*P[i], noalpha=noalpha, opthin=opthin)
+        truth = float(_mp_truth(oracle, s, 24.0, 3000.0))
+        assert abs(got[i] - truth) <= 1e-13 * abs(truth)
+
+
+def test_fastmath():
+    """The branch-free exp/expm1 of csrc/mbb_fastmath.cuh against mpmath, in ulps."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.RandomState(3)
+    x = np.concatenate([rng.uniform(-60, 60, 3000), rng.uniform(-1, 1, 3000),
+                        rng.uniform(-700, 700, 500), [0.0, 1e-300, -1e-300, 1e-17, 0.34657, -0.34658]])
+    for mode, fn in ((0, mp.exp), (1, mp.expm1)):
+        got = emu.fastmath(mode, x)
+        worst = 0.0
+        for xi, gi in zip(x, got):
+            t = fn(mp.mpf(float(xi)))
+            if t == 0:
+                assert gi == 0.0
+                continue
+            ulp = abs(float(t)) * 2.0**-52
+            worst = max(worst, abs(float(mp.mpf(float(gi)) - t)) / ulp)
+        assert worst < 2.0, (mode, worst)
+    # saturation instead of garbage outside the double range
+    big = emu.fastmath(0, np.array([800.0, 1e6, -800.0, -1e6]))
+    assert big[0] > 1e300 and big[1] > 1e300 and 0.0 <= big[2] < 1e-300 and 0.0 <= big[3] < 1e-300
+    em = emu.fastmath(1, np.array([800.0, -800.0, -50.0]))
+    assert em[0] > 1e300 and em[1] == -1.0 and em[2] == -1.0
