@@ -187,6 +187,33 @@ struct LaunchThread {
   }
 };
 
+constexpr int kMaxDeltaNB = 8;
+
+template <bool THIN, bool ALPHA, int NB>
+struct DeltaLauncher {
+  static void go(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, int nb) {
+    if (nb == NB) {
+      const unsigned grid = (unsigned)((a.n + MBB_DELTA_BLOCK - 1) / MBB_DELTA_BLOCK);
+      ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
+      loglike_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, st>>>(a, m, c->pri, d, c->small);
+    } else {
+      DeltaLauncher<THIN, ALPHA, NB - 1>::go(c, st, a, d, nb);
+    }
+  }
+};
+template <bool THIN, bool ALPHA>
+struct DeltaLauncher<THIN, ALPHA, 0> {
+  static void go(mbb_ctx*, cudaStream_t, const EvalArgs&, const DataRef&, int) {}
+};
+
+template <bool THIN, bool ALPHA, bool FAST>
+struct LaunchDelta {
+  static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
+    DeltaLauncher<THIN, ALPHA, kMaxDeltaNB>::go(c, st, a, d, c->nb);
+    *err = cudaSuccess;
+  }
+};
+
 template <bool THIN, bool ALPHA, bool FAST>
 struct LaunchWarp {
   static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
@@ -467,7 +494,8 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a) {
   d.nb = c->nb;
   const bool thin = c->opthin != 0, alpha = c->noalpha == 0, fast = c->math_mode == MBB_MATH_FAST;
   cudaError_t err = cudaSuccess;
-  if (c->nn <= kSmallMaxNodes) dispatch3<LaunchThread>(thin, alpha, fast, c, st, a, d, &err);
+  if (fast && c->nn == c->nb && c->nb <= kMaxDeltaNB) dispatch3<LaunchDelta>(thin, alpha, true, c, st, a, d, &err);
+  else if (c->nn <= kSmallMaxNodes) dispatch3<LaunchThread>(thin, alpha, fast, c, st, a, d, &err);
   else dispatch3<LaunchWarp>(thin, alpha, fast, c, st, a, d, &err);
   CK(err);
   c->launches += 1;

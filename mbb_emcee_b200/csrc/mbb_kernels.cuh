@@ -115,6 +115,103 @@ loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const D
 }
 
 // ---------------------------------------------------------------------------
+// Delta-band specialisation of the thread kernel: every band is one node (the
+// reference's default, non-response mode -- likelihood.py:817 -- and the
+// BASELINE cfg1/cfg5 workloads), FAST arithmetic, band count known at compile
+// time.  Fully unrolled: the polynomial coefficients and node constants stay
+// in (uniform) registers for the whole evaluation and the NB independent
+// exp/expm1 chains interleave, which is what lifts FP64-pipe utilisation.
+// ---------------------------------------------------------------------------
+#ifndef MBB_DELTA_MINB
+#define MBB_DELTA_MINB 3
+#endif
+#ifndef MBB_DELTA_BLOCK
+#define MBB_DELTA_BLOCK 256
+#endif
+#ifndef MBB_DELTA_EARLY
+#define MBB_DELTA_EARLY 1
+#endif
+template <bool THIN, bool ALPHA, int NB>
+__global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
+loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
+                     const SmallTab t) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  double p[5];
+  load_pars(a, e, p);
+  const long long src = source_of(a, e);
+  double diff[NB], iv[NB];
+#if MBB_DELTA_EARLY
+  // data loads issued next to the parameter loads: one exposed global latency
+  {
+    const double* __restrict__ fl = d.flux + src * NB;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) diff[b] = __ldg(fl + b);
+    if (!d.cinv) {
+      const double* __restrict__ ivp = d.ivar + src * NB;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) iv[b] = __ldg(ivp + b);
+    }
+  }
+#endif
+  int st = ST_OK;
+  double lnl;
+  if (below_lowlim(pr, p)) {
+    st = ST_BELOW_LOWLIM;
+    lnl = -kInf;
+  } else {
+    FastSed s;
+    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm, m.nu_norm);
+    st = s.status;
+    if (st != ST_OK) {
+      lnl = qnan();
+    } else {
+#if !MBB_DELTA_EARLY
+      {
+        const double* __restrict__ fl = d.flux + src * NB;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) diff[b] = __ldg(fl + b);
+        if (!d.cinv) {
+          const double* __restrict__ ivp = d.ivar + src * NB;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) iv[b] = __ldg(ivp + b);
+        }
+      }
+#endif
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const double f =
+            node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
+        diff[b] = fma(-f, t.w[b], diff[b]);
+      }
+      double chi = 0.0;
+      if (d.cinv) {
+        const double* __restrict__ ci = d.cinv + src * (NB * NB);
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+          double row = 0.0;
+#pragma unroll
+          for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
+          chi = fma(diff[r], row, chi);
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) chi = fma(diff[b] * diff[b], iv[b], chi);
+      }
+      double pen, gp;
+      prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+      lnl = -0.5 * chi;
+      lnl += pen;
+      if (pr.any_gprior) lnl += gp;
+      if (st != ST_OK) lnl = qnan();
+      else if (lnl != lnl) st = ST_NONFINITE;
+    }
+  }
+  a.out[e] = lnl;
+  if (a.status) a.status[e] = st;
+}
+
+// ---------------------------------------------------------------------------
 // TMA bulk copy + mbarrier helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) {

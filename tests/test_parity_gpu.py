@@ -383,6 +383,32 @@ def test_chain_post_golden(golden, name, opthin, noalpha):
     assert relerr(res.peaklambda, g[name + "_peaklambda"]).max() < TOL
     res.compute_dustmass(kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
     assert relerr(res.dustmass, g[name + "_dustmass"]).max() < TOL
+    # L_IR: fixed-rule quadrature vs the reference's adaptive quad (requested epsrel 1.49e-8,
+    # observed error of the reference vs a 40-digit truth up to 2.7e-8 with alpha on;
+    # see test_device_logic_cpu.py::test_freq_integrate for the 1e-13 truth check)
+    res.compute_lir(wavemin=cfg["lir"][0], wavemax=cfg["lir"][1])
+    assert relerr(res.lir, g[name + "_lir"]).max() < 1e-7
     # the allclose-dedupe: step 5 of walker 0 is within 3e-6 of step 4
     assert res.peaklambda[0, 5] == res.peaklambda[0, 4]
     assert res.dustmass[0, 5] == res.dustmass[0, 4]
+    assert res.lir[0, 5] == res.lir[0, 4]
+
+
+@pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
+def test_freq_integrate_golden(golden, oracle, name, opthin, noalpha):
+    """modified_blackbody.freq_integrate on the device vs the reference (2e-8)
+    and vs the CPU emulation of the same quadrature (1e-13)."""
+    from mbb_emcee_b200 import modified_blackbody
+    import hostemu_lib as emu
+    g = golden.sed
+    tag = name + "_wn250"
+    P = g[tag + "_P"][:12]
+    ref = g[tag + "_freqint"][:12]
+    want, st = emu.lir(opthin, noalpha, P, 250.0, 24.0, 3000.0)
+    for i in range(len(P)):
+        m = modified_blackbody(P[i, 0], P[i, 1], P[i, 2], P[i, 3], P[i, 4], wavenorm=250.0,
+                               noalpha=noalpha, opthin=opthin)
+        got = m.freq_integrate(24.0, 3000.0)
+        assert abs(got - ref[i]) <= 1e-7 * abs(ref[i])
+        assert abs(got - want[i]) <= 1e-13 * abs(want[i])
+        assert abs(m.max_wave() - g[tag + "_maxwave"][i]) <= TOL * g[tag + "_maxwave"][i]
