@@ -135,12 +135,31 @@ int mbb_sed_consts(mbb_ctx *ctx, int64_t n, const double *pars, int layout,
  * (results.py:553-566).  which: bit0 peak lambda, bit1 L_IR, bit2 dust mass;
  * outputs [nwalkers][nsteps], NULL where not requested.
  * L_IR: integral of f_nu over [lir_min, lir_max]*(1+z) um in the observer
- * frame times 3.11749657e4*dl_mpc^2*1e-17 (results.py:665-673).  */
+ * frame times 3.11749657e4*dl_mpc^2*1e-17 (results.py:665-673); dl_mpc <= 0
+ * selects prefactor 1, i.e. modified_blackbody.freq_integrate (:639-674).
+ * The SED flags and wavenorm are those of mbb_set_model.  */
 int mbb_chain_post(mbb_ctx *ctx, int64_t nwalkers, int64_t nsteps,
                    const double *chain, int which, double z, double dl_mpc,
                    double lir_min_um, double lir_max_um, double kappa,
                    double kappa_wave_um, double *out_peak, double *out_lir,
                    double *out_dustmass, int32_t *out_status, int mem);
+
+/* ---- device-resident ensemble sampler for nsrc sources at once:
+ * what mbb_fitter.run asks emcee for (mbb_fit.py:525-542 -> emcee 2.2 stretch
+ * move, two half-ensembles per iteration), with proposal, log-probability and
+ * accept/reject all on the GPU.  pos[nsrc][nwalkers][5] and
+ * lnprob[nsrc][nwalkers] are updated in place (lnprob is computed first unless
+ * have_lnprob != 0).  Random numbers: Philox4x32-10 keyed by `seed`, counter =
+ * (source*nwalkers/2 + walker-in-half, 2*(step0+t)+half, stream): pass step0 =
+ * iterations already done to continue a run (burn-in then main chain).
+ * naccept/status [nsrc][nwalkers] may be NULL.  chain[nsteps/thin][nsrc][nwalkers][5]
+ * and chain_lnprob[nsteps/thin][nsrc][nwalkers] (MBB_DEVICE only, may be NULL)
+ * receive every thin-th ensemble. */
+int mbb_ensemble_run(mbb_ctx *ctx, int64_t nsrc, int nwalkers, int64_t nsteps,
+                     double a, uint64_t seed, uint64_t step0, double *pos,
+                     double *lnprob, int have_lnprob, int32_t *naccept,
+                     int32_t *status, double *chain, double *chain_lnprob,
+                     int thin, int mem);
 
 /* ---- measurement aid: sustained DFMA rate of this device in TFLOP/s
  * (2 flops per DFMA), the FP64 roofline denominator bench.py reports. */

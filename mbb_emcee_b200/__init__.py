@@ -13,6 +13,7 @@ from .utility import *              # noqa: F401,F403
 from .response import *             # noqa: F401,F403
 from .mbb_fit import *              # noqa: F401,F403
 from .results import *              # noqa: F401,F403
+from .batch_fit import batch_fitter     # noqa: F401
 from .ensemble import EnsembleSampler  # noqa: F401
 from ._native import MBBNativeError    # noqa: F401
 

@@ -78,6 +78,8 @@ def load_library():
             "mbb_sed_consts": (i32, [vp, i64, vp, i32, i32, vp, vp, i32]),
             "mbb_chain_post": (i32, [vp, i64, i64, vp, i32, dbl, dbl, dbl, dbl, dbl, dbl,
                                      vp, vp, vp, vp, i32]),
+            "mbb_ensemble_run": (i32, [vp, i64, i32, i64, dbl, ctypes.c_uint64, ctypes.c_uint64, vp, vp,
+                                       i32, vp, vp, vp, vp, i32, i32]),
             "mbb_fp64_peak": (i32, [vp, i32, ctypes.POINTER(dbl)]),
         }
         for name, (res, args) in sig.items():
@@ -92,7 +94,7 @@ EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ct
                     "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
                     "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_bands",
                     "mbb_set_data", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
-                    "mbb_chain_post", "mbb_fp64_peak"]
+                    "mbb_chain_post", "mbb_ensemble_run", "mbb_fp64_peak"]
 
 
 def _f64(a):
@@ -251,6 +253,31 @@ class Context(object):
                                           float(kappa), float(kappa_wave), _ptr(pk), _ptr(lir),
                                           _ptr(dm), _ptr(st), HOST))
         return pk, lir, dm, st
+
+    def ensemble_run(self, pos, nsteps, seed=0, step0=0, a=2.0, lnprob=None):
+        """Device-resident stretch-move sampler (host arrays in/out).
+        pos[nsrc][nwalkers][5]; returns (pos, lnprob, naccept, status)."""
+        pos = np.array(pos, dtype=np.float64, order="C")
+        nsrc, nw = pos.shape[0], pos.shape[1]
+        have = lnprob is not None
+        lnp = np.array(lnprob, dtype=np.float64, order="C") if have else np.empty((nsrc, nw))
+        nacc = np.zeros((nsrc, nw), dtype=np.int32)
+        st = np.zeros((nsrc, nw), dtype=np.int32)
+        self._ck(self._lib.mbb_ensemble_run(self._h, nsrc, nw, int(nsteps), float(a), int(seed),
+                                            int(step0), _ptr(pos), _ptr(lnp), int(have), _ptr(nacc),
+                                            _ptr(st), None, None, 1, HOST))
+        return pos, lnp, nacc, st
+
+    def ensemble_run_device(self, nsrc, nwalkers, nsteps, pos_ptr, lnprob_ptr, have_lnprob=False,
+                            seed=0, step0=0, a=2.0, naccept_ptr=0, status_ptr=0, chain_ptr=0,
+                            chain_lnprob_ptr=0, thin=1):
+        """Raw device pointers; asynchronous (call sync())."""
+        def vp(x):
+            return ctypes.c_void_p(x) if x else None
+        self._ck(self._lib.mbb_ensemble_run(self._h, int(nsrc), int(nwalkers), int(nsteps), float(a),
+                                            int(seed), int(step0), vp(pos_ptr), vp(lnprob_ptr),
+                                            int(bool(have_lnprob)), vp(naccept_ptr), vp(status_ptr),
+                                            vp(chain_ptr), vp(chain_lnprob_ptr), int(thin), DEVICE))
 
     def sync(self):
         self._ck(self._lib.mbb_sync(self._h))

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/mbb_b200.h"
+#include "mbb_ensemble.cuh"
 #include "mbb_kernels.cuh"
 
 using namespace mbb;
@@ -122,6 +123,9 @@ struct mbb_ctx {
   DevBuf<double> d_in, d_out, d_aux0, d_aux1;
   DevBuf<int> d_st, d_src, d_owner, d_work;
   DevBuf<unsigned> d_count;
+  // ensemble sampler scratch
+  DevBuf<double> d_epos, d_elnp, d_eq, d_eqlnp;
+  DevBuf<int> d_enacc, d_est, d_eqst;
 };
 
 namespace {
@@ -312,6 +316,8 @@ int mbb_ctx_destroy(mbb_ctx* c) {
   c->d_in.release(); c->d_out.release(); c->d_aux0.release(); c->d_aux1.release();
   c->d_st.release(); c->d_src.release(); c->d_owner.release(); c->d_work.release();
   c->d_count.release();
+  c->d_epos.release(); c->d_elnp.release(); c->d_eq.release(); c->d_eqlnp.release();
+  c->d_enacc.release(); c->d_est.release(); c->d_eqst.release();
   for (auto& sl : c->slots) {
     sl.hin.release(); sl.hout.release(); sl.hst.release(); sl.hsrc.release();
     sl.din.release(); sl.dout.release(); sl.dst.release(); sl.dsrc.release();
@@ -818,6 +824,93 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
                          c->stream));
     if (out_status)
       CK(cudaMemcpyAsync(out_status, dst, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, double a, uint64_t seed,
+                     uint64_t step0, double* pos, double* lnprob, int have_lnprob, int32_t* naccept,
+                     int32_t* status, double* chain, double* chain_lnprob, int thin, int mem) {
+  if (!c) return fail("null context");
+  if (nsrc <= 0 || nsteps < 0) return fail("nsrc must be positive, nsteps non-negative");
+  if (nwalkers < 2 || (nwalkers & 1)) return fail("the number of walkers must be even");
+  if (nwalkers <= 10) return fail("need more than 2*dim = 10 walkers");
+  if (!(a > 1.0)) return fail("stretch scale a must be > 1");
+  if (!pos || !lnprob) return fail("null pos/lnprob pointer");
+  if (!c->bands_set || (!c->has_ivar && !c->has_cinv)) return fail("bands/data not set");
+  if (nsrc > c->nsrc) return fail("more sources than mbb_set_data provided");
+  if (thin < 1) thin = 1;
+  Use u(c);
+  const int h = nwalkers / 2;
+  const long long nwk = nsrc * nwalkers, nh = nsrc * h;
+  if (nwk >= (1LL << 31)) return fail("too many walkers for one call (>= 2^31); shard the sources");
+  double *dpos = pos, *dlnp = lnprob;
+  int *dnacc = naccept, *dst = status;
+  if (mem != MBB_DEVICE) {
+    CK(c->d_epos.reserve((size_t)nwk * 5));
+    CK(c->d_elnp.reserve((size_t)nwk));
+    CK(cudaMemcpyAsync(c->d_epos.p, pos, (size_t)nwk * 5 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (have_lnprob)
+      CK(cudaMemcpyAsync(c->d_elnp.p, lnprob, (size_t)nwk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dpos = c->d_epos.p;
+    dlnp = c->d_elnp.p;
+    dnacc = nullptr;
+    dst = nullptr;
+    if (chain || chain_lnprob) return fail("chain output needs MBB_DEVICE buffers (it is large); keep it on the device");
+  }
+  if (!dnacc) { CK(c->d_enacc.reserve((size_t)nwk)); dnacc = c->d_enacc.p; }
+  if (!dst) { CK(c->d_est.reserve((size_t)nwk)); dst = c->d_est.p; }
+  CK(cudaMemsetAsync(dnacc, 0, (size_t)nwk * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(dst, 0, (size_t)nwk * sizeof(int), c->stream));
+  CK(c->d_eq.reserve((size_t)nh * 5));
+  CK(c->d_eqlnp.reserve((size_t)nh));
+  CK(c->d_eqst.reserve((size_t)nh));
+  begin_timing(c);
+  if (!have_lnprob) {
+    // log-probability of the starting ensemble (emcee computes it once up front)
+    EvalArgs e{};
+    e.n = nwk; e.e0 = 0; e.wps = nwalkers; e.layout = MBB_AOS;
+    e.pars = dpos; e.src_index = nullptr; e.out = dlnp; e.status = dst;
+    if (launch_loglike(c, c->stream, e)) return 1;
+  }
+  EnsArgs g;
+  g.pos = dpos; g.lnp = dlnp; g.nacc = dnacc; g.status = dst;
+  g.q = c->d_eq.p; g.qlnp = c->d_eqlnp.p; g.qst = c->d_eqst.p;
+  g.nsrc = nsrc; g.nw = nwalkers; g.h = h; g.seed = seed; g.a = a;
+  const unsigned grid = (unsigned)((nh + 255) / 256);
+  int64_t kept = 0;
+  for (int64_t it = 0; it < nsteps; ++it) {
+    for (int half = 0; half < 2; ++half) {
+      g.half = half;
+      g.hstep = 2 * (step0 + (uint64_t)it) + (uint64_t)half;
+      ens_propose_kernel<<<grid, 256, 0, c->stream>>>(g);
+      EvalArgs e{};
+      e.n = nh; e.e0 = 0; e.wps = h; e.layout = MBB_AOS;
+      e.pars = g.q; e.src_index = nullptr; e.out = g.qlnp; e.status = g.qst;
+      if (launch_loglike(c, c->stream, e)) return 1;
+      ens_accept_kernel<<<grid, 256, 0, c->stream>>>(g);
+      c->launches += 2;
+    }
+    if ((chain || chain_lnprob) && ((it + 1) % thin == 0)) {
+      if (chain)
+        CK(cudaMemcpyAsync(chain + (size_t)kept * nwk * 5, dpos, (size_t)nwk * 5 * sizeof(double),
+                           cudaMemcpyDeviceToDevice, c->stream));
+      if (chain_lnprob)
+        CK(cudaMemcpyAsync(chain_lnprob + (size_t)kept * nwk, dlnp, (size_t)nwk * sizeof(double),
+                           cudaMemcpyDeviceToDevice, c->stream));
+      ++kept;
+    }
+  }
+  end_timing(c);
+  CK(cudaGetLastError());
+  if (mem != MBB_DEVICE) {
+    CK(cudaMemcpyAsync(pos, dpos, (size_t)nwk * 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(lnprob, dlnp, (size_t)nwk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (naccept)
+      CK(cudaMemcpyAsync(naccept, dnacc, (size_t)nwk * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (status)
+      CK(cudaMemcpyAsync(status, dst, (size_t)nwk * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
   return 0;

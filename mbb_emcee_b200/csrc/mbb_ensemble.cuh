@@ -1,0 +1,101 @@
+// Device-resident affine-invariant ensemble sampler for many sources at once
+// (SURVEY.md 8f row 1).  The stretch move of Goodman & Weare (2010) with the
+// scheduling of emcee 2.2 (two half-ensembles per iteration, reference
+// mbb_fit.py:80-81, 533-542 drives exactly this through emcee), but with the
+// proposals, the log-probability and the accept/reject step all on the GPU, so
+// walker positions never cross PCIe.
+//
+// Randomness is counter-based (Philox4x32-10, Salmon et al. 2011): the draws
+// of walker `w` of source `s` at half-step `h` of iteration `t` depend only on
+// (seed, s*nw/2 + w, 2t+h), so results are independent of launch geometry and
+// can be replayed on the host (tests/test_ensemble_gpu.py does exactly that
+// with a numpy Philox and the CPU oracle).  Statistically equivalent to, not
+// bit-identical with, emcee's Mersenne-Twister stream.
+#pragma once
+#include "mbb_kernels.cuh"
+#include "mbb_philox.cuh"
+
+namespace mbb {
+
+struct Draw {
+  double z;      // stretch factor ((a-1)u+1)^2/a
+  double lnu;    // log of the acceptance uniform
+  int partner;   // index into the complementary half
+};
+
+__device__ __forceinline__ Draw stretch_draw(unsigned long long seed, unsigned long long widx,
+                                             unsigned long long hstep, double a, int ncomp) {
+  const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+  const Philox r = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)hstep,
+                                 (unsigned)(hstep >> 32) << 1, k0, k1);
+  const Philox s = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)hstep,
+                                 ((unsigned)(hstep >> 32) << 1) | 1u, k0, k1);
+  Draw d;
+  // emcee: zz = ((a - 1.) * rand + 1) ** 2. / a   -- separate roundings, no FMA
+  const double t = __dadd_rn(__dmul_rn(a - 1.0, u53(r.c[0], r.c[1])), 1.0);
+  d.z = __ddiv_rn(__dmul_rn(t, t), a);
+  d.partner = (int)(((unsigned long long)r.c[2] * (unsigned long long)ncomp) >> 32);
+  d.lnu = log(u53(s.c[0], s.c[1]));
+  return d;
+}
+
+struct EnsArgs {
+  double* pos;              // [nsrc][nw][5]
+  double* lnp;              // [nsrc][nw]
+  int* nacc;                // [nsrc][nw]
+  int* status;              // [nsrc][nw], first non-trivial status seen (sticky)
+  double* q;                // [nsrc*h][5] proposal scratch
+  double* qlnp;             // [nsrc*h]
+  int* qst;                 // [nsrc*h]
+  long long nsrc;
+  int nw, h, half;          // h = nw/2; half 0 updates walkers [0,h) against [h,nw)
+  unsigned long long seed, hstep;   // hstep = 2*iteration + half
+  double a;
+};
+
+// q = c[j] - z (c[j] - s), in emcee's operation order
+__global__ void __launch_bounds__(256) ens_propose_kernel(const EnsArgs g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nsrc * g.h) return;
+  const long long src = i / g.h;
+  const int k = (int)(i - src * g.h);
+  const Draw d = stretch_draw(g.seed, (unsigned long long)i, g.hstep, g.a, g.h);
+  const int own = g.half == 0 ? k : g.h + k;
+  const int oth = (g.half == 0 ? g.h : 0) + d.partner;
+  const double* s = g.pos + (src * g.nw + own) * 5;
+  const double* c = g.pos + (src * g.nw + oth) * 5;
+  double* q = g.q + i * 5;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const double cj = c[j];
+    q[j] = __dsub_rn(cj, __dmul_rn(d.z, __dsub_rn(cj, s[j])));
+  }
+}
+
+// accept where (dim-1) ln z + lnp(q) - lnp(s) > ln u   (emcee 2.2 _propose_stretch)
+__global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nsrc * g.h) return;
+  const long long src = i / g.h;
+  const int k = (int)(i - src * g.h);
+  const Draw d = stretch_draw(g.seed, (unsigned long long)i, g.hstep, g.a, g.h);
+  const int own = g.half == 0 ? k : g.h + k;
+  const long long w = src * g.nw + own;
+  const double newlnp = g.qlnp[i];
+  const int st = g.qst[i];
+  if (st > ST_BELOW_LOWLIM) {          // the reference would have raised here
+    if (g.status[w] <= ST_BELOW_LOWLIM) g.status[w] = st;
+    return;
+  }
+  const double lnpdiff = 4.0 * log(d.z) + newlnp - g.lnp[w];
+  if (lnpdiff > d.lnu) {
+    const double* q = g.q + i * 5;
+    double* p = g.pos + w * 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) p[j] = q[j];
+    g.lnp[w] = newlnp;
+    g.nacc[w] += 1;
+  }
+}
+
+}  // namespace mbb

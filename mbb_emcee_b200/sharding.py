@@ -1,0 +1,59 @@
+"""Sharding of independent work across one-process-per-GPU ranks.
+
+Every (source, walker) evaluation and every chain sample is independent
+(SURVEY.md 8e), so multi-GPU use is: cut the unit range into contiguous
+per-rank pieces, run the single-GPU path on each, and gather once at the end.
+Nothing on the evaluation path communicates.  These helpers are the whole of
+the host-side logic; they work with any ``torch.distributed`` backend (NCCL on
+the GPU box, gloo in the CPU tests).
+"""
+import os
+
+import numpy as np
+
+__all__ = ["rank_world", "shard_range", "shard_sources", "gather_concat"]
+
+
+def rank_world():
+    """(rank, world_size) from the torchrun environment (0, 1 when absent)."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced [lo, hi) of ``n`` units for ``rank`` (sizes differ by <= 1)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    base, extra = divmod(int(n), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sources(nsrc, nwalkers, rank, world):
+    """Evaluation index range owned by ``rank`` when sources (never the walkers
+    of one source) are split across ranks: (src_lo, src_hi, eval_lo, eval_hi)."""
+    lo, hi = shard_range(nsrc, rank, world)
+    return lo, hi, lo * nwalkers, hi * nwalkers
+
+
+def gather_concat(local, group=None):
+    """The one final gather: every rank's 1-D/2-D float64 array, concatenated
+    along axis 0 in rank order, on every rank.  Shards may differ in length."""
+    import torch
+    import torch.distributed as dist
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    width = int(np.prod(local.shape[1:])) if local.ndim > 1 else 1
+    pad = torch.zeros((max(sizes), width), dtype=torch.float64, device=dev)
+    pad[:local.shape[0]] = torch.from_numpy(local.reshape(local.shape[0], width)).to(dev)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = np.concatenate([p[:s].cpu().numpy() for p, s in zip(parts, sizes)], axis=0)
+    return out.reshape((-1,) + local.shape[1:]) if local.ndim > 1 else out.ravel()

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../mbb_emcee_b200/csrc/mbb_model.cuh"
+#include "../../mbb_emcee_b200/csrc/mbb_philox.cuh"
 
 using namespace mbb;
 
@@ -161,6 +162,12 @@ void emu_fastmath(int mode, long long n, const double* x, double* out) {
     else if (mode == 2) out[i] = rcp_fast(x[i]);
     else out[i] = div_fast(x[i], x[i] + 1.0);
   }
+}
+
+void emu_philox(const unsigned* ctr, const unsigned* key, unsigned* out, double* u) {
+  const Philox r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = r.c[i];
+  *u = u53(r.c[0], r.c[1]);
 }
 
 void emu_fnu(int thin, int alpha, long long n, const double* pars, double wavenorm, int nfreq,

@@ -99,3 +99,12 @@ def fastmath(mode, x):
     out = np.empty_like(x)
     lib().emu_fastmath(int(mode), ctypes.c_longlong(x.size), _p(x), _p(out))
     return out
+
+
+def philox(ctr, key):
+    c = np.ascontiguousarray(ctr, dtype=np.uint32)
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    u = ctypes.c_double()
+    lib().emu_philox(_p(c), _p(k), _p(out), ctypes.byref(u))
+    return out, u.value

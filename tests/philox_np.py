@@ -1,0 +1,71 @@
+"""TEST INFRASTRUCTURE: numpy Philox4x32-10 and the stretch-move draws of
+csrc/mbb_ensemble.cuh, for replaying the device sampler on the host."""
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised over uint64 arrays holding 32-bit values."""
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) & MASK for x in (c0, c1, c2, c3))
+    k0 = np.uint64(k0 & 0xFFFFFFFF)
+    k1 = np.uint64(k1 & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ k0
+        n1 = p1 & MASK
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ k1
+        n3 = p0 & MASK
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = np.uint64((int(k0) + W0) & 0xFFFFFFFF)
+        k1 = np.uint64((int(k1) + W1) & 0xFFFFFFFF)
+    return c0, c1, c2, c3
+
+
+def u53(hi, lo):
+    m = ((hi >> np.uint64(5)) << np.uint64(26)) | (lo >> np.uint64(6))
+    return (m.astype(np.float64) + 0.5) * 1.1102230246251565e-16
+
+
+def stretch_draw(seed, widx, hstep, a, ncomp):
+    """(z, ln u, partner) for walker indices ``widx`` at half-step ``hstep``."""
+    widx = np.asarray(widx, dtype=np.uint64)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    lo, hi = widx & MASK, widx >> np.uint64(32)
+    h_lo = np.uint64(hstep & 0xFFFFFFFF)
+    h_hi = ((hstep >> 32) << 1) & 0xFFFFFFFF
+    r = philox4x32_10(lo, hi, np.full_like(lo, h_lo), np.full_like(lo, np.uint64(h_hi)), k0, k1)
+    s = philox4x32_10(lo, hi, np.full_like(lo, h_lo), np.full_like(lo, np.uint64(h_hi | 1)), k0, k1)
+    t = (a - 1.0) * u53(r[0], r[1]) + 1.0
+    z = (t * t) / a
+    partner = ((r[2] * np.uint64(ncomp)) >> np.uint64(32)).astype(np.int64)
+    return z, np.log(u53(s[0], s[1])), partner
+
+
+def replay(lnprob_rows, p0, nsteps, seed, a=2.0, step0=0, lnp0=None):
+    """Host replay of mbb_ensemble_run: p0[nsrc][nw][5]; lnprob_rows(src, Q[m,5]) -> [m]."""
+    pos = np.array(p0, dtype=np.float64)
+    nsrc, nw = pos.shape[:2]
+    h = nw // 2
+    lnp = np.array([lnprob_rows(s, pos[s]) for s in range(nsrc)]) if lnp0 is None else np.array(lnp0)
+    nacc = np.zeros((nsrc, nw), dtype=np.int64)
+    for it in range(nsteps):
+        for half in (0, 1):
+            hstep = 2 * (step0 + it) + half
+            for s in range(nsrc):
+                widx = s * h + np.arange(h)
+                z, lnu, partner = stretch_draw(seed, widx, hstep, a, h)
+                own = np.arange(h) + (0 if half == 0 else h)
+                oth = partner + (h if half == 0 else 0)
+                c = pos[s, oth]
+                q = c - z[:, None] * (c - pos[s, own])
+                newlnp = np.asarray(lnprob_rows(s, q))
+                with np.errstate(invalid="ignore"):
+                    acc = (4.0 * np.log(z) + newlnp - lnp[s, own]) > lnu
+                pos[s, own[acc]] = q[acc]
+                lnp[s, own[acc]] = newlnp[acc]
+                nacc[s, own[acc]] += 1
+    return pos, lnp, nacc

@@ -191,3 +191,17 @@ def test_fastmath():
     assert big[0] > 1e300 and big[1] > 1e300 and 0.0 <= big[2] < 1e-300 and 0.0 <= big[3] < 1e-300
     em = emu.fastmath(1, np.array([800.0, -800.0, -50.0]))
     assert em[0] > 1e300 and em[1] == -1.0 and em[2] == -1.0
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10, for the C++ generator
+    the device sampler uses and for the numpy twin the replay tests use."""
+    import philox_np
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd))]
+    for ctr, key, want in kat:
+        out, u = emu.philox(ctr, key)
+        assert tuple(int(x) for x in out) == want
+        got = philox_np.philox4x32_10(*[np.array([c], dtype=np.uint64) for c in ctr], key[0], key[1])
+        assert tuple(int(g[0]) for g in got) == want
+        assert u == philox_np.u53(got[0], got[1])[0] and 0.0 < u < 1.0

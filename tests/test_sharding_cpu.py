@@ -1,0 +1,77 @@
+"""CPU, world_size 2 over gloo: the N>1 path (shard -> evaluate -> one gather).
+
+The per-rank evaluation is stood in for by the host emulation of the device
+code (there is no GPU here); what is under test is the host-side logic the
+multi-GPU runs rely on: balanced contiguous shards, walkers of a source never
+split, rank-ordered gather equal to the single-process result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_shard_range_properties():
+    from mbb_emcee_b200.sharding import shard_range, shard_sources
+    for n in (0, 1, 7, 100000, 100003):
+        for world in (1, 2, 3, 8):
+            pieces = [shard_range(n, r, world) for r in range(world)]
+            assert pieces[0][0] == 0 and pieces[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+            sizes = [hi - lo for lo, hi in pieces]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_sources(10, 512, 1, 4) == (3, 6, 1536, 3072)
+    with pytest.raises(ValueError):
+        shard_range(5, 2, 2)
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import hostemu_lib as emu
+    from mbb_emcee_b200.sharding import gather_concat, rank_world, shard_sources
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    assert rank_world() == (rank, world)
+    d = np.load(os.path.join(tmp, "problem.npz"))
+    nsrc, nw = d["flux"].shape[0], int(d["nw"])
+    s_lo, s_hi, e_lo, e_hi = shard_sources(nsrc, nw, rank, world)
+    ep = emu.priors_struct([1, 0.1, 1, 0.1, 1e-3], [0, 1, 1, 1, 0, 0],
+                           [np.inf, 20, 1500, 20, np.inf, np.inf], [0] * 6, [0] * 6, [1] * 6)
+    off = np.arange(7, dtype=np.int32)
+    ll, st = emu.loglike(True, True, True, d["P"][e_lo:e_hi], 500.0, ep, off, d["waves"], np.ones(6),
+                         np.zeros(6), d["flux"][s_lo:s_hi], ivar=d["ivar"][s_lo:s_hi], wps=nw)
+    full = gather_concat(ll)
+    both = gather_concat(np.stack([ll, st.astype(np.float64)], axis=1))
+    if rank == 0:
+        np.savez(os.path.join(tmp, "gathered.npz"), ll=full, both=both)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    import hostemu_lib as emu
+    rng = np.random.RandomState(5)
+    nsrc, nw = 7, 16                      # odd source count: shards of 4 and 3 sources
+    waves = np.array([70.0, 100.0, 160.0, 250.0, 350.0, 500.0])
+    flux = rng.uniform(5, 80, (nsrc, 6))
+    ivar = 1.0 / rng.uniform(1, 6, (nsrc, 6))**2
+    P = np.column_stack([rng.uniform(8, 25, nsrc * nw), rng.uniform(1.2, 2.4, nsrc * nw),
+                         np.full(nsrc * nw, 1300.0), np.full(nsrc * nw, 4.0),
+                         rng.uniform(5, 100, nsrc * nw)])
+    np.savez(tmp_path / "problem.npz", P=P, flux=flux, ivar=ivar, waves=waves, nw=nw)
+    emu.lib()                             # build once before forking workers
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ep = emu.priors_struct([1, 0.1, 1, 0.1, 1e-3], [0, 1, 1, 1, 0, 0],
+                           [np.inf, 20, 1500, 20, np.inf, np.inf], [0] * 6, [0] * 6, [1] * 6)
+    want, st = emu.loglike(True, True, True, P, 500.0, ep, np.arange(7, dtype=np.int32), waves,
+                           np.ones(6), np.zeros(6), flux, ivar=ivar, wps=nw)
+    got = np.load(tmp_path / "gathered.npz")
+    assert np.array_equal(got["ll"], want)
+    assert np.array_equal(got["both"][:, 0], want) and np.array_equal(got["both"][:, 1], st)
