@@ -383,6 +383,64 @@ def run_b200(args):
                "gpu_launches_per_step": int(e2e_launches),
                "api": "mbb_loglike(MBB_HOST) with pinned host arrays; pipelined H2D/kernel/D2H",
                "matches_device_path": same}
+    # ---- batch fit: the device-resident ensemble sampler on the same workload ----
+    batch = None
+    if not args.no_e2e:
+        import ctypes
+        K = 10
+        lnp = torch.empty(n, dtype=torch.float64, device=dev)
+        nacc = torch.zeros(n, dtype=torch.int32, device=dev)
+        Pw = P.clone()
+        ctx.ensemble_run_device(W["nsrc"], nw, 2, Pw.data_ptr(), lnp.data_ptr(), False, seed=7,
+                                naccept_ptr=nacc.data_ptr())          # warm-up (+ initial lnprob)
+        ctx.sync()
+        barrier()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(lstream)
+        ctx.ensemble_run_device(W["nsrc"], nw, K, Pw.data_ptr(), lnp.data_ptr(), True, seed=7, step0=2,
+                                naccept_ptr=nacc.data_ptr())
+        e1.record(lstream)
+        ctx.sync()
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+        samp_launches = ctx.launch_count() - l0
+        acc_frac = float(nacc.double().mean().item()) / K
+        # same through host buffers: positions up, K iterations, positions + lnprob down
+        Ph = torch.empty((n, 5), dtype=torch.float64).pin_memory()
+        Lh = torch.empty(n, dtype=torch.float64).pin_memory()
+        Ph.copy_(P)
+        Phn, Lhn = Ph.numpy(), Lh.numpy()
+        torch.cuda.synchronize()
+
+        def fit_host(k):
+            rc = ctx._lib.mbb_ensemble_run(ctx._h, W["nsrc"], nw, k, 2.0, 7, 0,
+                                           ctypes.c_void_p(Phn.ctypes.data), ctypes.c_void_p(Lhn.ctypes.data),
+                                           0, None, None, None, None, 1, 0)
+            if rc != 0:
+                raise RuntimeError(ctx._lib.mbb_last_error().decode())
+
+        fit_host(1)
+        barrier()
+        t1 = time.perf_counter()
+        fit_host(K)
+        host_ms = 1e3 * (time.perf_counter() - t1)
+        barrier()
+        tb = torch.tensor([dev_ms, host_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        dev_ms, host_ms = float(tb[0].item()), float(tb[1].item())
+        batch = {"api": "batch_fitter / mbb_ensemble_run: stretch-move sampler resident on the device "
+                        "(Philox draws, proposal, likelihood, accept/reject fused per half-step)",
+                 "iterations_per_call": K, "evals_per_iteration": int(n * world),
+                 "device_resident": {"value": n * world * K / (dev_ms * 1e-3), "unit": UNIT,
+                                     "ms_per_iteration": dev_ms / K, "gpu_launches": int(samp_launches)},
+                 "e2e": {"value": n * world * (K + 1) / (host_ms * 1e-3), "unit": UNIT,
+                         "ms_per_call": host_ms, "h2d_bytes_per_call": int(n * 40),
+                         "d2h_bytes_per_call": int(n * 48),
+                         "note": "host call: walker positions uploaded, initial log-probability + K "
+                                 "iterations, positions and log-probabilities downloaded"},
+                 "mean_acceptance_fraction": acc_frac}
     clocks = sampler.stop()
 
     if rank == 0:
@@ -426,6 +484,7 @@ def run_b200(args):
                                  else "fallback"}},
             "cpu_baseline": cb,
             "e2e": e2e,
+            "batch_fit": batch,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"status_errors": nbad, "neg_inf": nneg, "wall_s_timed_region": wall,

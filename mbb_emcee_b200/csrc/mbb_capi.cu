@@ -92,6 +92,7 @@ struct mbb_ctx {
   std::vector<unsigned char> h_scalar;
   std::vector<double> h_packed;   // [freq|w|lhi|llo|rcube] x nn_pad
   DevBuf<double> d_packed;
+  DevBuf<NodeRec> d_nodes;
   DevBuf<int> d_off;
   DevBuf<unsigned char> d_scalar;
   SmallTab small;
@@ -124,6 +125,30 @@ struct mbb_ctx {
   DevBuf<int> d_st, d_src, d_owner, d_work;
   DevBuf<unsigned> d_count;
   // ensemble sampler scratch
+  // per-stream scratch of the split warp path (main stream + 3 pipeline slots)
+  struct Scratch {
+    cudaStream_t st = nullptr;
+    bool used = false;
+    DevBuf<double> c;
+    DevBuf<int> s;
+  };
+  Scratch scratch[4];
+  cudaError_t scratch_for(cudaStream_t st, size_t cap, double** c_out, int** s_out) {
+    Scratch* sc = nullptr;
+    for (auto& x : scratch)
+      if (x.used && x.st == st) sc = &x;
+    if (!sc)
+      for (auto& x : scratch)
+        if (!x.used) { sc = &x; x.used = true; x.st = st; break; }
+    if (!sc) return cudaErrorMemoryAllocation;
+    cudaError_t e = sc->c.reserve(cap * kScratchStride);
+    if (e != cudaSuccess) return e;
+    e = sc->s.reserve(cap);
+    if (e != cudaSuccess) return e;
+    *c_out = sc->c.p;
+    *s_out = sc->s.p;
+    return cudaSuccess;
+  }
   DevBuf<double> d_epos, d_elnp, d_eq, d_eqlnp;
   DevBuf<int> d_enacc, d_est, d_eqst;
 };
@@ -210,6 +235,31 @@ struct DeltaLauncher<THIN, ALPHA, 0> {
   static void go(mbb_ctx*, cudaStream_t, const EvalArgs&, const DataRef&, int) {}
 };
 
+template <bool THIN, bool ALPHA, int NB>
+struct EnsDeltaLauncher {
+  static void go(mbb_ctx* c, const EnsArgs& g, const DataRef& d, int nb) {
+    if (nb == NB) {
+      const long long nh = g.nsrc * g.h;
+      const unsigned grid = (unsigned)((nh + MBB_DELTA_BLOCK - 1) / MBB_DELTA_BLOCK);
+      ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
+      ens_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, c->stream>>>(g, m, c->pri, d, c->small);
+    } else {
+      EnsDeltaLauncher<THIN, ALPHA, NB - 1>::go(c, g, d, nb);
+    }
+  }
+};
+template <bool THIN, bool ALPHA>
+struct EnsDeltaLauncher<THIN, ALPHA, 0> {
+  static void go(mbb_ctx*, const EnsArgs&, const DataRef&, int) {}
+};
+
+template <bool THIN, bool ALPHA, bool FAST>
+struct LaunchEnsDelta {
+  static void run(mbb_ctx* c, const EnsArgs& g, const DataRef& d) {
+    EnsDeltaLauncher<THIN, ALPHA, kMaxDeltaNB>::go(c, g, d, c->nb);
+  }
+};
+
 template <bool THIN, bool ALPHA, bool FAST>
 struct LaunchDelta {
   static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
@@ -218,26 +268,51 @@ struct LaunchDelta {
   }
 };
 
+// split warp path: setup kernel + lean nodes kernel, in chunks that bound the scratch
 template <bool THIN, bool ALPHA, bool FAST>
-struct LaunchWarp {
-  static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
+struct LaunchSplit {
+  static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a0, const DataRef& d, cudaError_t* err) {
+    const long long kChunk = 1LL << 22;
+    const long long cap = a0.n < kChunk ? a0.n : kChunk;
+    *err = cudaSuccess;
     NodeTab t;
-    t.packed = c->d_packed.p;
+    t.nodes = c->d_nodes.p;
     t.band_off = c->d_off.p;
     t.scalar_path = c->d_scalar.p;
     t.nb = c->nb;
     t.nn = c->nn;
-    t.nn_pad = c->nn_pad;
-    size_t smem = warp_kernel_smem(c->nn_pad, c->nb, true);
-    t.in_smem = smem <= c->smem_optin ? 1 : 0;
-    if (!t.in_smem) smem = warp_kernel_smem(c->nn_pad, c->nb, false);
-    auto kern = loglike_warp_kernel<THIN, ALPHA, FAST>;
-    *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = nodes_kernel_smem(c->nn, true);
+    const bool in_smem = smem <= c->smem_optin;
+    if (!in_smem) smem = nodes_kernel_smem(c->nn, false);
+    auto nodes = in_smem ? loglike_nodes_kernel<THIN, ALPHA, FAST, true>
+                         : loglike_nodes_kernel<THIN, ALPHA, FAST, false>;
+    *err = cudaFuncSetAttribute(nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (*err != cudaSuccess) return;
-    const long long ntiles = (a.n + kWarpTile - 1) / kWarpTile;
-    unsigned grid = (unsigned)(ntiles < c->sm_count ? ntiles : c->sm_count);
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nodes, 512, smem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
     ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
-    kern<<<grid, kWarpTile, smem, st>>>(a, m, c->pri, d, t);
+    for (long long off = 0; off < a0.n; off += cap) {
+      EvalArgs a = a0;
+      a.n = (a0.n - off) < cap ? (a0.n - off) : cap;
+      a.e0 = a0.e0 + off;
+      a.soa_stride = a0.soa_stride ? a0.soa_stride : a0.n;
+      a.pars = a0.layout == MBB_AOS ? a0.pars + off * 5 : a0.pars + off;
+      a.out = a0.out + off;
+      a.status = a0.status ? a0.status + off : nullptr;
+      a.src_index = a0.src_index ? a0.src_index + off : nullptr;
+      double* scratch = nullptr;
+      int* sst = nullptr;
+      *err = c->scratch_for(st, (size_t)cap, &scratch, &sst);
+      if (*err != cudaSuccess) return;
+      loglike_setup_kernel<THIN, ALPHA, FAST><<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(
+          a, m, c->pri, scratch, sst);
+      const long long want = (a.n + 15) / 16;
+      const long long resident = (long long)c->sm_count * per_sm;
+      const unsigned grid = (unsigned)(want < resident ? want : resident);
+      nodes<<<grid, 512, smem, st>>>(a, c->pri.any_gprior, d, t, scratch, sst);
+      c->launches += 1;   // the caller counts one launch per call; add the second kernel
+    }
   }
 };
 
@@ -310,12 +385,13 @@ int mbb_ctx_destroy(mbb_ctx* c) {
   if (!c) return 0;
   Use u(c);
   cudaStreamSynchronize(c->stream);
-  c->d_packed.release(); c->d_off.release(); c->d_scalar.release();
+  c->d_packed.release(); c->d_nodes.release(); c->d_off.release(); c->d_scalar.release();
   c->d_flux.release(); c->d_ivar.release(); c->d_cinv.release();
   c->h_in.release(); c->h_out.release(); c->h_st.release(); c->h_src.release();
   c->d_in.release(); c->d_out.release(); c->d_aux0.release(); c->d_aux1.release();
   c->d_st.release(); c->d_src.release(); c->d_owner.release(); c->d_work.release();
   c->d_count.release();
+  for (auto& x : c->scratch) { x.c.release(); x.s.release(); }
   c->d_epos.release(); c->d_elnp.release(); c->d_eq.release(); c->d_eqlnp.release();
   c->d_enacc.release(); c->d_est.release(); c->d_eqst.release();
   for (auto& sl : c->slots) {
@@ -411,6 +487,19 @@ int mbb_set_bands(mbb_ctx* c, int nbands, const int32_t* band_off, const double*
   CK(c->d_scalar.reserve(nbands));
   CK(cudaMemcpyAsync(c->d_packed.p, c->h_packed.data(), c->h_packed.size() * sizeof(double),
                      cudaMemcpyHostToDevice, c->stream));
+  {
+    std::vector<NodeRec> recs((size_t)nn);
+    for (int i = 0; i < nn; ++i) {
+      recs[i].freq = c->h_packed[i];
+      recs[i].w = c->h_packed[np + i];
+      recs[i].lhi = c->h_packed[2 * np + i];
+      recs[i].llo = c->h_packed[3 * np + i];
+      recs[i].rcube = c->h_packed[4 * np + i];
+      recs[i].pad = 0.0;
+    }
+    CK(c->d_nodes.reserve((size_t)nn));
+    CK(cudaMemcpy(c->d_nodes.p, recs.data(), (size_t)nn * sizeof(NodeRec), cudaMemcpyHostToDevice));
+  }
   CK(cudaMemcpyAsync(c->d_off.p, c->h_off.data(), (nbands + 1) * sizeof(int), cudaMemcpyHostToDevice,
                      c->stream));
   CK(cudaMemcpyAsync(c->d_scalar.p, c->h_scalar.data(), nbands, cudaMemcpyHostToDevice, c->stream));
@@ -502,7 +591,7 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a) {
   cudaError_t err = cudaSuccess;
   if (fast && c->nn == c->nb && c->nb <= kMaxDeltaNB) dispatch3<LaunchDelta>(thin, alpha, true, c, st, a, d, &err);
   else if (c->nn <= kSmallMaxNodes) dispatch3<LaunchThread>(thin, alpha, fast, c, st, a, d, &err);
-  else dispatch3<LaunchWarp>(thin, alpha, fast, c, st, a, d, &err);
+  else dispatch3<LaunchSplit>(thin, alpha, fast, c, st, a, d, &err);
   CK(err);
   c->launches += 1;
   CK(cudaGetLastError());
@@ -879,11 +968,25 @@ int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, dou
   g.q = c->d_eq.p; g.qlnp = c->d_eqlnp.p; g.qst = c->d_eqst.p;
   g.nsrc = nsrc; g.nw = nwalkers; g.h = h; g.seed = seed; g.a = a;
   const unsigned grid = (unsigned)((nh + 255) / 256);
+  // delta-band FAST configurations take the fused one-kernel half-step
+  static const bool no_fuse = getenv("MBB_B200_NO_FUSED_SAMPLER") != nullptr;
+  const bool fused = !no_fuse && c->math_mode == MBB_MATH_FAST && c->nn == c->nb && c->nb <= kMaxDeltaNB;
+  DataRef dref;
+  dref.flux = c->d_flux.p;
+  dref.ivar = c->has_ivar ? c->d_ivar.p : nullptr;
+  dref.cinv = c->has_cinv ? c->d_cinv.p : nullptr;
+  dref.nsrc = c->nsrc;
+  dref.nb = c->nb;
   int64_t kept = 0;
   for (int64_t it = 0; it < nsteps; ++it) {
     for (int half = 0; half < 2; ++half) {
       g.half = half;
       g.hstep = 2 * (step0 + (uint64_t)it) + (uint64_t)half;
+      if (fused) {
+        dispatch3<LaunchEnsDelta>(c->opthin != 0, c->noalpha == 0, true, c, g, dref);
+        c->launches += 1;
+        continue;
+      }
       ens_propose_kernel<<<grid, 256, 0, c->stream>>>(g);
       EvalArgs e{};
       e.n = nh; e.e0 = 0; e.wps = h; e.layout = MBB_AOS;

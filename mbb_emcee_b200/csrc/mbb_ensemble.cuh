@@ -98,4 +98,44 @@ __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
   }
 }
 
+// Fused half-step for delta-band configurations: draw, propose, evaluate and
+// accept in one kernel; the proposal never leaves registers.  Same draws, same
+// arithmetic, hence the same chain as the three-kernel pipeline above.
+template <bool THIN, bool ALPHA, int NB>
+__global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
+ens_delta_kernel(const EnsArgs g, const ModelP m, const Priors pr, const DataRef d, const SmallTab t) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nsrc * g.h) return;
+  const unsigned ih = (unsigned)g.h;
+  const long long src = (g.nsrc * g.h < (1LL << 32)) ? (long long)((unsigned)i / ih) : i / g.h;
+  const int k = (int)(i - src * g.h);
+  const Draw dr = stretch_draw(g.seed, (unsigned long long)i, g.hstep, g.a, g.h);
+  const int own = g.half == 0 ? k : g.h + k;
+  const int oth = (g.half == 0 ? g.h : 0) + dr.partner;
+  const long long w = src * g.nw + own;
+  const double* __restrict__ s = g.pos + w * 5;
+  const double* __restrict__ c = g.pos + (src * g.nw + oth) * 5;
+  double q[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const double cj = c[j];
+    q[j] = __dsub_rn(cj, __dmul_rn(dr.z, __dsub_rn(cj, s[j])));
+  }
+  const double old = g.lnp[w];
+  int st;
+  const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, m, pr, d, t, st);
+  if (st > ST_BELOW_LOWLIM) {
+    if (g.status[w] <= ST_BELOW_LOWLIM) g.status[w] = st;
+    return;
+  }
+  const double lnpdiff = 4.0 * log(dr.z) + newlnp - old;
+  if (lnpdiff > dr.lnu) {
+    double* p = g.pos + w * 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) p[j] = q[j];
+    g.lnp[w] = newlnp;
+    g.nacc[w] += 1;
+  }
+}
+
 }  // namespace mbb

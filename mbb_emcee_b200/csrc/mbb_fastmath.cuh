@@ -145,4 +145,129 @@ MBB_HD double exp_prod_fast(double b, double l_hi, double l_lo) {
   return fma(r, e, r);
 }
 
+// ---------------------------------------------------------------------------
+// Table-driven variants: x = (64 m + j - 32) ln2/64 + r, |r| <= ln2/128,
+// T[j] = 2^((j-32)/64) in [0.71, 1.40), so that |x| < 0.34 always has m == 0:
+//   exp(x)   = 2^m T[j] (1 + p),      p = expm1(r) = r h(r), h of degree 4
+//   expm1(x) = 2^m T[j] p + (2^m T[j] - 1), with the separately rounded table
+//              entry T[j]-1 when m == 0 (no cancellation for small |x|).
+// 10-11 FP64 instructions instead of 17-18; the 1 KB table {T[j], T[j]-1}
+// lives in global memory and stays L1-resident (one LDG.128 per call).
+// ---------------------------------------------------------------------------
+struct ExpTabEntry {
+  double t, tm1;
+};
+
+#if defined(__CUDACC__)
+__device__ const ExpTabEntry kExpTab_dev[64] = {
+#include "mbb_exptab.inc"
+};
+__device__ __constant__ double kTabPoly_dev[5] = {1.0, 0.49999999999962602, 0.16666666666661323,
+                                                 0.041666717628250034, 0.0083333406135586794};
+#endif
+
+MBB_HD ExpTabEntry exp_tab_entry(int j) {
+#if defined(__CUDA_ARCH__)
+  const double2 v = __ldg(reinterpret_cast<const double2*>(kExpTab_dev) + j);
+  ExpTabEntry e;
+  e.t = v.x;
+  e.tm1 = v.y;
+  return e;
+#else
+  static const ExpTabEntry tab[64] = {
+#include "mbb_exptab.inc"
+  };
+  return tab[j];
+#endif
+}
+
+MBB_HD double tab_poly_coef(int i) {
+#if defined(__CUDA_ARCH__)
+  return kTabPoly_dev[i];
+#else
+  const double c[5] = {1.0, 0.49999999999962602, 0.16666666666661323, 0.041666717628250034,
+                       0.0083333406135586794};
+  return c[i];
+#endif
+}
+
+// x = (64 m + j - 32) ln2/64 + r; returns p = expm1(r)
+template <int MMAX = 1023>
+MBB_HD double reduce_tab(double x, int& m, int& j) {
+  const double kMagic = 6755399441055744.0;
+  const double k64Log2e = 92.332482616893657;                 // 64 / ln 2
+  const double kLn2Hi64 = 6.93147180369123816490e-01 / 64.0;  // exact scalings of the fdlibm split
+  const double kLn2Lo64 = 1.90821492927058770002e-10 / 64.0;
+  const double t = fma(x, k64Log2e, kMagic);
+  const double kf = t - kMagic;
+#if defined(__CUDA_ARCH__)
+  const int k = __double2loint(t);
+#else
+  const int k = (int)kf;
+#endif
+  double r = fma(-kf, kLn2Hi64, x);
+  r = fma(-kf, kLn2Lo64, r);
+  j = (k + 32) & 63;
+  m = (k + 32) >> 6;
+  m = m > MMAX ? MMAX : m;
+  m = m < -1022 ? -1022 : m;
+  double h = tab_poly_coef(4);
+#pragma unroll
+  for (int i = 3; i >= 0; --i) h = fma(h, r, tab_poly_coef(i));
+  return h * r;
+}
+
+// MMAX caps the result at < 2^(MMAX+1): exp_tab<10> saturates near 2e3, which is
+// what callers want when the value only feeds expm1(-t) (keeps its argument
+// inside the range where the integer exponent extraction is valid).
+template <int MMAX = 1023>
+MBB_HD double exp_tab(double x) {
+  int m, j;
+  const double p = reduce_tab<MMAX>(x, m, j);
+  const double T = exp_tab_entry(j).t;
+  return scale2(fma(T, p, T), m);
+}
+
+MBB_HD double expm1_tab(double x) {
+  int m, j;
+  const double p = reduce_tab(x, m, j);
+  const ExpTabEntry e = exp_tab_entry(j);
+  const double sT = scale2(e.t, m);
+  const double base = (m == 0) ? e.tm1 : sT - 1.0;
+  return fma(sT, p, base);
+}
+
+template <int MMAX = 1023>
+MBB_HD double exp_prod_tab(double b, double l_hi, double l_lo) {
+  const double y = b * l_hi;
+  const double e = fma(b, l_lo, fma(b, l_hi, -y));
+  const double r = exp_tab<MMAX>(y);
+  return fma(r, e, r);
+}
+
+// which lean exp family the FAST model code uses (A/B switch for measurements)
+#ifndef MBB_USE_EXPTAB
+#define MBB_USE_EXPTAB 1
+#endif
+#if MBB_USE_EXPTAB
+MBB_HD double exp_l(double x) { return exp_tab(x); }
+MBB_HD double expm1_l(double x) { return expm1_tab(x); }
+MBB_HD double exp_prod_l(double b, double hi, double lo) { return exp_prod_tab(b, hi, lo); }
+// saturating at ~2e3: for optical depths t that only feed expm1(-t)
+MBB_HD double exp_tau(double x) { return exp_tab<10>(x); }
+MBB_HD double exp_prod_tau(double b, double hi, double lo) { return exp_prod_tab<10>(b, hi, lo); }
+#else
+MBB_HD double exp_l(double x) { return exp_fast(x); }
+MBB_HD double expm1_l(double x) { return expm1_fast(x); }
+MBB_HD double exp_prod_l(double b, double hi, double lo) { return exp_prod_fast(b, hi, lo); }
+MBB_HD double exp_tau(double x) { return fmin(exp_fast(x), 2000.0); }
+MBB_HD double exp_prod_tau(double b, double hi, double lo) { return fmin(exp_prod_fast(b, hi, lo), 2000.0); }
+#endif
+// The lean exp family extracts the binary exponent from the low 32 bits of
+// x*64/ln2 + 1.5*2^52: valid for |x| < 2^31 ln2/64 ~ 2.3e7.  fast_setup gates
+// the parameters (T >= 1e-3 K, beta, alpha <= 300) so every argument formed
+// from them stays far inside that range.
+constexpr double kFastMaxIndex = 300.0;
+constexpr double kFastMinT = 1e-3;
+
 }  // namespace mbb

@@ -4,17 +4,18 @@
 //                          delta / few-node configs such as BASELINE cfg1/cfg5)
 //                          travel in the kernel parameter block, i.e. the
 //                          constant bank -- uniform across the warp, no loads.
-//   loglike_warp_kernel    persistent, one CTA per SM.  The passband node
-//                          tables (up to ~5.6k nodes) are staged ONCE per CTA
-//                          into shared memory by a TMA bulk copy
-//                          (cp.async.bulk + mbarrier).  Each tile of 512
-//                          evaluations runs in two phases: (1) thread-per-
-//                          evaluation setup (limits, per-walker constants incl.
-//                          the merge-point root solve, prior terms incl. the
-//                          lambda_peak solve) -> shared memory; (2) warp-per-
-//                          evaluation node loop, lanes striding the nodes of a
-//                          band, warp-shuffle reduction per band, then the
-//                          chi-square (diagonal or full inverse covariance).
+//   loglike_delta_kernel   the same with every band a single node and the band
+//                          count a template parameter (fully unrolled).
+//   loglike_setup_kernel + loglike_nodes_kernel   tabulated passbands:
+//                          (1) thread-per-evaluation setup (limits, per-walker
+//                          constants incl. the merge-point root solve, prior
+//                          terms incl. the lambda_peak solve) -> scratch;
+//                          (2) persistent warp-per-evaluation node loops: the
+//                          node table (up to ~4.8k nodes of 48 B) is staged
+//                          ONCE per CTA into shared memory by TMA bulk copies
+//                          (cp.async.bulk + mbarrier), lanes stride the nodes
+//                          of a band, warp-shuffle reduction per band, then
+//                          the chi-square (diagonal or full inverse covariance).
 //   fnu_kernel, sed_consts_kernel, chain_* kernels: the API's other entries.
 #pragma once
 #include <cuda_runtime.h>
@@ -25,8 +26,6 @@ namespace mbb {
 
 constexpr int kSmallMaxNodes = 32;
 constexpr int kMaxBands = kMaxBandsPerThread;
-constexpr int kWarpTile = 512;     // evaluations per tile == threads per CTA
-constexpr int kSedcStride = 12;    // doubles per evaluation kept in smem
 
 struct EvalArgs {
   const double* pars;
@@ -35,6 +34,7 @@ struct EvalArgs {
   int* status;
   long long n;
   long long e0;       // global index of evaluation 0 (chunked host path)
+  long long soa_stride;  // element stride between parameters in SoA layout (0 = n)
   long long wps;      // walkers per source (when src_index == nullptr)
   int layout;         // 0 = [n][5], 1 = [5][n]
 };
@@ -63,14 +63,21 @@ struct SmallTab {
   int nb;
 };
 
+// One quadrature node as the nodes kernel reads it: 48 bytes, 16-byte aligned,
+// so a lane fetches it with LDS.128 + LDS.128 + LDS.64 from one address
+// (stride 12 words: conflict-free for 128-bit accesses).
+struct __align__(16) NodeRec {
+  double freq, w;       // 299792.458/lambda_i [GHz], sedmult*normfac
+  double lhi, llo;      // ln(lambda_i/lambda_norm), double-double
+  double rcube, pad;    // (lambda_norm/lambda_i)^3
+};
+
 struct NodeTab {
-  const double* packed;   // [freq | w | lhi | llo | rcube], each nn_pad doubles
+  const NodeRec* nodes;   // [nn]
   const int* band_off;    // nb + 1
   const unsigned char* scalar_path;
   int nb;
   int nn;
-  int nn_pad;             // even, so every sub-array is 16-byte aligned
-  int in_smem;            // stage the packed table into shared memory
 };
 
 __device__ __forceinline__ void load_pars(const EvalArgs& a, long long e, double p[5]) {
@@ -79,8 +86,9 @@ __device__ __forceinline__ void load_pars(const EvalArgs& a, long long e, double
 #pragma unroll
     for (int i = 0; i < 5; ++i) p[i] = __ldg(q + i);
   } else {
+    const long long sd = a.soa_stride ? a.soa_stride : a.n;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) p[i] = __ldg(a.pars + (long long)i * a.n + e);
+    for (int i = 0; i < 5; ++i) p[i] = __ldg(a.pars + (long long)i * sd + e);
   }
 }
 
@@ -128,9 +136,93 @@ loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const D
 #ifndef MBB_DELTA_BLOCK
 #define MBB_DELTA_BLOCK 256
 #endif
-#ifndef MBB_DELTA_EARLY
-#define MBB_DELTA_EARLY 1
+#ifndef MBB_DELTA_LATE
+#define MBB_DELTA_LATE 0
 #endif
+// one evaluation, all bands single-node, FAST arithmetic, NB compile-time
+template <bool THIN, bool ALPHA, int NB>
+__device__ __forceinline__ double delta_eval(const double p[5], long long src, const ModelP& m,
+                                             const Priors& pr, const DataRef& d, const SmallTab& t,
+                                             int& st) {
+  const double* __restrict__ fl = d.flux + src * NB;
+  const double* __restrict__ ivp = d.ivar + src * NB;
+#if !MBB_DELTA_LATE
+  double diff[NB], iv[NB];
+  {
+    // data loads issued next to the parameter loads: one exposed global latency
+#pragma unroll
+    for (int b = 0; b < NB; ++b) diff[b] = __ldg(fl + b);
+    if (!d.cinv) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) iv[b] = __ldg(ivp + b);
+    }
+  }
+#endif
+  st = ST_OK;
+  if (below_lowlim(pr, p)) {
+    st = ST_BELOW_LOWLIM;
+    return -kInf;
+  }
+  FastSed s;
+  fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm, m.nu_norm);
+  st = s.status;
+  if (st != ST_OK) return qnan();
+  double chi = 0.0;
+#if MBB_DELTA_LATE
+  if (!d.cinv) {
+    // register-lean form: nothing but chi stays live across bands
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const double f = node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
+      const double df = fma(-f, t.w[b], __ldg(fl + b));
+      chi = fma(df * df, __ldg(ivp + b), chi);
+    }
+  } else {
+    double diff[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const double f = node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
+      diff[b] = fma(-f, t.w[b], __ldg(fl + b));
+    }
+    const double* __restrict__ ci = d.cinv + src * (NB * NB);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      double row = 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
+      chi = fma(diff[r], row, chi);
+    }
+  }
+#else
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const double f = node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
+    diff[b] = fma(-f, t.w[b], diff[b]);
+  }
+  if (d.cinv) {
+    const double* __restrict__ ci = d.cinv + src * (NB * NB);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      double row = 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
+      chi = fma(diff[r], row, chi);
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) chi = fma(diff[b] * diff[b], iv[b], chi);
+  }
+#endif
+  double pen, gp;
+  prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+  double lnl = -0.5 * chi;
+  lnl += pen;
+  if (pr.any_gprior) lnl += gp;
+  if (st != ST_OK) return qnan();
+  if (lnl != lnl) st = ST_NONFINITE;
+  return lnl;
+}
+
 template <bool THIN, bool ALPHA, int NB>
 __global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
 loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
@@ -139,74 +231,8 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
   if (e >= a.n) return;
   double p[5];
   load_pars(a, e, p);
-  const long long src = source_of(a, e);
-  double diff[NB], iv[NB];
-#if MBB_DELTA_EARLY
-  // data loads issued next to the parameter loads: one exposed global latency
-  {
-    const double* __restrict__ fl = d.flux + src * NB;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) diff[b] = __ldg(fl + b);
-    if (!d.cinv) {
-      const double* __restrict__ ivp = d.ivar + src * NB;
-#pragma unroll
-      for (int b = 0; b < NB; ++b) iv[b] = __ldg(ivp + b);
-    }
-  }
-#endif
-  int st = ST_OK;
-  double lnl;
-  if (below_lowlim(pr, p)) {
-    st = ST_BELOW_LOWLIM;
-    lnl = -kInf;
-  } else {
-    FastSed s;
-    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm, m.nu_norm);
-    st = s.status;
-    if (st != ST_OK) {
-      lnl = qnan();
-    } else {
-#if !MBB_DELTA_EARLY
-      {
-        const double* __restrict__ fl = d.flux + src * NB;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) diff[b] = __ldg(fl + b);
-        if (!d.cinv) {
-          const double* __restrict__ ivp = d.ivar + src * NB;
-#pragma unroll
-          for (int b = 0; b < NB; ++b) iv[b] = __ldg(ivp + b);
-        }
-      }
-#endif
-#pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const double f =
-            node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
-        diff[b] = fma(-f, t.w[b], diff[b]);
-      }
-      double chi = 0.0;
-      if (d.cinv) {
-        const double* __restrict__ ci = d.cinv + src * (NB * NB);
-#pragma unroll
-        for (int r = 0; r < NB; ++r) {
-          double row = 0.0;
-#pragma unroll
-          for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
-          chi = fma(diff[r], row, chi);
-        }
-      } else {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) chi = fma(diff[b] * diff[b], iv[b], chi);
-      }
-      double pen, gp;
-      prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
-      lnl = -0.5 * chi;
-      lnl += pen;
-      if (pr.any_gprior) lnl += gp;
-      if (st != ST_OK) lnl = qnan();
-      else if (lnl != lnl) st = ST_NONFINITE;
-    }
-  }
+  int st;
+  const double lnl = delta_eval<THIN, ALPHA, NB>(p, source_of(a, e), m, pr, d, t, st);
   a.out[e] = lnl;
   if (a.status) a.status[e] = st;
 }
@@ -252,181 +278,161 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Shared-memory footprint of the warp kernel (bytes); host and device agree.
-__host__ __device__ inline size_t warp_kernel_smem(int nn_pad, int nb, bool tables_in_smem) {
-  size_t doubles = (tables_in_smem ? (size_t)5 * nn_pad : 0)    // node tables
-                   + (size_t)kWarpTile * kSedcStride              // per-eval constants
-                   + (size_t)kWarpTile * 2                        // pen, gp
-                   + (size_t)(kWarpTile / 32) * kMaxBands         // per-warp diff scratch
-                   + 2;                                           // mbarrier (+pad)
-  size_t ints = (size_t)kWarpTile                                 // status
-                + (size_t)(kMaxBands + 1);                        // band offsets
-  return doubles * 8 + ints * 4 + kMaxBands;                      // + scalar_path bytes
+// ---------------------------------------------------------------------------
+// The warp path: a thread-per-evaluation SETUP kernel
+// writes 14 doubles + status per evaluation to a scratch array, then a lean
+// NODES kernel (64 registers -> 2 CTAs x 512 threads per SM, twice the
+// resident warps of the fused kernel) does the node loops.  The scratch costs
+// 116 B/evaluation of traffic against >= 1e5 flops of node work.
+// ---------------------------------------------------------------------------
+constexpr int kScratchStride = 14;   // c[0..11], pen, gp
+
+template <bool THIN, bool ALPHA, bool FAST>
+__global__ void __launch_bounds__(128)
+loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* __restrict__ scratch,
+                     int* __restrict__ sst) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  double p[5];
+  load_pars(a, e, p);
+  int st = ST_OK;
+  double pen = 0.0, gp = 0.0;
+  double c[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) c[i] = 0.0;
+  if (below_lowlim(pr, p)) {
+    st = ST_BELOW_LOWLIM;
+  } else if (FAST) {
+    FastSed s;
+    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm, m.nu_norm);
+    st = s.status;
+    if (st == ST_OK) prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+    c[0] = s.hokt9; c[2] = s.beta; c[3] = s.alpha; c[6] = s.xmerge;
+    c[8] = s.amp_grey; c[9] = s.amp_pow; c[10] = s.q_hi; c[11] = s.q_lo;
+  } else {
+    Sed s;
+    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
+    st = s.status;
+    if (st == ST_OK) prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+    c[0] = s.hokt9; c[1] = s.hokt_e9; c[2] = s.beta; c[3] = s.alpha;
+    c[4] = s.x0; c[5] = s.normfac; c[6] = s.xmerge; c[7] = s.kappa;
+  }
+  double2* o = reinterpret_cast<double2*>(scratch + e * kScratchStride);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) o[i] = make_double2(c[2 * i], c[2 * i + 1]);
+  o[6] = make_double2(pen, gp);
+  sst[e] = st;
 }
 
-// ---------------------------------------------------------------------------
-// warp-per-evaluation persistent kernel
-// ---------------------------------------------------------------------------
-template <bool THIN, bool ALPHA, bool FAST>
-__global__ void __launch_bounds__(kWarpTile, 1)
-loglike_warp_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
-                    const NodeTab t) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sm = reinterpret_cast<double*>(smem_raw);
-  const int nn_pad = t.nn_pad;
-  double* tab = sm;                                   // 5 * nn_pad (if in_smem)
-  double* sedc = tab + (t.in_smem ? 5 * nn_pad : 0);  // kWarpTile * kSedcStride
-  double* s_pen = sedc + kWarpTile * kSedcStride;
-  double* s_gp = s_pen + kWarpTile;
-  double* s_diff = s_gp + kWarpTile;                  // (kWarpTile/32) * kMaxBands
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_diff + (kWarpTile / 32) * kMaxBands);
-  int* s_status = reinterpret_cast<int*>(bar + 2);
-  int* s_off = s_status + kWarpTile;
-  unsigned char* s_scalar = reinterpret_cast<unsigned char*>(s_off + kMaxBands + 1);
+__host__ __device__ inline size_t nodes_kernel_smem(int nn, bool tables_in_smem) {
+  return (tables_in_smem ? (size_t)nn * sizeof(NodeRec) : 0) + (size_t)16 * kMaxBands * 8 + 16 +
+         (size_t)(kMaxBands + 1) * 4 + kMaxBands;
+}
 
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
+template <bool THIN, bool ALPHA, bool FAST, bool IN_SMEM>
+__global__ void __launch_bounds__(512, 2)
+loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, const NodeTab t,
+                     const double* __restrict__ scratch, const int* __restrict__ sst) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NodeRec* s_nodes = reinterpret_cast<NodeRec*>(smem_raw);
+  double* s_diff = reinterpret_cast<double*>(smem_raw + (IN_SMEM ? (size_t)t.nn * sizeof(NodeRec) : 0));
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_diff + 16 * kMaxBands);
+  int* s_off = reinterpret_cast<int*>(bar + 2);
+  unsigned char* s_scalar = reinterpret_cast<unsigned char*>(s_off + kMaxBands + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = t.nb;
 
-  // ---- stage the passband tables once per CTA (TMA bulk copy) -------------
-  if (t.in_smem) {
+  if (IN_SMEM) {                       // stage the node table once per CTA (TMA bulk copy)
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-      const unsigned bytes = (unsigned)(5 * nn_pad * sizeof(double));
+      const unsigned bytes = (unsigned)(t.nn * sizeof(NodeRec));
       mbar_expect_tx(bar, bytes);
-      // <= 64 KiB per copy keeps each request comfortably inside the engine's limits
       unsigned done = 0;
-      while (done < bytes) {
+      while (done < bytes) {           // <= 64 KiB per request
         unsigned chunk = bytes - done;
         if (chunk > 65536u) chunk = 65536u;
-        bulk_g2s(reinterpret_cast<unsigned char*>(tab) + done,
-                 reinterpret_cast<const unsigned char*>(t.packed) + done, chunk, bar);
+        bulk_g2s(smem_raw + done, reinterpret_cast<const unsigned char*>(t.nodes) + done, chunk, bar);
         done += chunk;
       }
     }
   }
   for (int i = tid; i <= nb; i += blockDim.x) s_off[i] = t.band_off[i];
   for (int i = tid; i < nb; i += blockDim.x) s_scalar[i] = t.scalar_path[i];
-  if (t.in_smem) mbar_wait(bar, 0);
+  if (IN_SMEM) mbar_wait(bar, 0);
   __syncthreads();
 
-  const double* g_tab = t.in_smem ? tab : t.packed;
-  const double* n_freq = g_tab;
-  const double* n_w = g_tab + nn_pad;
-  const double* n_lhi = g_tab + 2 * nn_pad;
-  const double* n_llo = g_tab + 3 * nn_pad;
-  const double* n_rc = g_tab + 4 * nn_pad;
+  const NodeRec* __restrict__ nodes = IN_SMEM ? s_nodes : t.nodes;
+  double* wdiff = s_diff + warp * kMaxBands;
 
-  const long long ntiles = (a.n + kWarpTile - 1) / kWarpTile;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    // ---- phase 1: one thread per evaluation ------------------------------
-    {
-      const long long e = tile * kWarpTile + tid;
-      int st = ST_OK;
-      double pen = 0.0, gp = 0.0;
-      double* c = sedc + tid * kSedcStride;
-      if (e < a.n) {
-        double p[5];
-        load_pars(a, e, p);
-        if (below_lowlim(pr, p)) {
-          st = ST_BELOW_LOWLIM;
-        } else {
-          if (FAST) {
-            FastSed s;
-            fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm, m.nu_norm);
-            st = s.status;
-            if (st == ST_OK) prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
-            c[0] = s.hokt9; c[2] = s.beta; c[3] = s.alpha; c[6] = s.xmerge;
-            c[8] = s.amp_grey; c[9] = s.amp_pow; c[10] = s.q_hi; c[11] = s.q_lo;
-          } else {
-            Sed s;
-            sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
-            st = s.status;
-            if (st == ST_OK) prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
-            c[0] = s.hokt9; c[1] = s.hokt_e9; c[2] = s.beta; c[3] = s.alpha;
-            c[4] = s.x0; c[5] = s.normfac; c[6] = s.xmerge; c[7] = s.kappa;
-          }
-        }
-      } else {
-        st = -1;   // beyond the end
-      }
-      s_pen[tid] = pen;
-      s_gp[tid] = gp;
-      s_status[tid] = st;
-    }
-    __syncthreads();
-
-    // ---- phase 2: one warp per evaluation, lanes stride the nodes --------
-    for (int k = 0; k < 32; ++k) {
-      const int slot = warp * 32 + k;
-      const int st = s_status[slot];
-      if (st < 0) break;
-      const long long e = tile * kWarpTile + slot;
-      if (st != ST_OK) {
-        if (lane == 0) {
-          a.out[e] = (st == ST_BELOW_LOWLIM) ? -kInf : qnan();
-          if (a.status) a.status[e] = st;
-        }
-        continue;
-      }
-      const double* c = sedc + slot * kSedcStride;
-      Sed s;
-      FastSed fs;
-      if (FAST) {
-        fs.hokt9 = c[0]; fs.beta = c[2]; fs.alpha = c[3]; fs.xmerge = c[6];
-        fs.amp_grey = c[8]; fs.amp_pow = c[9]; fs.q_hi = c[10]; fs.q_lo = c[11];
-      } else {
-        s.hokt9 = c[0]; s.hokt_e9 = c[1]; s.beta = c[2]; s.alpha = c[3];
-        s.x0 = c[4]; s.normfac = c[5]; s.xmerge = c[6]; s.kappa = c[7];
-      }
-      const long long src = source_of(a, e);
-      const double* fl = d.flux + src * d.nb;
-      double* wdiff = s_diff + warp * kMaxBands;
-      double chi = 0.0;
-      for (int b = 0; b < nb; ++b) {
-        const double hk = FAST ? fs.hokt9 : (s_scalar[b] ? s.hokt_e9 : s.hokt9);
-        const int i1 = s_off[b + 1];
-        double acc = 0.0;
-        for (int i = s_off[b] + lane; i < i1; i += 32) {
-          const double cx = hk * n_freq[i];
-          double f;
-          if (FAST) f = node_fnu_fast<THIN, ALPHA>(fs, cx, n_lhi[i], n_llo[i], n_rc[i]);
-          else f = node_fnu<THIN, ALPHA>(s, cx);
-          acc = fma(f, n_w[i], acc);
-        }
-        acc = warp_sum(acc);
-        const double df = __ldg(fl + b) - acc;
-        if (d.cinv) {
-          if (lane == 0) wdiff[b] = df;
-        } else {
-          chi = fma(df * df, __ldg(d.ivar + src * d.nb + b), chi);
-        }
-      }
-      if (d.cinv) {
-        __syncwarp();
-        const double* ci = d.cinv + src * (long long)nb * nb;
-        double part = 0.0;
-        for (int r = lane; r < nb; r += 32) {
-          double row = 0.0;
-          for (int cc = 0; cc < nb; ++cc) row = fma(__ldg(ci + r * nb + cc), wdiff[cc], row);
-          part = fma(wdiff[r], row, part);
-        }
-        chi = warp_sum(part);
-        __syncwarp();
-      }
+  const long long wstride = (long long)gridDim.x * 16;
+  for (long long e = (long long)blockIdx.x * 16 + warp; e < a.n; e += wstride) {
+    const int st = __ldg(sst + e);
+    if (st != ST_OK) {
       if (lane == 0) {
-        double lnl = -0.5 * chi;
-        lnl += s_pen[slot];
-        if (pr.any_gprior) lnl += s_gp[slot];
-        int so = ST_OK;
-        if (lnl != lnl) so = ST_NONFINITE;
-        a.out[e] = lnl;
-        if (a.status) a.status[e] = so;
+        a.out[e] = (st == ST_BELOW_LOWLIM) ? -kInf : qnan();
+        if (a.status) a.status[e] = st;
+      }
+      continue;
+    }
+    const double2* c2 = reinterpret_cast<const double2*>(scratch + e * kScratchStride);
+    const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
+    const double2 c89 = __ldg(c2 + 4), cab = __ldg(c2 + 5), cpg = __ldg(c2 + 6);
+    Sed s;
+    FastSed fs;
+    if (FAST) {
+      fs.hokt9 = c01.x; fs.beta = c23.x; fs.alpha = c23.y; fs.xmerge = c67.x;
+      fs.amp_grey = c89.x; fs.amp_pow = c89.y; fs.q_hi = cab.x; fs.q_lo = cab.y;
+    } else {
+      s.hokt9 = c01.x; s.hokt_e9 = c01.y; s.beta = c23.x; s.alpha = c23.y;
+      s.x0 = c45.x; s.normfac = c45.y; s.xmerge = c67.x; s.kappa = c67.y;
+    }
+    const long long src = source_of(a, e);
+    const double* fl = d.flux + src * d.nb;
+    double chi = 0.0;
+    for (int b = 0; b < nb; ++b) {
+      const double hk = FAST ? fs.hokt9 : (s_scalar[b] ? s.hokt_e9 : s.hokt9);
+      const int i1 = s_off[b + 1];
+      double acc = 0.0;
+      for (int i = s_off[b] + lane; i < i1; i += 32) {
+        const double2 fw = *reinterpret_cast<const double2*>(&nodes[i].freq);
+        const double cx = hk * fw.x;
+        double f;
+        if (FAST) {
+          const double2 ll = *reinterpret_cast<const double2*>(&nodes[i].lhi);
+          f = node_fnu_fast<THIN, ALPHA>(fs, cx, ll.x, ll.y, THIN ? 0.0 : nodes[i].rcube);
+        } else {
+          f = node_fnu<THIN, ALPHA>(s, cx);
+        }
+        acc = fma(f, fw.y, acc);
+      }
+      acc = warp_sum(acc);
+      const double df = __ldg(fl + b) - acc;
+      if (d.cinv) {
+        if (lane == 0) wdiff[b] = df;
+      } else {
+        chi = fma(df * df, __ldg(d.ivar + src * d.nb + b), chi);
       }
     }
-    __syncthreads();
+    if (d.cinv) {
+      __syncwarp();
+      const double* ci = d.cinv + src * (long long)nb * nb;
+      double part = 0.0;
+      for (int r = lane; r < nb; r += 32) {
+        double row = 0.0;
+        for (int cc = 0; cc < nb; ++cc) row = fma(__ldg(ci + r * nb + cc), wdiff[cc], row);
+        part = fma(wdiff[r], row, part);
+      }
+      chi = warp_sum(part);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      double lnl = -0.5 * chi;
+      lnl += cpg.x;
+      if (any_gprior) lnl += cpg.y;
+      a.out[e] = lnl;
+      if (a.status) a.status[e] = (lnl != lnl) ? ST_NONFINITE : ST_OK;
+    }
   }
 }
 

@@ -220,16 +220,16 @@ MBB_HD_NOINLINE void sed_setup(Sed& s, double T, double beta, double lambda0, do
 // `nu_norm` = 299792.458 / wavenorm [GHz], precomputed on the host.
 // ---------------------------------------------------------------------------
 MBB_HD double merge_residual_fast(double x, double alpha, double beta, double inv_x0) {
-  const double t = exp_fast(beta * log(x * inv_x0));
+  const double t = exp_tau(beta * log(x * inv_x0));
   // t/expm1(t): -> 1 as t -> 0, -> 0 as t -> inf (saturating expm1_fast)
-  const double bterm = t < 1e-280 ? 1.0 : t * rcp_fast(expm1_fast(t));
-  return x + expm1_fast(-x) * (3.0 + alpha + beta * bterm);
+  const double bterm = t < 1e-280 ? 1.0 : t * rcp_fast(expm1_l(t));
+  return x + expm1_l(-x) * (3.0 + alpha + beta * bterm);
 }
 
 MBB_HD double thin_merge_root_fast(double a) {
   double x = a;
   for (int it = 0; it < 12; ++it) {
-    const double e = a * exp_fast(-x);
+    const double e = a * exp_l(-x);
     const double dx = div_fast((x - a) + e, 1.0 - e);
     x -= dx;
     if (fabs(dx) <= 1.2e-16 * x) break;
@@ -248,6 +248,9 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
   if (!finite_d(T) || !finite_d(fnorm) || (!THIN && !finite_d(lambda0)) || (ALPHA && !finite_d(alpha)) ||
       !finite_d(beta))
     f.status = ST_NONFINITE;
+  // range of validity of the lean exp family (mbb_fastmath.cuh)
+  if (f.status == ST_OK && (!(T >= kFastMinT) || beta > kFastMaxIndex || (ALPHA && alpha > kFastMaxIndex)))
+    f.status = ST_OVERFLOW;
   f.hokt9 = 1e9 * kH / (kK * T);
   if (f.status != ST_OK) return;
   const double xn = f.hokt9 * nu_norm;
@@ -259,9 +262,9 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
     inv_x0 = rcp_fast(f.x0);
     f.q_hi = log(r);
     f.q_lo = 0.0;
-    tn_fac = -expm1_fast(-exp_prod_fast(beta, f.q_hi, f.q_lo));     // 1 - exp(-(xn/x0)^beta)
+    tn_fac = -expm1_l(-exp_prod_tau(beta, f.q_hi, f.q_lo));     // 1 - exp(-(xn/x0)^beta)
   }
-  const double em_n = expm1_fast(xn);
+  const double em_n = expm1_l(xn);
   const double grey_at_norm = THIN ? fnorm * em_n : div_fast(fnorm * em_n, tn_fac);
   if (!ALPHA) {
     f.amp_grey = grey_at_norm;
@@ -298,14 +301,14 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
   // R = grey(xmerge) xmerge^alpha / (grey(xnorm) xnorm^alpha), built from ratios
   const double xm = f.xmerge;
   const double lmn = log(div_fast(xm, xn));
-  const double inv_em_m = rcp_fast(expm1_fast(xm));
+  const double inv_em_m = rcp_fast(expm1_l(xm));
   double R;
   if (THIN) {
-    R = exp_fast((3.0 + beta + alpha) * lmn) * inv_em_m * em_n;        // times grey_at_norm/fnorm
+    R = exp_l((3.0 + beta + alpha) * lmn) * inv_em_m * em_n;        // times grey_at_norm/fnorm
     // (amp_grey = fnorm*em_n when xn <= xm) -> amp_pow = fnorm * R
   } else {
-    const double tm = exp_fast(beta * (lmn + f.q_hi));
-    R = -expm1_fast(-tm) * exp_fast((3.0 + alpha) * lmn) * inv_em_m * div_fast(em_n, tn_fac);
+    const double tm = exp_tau(beta * (lmn + f.q_hi));
+    R = -expm1_l(-tm) * exp_l((3.0 + alpha) * lmn) * inv_em_m * div_fast(em_n, tn_fac);
   }
   // here R = amp_pow / fnorm when the normalisation wavelength sits on the grey side
   if (xn > xm) {
@@ -349,12 +352,12 @@ MBB_HD double node_fnu(const Sed& s, double cx) {
 // rcube = (wavenorm/wave_i)^3, cx = hokt9 * freq_i.
 template <bool THIN, bool ALPHA>
 MBB_HD double node_fnu_fast(const FastSed& s, double cx, double l_hi, double l_lo, double rcube) {
-  if (ALPHA && cx > s.xmerge) return s.amp_pow * exp_prod_fast(s.alpha, l_hi, l_lo);
-  const double em = expm1_fast(cx);
-  if (THIN) return div_fast(s.amp_grey * exp_prod_fast(-(s.beta + 3.0), l_hi, l_lo), em);
+  if (ALPHA && cx > s.xmerge) return s.amp_pow * exp_prod_l(s.alpha, l_hi, l_lo);
+  const double em = expm1_l(cx);
+  if (THIN) return div_fast(s.amp_grey * exp_prod_l(-(s.beta + 3.0), l_hi, l_lo), em);
   // t = (cx/x0)^beta = exp(beta * (q - L_i))
-  const double t = exp_prod_fast(s.beta, s.q_hi - l_hi, s.q_lo - l_lo);
-  return div_fast(s.amp_grey * (-expm1_fast(-t)) * rcube, em);
+  const double t = exp_prod_tau(s.beta, s.q_hi - l_hi, s.q_lo - l_lo);
+  return div_fast(s.amp_grey * (-expm1_l(-t)) * rcube, em);
 }
 
 // ---------------------------------------------------------------------------

@@ -154,12 +154,14 @@ void emu_lir(int thin, int alpha, long long n, const double* pars, double waveno
   DISPATCH2(run_lir, thin, alpha, n, pars, wavenorm, fmin, fmax, prefac, out, status);
 }
 
-// element-wise checks of the lean math (mode 0 exp, 1 expm1, 2 reciprocal, 3 a/b with b = x+1)
+// element-wise checks of the lean math (mode 0 exp, 1 expm1, 2 reciprocal, 3 a/b with b = x+1, 4/5 table-driven exp/expm1)
 void emu_fastmath(int mode, long long n, const double* x, double* out) {
   for (long long i = 0; i < n; ++i) {
     if (mode == 0) out[i] = exp_fast(x[i]);
     else if (mode == 1) out[i] = expm1_fast(x[i]);
     else if (mode == 2) out[i] = rcp_fast(x[i]);
+    else if (mode == 4) out[i] = exp_tab(x[i]);
+    else if (mode == 5) out[i] = expm1_tab(x[i]);
     else out[i] = div_fast(x[i], x[i] + 1.0);
   }
 }
