@@ -144,6 +144,14 @@ int mbb_chain_post(mbb_ctx *ctx, int64_t nwalkers, int64_t nsteps,
                    double kappa_wave_um, double *out_peak, double *out_lir,
                    double *out_dustmass, int32_t *out_status, int mem);
 
+/* ---- predicted band flux for every chain sample: mbb_results._predict_flux
+ * (results.py:895-944) through band `band` of the table set by mbb_set_bands
+ * (a single node of weight 1 = flux density at one wavelength).  Same dedupe
+ * as mbb_chain_post; SED flags / wavenorm from mbb_set_model. */
+int mbb_chain_flux(mbb_ctx *ctx, int64_t nwalkers, int64_t nsteps,
+                   const double *chain, int band, double *out_flux,
+                   int32_t *out_status, int mem);
+
 /* ---- device-resident ensemble sampler for nsrc sources at once:
  * what mbb_fitter.run asks emcee for (mbb_fit.py:525-542 -> emcee 2.2 stretch
  * move, two half-ensembles per iteration), with proposal, log-probability and

@@ -78,6 +78,7 @@ def load_library():
             "mbb_sed_consts": (i32, [vp, i64, vp, i32, i32, vp, vp, i32]),
             "mbb_chain_post": (i32, [vp, i64, i64, vp, i32, dbl, dbl, dbl, dbl, dbl, dbl,
                                      vp, vp, vp, vp, i32]),
+            "mbb_chain_flux": (i32, [vp, i64, i64, vp, i32, vp, vp, i32]),
             "mbb_ensemble_run": (i32, [vp, i64, i32, i64, dbl, ctypes.c_uint64, ctypes.c_uint64, vp, vp,
                                        i32, vp, vp, vp, vp, i32, i32]),
             "mbb_fp64_peak": (i32, [vp, i32, ctypes.POINTER(dbl)]),
@@ -94,7 +95,7 @@ EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ct
                     "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
                     "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_bands",
                     "mbb_set_data", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
-                    "mbb_chain_post", "mbb_ensemble_run", "mbb_fp64_peak"]
+                    "mbb_chain_post", "mbb_chain_flux", "mbb_ensemble_run", "mbb_fp64_peak"]
 
 
 def _f64(a):
@@ -253,6 +254,14 @@ class Context(object):
                                           float(kappa), float(kappa_wave), _ptr(pk), _ptr(lir),
                                           _ptr(dm), _ptr(st), HOST))
         return pk, lir, dm, st
+
+    def chain_flux(self, chain, band=0):
+        chain = _f64(chain)
+        nw, ns = chain.shape[0], chain.shape[1]
+        out = np.empty((nw, ns))
+        st = np.empty((nw, ns), dtype=np.int32)
+        self._ck(self._lib.mbb_chain_flux(self._h, nw, ns, _ptr(chain), int(band), _ptr(out), _ptr(st), HOST))
+        return out, st
 
     def ensemble_run(self, pos, nsteps, seed=0, step0=0, a=2.0, lnprob=None):
         """Device-resident stretch-move sampler (host arrays in/out).

@@ -434,7 +434,8 @@ int mbb_set_model(mbb_ctx* c, double wavenorm, int opthin, int noalpha) {
   c->wavenorm = wavenorm;
   c->opthin = opthin ? 1 : 0;
   c->noalpha = noalpha ? 1 : 0;
-  if (changed && c->bands_set) return fail("set the model before the bands (tables depend on wavenorm)");
+  // the node tables hold log(lambda/wavenorm): a new wavenorm invalidates them
+  if (changed) c->bands_set = false;
   return 0;
 }
 
@@ -911,6 +912,57 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
     if (which & 4)
       CK(cudaMemcpyAsync(out_dustmass, ddm, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost,
                          c->stream));
+    if (out_status)
+      CK(cudaMemcpyAsync(out_status, dst, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int mbb_chain_flux(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* chain, int band,
+                   double* out_flux, int32_t* out_status, int mem) {
+  if (!c) return fail("null context");
+  if (nwalkers <= 0 || nsteps <= 0) return fail("empty chain");
+  if (!chain || !out_flux) return fail("null pointer");
+  if (!c->bands_set) return fail("mbb_set_bands has not been called");
+  if (band < 0 || band >= c->nb) return fail("band index out of range");
+  const int64_t ns = nwalkers * nsteps;
+  if (ns >= (int64_t)1 << 31) return fail("chain too long for one call (>= 2^31 samples); shard it");
+  Use u(c);
+  const double* dchain = chain;
+  double* dout = out_flux;
+  int* dst = out_status;
+  if (mem != MBB_DEVICE) {
+    CK(c->d_in.reserve((size_t)ns * 5));
+    CK(cudaMemcpyAsync(c->d_in.p, chain, (size_t)ns * 5 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dchain = c->d_in.p;
+    CK(c->d_out.reserve((size_t)ns));
+    dout = c->d_out.p;
+    CK(c->d_st.reserve((size_t)ns));
+    dst = c->d_st.p;
+  }
+  CK(c->d_owner.reserve((size_t)ns));
+  CK(c->d_work.reserve((size_t)ns));
+  CK(c->d_count.reserve(1));
+  CK(cudaMemsetAsync(c->d_count.p, 0, sizeof(unsigned), c->stream));
+  begin_timing(c);
+  chain_dedupe_kernel<<<(unsigned)((nwalkers + 63) / 64), 64, 0, c->stream>>>(
+      dchain, nwalkers, nsteps, c->d_owner.p, c->d_work.p, c->d_count.p);
+  const unsigned grid = (unsigned)((ns + 127) / 128);
+  const int i0 = c->h_off[band], i1 = c->h_off[band + 1], sp = c->h_scalar[band];
+  const bool thin = c->opthin != 0, alpha = c->noalpha == 0;
+#define FLX(T, A) chain_flux_kernel<T, A><<<grid, 128, 0, c->stream>>>(dchain, c->d_work.p, c->d_count.p, \
+                                    c->wavenorm, c->d_nodes.p, i0, i1, sp, dout, dst)
+  if (thin) { if (alpha) FLX(true, true); else FLX(true, false); }
+  else { if (alpha) FLX(false, true); else FLX(false, false); }
+#undef FLX
+  chain_fill_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(c->d_owner.p, nwalkers, nsteps, dout,
+                                                                         nullptr, nullptr, dst);
+  end_timing(c);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  if (mem != MBB_DEVICE) {
+    CK(cudaMemcpyAsync(out_flux, dout, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (out_status)
       CK(cudaMemcpyAsync(out_status, dst, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

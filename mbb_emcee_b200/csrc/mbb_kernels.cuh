@@ -623,6 +623,31 @@ chain_lir_kernel(const double* __restrict__ chain, const int* __restrict__ work,
   }
 }
 
+// Predicted band flux for every unique chain sample (results._predict_flux,
+// results.py:895-944): one thread per sample, nodes of one band serially, in
+// the reference's arithmetic (FAITHFUL) -- the SED is built with the default
+// wavenorm the reference uses there (results.py:935-938).
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(128)
+chain_flux_kernel(const double* __restrict__ chain, const int* __restrict__ work,
+                  const unsigned* __restrict__ nwork, double wavenorm, const NodeRec* __restrict__ nodes,
+                  int i0, int i1, int scalar_path, double* __restrict__ out, int* __restrict__ status) {
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *nwork) return;
+  const long long idx = work[j];
+  const double* p = chain + idx * 5;
+  Sed s;
+  sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+  double acc = qnan();
+  if (s.status == ST_OK) {
+    acc = 0.0;
+    const double hk = scalar_path ? s.hokt_e9 : s.hokt9;
+    for (int i = i0; i < i1; ++i) acc = fma(node_fnu<THIN, ALPHA>(s, hk * nodes[i].freq), nodes[i].w, acc);
+  }
+  out[idx] = acc;
+  if (status) status[idx] = s.status;
+}
+
 // Pass 3: repeated steps copy their owner's value.
 __global__ void chain_fill_kernel(const int* __restrict__ owner, long long nwalkers,
                                   long long nsteps, double* __restrict__ a0,

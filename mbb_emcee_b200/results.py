@@ -400,6 +400,42 @@ class mbb_results(object):
                                    kappa_wave=self._kappa_wave)[2]
         self._has_dustmass = True
 
+    # ---------------------------------------------------------- predicted flux
+    def _predict_flux(self, spec, maxidx=None):
+        """Predicted flux density [mJy] for every chain sample at a wavelength
+        (float, microns) or through a named response of the fit (reference
+        results.py:895-944; like the reference, the SED is built with the
+        default wavenorm=500)."""
+        if maxidx is not None:
+            raise NotImplementedError("maxidx is dead code in the reference")
+        if isinstance(spec, str):
+            if not self._response_integrate:
+                raise Exception("Asked for response integration, but no response "
+                                "functions available from original fit")
+            if spec not in self._responsewheel:
+                raise ValueError("Do not have response function matching "
+                                 "{:s}".format(spec))
+            wv, wt, isdelta = self._responsewheel[spec].node_table()
+        else:
+            w = float(spec)
+            if w <= 0:
+                raise ValueError("Invalid wavelength {:f}".format(w))
+            wv, wt, isdelta = np.array([w]), np.array([1.0]), True
+        ctx = self.context
+        ctx.set_model(500.0, self._opthin, self._noalpha)
+        ctx.set_bands(np.array([0, len(wv)], dtype=np.int32), wv, wt,
+                      np.array([1 if isdelta else 0], dtype=np.uint8))
+        flux, status = ctx.chain_flux(self.chain, 0)
+        _native.raise_for_status(status, self.chain)
+        return flux
+
+    def predflux_cen(self, spec, percentile=68.3, maxidx=None, lowlim=None, uplim=None):
+        """Central confidence interval of the predicted flux (reference :946-985)."""
+        if not self._fitset:
+            return None
+        return self._parcen_internal(self._predict_flux(spec, maxidx).flatten(), percentile,
+                                     lowlim=lowlim, uplim=uplim)
+
     # ---------------------------------------------------------------- choices
     def choice(self, nsamples=1, getpeaklambda=False, getlir=False,
                getdustmass=False):

@@ -412,3 +412,25 @@ def test_freq_integrate_golden(golden, oracle, name, opthin, noalpha):
         assert abs(got - ref[i]) <= 1e-7 * abs(ref[i])
         assert abs(got - want[i]) <= 1e-13 * abs(want[i])
         assert abs(m.max_wave() - g[tag + "_maxwave"][i]) <= TOL * g[tag + "_maxwave"][i]
+
+
+def test_predict_flux_vs_oracle(oracle):
+    """mbb_results._predict_flux (results.py:895-944): a wavelength and a passband."""
+    from mbb_emcee_b200 import mbb_fitter, mbb_results, synthetic
+    rng = np.random.RandomState(8)
+    chain = synthetic.random_walk_chain((14.0, 1.8, 400.0, 3.0, 30.0), 4, 12, rng)
+    fit = mbb_fitter(nwalkers=12, response=True, device=0)
+    fit.set_data(["SPIRE_250um", "SPIRE_500um"], [30.0, 20.0], [3.0, 2.0])
+    res = mbb_results.from_chain(chain, device=0)
+    res._response_integrate = True
+    res._responsewheel = fit.like._responsewheel
+    got_w = res._predict_flux(350.0)
+    got_b = res._predict_flux("SPIRE_250um")
+    band = oracle.band_from_response(fit.like._responsewheel["SPIRE_250um"])
+    for w in range(4):
+        for t in range(12):
+            s = oracle.make_sed(*chain[w, t])                    # default wavenorm, thick + alpha
+            assert abs(got_w[w, t] - oracle.sed_call(s, 350.0)[0]) <= TOL * got_w[w, t]
+            assert abs(got_b[w, t] - oracle.band_flux(s, band)) <= TOL * got_b[w, t]
+    cen = res.predflux_cen(350.0)
+    assert cen.shape == (3,) and cen[0] > 0
