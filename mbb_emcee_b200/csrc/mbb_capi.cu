@@ -878,7 +878,7 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
     dc.opthin = c->opthin;
   }
   begin_timing(c);
-  chain_dedupe_kernel<<<(unsigned)((nwalkers + 63) / 64), 64, 0, c->stream>>>(
+  chain_dedupe_kernel<<<(unsigned)((nwalkers + 3) / 4), 128, 0, c->stream>>>(
       dchain, nwalkers, nsteps, c->d_owner.p, c->d_work.p, c->d_count.p);
   chain_unique_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(
       dchain, c->d_work.p, c->d_count.p, which, dc, dpk, ddm, dst);
@@ -946,7 +946,7 @@ int mbb_chain_flux(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
   CK(c->d_count.reserve(1));
   CK(cudaMemsetAsync(c->d_count.p, 0, sizeof(unsigned), c->stream));
   begin_timing(c);
-  chain_dedupe_kernel<<<(unsigned)((nwalkers + 63) / 64), 64, 0, c->stream>>>(
+  chain_dedupe_kernel<<<(unsigned)((nwalkers + 3) / 4), 128, 0, c->stream>>>(
       dchain, nwalkers, nsteps, c->d_owner.p, c->d_work.p, c->d_count.p);
   const unsigned grid = (unsigned)((ns + 127) / 128);
   const int i0 = c->h_off[band], i1 = c->h_off[band + 1], sp = c->h_scalar[band];

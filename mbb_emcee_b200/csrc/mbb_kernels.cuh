@@ -487,35 +487,56 @@ sed_consts_kernel(const EvalArgs a, const ModelP m, int want_peak) {
 // ---------------------------------------------------------------------------
 // chain post-processing (results.py:534-801)
 // ---------------------------------------------------------------------------
-// Pass 1, one thread per walker: the sequential allclose-dedupe of _map_chain
+// Pass 1: the sequential allclose-dedupe of _map_chain
 // (results.py:553-566).  owner[w][t] = step index whose value step t reuses
 // (t itself when it must be computed).  np.allclose(prev, cur): every
 // |prev_i - cur_i| <= 1e-8 + 1e-5*|cur_i|.
-__global__ void chain_dedupe_kernel(const double* __restrict__ chain, long long nwalkers,
-                                    long long nsteps, int* __restrict__ owner,
-                                    int* __restrict__ work, unsigned* __restrict__ nwork) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per walker: 32 consecutive steps are loaded coalesced (one step per
+// lane), the sequential rule is then replayed with shuffles (all lanes follow
+// the same uniform scan), owners are stored coalesced and the new samples of the
+// chunk are appended to the work list with ONE atomic per chunk.
+__global__ void __launch_bounds__(128)
+chain_dedupe_kernel(const double* __restrict__ chain, long long nwalkers, long long nsteps,
+                    int* __restrict__ owner, int* __restrict__ work, unsigned* __restrict__ nwork) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= nwalkers) return;
   const double* base = chain + w * nsteps * 5;
-  double prev[5];
+  double prev[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   long long prev_t = 0;
-  for (long long tt = 0; tt < nsteps; ++tt) {
+  for (long long t0 = 0; t0 < nsteps; t0 += 32) {
+    const long long t = t0 + lane;
     double cur[5];
-    bool same = tt > 0;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      cur[i] = base[tt * 5 + i];
-      if (tt > 0) same = same && (fabs(prev[i] - cur[i]) <= 1e-8 + 1e-5 * fabs(cur[i]));
+    for (int i = 0; i < 5; ++i) cur[i] = t < nsteps ? base[t * 5 + i] : 0.0;
+    const int cnt = (int)((nsteps - t0) < 32 ? (nsteps - t0) : 32);
+    long long my_owner = t;
+    bool my_new = false;
+    for (int j = 0; j < cnt; ++j) {
+      double c[5];
+      bool same = (t0 + j) > 0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        c[i] = __shfl_sync(0xffffffffu, cur[i], j);
+        same = same && (fabs(prev[i] - c[i]) <= 1e-8 + 1e-5 * fabs(c[i]));
+      }
+      if (!same) {
+        prev_t = t0 + j;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) prev[i] = c[i];
+      }
+      if (lane == j) {
+        my_owner = prev_t;
+        my_new = !same;
+      }
     }
-    if (same) {
-      owner[w * nsteps + tt] = (int)prev_t;
-    } else {
-      owner[w * nsteps + tt] = (int)tt;
-      prev_t = tt;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) prev[i] = cur[i];
-      unsigned slot = atomicAdd(nwork, 1u);
-      work[slot] = (int)(w * nsteps + tt);   // flat sample index (fits: checked on host)
+    const unsigned mask = __ballot_sync(0xffffffffu, my_new);
+    unsigned slot0 = 0;
+    if (lane == 0 && mask) slot0 = atomicAdd(nwork, (unsigned)__popc(mask));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (t < nsteps) {
+      owner[w * nsteps + t] = (int)my_owner;
+      if (my_new) work[slot0 + __popc(mask & ((1u << lane) - 1u))] = (int)(w * nsteps + t);
     }
   }
 }

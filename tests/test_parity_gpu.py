@@ -434,3 +434,54 @@ def test_predict_flux_vs_oracle(oracle):
             assert abs(got_b[w, t] - oracle.band_flux(s, band)) <= TOL * got_b[w, t]
     cen = res.predflux_cen(350.0)
     assert cen.shape == (3,) and cen[0] > 0
+
+
+def test_chain_post_full_size_properties(oracle):
+    """BASELINE configs[3]: a 10^7-sample chain (500 walkers x 20000 steps, 35% of
+    the steps new).  Size-independent properties + an oracle-checked sample."""
+    import hostemu_lib as emu
+    from mbb_emcee_b200 import mbb_results, synthetic
+    cfg = synthetic.CONFIGS["cfg4"]
+    rng = np.random.RandomState(cfg["seed"])
+    nw, ns = 500, 20000
+    chain = synthetic.random_walk_chain(cfg["truth"], nw, ns, rng)
+    res = mbb_results.from_chain(chain, wavenorm=cfg["wavenorm"], redshift=cfg["z"],
+                                 lumdist=cfg["lumdist"], device=0)
+    res.compute_peaklambda()
+    res.compute_dustmass(kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
+    res.compute_lir(*cfg["lir"])
+    for arr in (res.peaklambda, res.dustmass, res.lir):
+        assert arr.shape == (nw, ns) and np.isfinite(arr).all() and (arr > 0).all()
+    # (1) idempotence of the dedupe: exact repeats carry their predecessor's value
+    same = np.all(chain[:, 1:, :] == chain[:, :-1, :], axis=2)
+    assert 0.5 < same.mean() < 0.8
+    for arr in (res.peaklambda, res.dustmass, res.lir):
+        assert np.array_equal(arr[:, 1:][same], arr[:, :-1][same])
+    # (2) linearity in fnorm: dust mass and L_IR scale with it, the peak does not
+    chain2 = chain.copy()
+    chain2[:, :, 4] *= 2.0
+    res2 = mbb_results.from_chain(chain2[:40], wavenorm=cfg["wavenorm"], redshift=cfg["z"],
+                                  lumdist=cfg["lumdist"], device=0)
+    res2.compute_peaklambda()
+    res2.compute_dustmass(kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
+    res2.compute_lir(*cfg["lir"])
+    new = ~np.concatenate([np.zeros((40, 1), bool), same[:40]], axis=1)
+    assert relerr(res2.dustmass[new], 2.0 * res.dustmass[:40][new]).max() < 1e-14
+    assert relerr(res2.lir[new], 2.0 * res.lir[:40][new]).max() < 1e-13
+    assert np.array_equal(res2.peaklambda[new], res.peaklambda[:40][new])
+    # (3) a random sample of new steps against the oracle / the CPU emulation
+    wi = rng.randint(0, nw, 60)
+    ti = rng.randint(1, ns, 60)
+    c = oracle.dustmass_consts(cfg["z"], cfg["wavenorm"], cfg["kappa_wave"], cfg["lumdist"])
+    pref = oracle.LIR_PREFAC * cfg["lumdist"]**2
+    for w, t in zip(wi, ti):
+        while same[w, t - 1] and t > 1:       # walk back to the step that was actually computed
+            t -= 1
+        if np.allclose(chain[w, t - 1], chain[w, t]):
+            continue                          # moved by < 1e-5: reference reuses the predecessor
+        st = chain[w, t]
+        assert abs(res.peaklambda[w, t] - oracle.peaklambda_step(st)) <= TOL * res.peaklambda[w, t]
+        dm = oracle.dustmass_step(st, cfg["kappa"], cfg["wavenorm"], False, *c)
+        assert abs(res.dustmass[w, t] - dm) <= TOL * dm
+        lir_emu, _ = emu.lir(False, False, st, 500.0, 8.0 * 3.0, 1000.0 * 3.0, prefac=pref)
+        assert abs(res.lir[w, t] - lir_emu[0]) <= 1e-13 * lir_emu[0]
