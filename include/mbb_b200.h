@@ -40,6 +40,7 @@ typedef struct mbb_ctx mbb_ctx;
 enum { MBB_AOS = 0, MBB_SOA = 1 };
 enum { MBB_HOST = 0, MBB_DEVICE = 1 };
 enum { MBB_MATH_FAITHFUL = 0, MBB_MATH_FAST = 1 };
+enum { MBB_LIR_QUADPACK = 0, MBB_LIR_GAUSS = 1 };
 
 /* per-evaluation status codes written to `status[]`; 0/1 are normal outcomes,
  * the others correspond to exceptions the reference raises. */
@@ -78,6 +79,17 @@ int mbb_last_kernel_ms(mbb_ctx *ctx, float *ms);
  *      likelihood._set_sed (likelihood.py:765-768) ------------------------- */
 int mbb_set_model(mbb_ctx *ctx, double wavenorm, int opthin, int noalpha);
 int mbb_set_math_mode(mbb_ctx *ctx, int mode);
+
+/* ---- how mbb_chain_post integrates f_nu for L_IR / freq_integrate
+ * (modified_blackbody.py:671 -> scipy.integrate.quad):
+ *   MBB_LIR_QUADPACK (default) replays QUADPACK dqagse (21-point Gauss-Kronrod,
+ *     epsabs = epsrel = 1.49e-8, limit 50, epsilon extrapolation) on the
+ *     reference's integrand: the reference's number to ~1e-15, including its
+ *     own ~1e-8 quadrature error;
+ *   MBB_LIR_GAUSS integrates the power-law part analytically and the grey
+ *     body by a fixed 128-node Gauss-Legendre rule in ln(x): the true integral
+ *     to ~1e-15, faster. */
+int mbb_set_lir_method(mbb_ctx *ctx, int method);
 
 /* ---- passbands: replaces response.__call__ (response.py:544-576).
  * Band b owns nodes [band_off[b], band_off[b+1]).  node_wave_um are the

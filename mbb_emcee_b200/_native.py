@@ -19,6 +19,7 @@ _LIBNAME = os.path.join(_HERE, "csrc", "libmbb_b200.so")
 AOS, SOA = 0, 1
 HOST, DEVICE = 0, 1
 MATH_FAITHFUL, MATH_FAST = 0, 1
+LIR_QUADPACK, LIR_GAUSS = 0, 1
 
 STATUS_NAMES = {0: "ok", 1: "below lower limit", 2: "bad alpha", 3: "bad beta",
                 4: "bracket low", 5: "bracket high", 6: "no convergence",
@@ -70,6 +71,7 @@ def load_library():
             "mbb_last_kernel_ms": (i32, [vp, ctypes.POINTER(ctypes.c_float)]),
             "mbb_set_model": (i32, [vp, dbl, i32, i32]),
             "mbb_set_math_mode": (i32, [vp, i32]),
+            "mbb_set_lir_method": (i32, [vp, i32]),
             "mbb_set_bands": (i32, [vp, i32, vp, vp, vp, vp]),
             "mbb_set_data": (i32, [vp, i32, i32, vp, vp, vp]),
             "mbb_set_priors": (i32, [vp, vp, vp, vp, vp, vp, vp]),
@@ -93,7 +95,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ctx_create",
                     "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
-                    "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_bands",
+                    "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_lir_method", "mbb_set_bands",
                     "mbb_set_data", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
                     "mbb_chain_post", "mbb_chain_flux", "mbb_ensemble_run", "mbb_fp64_peak"]
 
@@ -172,6 +174,11 @@ class Context(object):
     def set_math_mode(self, mode):
         self._ck(self._lib.mbb_set_math_mode(self._h, int(mode)))
         self.math_mode = int(mode)
+
+    def set_lir_method(self, method):
+        """'quadpack' (default; the reference's number) or 'gauss' (the true integral)."""
+        m = {"quadpack": LIR_QUADPACK, "gauss": LIR_GAUSS}.get(method, method)
+        self._ck(self._lib.mbb_set_lir_method(self._h, int(m)))
 
     def set_bands(self, band_off, node_wave, node_weight, scalar_path=None):
         off = np.ascontiguousarray(band_off, dtype=np.int32)

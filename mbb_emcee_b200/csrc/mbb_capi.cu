@@ -85,6 +85,7 @@ struct mbb_ctx {
   double wavenorm = 500.0;
   int opthin = 0, noalpha = 0;
   int math_mode = MBB_MATH_FAST;
+  int lir_method = MBB_LIR_QUADPACK;
 
   // passbands
   int nb = 0, nn = 0, nn_pad = 0;
@@ -443,6 +444,13 @@ int mbb_set_math_mode(mbb_ctx* c, int mode) {
   if (!c) return fail("null context");
   if (mode != MBB_MATH_FAITHFUL && mode != MBB_MATH_FAST) return fail("unknown math mode");
   c->math_mode = mode;
+  return 0;
+}
+
+int mbb_set_lir_method(mbb_ctx* c, int method) {
+  if (!c) return fail("null context");
+  if (method != MBB_LIR_QUADPACK && method != MBB_LIR_GAUSS) return fail("unknown L_IR method");
+  c->lir_method = method;
   return 0;
 }
 
@@ -891,10 +899,15 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
     const double prefac = dl_mpc > 0.0 ? 3.11749657e4 * (dl_mpc * dl_mpc) : 1.0;
     const unsigned grid = (unsigned)((ns + 127) / 128);
     const bool thin = c->opthin != 0, alpha = c->noalpha == 0;
-#define LIR(T, A) chain_lir_kernel<T, A><<<grid, 128, 0, c->stream>>>(dchain, c->d_work.p, c->d_count.p, \
+#define LIR(K, T, A) K<T, A><<<grid, 128, 0, c->stream>>>(dchain, c->d_work.p, c->d_count.p, \
                                    c->wavenorm, fmin, fmax, prefac, dlir, dst)
-    if (thin) { if (alpha) LIR(true, true); else LIR(true, false); }
-    else { if (alpha) LIR(false, true); else LIR(false, false); }
+    if (c->lir_method == MBB_LIR_GAUSS) {
+      if (thin) { if (alpha) LIR(chain_lir_kernel, true, true); else LIR(chain_lir_kernel, true, false); }
+      else { if (alpha) LIR(chain_lir_kernel, false, true); else LIR(chain_lir_kernel, false, false); }
+    } else {
+      if (thin) { if (alpha) LIR(chain_lir_qags_kernel, true, true); else LIR(chain_lir_qags_kernel, true, false); }
+      else { if (alpha) LIR(chain_lir_qags_kernel, false, true); else LIR(chain_lir_qags_kernel, false, false); }
+    }
 #undef LIR
     c->launches += 1;
   }

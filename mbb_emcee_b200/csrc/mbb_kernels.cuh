@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include "mbb_model.cuh"
+#include "mbb_quadpack.cuh"
 
 namespace mbb {
 
@@ -642,6 +643,34 @@ chain_lir_kernel(const double* __restrict__ chain, const int* __restrict__ work,
       if (status) status[idx] = (v == v) ? ST_OK : ST_NONFINITE;
     }
   }
+}
+
+// L_IR by replaying scipy.integrate.quad (QUADPACK dqagse, epsabs = epsrel =
+// 1.49e-8, limit 50) on the reference's own integrand (modified_blackbody.py:
+// 671, numpy formulation of f_nu): one thread per unique sample.  Reproduces
+// the reference's value to ~1e-15 -- including its ~1e-8 quadrature error.
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(128)
+chain_lir_qags_kernel(const double* __restrict__ chain, const int* __restrict__ work,
+                      const unsigned* __restrict__ nwork, double wavenorm, double fmin_ghz,
+                      double fmax_ghz, double prefac, double* __restrict__ out_lir,
+                      int* __restrict__ status) {
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *nwork) return;
+  const long long idx = work[j];
+  const double* p = chain + idx * 5;
+  Sed s;
+  sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+  double v = qnan();
+  int st = s.status;
+  if (st == ST_OK) {
+    const QagsOut q = qagse([&](double nu) { return node_fnu<THIN, ALPHA>(s, s.hokt_e9 * nu); },
+                            fmin_ghz, fmax_ghz, 1.49e-8, 1.49e-8);
+    v = prefac * (1e-17 * q.result);
+    if (v != v) st = ST_NONFINITE;
+  }
+  out_lir[idx] = v;
+  if (status) status[idx] = st;
 }
 
 // Predicted band flux for every unique chain sample (results._predict_flux,

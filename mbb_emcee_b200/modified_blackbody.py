@@ -178,9 +178,11 @@ class modified_blackbody(object):
         _native.raise_for_status(status, self._pars)
         return float(consts[0, 5])
 
-    def freq_integrate(self, minwave, maxwave):
+    def freq_integrate(self, minwave, maxwave, method="quadpack"):
         """Integral of f_nu over [minwave, maxwave] microns, erg/s/cm^2
-        (reference :639-674)."""
+        (reference :639-674).  ``method``: "quadpack" replays the reference's
+        scipy.integrate.quad call (its value to ~1e-15), "gauss" is the
+        fixed-rule quadrature (the true integral to ~1e-15)."""
         minwave = float(minwave)
         maxwave = float(maxwave)
         if minwave <= 0.0:
@@ -189,9 +191,9 @@ class modified_blackbody(object):
             minwave, maxwave = maxwave, minwave
         # unit prefactor so the chain kernel returns 1e-17 * integral
         chain = self._pars.reshape(1, 1, 5)
-        dl = (1.0 / 3.11749657e4) ** 0.5
+        self._ctx.set_lir_method(method)
         _, lir, _, status = self._device(
-            lambda ctx: ctx.chain_post(chain, 2, z=0.0, dl_mpc=dl, lir_min=minwave,
+            lambda ctx: ctx.chain_post(chain, 2, z=0.0, dl_mpc=-1.0, lir_min=minwave,
                                        lir_max=maxwave))
         _native.raise_for_status(status, self._pars)
         return float(lir[0, 0])

@@ -333,8 +333,13 @@ class mbb_results(object):
         return self._parcen_internal(self.lir.flatten(), percentile,
                                      lowlim=lowlim, uplim=uplim)
 
-    def compute_lir(self, wavemin=8.0, wavemax=1000.0, maxidx=None):
-        """L_IR in 10^12 L_sun for every chain sample (reference :627-674)."""
+    def compute_lir(self, wavemin=8.0, wavemax=1000.0, maxidx=None, method="quadpack"):
+        """L_IR in 10^12 L_sun for every chain sample (reference :627-674).
+
+        ``method`` (extension): "quadpack" (default) replays the reference's
+        scipy.integrate.quad call and returns the reference's numbers to
+        ~1e-15; "gauss" is a fixed-rule quadrature accurate to ~1e-15 of the
+        true integral (the reference itself is only good to ~1e-8 there)."""
         if not self._fitset:
             raise Exception("Fit results not loaded")
         if self._z is None:
@@ -350,6 +355,7 @@ class mbb_results(object):
             raise ValueError("Invalid wavemax: {:f}".format(self._lir_max))
         if self._lir_min > self._lir_max:
             self._lir_min, self._lir_max = self._lir_max, self._lir_min
+        self.context.set_lir_method(method)
         self.lir = self._post(2, 500.0, self._opthin, self._noalpha, z=self._z,
                               dl_mpc=self.lumdist, lir_min=self._lir_min,
                               lir_max=self._lir_max)[1]

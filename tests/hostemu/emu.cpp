@@ -13,6 +13,7 @@
 
 #include "../../mbb_emcee_b200/csrc/mbb_model.cuh"
 #include "../../mbb_emcee_b200/csrc/mbb_philox.cuh"
+#include "../../mbb_emcee_b200/csrc/mbb_quadpack.cuh"
 
 using namespace mbb;
 
@@ -95,6 +96,21 @@ void run_lir(long long n, const double* pars, double wavenorm, double fmin, doub
     out[e] = prefac * (1e-17 * (s.normfac * (acc + sp.pow_part) / s.hokt_e9));
   }
 }
+template <bool THIN, bool ALPHA>
+void run_qags(long long n, const double* pars, double wavenorm, double fmin, double fmax, double prefac,
+              double* out, int* neval, int* status) {
+  for (long long e = 0; e < n; ++e) {
+    const double* p = pars + 5 * e;
+    Sed s;
+    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+    status[e] = s.status;
+    if (s.status != ST_OK) { out[e] = kInf - kInf; neval[e] = 0; continue; }
+    const QagsOut q = qagse([&](double nu) { return node_fnu<THIN, ALPHA>(s, s.hokt_e9 * nu); }, fmin, fmax,
+                            1.49e-8, 1.49e-8);
+    out[e] = prefac * (1e-17 * q.result);
+    neval[e] = q.neval;
+  }
+}
 }  // namespace
 
 #define DISPATCH2(fn, thin, alpha, ...)                         \
@@ -164,6 +180,31 @@ void emu_fastmath(int mode, long long n, const double* x, double* out) {
     else if (mode == 5) out[i] = expm1_tab(x[i]);
     else out[i] = div_fast(x[i], x[i] + 1.0);
   }
+}
+
+void emu_qags(int thin, int alpha, long long n, const double* pars, double wavenorm, double fmin, double fmax,
+              double prefac, double* out, int* neval, int* status) {
+  DISPATCH2(run_qags, thin, alpha, n, pars, wavenorm, fmin, fmax, prefac, out, neval, status);
+}
+
+// QAGS on a few textbook integrands (kind), to compare with scipy.integrate.quad
+void emu_qags_test(int kind, double a, double b, double epsabs, double epsrel, double* result, double* abserr,
+                   int* neval, int* ier) {
+  auto f = [kind](double x) -> double {
+    switch (kind) {
+      case 0: return sqrt(x);
+      case 1: return log(x);
+      case 2: return 1.0 / sqrt(x);
+      case 3: return sqrt(fabs(x - 0.3));
+      case 4: return cos(50.0 * x);
+      case 5: return exp(-x * x);
+      case 6: return fabs(x - 1.0 / 3.0);
+      case 7: return 1.0 / (1.0 + 1000.0 * (x - 0.5) * (x - 0.5));
+      default: return x;
+    }
+  };
+  const QagsOut q = qagse(f, a, b, epsabs, epsrel);
+  *result = q.result; *abserr = q.abserr; *neval = q.neval; *ier = q.ier;
 }
 
 void emu_philox(const unsigned* ctr, const unsigned* key, unsigned* out, double* u) {

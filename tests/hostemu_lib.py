@@ -108,3 +108,26 @@ def philox(ctr, key):
     u = ctypes.c_double()
     lib().emu_philox(_p(c), _p(k), _p(out), ctypes.byref(u))
     return out, u.value
+
+
+def qags(opthin, noalpha, pars, wavenorm, minwave, maxwave, prefac=1.0):
+    """freq_integrate by the QUADPACK replay (csrc/mbb_quadpack.cuh)."""
+    P = _c(pars).reshape(-1, 5)
+    n = P.shape[0]
+    out = np.empty(n)
+    nev = np.empty(n, dtype=np.int32)
+    st = np.empty(n, dtype=np.int32)
+    fmin, fmax = 299792458e-3 / maxwave, 299792458e-3 / minwave
+    lib().emu_qags(int(opthin), int(not noalpha), ctypes.c_longlong(n), _p(P), ctypes.c_double(wavenorm),
+                   ctypes.c_double(fmin), ctypes.c_double(fmax), ctypes.c_double(prefac), _p(out), _p(nev),
+                   _p(st))
+    return out, nev, st
+
+
+def qags_test(kind, a, b, epsabs=1.49e-8, epsrel=1.49e-8):
+    r, e = ctypes.c_double(), ctypes.c_double()
+    nv, ier = ctypes.c_int(), ctypes.c_int()
+    lib().emu_qags_test(int(kind), ctypes.c_double(a), ctypes.c_double(b), ctypes.c_double(epsabs),
+                        ctypes.c_double(epsrel), ctypes.byref(r), ctypes.byref(e), ctypes.byref(nv),
+                        ctypes.byref(ier))
+    return r.value, e.value, nv.value, ier.value

@@ -206,3 +206,33 @@ def test_philox_known_answers():
         got = philox_np.philox4x32_10(*[np.array([c], dtype=np.uint64) for c in ctr], key[0], key[1])
         assert tuple(int(g[0]) for g in got) == want
         assert u == philox_np.u53(got[0], got[1])[0] and 0.0 < u < 1.0
+
+
+def test_qags_matches_scipy(golden):
+    """The QUADPACK replay (csrc/mbb_quadpack.cuh) against scipy.integrate.quad:
+    identical result / error estimate / neval on integrands that exercise the
+    bisection order and the epsilon-algorithm extrapolation, and the
+    reference's freq_integrate values to 1e-15."""
+    import warnings
+    from scipy.integrate import quad
+    fs = [np.sqrt, np.log, lambda x: 1 / np.sqrt(x), lambda x: np.sqrt(abs(x - 0.3)),
+          lambda x: np.cos(50 * x), lambda x: np.exp(-x * x), lambda x: abs(x - 1 / 3.),
+          lambda x: 1 / (1 + 1000 * (x - .5)**2)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for kind, f in enumerate(fs):
+            for a, b in ((0.0, 1.0), (0.0, 2.5), (1e-3, 7.0)):
+                res, err, info = quad(f, a, b, full_output=1)[:3]
+                got = emu.qags_test(kind, a, b)
+                assert abs(got[0] - res) <= 4e-16 * abs(res), (kind, a, b)
+                assert abs(got[1] - err) <= 1e-3 * abs(err) + 1e-18
+                assert got[2] == info["neval"]
+    g = golden.sed
+    for name, opthin, noalpha in VARIANTS:
+        for wn in (500.0, 250.0):
+            tag = "%s_wn%d" % (name, int(wn))
+            ref = g[tag + "_freqint"]
+            m = np.isfinite(ref)
+            got, nev, st = emu.qags(opthin, noalpha, g[tag + "_P"][m], wn, 24.0, 3000.0)
+            assert (st == 0).all()
+            assert relerr(got, ref[m]).max() < 1e-15

@@ -383,11 +383,23 @@ def test_chain_post_golden(golden, name, opthin, noalpha):
     assert relerr(res.peaklambda, g[name + "_peaklambda"]).max() < TOL
     res.compute_dustmass(kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
     assert relerr(res.dustmass, g[name + "_dustmass"]).max() < TOL
-    # L_IR: fixed-rule quadrature vs the reference's adaptive quad (requested epsrel 1.49e-8,
-    # observed error of the reference vs a 40-digit truth up to 2.7e-8 with alpha on;
-    # see test_device_logic_cpu.py::test_freq_integrate for the 1e-13 truth check)
+    # L_IR, default method: replay of the reference's scipy.integrate.quad call.
+    # Same subdivision sequence => 1e-15 agreement.  The adaptive algorithm is
+    # chaotic at the ulp level, though: where a termination / ordering test of
+    # QUADPACK is decided by the last bit of an integrand value (libdevice pow
+    # vs glibc pow), the two runs subdivide differently and differ by the
+    # quadrature's own error (<= ~3e-8).  Require the first for the bulk.
     res.compute_lir(wavemin=cfg["lir"][0], wavemax=cfg["lir"][1])
-    assert relerr(res.lir, g[name + "_lir"]).max() < 1e-7
+    dev = relerr(res.lir, g[name + "_lir"])
+    assert dev.max() < 1e-7
+    assert np.mean(dev < TOL) >= 0.9, np.mean(dev < TOL)
+    lir_q = res.lir.copy()
+    # L_IR, fixed-rule quadrature: the true integral (1e-13 vs 40-digit mpmath in
+    # test_device_logic_cpu.py::test_freq_integrate); the reference's own quad error
+    # reaches 2.7e-8 with the merge kink inside the range
+    res.compute_lir(wavemin=cfg["lir"][0], wavemax=cfg["lir"][1], method="gauss")
+    assert relerr(res.lir, lir_q).max() < 1e-7
+    res.lir = lir_q
     # the allclose-dedupe: step 5 of walker 0 is within 3e-6 of step 4
     assert res.peaklambda[0, 5] == res.peaklambda[0, 4]
     assert res.dustmass[0, 5] == res.dustmass[0, 4]
@@ -396,8 +408,9 @@ def test_chain_post_golden(golden, name, opthin, noalpha):
 
 @pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
 def test_freq_integrate_golden(golden, oracle, name, opthin, noalpha):
-    """modified_blackbody.freq_integrate on the device vs the reference (2e-8)
-    and vs the CPU emulation of the same quadrature (1e-13)."""
+    """modified_blackbody.freq_integrate on the device: the QUADPACK replay
+    reproduces the reference to 1e-12; the fixed-rule quadrature agrees with the
+    CPU emulation of the same rule to 1e-13 (and with the truth, see CPU tests)."""
     from mbb_emcee_b200 import modified_blackbody
     import hostemu_lib as emu
     g = golden.sed
@@ -405,13 +418,18 @@ def test_freq_integrate_golden(golden, oracle, name, opthin, noalpha):
     P = g[tag + "_P"][:12]
     ref = g[tag + "_freqint"][:12]
     want, st = emu.lir(opthin, noalpha, P, 250.0, 24.0, 3000.0)
+    nclose = 0
     for i in range(len(P)):
         m = modified_blackbody(P[i, 0], P[i, 1], P[i, 2], P[i, 3], P[i, 4], wavenorm=250.0,
                                noalpha=noalpha, opthin=opthin)
-        got = m.freq_integrate(24.0, 3000.0)
+        got = m.freq_integrate(24.0, 3000.0)                          # QUADPACK replay
+        nclose += abs(got - ref[i]) <= TOL * abs(ref[i])
+        assert abs(got - ref[i]) <= 1e-7 * abs(ref[i])
+        got = m.freq_integrate(24.0, 3000.0, method="gauss")
         assert abs(got - ref[i]) <= 1e-7 * abs(ref[i])
         assert abs(got - want[i]) <= 1e-13 * abs(want[i])
         assert abs(m.max_wave() - g[tag + "_maxwave"][i]) <= TOL * g[tag + "_maxwave"][i]
+    assert nclose >= len(P) - 2        # see test_chain_post_golden on the rare subdivision flips
 
 
 def test_predict_flux_vs_oracle(oracle):
@@ -449,7 +467,18 @@ def test_chain_post_full_size_properties(oracle):
                                  lumdist=cfg["lumdist"], device=0)
     res.compute_peaklambda()
     res.compute_dustmass(kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
-    res.compute_lir(*cfg["lir"])
+    res.compute_lir(*cfg["lir"], method="gauss")
+    lir_gauss = res.lir.copy()
+    res.compute_lir(*cfg["lir"])                      # default: QUADPACK replay
+    # the replay inherits the reference's quadrature error; where that error is
+    # largest it must still BE the reference's number (checked against scipy below)
+    dev = relerr(res.lir, lir_gauss)
+    assert np.median(dev) < 1e-8
+    pref0 = oracle.LIR_PREFAC * cfg["lumdist"]**2
+    for flat in np.argsort(dev, axis=None)[-4:]:
+        w, t = np.unravel_index(flat, dev.shape)
+        ref = pref0 * oracle.lir_step(chain[w, t], cfg["z"], 8.0, 1000.0, False, False)
+        assert abs(res.lir[w, t] - ref) <= 1e-7 * ref, (dev[w, t], res.lir[w, t], ref)
     for arr in (res.peaklambda, res.dustmass, res.lir):
         assert arr.shape == (nw, ns) and np.isfinite(arr).all() and (arr > 0).all()
     # (1) idempotence of the dedupe: exact repeats carry their predecessor's value
@@ -464,16 +493,17 @@ def test_chain_post_full_size_properties(oracle):
                                   lumdist=cfg["lumdist"], device=0)
     res2.compute_peaklambda()
     res2.compute_dustmass(kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
-    res2.compute_lir(*cfg["lir"])
+    res2.compute_lir(*cfg["lir"], method="gauss")
     new = ~np.concatenate([np.zeros((40, 1), bool), same[:40]], axis=1)
     assert relerr(res2.dustmass[new], 2.0 * res.dustmass[:40][new]).max() < 1e-14
-    assert relerr(res2.lir[new], 2.0 * res.lir[:40][new]).max() < 1e-13
+    assert relerr(res2.lir[new], 2.0 * lir_gauss[:40][new]).max() < 1e-13
     assert np.array_equal(res2.peaklambda[new], res.peaklambda[:40][new])
     # (3) a random sample of new steps against the oracle / the CPU emulation
     wi = rng.randint(0, nw, 60)
     ti = rng.randint(1, ns, 60)
     c = oracle.dustmass_consts(cfg["z"], cfg["wavenorm"], cfg["kappa_wave"], cfg["lumdist"])
     pref = oracle.LIR_PREFAC * cfg["lumdist"]**2
+    nchk = nclose = 0
     for w, t in zip(wi, ti):
         while same[w, t - 1] and t > 1:       # walk back to the step that was actually computed
             t -= 1
@@ -484,4 +514,9 @@ def test_chain_post_full_size_properties(oracle):
         dm = oracle.dustmass_step(st, cfg["kappa"], cfg["wavenorm"], False, *c)
         assert abs(res.dustmass[w, t] - dm) <= TOL * dm
         lir_emu, _ = emu.lir(False, False, st, 500.0, 8.0 * 3.0, 1000.0 * 3.0, prefac=pref)
-        assert abs(res.lir[w, t] - lir_emu[0]) <= 1e-13 * lir_emu[0]
+        assert abs(lir_gauss[w, t] - lir_emu[0]) <= 1e-13 * lir_emu[0]
+        lir_ref = pref * oracle.lir_step(st, cfg["z"], 8.0, 1000.0, False, False)
+        nchk += 1
+        nclose += abs(res.lir[w, t] - lir_ref) <= TOL * lir_ref
+        assert abs(res.lir[w, t] - lir_ref) <= 1e-7 * lir_ref
+    assert nclose >= 0.9 * nchk, (nclose, nchk)
