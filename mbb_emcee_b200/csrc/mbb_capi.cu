@@ -92,7 +92,6 @@ struct mbb_ctx {
   std::vector<int> h_off;
   std::vector<unsigned char> h_scalar;
   std::vector<double> h_packed;   // [freq|w|lhi|llo|rcube] x nn_pad
-  DevBuf<double> d_packed;
   DevBuf<NodeRec> d_nodes;
   DevBuf<int> d_off;
   DevBuf<unsigned char> d_scalar;
@@ -386,7 +385,7 @@ int mbb_ctx_destroy(mbb_ctx* c) {
   if (!c) return 0;
   Use u(c);
   cudaStreamSynchronize(c->stream);
-  c->d_packed.release(); c->d_nodes.release(); c->d_off.release(); c->d_scalar.release();
+  c->d_nodes.release(); c->d_off.release(); c->d_scalar.release();
   c->d_flux.release(); c->d_ivar.release(); c->d_cinv.release();
   c->h_in.release(); c->h_out.release(); c->h_st.release(); c->h_src.release();
   c->d_in.release(); c->d_out.release(); c->d_aux0.release(); c->d_aux1.release();
@@ -491,11 +490,8 @@ int mbb_set_bands(mbb_ctx* c, int nbands, const int32_t* band_off, const double*
     c->h_packed[4 * np + i] = (double)(r * r * r);
   }
   for (int i = nn; i < np; ++i) c->h_packed[i] = 1.0;   // harmless padding node, weight 0
-  CK(c->d_packed.reserve(c->h_packed.size()));
   CK(c->d_off.reserve(nbands + 1));
   CK(c->d_scalar.reserve(nbands));
-  CK(cudaMemcpyAsync(c->d_packed.p, c->h_packed.data(), c->h_packed.size() * sizeof(double),
-                     cudaMemcpyHostToDevice, c->stream));
   {
     std::vector<NodeRec> recs((size_t)nn);
     for (int i = 0; i < nn; ++i) {

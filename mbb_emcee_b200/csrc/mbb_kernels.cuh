@@ -137,9 +137,6 @@ loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const D
 #ifndef MBB_DELTA_BLOCK
 #define MBB_DELTA_BLOCK 256
 #endif
-#ifndef MBB_DELTA_LATE
-#define MBB_DELTA_LATE 0
-#endif
 // one evaluation, all bands single-node, FAST arithmetic, NB compile-time
 template <bool THIN, bool ALPHA, int NB>
 __device__ __forceinline__ double delta_eval(const double p[5], long long src, const ModelP& m,
@@ -147,7 +144,6 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, c
                                              int& st) {
   const double* __restrict__ fl = d.flux + src * NB;
   const double* __restrict__ ivp = d.ivar + src * NB;
-#if !MBB_DELTA_LATE
   double diff[NB], iv[NB];
   {
     // data loads issued next to the parameter loads: one exposed global latency
@@ -158,7 +154,6 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, c
       for (int b = 0; b < NB; ++b) iv[b] = __ldg(ivp + b);
     }
   }
-#endif
   st = ST_OK;
   if (below_lowlim(pr, p)) {
     st = ST_BELOW_LOWLIM;
@@ -169,32 +164,6 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, c
   st = s.status;
   if (st != ST_OK) return qnan();
   double chi = 0.0;
-#if MBB_DELTA_LATE
-  if (!d.cinv) {
-    // register-lean form: nothing but chi stays live across bands
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const double f = node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
-      const double df = fma(-f, t.w[b], __ldg(fl + b));
-      chi = fma(df * df, __ldg(ivp + b), chi);
-    }
-  } else {
-    double diff[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const double f = node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
-      diff[b] = fma(-f, t.w[b], __ldg(fl + b));
-    }
-    const double* __restrict__ ci = d.cinv + src * (NB * NB);
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      double row = 0.0;
-#pragma unroll
-      for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
-      chi = fma(diff[r], row, chi);
-    }
-  }
-#else
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     const double f = node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
@@ -213,7 +182,6 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, c
 #pragma unroll
     for (int b = 0; b < NB; ++b) chi = fma(diff[b] * diff[b], iv[b], chi);
   }
-#endif
   double pen, gp;
   prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
   double lnl = -0.5 * chi;

@@ -33,8 +33,10 @@ def main():
                        "%.0f%% of steps new; thick + alpha; z=2, dl=1.6e4 Mpc" % (100 * uniq),
            "samples": nw * ns}
     vp = ctypes.c_void_p
-    for name, which, wavenorm in (("peak_lambda", 1, 500.0), ("L_IR", 2, 500.0), ("dust_mass", 4, cfg["wavenorm"])):
+    for name, which, wavenorm in (("peak_lambda", 1, 500.0), ("L_IR_quadpack_replay", 2, 500.0),
+                                  ("L_IR_gauss", 2, 500.0), ("dust_mass", 4, cfg["wavenorm"])):
         ctx.set_model(wavenorm, False, False)
+        ctx.set_lir_method("gauss" if name.endswith("gauss") else "quadpack")
         args = [ctx._h, nw, ns, vp(ch.data_ptr()), which, cfg["z"], cfg["lumdist"], 8.0, 1000.0,
                 cfg["kappa"], cfg["kappa_wave"],
                 vp(out.data_ptr()) if which == 1 else None, vp(out.data_ptr()) if which == 2 else None,
