@@ -14,7 +14,8 @@ __all__ = ["MBBNativeError", "Context", "library_path", "load_library",
            "default_context", "raise_for_status", "STATUS_NAMES"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBNAME = os.path.join(_HERE, "csrc", "libmbb_b200.so")
+# MBB_B200_LIB: developer knob for A/B-timing alternative builds of the same library
+_LIBNAME = os.environ.get("MBB_B200_LIB") or os.path.join(_HERE, "csrc", "libmbb_b200.so")
 
 AOS, SOA = 0, 1
 HOST, DEVICE = 0, 1

@@ -88,11 +88,17 @@ struct mbb_ctx {
   int lir_method = MBB_LIR_QUADPACK;
 
   // passbands
-  int nb = 0, nn = 0, nn_pad = 0;
+  int nb = 0, nn = 0;
   std::vector<int> h_off;
   std::vector<unsigned char> h_scalar;
-  std::vector<double> h_packed;   // [freq|w|lhi|llo|rcube] x nn_pad
-  DevBuf<NodeRec> d_nodes;
+  std::vector<double> h_wave, h_weight;   // as given to mbb_set_bands
+  DevBuf<double2> d_node_fw;      // {freq, passband weight}: FAITHFUL kernels, chain_flux
+  DevBuf<double2> d_node_fast_a;  // {freq, weff}  FAST (depends on opthin)
+  DevBuf<double> d_node_fast_b;   // L' = log(wave/wavenorm)*64/ln2, FAST (depends on wavenorm)
+  double nu_max = 0.0, lmax = 0.0;
+  bool fast_tables_ok = false;    // FAST tables match the current (wavenorm, opthin)
+  DevBuf<ColdArgs> d_cold;        // SmallTab + priors + model for the kernels' cold paths
+  bool cold_ok = false;
   DevBuf<int> d_off;
   DevBuf<unsigned char> d_scalar;
   SmallTab small;
@@ -169,6 +175,7 @@ void default_priors(Priors& p) {
   p.has_uplim[1] = p.has_uplim[3] = 1;
   p.uplim[1] = p.uplim[3] = 20.0;
   p.any_gprior = 0;
+  p.always_terms = 0;
 }
 
 struct Use {
@@ -182,6 +189,75 @@ struct Use {
     if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
   }
 };
+
+ModelP model_of(const mbb_ctx* c) {
+  ModelP m;
+  m.wavenorm = c->wavenorm;
+  m.nu_norm = kUmToGHz / c->wavenorm;
+  m.nu_max = c->nu_max;
+  m.lmax = c->lmax;
+  return m;
+}
+
+// (Re)build the mode-dependent node tables: the FAST constants depend on
+// wavenorm (L') and on opthin (weff), which mbb_set_model may change after
+// mbb_set_bands.
+cudaError_t upload_cold(mbb_ctx* c);
+
+cudaError_t ensure_tables(mbb_ctx* c) {
+  if (c->fast_tables_ok) return c->cold_ok ? cudaSuccess : upload_cold(c);
+  const int nn = c->nn;
+  const bool thin = c->opthin != 0;
+  std::vector<double2> fw((size_t)nn), fa((size_t)nn);
+  std::vector<double> fb((size_t)nn + 1, 0.0);   // +1: padded to a multiple of 16 bytes for the bulk copy
+  c->nu_max = 0.0;
+  c->lmax = 0.0;
+  SmallTab& s = c->small;
+  memset(&s, 0, sizeof(s));
+  s.nb = c->nb;
+  for (int i = 0; i < nn; ++i) {
+    const FastNode n = fast_node(c->h_wave[i], c->h_weight[i], c->wavenorm, thin);
+    fw[i] = make_double2(n.freq, c->h_weight[i]);
+    fa[i] = make_double2(n.freq, n.weff);
+    fb[i] = n.lp;
+    if (n.freq > c->nu_max) c->nu_max = n.freq;
+    if (n.labs > c->lmax) c->lmax = n.labs;
+    if (nn <= kSmallMaxNodes) {
+      s.freq[i] = n.freq; s.w[i] = c->h_weight[i]; s.weff[i] = n.weff; s.lp[i] = n.lp;
+    }
+  }
+  if (nn <= kSmallMaxNodes) {
+    for (int b = 0; b <= c->nb; ++b) s.band_off[b] = c->h_off[b];
+    for (int b = 0; b < c->nb; ++b) s.scalar_path[b] = c->h_scalar[b];
+  }
+  cudaError_t e;
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
+  if ((e = c->d_node_fw.reserve((size_t)nn)) != cudaSuccess) return e;
+  if ((e = c->d_node_fast_a.reserve((size_t)nn)) != cudaSuccess) return e;
+  if ((e = c->d_node_fast_b.reserve((size_t)nn + 1)) != cudaSuccess) return e;
+  const size_t bytes = (size_t)nn * sizeof(double2);
+  if ((e = cudaMemcpy(c->d_node_fw.p, fw.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(c->d_node_fast_a.p, fa.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(c->d_node_fast_b.p, fb.data(), ((size_t)nn + 1) * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return e;
+  c->fast_tables_ok = true;
+  return upload_cold(c);
+}
+
+cudaError_t upload_cold(mbb_ctx* c) {
+  ColdArgs h;
+  h.t = c->small;
+  h.pr = c->pri;
+  h.m = model_of(c);
+  cudaError_t e;
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
+  for (auto& sl : c->slots)
+    if (sl.s && (e = cudaStreamSynchronize(sl.s)) != cudaSuccess) return e;
+  if ((e = c->d_cold.reserve(1)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(c->d_cold.p, &h, sizeof(h), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  c->cold_ok = true;
+  return cudaSuccess;
+}
 
 void begin_timing(mbb_ctx* c) { cudaEventRecord(c->ev0, c->stream); }
 void end_timing(mbb_ctx* c) {
@@ -210,7 +286,7 @@ template <bool THIN, bool ALPHA, bool FAST>
 struct LaunchThread {
   static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
     const unsigned grid = (unsigned)((a.n + 255) / 256);
-    ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
+    const ModelP m = model_of(c);
     loglike_thread_kernel<THIN, ALPHA, FAST><<<grid, 256, 0, st>>>(a, m, c->pri, d, c->small);
     *err = cudaSuccess;
   }
@@ -222,9 +298,17 @@ template <bool THIN, bool ALPHA, int NB>
 struct DeltaLauncher {
   static void go(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, int nb) {
     if (nb == NB) {
-      const unsigned grid = (unsigned)((a.n + MBB_DELTA_BLOCK - 1) / MBB_DELTA_BLOCK);
-      ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
-      loglike_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, st>>>(a, m, c->pri, d, c->small);
+      // persistent: one wave of CTAs walks the tiles; parameter tiles arrive by TMA when the
+      // buffer allows it (16-byte aligned; SoA rows 16-byte aligned too)
+      const long long ntiles = (a.n + kDeltaTile - 1) / kDeltaTile;
+      const long long resident = (long long)c->sm_count * MBB_DELTA_MINB;
+      const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
+      const long long sd = a.soa_stride ? a.soa_stride : a.n;
+      static const bool no_tma = getenv("MBB_B200_NO_TMA") != nullptr;
+      const int use_tma = !no_tma && ((uintptr_t)a.pars % 16 == 0) && (a.layout == MBB_AOS || sd % 2 == 0);
+      const ModelP m = model_of(c);
+      loglike_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, st>>>(a, m, c->pri, d, c->small,
+                                                                           c->d_cold.p, use_tma);
     } else {
       DeltaLauncher<THIN, ALPHA, NB - 1>::go(c, st, a, d, nb);
     }
@@ -241,8 +325,8 @@ struct EnsDeltaLauncher {
     if (nb == NB) {
       const long long nh = g.nsrc * g.h;
       const unsigned grid = (unsigned)((nh + MBB_DELTA_BLOCK - 1) / MBB_DELTA_BLOCK);
-      ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
-      ens_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, c->stream>>>(g, m, c->pri, d, c->small);
+      const ModelP m = model_of(c);
+      ens_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, c->stream>>>(g, m, c->pri, d, c->small, c->d_cold.p);
     } else {
       EnsDeltaLauncher<THIN, ALPHA, NB - 1>::go(c, g, d, nb);
     }
@@ -276,22 +360,23 @@ struct LaunchSplit {
     const long long cap = a0.n < kChunk ? a0.n : kChunk;
     *err = cudaSuccess;
     NodeTab t;
-    t.nodes = c->d_nodes.p;
+    t.a = FAST ? c->d_node_fast_a.p : c->d_node_fw.p;
+    t.b = c->d_node_fast_b.p;
     t.band_off = c->d_off.p;
     t.scalar_path = c->d_scalar.p;
     t.nb = c->nb;
     t.nn = c->nn;
-    size_t smem = nodes_kernel_smem(c->nn, true);
+    size_t smem = nodes_kernel_smem(c->nn, true, FAST);
     const bool in_smem = smem <= c->smem_optin;
-    if (!in_smem) smem = nodes_kernel_smem(c->nn, false);
+    if (!in_smem) smem = nodes_kernel_smem(c->nn, false, FAST);
     auto nodes = in_smem ? loglike_nodes_kernel<THIN, ALPHA, FAST, true>
                          : loglike_nodes_kernel<THIN, ALPHA, FAST, false>;
     *err = cudaFuncSetAttribute(nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (*err != cudaSuccess) return;
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nodes, 512, smem) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nodes, kNodesThreads, smem) != cudaSuccess || per_sm < 1)
       per_sm = 1;
-    ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
+    const ModelP m = model_of(c);
     for (long long off = 0; off < a0.n; off += cap) {
       EvalArgs a = a0;
       a.n = (a0.n - off) < cap ? (a0.n - off) : cap;
@@ -307,10 +392,10 @@ struct LaunchSplit {
       if (*err != cudaSuccess) return;
       loglike_setup_kernel<THIN, ALPHA, FAST><<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(
           a, m, c->pri, scratch, sst);
-      const long long want = (a.n + 15) / 16;
+      const long long want = (a.n + kNodesWarps - 1) / kNodesWarps;
       const long long resident = (long long)c->sm_count * per_sm;
       const unsigned grid = (unsigned)(want < resident ? want : resident);
-      nodes<<<grid, 512, smem, st>>>(a, c->pri.any_gprior, d, t, scratch, sst);
+      nodes<<<grid, kNodesThreads, smem, st>>>(a, c->pri.any_gprior, d, t, scratch, sst);
       c->launches += 1;   // the caller counts one launch per call; add the second kernel
     }
   }
@@ -320,7 +405,7 @@ template <bool THIN, bool ALPHA, bool UNUSED>
 struct LaunchFnu {
   static void run(mbb_ctx* c, const EvalArgs& a, const double* freq, int nfreq, int scalar_path) {
     dim3 grid((unsigned)((nfreq + 255) / 256), (unsigned)a.n);
-    ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
+    const ModelP m = model_of(c);
     fnu_kernel<THIN, ALPHA><<<grid, 256, 0, c->stream>>>(a, m, freq, nfreq, scalar_path);
   }
 };
@@ -329,7 +414,7 @@ template <bool THIN, bool ALPHA, bool UNUSED>
 struct LaunchConsts {
   static void run(mbb_ctx* c, const EvalArgs& a, int want_peak) {
     const unsigned grid = (unsigned)((a.n + 127) / 128);
-    ModelP m{c->wavenorm, kUmToGHz / c->wavenorm};
+    const ModelP m = model_of(c);
     sed_consts_kernel<THIN, ALPHA><<<grid, 128, 0, c->stream>>>(a, m, want_peak);
   }
 };
@@ -385,7 +470,7 @@ int mbb_ctx_destroy(mbb_ctx* c) {
   if (!c) return 0;
   Use u(c);
   cudaStreamSynchronize(c->stream);
-  c->d_nodes.release(); c->d_off.release(); c->d_scalar.release();
+  c->d_cold.release(); c->d_node_fw.release(); c->d_node_fast_a.release(); c->d_node_fast_b.release(); c->d_off.release(); c->d_scalar.release();
   c->d_flux.release(); c->d_ivar.release(); c->d_cinv.release();
   c->h_in.release(); c->h_out.release(); c->h_st.release(); c->h_src.release();
   c->d_in.release(); c->d_out.release(); c->d_aux0.release(); c->d_aux1.release();
@@ -430,12 +515,12 @@ int mbb_last_kernel_ms(mbb_ctx* c, float* ms) {
 int mbb_set_model(mbb_ctx* c, double wavenorm, int opthin, int noalpha) {
   if (!c) return fail("null context");
   if (!(wavenorm > 0.0)) return fail("wavenorm must be positive");
-  const bool changed = wavenorm != c->wavenorm;
+  // the FAST node tables hold log(lambda/wavenorm) and (thick) weights scaled by
+  // (wavenorm/lambda)^3: rebuilt lazily at the next launch
+  if (wavenorm != c->wavenorm || (opthin ? 1 : 0) != c->opthin) c->fast_tables_ok = false;
   c->wavenorm = wavenorm;
   c->opthin = opthin ? 1 : 0;
   c->noalpha = noalpha ? 1 : 0;
-  // the node tables hold log(lambda/wavenorm): a new wavenorm invalidates them
-  if (changed) c->bands_set = false;
   return 0;
 }
 
@@ -468,61 +553,20 @@ int mbb_set_bands(mbb_ctx* c, int nbands, const int32_t* band_off, const double*
   CK(cudaStreamSynchronize(c->stream));
   c->nb = nbands;
   c->nn = nn;
-  c->nn_pad = (nn + 1) & ~1;
   c->h_off.assign(band_off, band_off + nbands + 1);
   c->h_scalar.assign(nbands, 0);
   if (scalar_path)
     for (int b = 0; b < nbands; ++b) c->h_scalar[b] = scalar_path[b] ? 1 : 0;
-  const int np = c->nn_pad;
-  c->h_packed.assign((size_t)5 * np, 0.0);
-  for (int i = 0; i < nn; ++i) {
-    const double wv = node_wave_um[i];
-    // frequency exactly as the reference forms it: um_to_GHz / wave
-    // (modified_blackbody.py:551-554)
-    c->h_packed[i] = kUmToGHz / wv;
-    c->h_packed[np + i] = node_weight[i];
-    // L = log(wave / wavenorm) as hi + lo, from the x87 80-bit logl (64-bit mantissa)
-    long double l = logl((long double)wv) - logl((long double)c->wavenorm);
-    const double hi = (double)l;
-    c->h_packed[2 * np + i] = hi;
-    c->h_packed[3 * np + i] = (double)(l - (long double)hi);
-    long double r = (long double)c->wavenorm / (long double)wv;
-    c->h_packed[4 * np + i] = (double)(r * r * r);
-  }
-  for (int i = nn; i < np; ++i) c->h_packed[i] = 1.0;   // harmless padding node, weight 0
+  c->h_wave.assign(node_wave_um, node_wave_um + nn);
+  c->h_weight.assign(node_weight, node_weight + nn);
   CK(c->d_off.reserve(nbands + 1));
   CK(c->d_scalar.reserve(nbands));
-  {
-    std::vector<NodeRec> recs((size_t)nn);
-    for (int i = 0; i < nn; ++i) {
-      recs[i].freq = c->h_packed[i];
-      recs[i].w = c->h_packed[np + i];
-      recs[i].lhi = c->h_packed[2 * np + i];
-      recs[i].llo = c->h_packed[3 * np + i];
-      recs[i].rcube = c->h_packed[4 * np + i];
-      recs[i].pad = 0.0;
-    }
-    CK(c->d_nodes.reserve((size_t)nn));
-    CK(cudaMemcpy(c->d_nodes.p, recs.data(), (size_t)nn * sizeof(NodeRec), cudaMemcpyHostToDevice));
-  }
   CK(cudaMemcpyAsync(c->d_off.p, c->h_off.data(), (nbands + 1) * sizeof(int), cudaMemcpyHostToDevice,
                      c->stream));
   CK(cudaMemcpyAsync(c->d_scalar.p, c->h_scalar.data(), nbands, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (nn <= kSmallMaxNodes) {
-    SmallTab& s = c->small;
-    memset(&s, 0, sizeof(s));
-    s.nb = nbands;
-    for (int i = 0; i < nn; ++i) {
-      s.freq[i] = c->h_packed[i];
-      s.w[i] = c->h_packed[np + i];
-      s.lhi[i] = c->h_packed[2 * np + i];
-      s.llo[i] = c->h_packed[3 * np + i];
-      s.rcube[i] = c->h_packed[4 * np + i];
-    }
-    for (int b = 0; b <= nbands; ++b) s.band_off[b] = band_off[b];
-    for (int b = 0; b < nbands; ++b) s.scalar_path[b] = c->h_scalar[b];
-  }
+  c->fast_tables_ok = false;
+  CK(ensure_tables(c));
   c->bands_set = true;
   return 0;
 }
@@ -564,12 +608,14 @@ int mbb_set_priors(mbb_ctx* c, const double lowlim[5], const uint8_t has_uplim[6
   p.any_gprior = 0;
   for (int i = 0; i < 6; ++i) {
     p.has_uplim[i] = has_uplim[i] ? 1 : 0;
-    p.uplim[i] = uplim[i];
+    p.uplim[i] = has_uplim[i] ? uplim[i] : kInf;
     p.has_gprior[i] = has_gprior[i] ? 1 : 0;
     p.gmean[i] = gmean[i];
     p.givar[i] = givar[i];
     if (has_gprior[i]) p.any_gprior = 1;
   }
+  p.always_terms = (p.any_gprior || p.has_uplim[5]) ? 1 : 0;
+  c->cold_ok = false;
   return 0;
 }
 
@@ -585,7 +631,9 @@ bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a) {
+int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a_in) {
+  EvalArgs a = a_in;
+  set_wps_division(a);
   DataRef d;
   d.flux = c->d_flux.p;
   d.ivar = c->has_ivar ? c->d_ivar.p : nullptr;
@@ -593,6 +641,7 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a) {
   d.nsrc = c->nsrc;
   d.nb = c->nb;
   const bool thin = c->opthin != 0, alpha = c->noalpha == 0, fast = c->math_mode == MBB_MATH_FAST;
+  CK(ensure_tables(c));
   cudaError_t err = cudaSuccess;
   if (fast && c->nn == c->nb && c->nb <= kMaxDeltaNB) dispatch3<LaunchDelta>(thin, alpha, true, c, st, a, d, &err);
   else if (c->nn <= kSmallMaxNodes) dispatch3<LaunchThread>(thin, alpha, fast, c, st, a, d, &err);
@@ -961,7 +1010,7 @@ int mbb_chain_flux(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
   const int i0 = c->h_off[band], i1 = c->h_off[band + 1], sp = c->h_scalar[band];
   const bool thin = c->opthin != 0, alpha = c->noalpha == 0;
 #define FLX(T, A) chain_flux_kernel<T, A><<<grid, 128, 0, c->stream>>>(dchain, c->d_work.p, c->d_count.p, \
-                                    c->wavenorm, c->d_nodes.p, i0, i1, sp, dout, dst)
+                                    c->wavenorm, c->d_node_fw.p, i0, i1, sp, dout, dst)
   if (thin) { if (alpha) FLX(true, true); else FLX(true, false); }
   else { if (alpha) FLX(false, true); else FLX(false, false); }
 #undef FLX

@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
 // arithmetic, hence the same chain as the three-kernel pipeline above.
 template <bool THIN, bool ALPHA, int NB>
 __global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
-ens_delta_kernel(const EnsArgs g, const ModelP m, const Priors pr, const DataRef d, const SmallTab t) {
+ens_delta_kernel(const EnsArgs g, const ModelP m, const Priors pr, const DataRef d, const SmallTab t,
+                 const ColdArgs* __restrict__ cold) {
+  __shared__ __align__(16) double s_tab[kTabRepDoubles];
+  stage_exp_table(s_tab);
+  __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nsrc * g.h) return;
   const unsigned ih = (unsigned)g.h;
@@ -122,8 +126,10 @@ ens_delta_kernel(const EnsArgs g, const ModelP m, const Priors pr, const DataRef
     q[j] = __dsub_rn(cj, __dmul_rn(dr.z, __dsub_rn(cj, s[j])));
   }
   const double old = g.lnp[w];
+  double diff[NB];
+  delta_load_data<NB>(d, src, diff);
   int st;
-  const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, m, pr, d, t, st);
+  const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, diff, m, pr, d, t, cold, lane_exp_table(s_tab), st);
   if (st > ST_BELOW_LOWLIM) {
     if (g.status[w] <= ST_BELOW_LOWLIM) g.status[w] = st;
     return;

@@ -1,19 +1,41 @@
-// Lean FP64 exp / expm1 / reciprocal for the FAST arithmetic mode.
+// Lean FP64 exp / expm1 / division for the FAST arithmetic mode.
 //
 // Why not libdevice: on sm_100a its exp/expm1/division spend more issue slots on
-// integer fix-ups, special-case branches and UMOVs that materialise the
-// polynomial constants than on FP64 work (ncu, profiles/r01_*: 27% of the
-// executed instructions of the first likelihood kernel were FP64, the issue
-// stage -- not the FP64 pipe -- was the limiter).  These versions
-//   * keep the polynomial coefficients in __constant__ memory, so every DFMA
-//     takes its coefficient straight from the constant bank (no UMOV);
-//   * have no branches: saturation is done by clamping the integer exponent
-//     (integer pipe), valid for finite arguments -- callers screen NaN/inf;
-//   * replace IEEE division by MUFU.RCP64H + two Newton steps + one residual
-//     correction (<= 1 ulp).
-// Accuracy (tests/test_device_logic_cpu.py::test_fastmath): exp, expm1 <= 1.5
-// ulp over the ranges used; polynomial fits from tools/gen_poly.py (max
-// relative fit error 1.6e-17 and 4.9e-18).
+// integer fix-ups, special-case branches and constant materialisation than on
+// FP64 work (ncu, profiles/r01_*: 27% of the executed instructions of the first
+// likelihood kernel were FP64; the issue stage, not the FP64 pipe, was the
+// limiter).  The family below works in units of 1/64 octave:
+//
+//     exp(a*b) = 2^(y/64),  y = a*b*64/ln2 = 64 m + (j - 32) + f,  |f| <= 1/2
+//              = 2^m * T_j * 2^(f/64),        T_j = 2^((j-32)/64)
+//
+//   * the argument is handed over as a PRODUCT with the second factor already
+//     scaled by 64/ln2 (node tables hold log(lambda/lambda_norm)*64/ln2,
+//     per-walker constants are scaled once in the setup), so the reduction is
+//     3-4 FP64 instructions for any exp in the node loop -- no separate
+//     product, no Cody-Waite constants;
+//   * 2^(f/64) - 1 = f g(f) with g of degree 4 (4 DFMA + 1 DMUL);
+//   * no branches and, on the hot path, no clamps: the caller proves per walker
+//     that every exponent stays inside the double range (`safe` flag of
+//     FastSed); CLAMP=true instantiations saturate the binary exponent for the
+//     rest;
+//   * expm1(x) = sT p + (sT - 1) with sT = 2^m T_j: j = 32 (T = 1 exactly)
+//     covers |x| < ln2/128 and sT - 1 is exact (Sterbenz) for the neighbouring
+//     entries; the rounding of T_j (<= 2^-53) bounds the relative error of
+//     expm1 by 2^-53 sT/|sT - 1| <= 2e-14 (at |x| ~ 0.0054), <= 2e-16 for |x| > 1;
+//   * the 64-entry table is stored rotated and with pre-adjusted high words so
+//     that index and scale come straight from the low word of the magic-number
+//     sum: shift, mask, LDS.64, integer multiply-add.  In shared memory it is
+//     replicated 16x (8 KB, copy c in bank pair c) and lane l reads copy l & 15,
+//     so a lookup with 32 different indices is bank-conflict-free (2 wavefronts;
+//     ncu showed the unreplicated table at ~9 wavefronts per lookup and the
+//     shared-memory pipe, not the FP64 pipe, saturated);
+//   * reciprocal = MUFU.RCP64H seed + one cubic correction (3 FP64), arranged
+//     by the callers so that it runs beside the exp chains, not after them.
+// 9-10 FP64 instructions per exp, 10-11 per expm1, against 29/35 + ~30 fix-up
+// instructions in libdevice.  Accuracy (tests/test_device_logic_cpu.py, vs
+// mpmath): exp <= 1.5 ulp, expm1 <= 3 ulp away from the |x| ~ 0.01 band
+// described above; constants from tools/gen_poly.py.
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -22,100 +44,199 @@
 
 namespace mbb {
 
+constexpr double kMagic = 6755399441055744.0;            // 1.5*2^52: low word of x+kMagic = round(x)
+constexpr double kC64Hi = 92.332482616893657;            // 64/ln2 as a double-double
+constexpr double kC64Lo = 1.3027375194195861e-15;
+
+// Table entry i serves the exponent residue i = k & 63: T_j with j = (i + 32) & 63,
+// as a bit pattern whose high word is pre-adjusted by 0x80000 - (j << 14), so that
+// hi + (k << 14) is the high word of 2^m T_j, m = (k + 32) >> 6.
 #if defined(__CUDACC__)
-__device__ __constant__ double kExpC_dev[12] = {
-    1.0, 1.0, 0.50000000000000189, 0.1666666666666668, 0.041666666666487953, 0.008333333333319589,
-    0.0013888888952352863, 0.00019841269890076403, 2.4801485441561313e-05, 2.7557240887229869e-06,
-    2.763265472252779e-07, 2.5110049204818658e-08};
-__device__ __constant__ double kEm1C_dev[11] = {
-    0.5, 0.16666666666666671, 0.041666666666666671, 0.0083333333333261358, 0.0013888888888883748,
-    0.00019841269874820627, 2.4801587325547743e-05, 2.7557255400206422e-06, 2.7557273643110297e-07,
-    2.5105217004720745e-08, 2.0914686968086876e-09};
+__device__ const unsigned long long kExp2Tab_dev[64] = {
+#include "mbb_exptab.inc"
+};
+// f*g(f) = 2^(f/64) - 1 on |f| <= 0.5005, max abs error 2.4e-18
+__device__ __constant__ double kLeanG_dev[5] = {0.010830424696249145, 5.8649049550517742e-05,
+                                               2.1173137155457974e-07, 5.7328587073751599e-10,
+                                               1.2417854561126839e-12};
 #endif
 
-MBB_HD double exp_coef(int i) {
+inline const double* exp2_tab_host() {
+  static const unsigned long long tab[64] = {
+#include "mbb_exptab.inc"
+  };
+  return reinterpret_cast<const double*>(tab);
+}
+
+// The plain (unreplicated) table: global memory (L1-resident) on the device, a
+// static array on the host.  Index stride 1 (TS = 0 below).
+MBB_HD const double* exp2_tab_default() {
 #if defined(__CUDA_ARCH__)
-  return kExpC_dev[i];
+  return reinterpret_cast<const double*>(kExp2Tab_dev);
 #else
-  const double c[12] = {1.0, 1.0, 0.50000000000000189, 0.1666666666666668, 0.041666666666487953,
-                        0.008333333333319589, 0.0013888888952352863, 0.00019841269890076403,
-                        2.4801485441561313e-05, 2.7557240887229869e-06, 2.763265472252779e-07,
-                        2.5110049204818658e-08};
+  return exp2_tab_host();
+#endif
+}
+// shared-memory copy: entry i, copy c at double index i*16 + c  (TS = 4)
+constexpr int kTabRepShift = 4;
+constexpr int kTabRepDoubles = 64 << kTabRepShift;
+
+MBB_HD double lean_g_coef(int i) {
+#if defined(__CUDA_ARCH__)
+  return kLeanG_dev[i];
+#else
+  const double c[5] = {0.010830424696249145, 5.8649049550517742e-05, 2.1173137155457974e-07,
+                       5.7328587073751599e-10, 1.2417854561126839e-12};
   return c[i];
 #endif
 }
 
-MBB_HD double em1_coef(int i) {
+// ---- bit-level helpers (identical results on host and device) ----
+MBB_HD int hi32_of(double t) {
 #if defined(__CUDA_ARCH__)
-  return kEm1C_dev[i];
+  return __double2hiint(t);
 #else
-  const double c[11] = {0.5, 0.16666666666666671, 0.041666666666666671, 0.0083333333333261358,
-                        0.0013888888888883748, 0.00019841269874820627, 2.4801587325547743e-05,
-                        2.7557255400206422e-06, 2.7557273643110297e-07, 2.5105217004720745e-08,
-                        2.0914686968086876e-09};
-  return c[i];
+  unsigned long long u;
+  memcpy(&u, &t, 8);
+  return (int)(unsigned)(u >> 32);
+#endif
+}
+MBB_HD int lo32_of(double t) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(t);
+#else
+  unsigned long long u;
+  memcpy(&u, &t, 8);
+  return (int)(unsigned)(u & 0xffffffffu);
+#endif
+}
+MBB_HD double from_hilo(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, lo);
+#else
+  const unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+  double r;
+  memcpy(&r, &u, 8);
+  return r;
 #endif
 }
 
-// x = k ln2 + r, |r| <= ln2/2; k clamped to the normal exponent range.
-MBB_HD void reduce_ln2(double x, int& k, double& r) {
-  const double kMagic = 6755399441055744.0;          // 1.5 * 2^52
-  const double kLog2e = 1.4426950408889634;
-  const double kLn2Hi = 6.93147180369123816490e-01;  // fdlibm split of ln 2
-  const double kLn2Lo = 1.90821492927058770002e-10;
-  const double t = fma(x, kLog2e, kMagic);
+// min(x, ~cap) for x >= 0 (also +inf and NaN -> ~cap): one integer instruction on
+// the high word; when clamped the result lies in [cap, cap + one high-word step).
+template <int CAP_HI_WORD>
+MBB_HD double clamp_pos(double x) {
+  const int h = hi32_of(x);
+  return from_hilo(h < CAP_HI_WORD ? h : CAP_HI_WORD, lo32_of(x));
+}
+constexpr int kHi700 = 0x4085e000;      // high word of 700.0
+constexpr int kHi700C = 0x40ef8e00;     // high word of 64624.0 ~ 700*64/ln2
+
+// Reduced exponent: y = k + f in units of 1/64 octave, k = round(y), |f| <= 1/2.
+// Valid while |y| < 2^31 (callers gate their parameters).
+struct Red {
+  double f;
+  int k;
+};
+
+// y = a*(b_hi + b_lo)
+MBB_HD Red red_prod(double a, double b_hi, double b_lo) {
+  const double t = fma(a, b_hi, kMagic);
   const double kf = t - kMagic;
-#if defined(__CUDA_ARCH__)
-  k = __double2loint(t);
-#else
-  k = (int)kf;
-#endif
-  r = fma(-kf, kLn2Hi, x);
-  r = fma(-kf, kLn2Lo, r);
-  k = k > 1023 ? 1023 : k;
-  k = k < -1022 ? -1022 : k;
+  Red r;
+  r.f = fma(a, b_lo, fma(a, b_hi, -kf));
+  r.k = lo32_of(t);
+  return r;
 }
 
-// p * 2^k for p in [0.5, 2), k in [-1022, 1023] (exponent-field addition)
-MBB_HD double scale2(double p, int k) {
-#if defined(__CUDA_ARCH__)
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-#else
-  return ldexp(p, k);
-#endif
+// y = a*b, b a single double (node tables: the rounding of b costs |y| 2^-53 in y)
+MBB_HD Red red_prod1(double a, double b) {
+  const double t = fma(a, b, kMagic);
+  const double kf = t - kMagic;
+  Red r;
+  r.f = fma(a, b, -kf);
+  r.k = lo32_of(t);
+  return r;
 }
 
-MBB_HD double pow2i(int k) {   // 2^k, k in [-1022, 1023]
-#if defined(__CUDA_ARCH__)
-  return __hiloint2double((k + 1023) << 20, 0);
-#else
-  return ldexp(1.0, k);
-#endif
+// plain argument in natural units
+MBB_HD Red red_x(double x) { return red_prod(x, kC64Hi, kC64Lo); }
+
+// y = -yc for an argument already in 1/64-octave units (3 instructions)
+MBB_HD Red red_neg_scaled(double yc) {
+  const double t = kMagic - yc;
+  const double kf = t - kMagic;
+  Red r;
+  r.f = -(yc + kf);
+  r.k = lo32_of(t);
+  return r;
 }
 
-MBB_HD double exp_fast(double x) {
-  int k;
-  double r;
-  reduce_ln2(x, k, r);
-  double p = exp_coef(11);
+// y = (a_hi + a_lo) + b*c, all in 1/64-octave units (slow path of the optically
+// thick node: the two exponents may individually overflow)
+MBB_HD Red red_sum_prod(double a_hi, double a_lo, double b, double c) {
+  const double y = b * c;
+  const double ylo = fma(b, c, -y);
+  const double s = a_hi + y;
+  const double bb = s - a_hi;
+  const double err = (a_hi - (s - bb)) + (y - bb);
+  const double t = s + kMagic;
+  const double kf = t - kMagic;
+  Red r;
+  r.f = (s - kf) + (err + (a_lo + ylo));
+  r.k = lo32_of(t);
+  return r;
+}
+
+// 2^m T_j: table lookup + scaling.  TS = log2 of the index stride (0: plain
+// table, kTabRepShift: the replicated shared-memory copy, `tab` then points at
+// the calling lane's copy).  CLAMP=false: one integer multiply-add (the caller
+// guarantees m in [-1022, 1023]); CLAMP=true saturates m.
+template <int TS, bool CLAMP>
+MBB_HD double scaled_T(const double* tab, int k) {
+  const double tb = tab[(k & 63) << TS];
+  if (!CLAMP) return from_hilo(hi32_of(tb) + (int)((unsigned)k << 14), lo32_of(tb));
+  const int j = (k + 32) & 63;
+  int m = (k + 32) >> 6;
+  m = m > 1023 ? 1023 : m;
+  m = m < -1022 ? -1022 : m;
+  return from_hilo(hi32_of(tb) - 0x80000 + (j << 14) + (int)((unsigned)m << 20), lo32_of(tb));
+}
+
+// p = 2^(f/64) - 1
+MBB_HD double lean_p(double f) {
+  double g = lean_g_coef(4);
 #pragma unroll
-  for (int i = 10; i >= 0; --i) p = fma(p, r, exp_coef(i));
-  return scale2(p, k);
+  for (int i = 3; i >= 0; --i) g = fma(g, f, lean_g_coef(i));
+  return g * f;
 }
 
-MBB_HD double expm1_fast(double x) {
-  int k;
-  double r;
-  reduce_ln2(x, k, r);
-  double q = em1_coef(10);
-#pragma unroll
-  for (int i = 9; i >= 0; --i) q = fma(q, r, em1_coef(i));
-  q = fma(r * r, q, r);                 // expm1(r)
-  const double s = pow2i(k);
-  return fma(s, q, s - 1.0);
+template <int TS, bool CLAMP>
+MBB_HD double exp_red(const Red r, const double* tab) {
+  const double sT = scaled_T<TS, CLAMP>(tab, r.k);
+  return fma(sT, lean_p(r.f), sT);
 }
 
-// 1/b for normal b (no subnormal / zero handling)
+// scale * exp(y): the product scale*sT runs beside the polynomial, not after it
+template <int TS, bool CLAMP>
+MBB_HD double exp_red_times(const Red r, const double* tab, double scale) {
+  const double sT = scaled_T<TS, CLAMP>(tab, r.k) * scale;
+  return fma(sT, lean_p(r.f), sT);
+}
+
+template <int TS, bool CLAMP>
+MBB_HD double expm1_red(const Red r, const double* tab) {
+  const double sT = scaled_T<TS, CLAMP>(tab, r.k);
+  return fma(sT, lean_p(r.f), sT - 1.0);
+}
+
+// 1 - exp(y) for the reduced exponent of y (y <= 0 in every use)
+template <int TS, bool CLAMP>
+MBB_HD double one_minus_exp_red(const Red r, const double* tab) {
+  const double sT = scaled_T<TS, CLAMP>(tab, r.k);
+  return fma(-sT, lean_p(r.f), 1.0 - sT);
+}
+
+// 1/b for normal b (no subnormal / zero handling), <= 1 ulp
 MBB_HD double rcp_fast(double b) {
 #if defined(__CUDA_ARCH__)
   double r;
@@ -130,144 +251,43 @@ MBB_HD double rcp_fast(double b) {
 #endif
 }
 
-// a / b with one residual correction (<= 1 ulp)
+// a / b with one residual correction (<= 1 ulp): per-walker quotients
 MBB_HD double div_fast(double a, double b) {
   const double r = rcp_fast(b);
   const double y = a * r;
   return fma(fma(-b, y, a), r, y);
 }
 
-// exp(b * (l_hi + l_lo)), product carried in double-double
-MBB_HD double exp_prod_fast(double b, double l_hi, double l_lo) {
-  const double y = b * l_hi;
-  const double e = fma(b, l_lo, fma(b, l_hi, -y));
-  const double r = exp_fast(y);
-  return fma(r, e, r);
-}
-
-// ---------------------------------------------------------------------------
-// Table-driven variants: x = (64 m + j - 32) ln2/64 + r, |r| <= ln2/128,
-// T[j] = 2^((j-32)/64) in [0.71, 1.40), so that |x| < 0.34 always has m == 0:
-//   exp(x)   = 2^m T[j] (1 + p),      p = expm1(r) = r h(r), h of degree 4
-//   expm1(x) = 2^m T[j] p + (2^m T[j] - 1), with the separately rounded table
-//              entry T[j]-1 when m == 0 (no cancellation for small |x|).
-// 10-11 FP64 instructions instead of 17-18; the 1 KB table {T[j], T[j]-1}
-// lives in global memory and stays L1-resident (one LDG.128 per call).
-// ---------------------------------------------------------------------------
-struct ExpTabEntry {
-  double t, tm1;
-};
-
-#if defined(__CUDACC__)
-__device__ const ExpTabEntry kExpTab_dev[64] = {
-#include "mbb_exptab.inc"
-};
-__device__ __constant__ double kTabPoly_dev[5] = {1.0, 0.49999999999962602, 0.16666666666661323,
-                                                 0.041666717628250034, 0.0083333406135586794};
-#endif
-
-MBB_HD ExpTabEntry exp_tab_entry(int j) {
+// 1/b in 3 FP64 instructions (node loop): seed r0 = MUFU.RCP64H(b) with
+// |e| = |1 - b r0| <= 2^-19.9 (measured on B200, tools/rcp_probe.cu), then
+// r0 (1 + e + e^2): relative error e^3 ~ 2^-59.7 plus two roundings.
+MBB_HD double rcp_cubic(double b) {
 #if defined(__CUDA_ARCH__)
-  const double2 v = __ldg(reinterpret_cast<const double2*>(kExpTab_dev) + j);
-  ExpTabEntry e;
-  e.t = v.x;
-  e.tm1 = v.y;
-  return e;
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(b));
+  const double e = fma(-b, r0, 1.0);
+  return fma(fma(r0, e, r0), e, r0);
 #else
-  static const ExpTabEntry tab[64] = {
-#include "mbb_exptab.inc"
-  };
-  return tab[j];
+  return 1.0 / b;
 #endif
 }
 
-MBB_HD double tab_poly_coef(int i) {
-#if defined(__CUDA_ARCH__)
-  return kTabPoly_dev[i];
-#else
-  const double c[5] = {1.0, 0.49999999999962602, 0.16666666666661323, 0.041666717628250034,
-                       0.0083333406135586794};
-  return c[i];
-#endif
-}
+// a / b = a * rcp_cubic(b)  (<= 2 ulp)
+MBB_HD double div_lean(double a, double b) { return a * rcp_cubic(b); }
 
-// x = (64 m + j - 32) ln2/64 + r; returns p = expm1(r)
-template <int MMAX = 1023>
-MBB_HD double reduce_tab(double x, int& m, int& j) {
-  const double kMagic = 6755399441055744.0;
-  const double k64Log2e = 92.332482616893657;                 // 64 / ln 2
-  const double kLn2Hi64 = 6.93147180369123816490e-01 / 64.0;  // exact scalings of the fdlibm split
-  const double kLn2Lo64 = 1.90821492927058770002e-10 / 64.0;
-  const double t = fma(x, k64Log2e, kMagic);
-  const double kf = t - kMagic;
-#if defined(__CUDA_ARCH__)
-  const int k = __double2loint(t);
-#else
-  const int k = (int)kf;
-#endif
-  double r = fma(-kf, kLn2Hi64, x);
-  r = fma(-kf, kLn2Lo64, r);
-  j = (k + 32) & 63;
-  m = (k + 32) >> 6;
-  m = m > MMAX ? MMAX : m;
-  m = m < -1022 ? -1022 : m;
-  double h = tab_poly_coef(4);
-#pragma unroll
-  for (int i = 3; i >= 0; --i) h = fma(h, r, tab_poly_coef(i));
-  return h * r;
-}
+// generic saturating forms (per-walker setup code)
+MBB_HD double exp_l(double x) { return exp_red<0, true>(red_x(x), exp2_tab_default()); }
+MBB_HD double expm1_l(double x) { return expm1_red<0, true>(red_x(x), exp2_tab_default()); }
+// saturating near 700: for optical depths t that only feed 1 - exp(-t)
+MBB_HD double exp_tau(double x) { return clamp_pos<kHi700>(exp_l(x)); }
 
-// MMAX caps the result at < 2^(MMAX+1): exp_tab<10> saturates near 2e3, which is
-// what callers want when the value only feeds expm1(-t) (keeps its argument
-// inside the range where the integer exponent extraction is valid).
-template <int MMAX = 1023>
-MBB_HD double exp_tab(double x) {
-  int m, j;
-  const double p = reduce_tab<MMAX>(x, m, j);
-  const double T = exp_tab_entry(j).t;
-  return scale2(fma(T, p, T), m);
-}
-
-MBB_HD double expm1_tab(double x) {
-  int m, j;
-  const double p = reduce_tab(x, m, j);
-  const ExpTabEntry e = exp_tab_entry(j);
-  const double sT = scale2(e.t, m);
-  const double base = (m == 0) ? e.tm1 : sT - 1.0;
-  return fma(sT, p, base);
-}
-
-template <int MMAX = 1023>
-MBB_HD double exp_prod_tab(double b, double l_hi, double l_lo) {
-  const double y = b * l_hi;
-  const double e = fma(b, l_lo, fma(b, l_hi, -y));
-  const double r = exp_tab<MMAX>(y);
-  return fma(r, e, r);
-}
-
-// which lean exp family the FAST model code uses (A/B switch for measurements)
-#ifndef MBB_USE_EXPTAB
-#define MBB_USE_EXPTAB 1
-#endif
-#if MBB_USE_EXPTAB
-MBB_HD double exp_l(double x) { return exp_tab(x); }
-MBB_HD double expm1_l(double x) { return expm1_tab(x); }
-MBB_HD double exp_prod_l(double b, double hi, double lo) { return exp_prod_tab(b, hi, lo); }
-// saturating at ~2e3: for optical depths t that only feed expm1(-t)
-MBB_HD double exp_tau(double x) { return exp_tab<10>(x); }
-MBB_HD double exp_prod_tau(double b, double hi, double lo) { return exp_prod_tab<10>(b, hi, lo); }
-#else
-MBB_HD double exp_l(double x) { return exp_fast(x); }
-MBB_HD double expm1_l(double x) { return expm1_fast(x); }
-MBB_HD double exp_prod_l(double b, double hi, double lo) { return exp_prod_fast(b, hi, lo); }
-MBB_HD double exp_tau(double x) { return fmin(exp_fast(x), 2000.0); }
-MBB_HD double exp_prod_tau(double b, double hi, double lo) { return fmin(exp_prod_fast(b, hi, lo), 2000.0); }
-#endif
 // The lean exp family extracts the binary exponent from the low 32 bits of
-// x*64/ln2 + 1.5*2^52: valid for |x| < 2^31 ln2/64 ~ 2.3e7.  fast_setup gates
-// the parameters (T >= 1e-3 K, beta, alpha <= 300) so every argument formed
-// from them stays far inside that range.
+// a*b + 1.5*2^52: valid for |x| < 2^31 ln2/64 ~ 2.3e7.  fast_setup gates the
+// parameters (T >= 1e-3 K, beta, alpha <= 300) so every argument formed from
+// them stays far inside that range.
 constexpr double kFastMaxIndex = 300.0;
 constexpr double kFastMinT = 1e-3;
+// |exponent| (natural units) below which no CLAMP is needed
+constexpr double kSafeExp = 690.0;
 
 }  // namespace mbb

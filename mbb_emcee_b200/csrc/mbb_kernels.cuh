@@ -1,21 +1,23 @@
 // sm_100a kernels of the modified-blackbody likelihood hot path.
 //
-//   loglike_thread_kernel  one thread per evaluation; node tables (<= 32 nodes:
-//                          delta / few-node configs such as BASELINE cfg1/cfg5)
+//   loglike_thread_kernel  one thread per evaluation; node tables (<= 32 nodes)
 //                          travel in the kernel parameter block, i.e. the
 //                          constant bank -- uniform across the warp, no loads.
-//   loglike_delta_kernel   the same with every band a single node and the band
-//                          count a template parameter (fully unrolled).
+//                          Generic: FAITHFUL arithmetic, or FAST with mixed
+//                          delta / few-node bands.
+//   loglike_delta_kernel   every band a single node (BASELINE cfg1/cfg5), FAST,
+//                          band count a template parameter (fully unrolled);
+//                          the 1 KB exp table is staged into shared memory.
 //   loglike_setup_kernel + loglike_nodes_kernel   tabulated passbands:
 //                          (1) thread-per-evaluation setup (limits, per-walker
 //                          constants incl. the merge-point root solve, prior
 //                          terms incl. the lambda_peak solve) -> scratch;
 //                          (2) persistent warp-per-evaluation node loops: the
-//                          node table (up to ~4.8k nodes of 48 B) is staged
-//                          ONCE per CTA into shared memory by TMA bulk copies
-//                          (cp.async.bulk + mbarrier), lanes stride the nodes
-//                          of a band, warp-shuffle reduction per band, then
-//                          the chi-square (diagonal or full inverse covariance).
+//                          node table is staged ONCE per CTA into shared memory
+//                          by TMA bulk copies (cp.async.bulk + mbarrier), lanes
+//                          stride the nodes of a band, warp-shuffle reduction
+//                          per band, then the chi-square (diagonal or full
+//                          inverse covariance).
 //   fnu_kernel, sed_consts_kernel, chain_* kernels: the API's other entries.
 #pragma once
 #include <cuda_runtime.h>
@@ -38,12 +40,23 @@ struct EvalArgs {
   long long soa_stride;  // element stride between parameters in SoA layout (0 = n)
   long long wps;      // walkers per source (when src_index == nullptr)
   int layout;         // 0 = [n][5], 1 = [5][n]
+  // floor(g / wps) for 32-bit g without a division (Granlund & Montgomery 1994):
+  // t = umulhi(wps_mul, g); q = (t + ((g - t) >> wps_sh1)) >> wps_sh2
+  unsigned wps_mul;
+  int wps_sh1, wps_sh2;
 };
 
-struct ModelP {
-  double wavenorm;
-  double nu_norm;     // 299792.458 / wavenorm [GHz]
-};
+// fills the division constants from a.wps (host side)
+inline void set_wps_division(EvalArgs& a) {
+  a.wps_mul = 0; a.wps_sh1 = 0; a.wps_sh2 = 0;
+  const unsigned long long d = (unsigned long long)(a.wps > 0 ? a.wps : 1);
+  if (d >> 32) return;                       // device falls back to 64-bit division
+  int l = 0;
+  while ((1ull << l) < d) ++l;               // ceil(log2 d)
+  a.wps_mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  a.wps_sh1 = l < 1 ? l : 1;
+  a.wps_sh2 = l > 1 ? l - 1 : 0;
+}
 
 struct DataRef {
   const double* flux;   // [nsrc][nb]
@@ -53,28 +66,33 @@ struct DataRef {
   int nb;
 };
 
+// <= 32 nodes: the whole table in the kernel parameter block
 struct SmallTab {
   double freq[kSmallMaxNodes];
-  double w[kSmallMaxNodes];
-  double lhi[kSmallMaxNodes];
-  double llo[kSmallMaxNodes];
-  double rcube[kSmallMaxNodes];
+  double w[kSmallMaxNodes];      // passband weight sedmult*normfac (FAITHFUL)
+  double weff[kSmallMaxNodes];   // FAST: w (thin) or w (wavenorm/wave)^3 (thick)
+  double lp[kSmallMaxNodes];     // FAST: log(wave/wavenorm)*64/ln2
   int band_off[kSmallMaxNodes + 1];
   unsigned char scalar_path[kSmallMaxNodes];
   int nb;
 };
 
-// One quadrature node as the nodes kernel reads it: 48 bytes, 16-byte aligned,
-// so a lane fetches it with LDS.128 + LDS.128 + LDS.64 from one address
-// (stride 12 words: conflict-free for 128-bit accesses).
-struct __align__(16) NodeRec {
-  double freq, w;       // 299792.458/lambda_i [GHz], sedmult*normfac
-  double lhi, llo;      // ln(lambda_i/lambda_norm), double-double
-  double rcube, pad;    // (lambda_norm/lambda_i)^3
+// Everything a cold path needs, in GLOBAL memory: a noinline device function
+// cannot address the kernel parameter block, and handing it references to
+// parameters would make the compiler copy them to the local stack.
+struct ColdArgs {
+  SmallTab t;
+  Priors pr;
+  ModelP m;
 };
 
+// Node table of the warp path, as two arrays so that a lane fetches a node
+// with one conflict-free LDS.128 and one conflict-free LDS.64:
+//   a[i] = {freq_i [GHz], weight_i}   (weight = weff for FAST, w for FAITHFUL)
+//   b[i] = L'_i                       (FAST only)
 struct NodeTab {
-  const NodeRec* nodes;   // [nn]
+  const double2* a;
+  const double* b;
   const int* band_off;    // nb + 1
   const unsigned char* scalar_path;
   int nb;
@@ -96,114 +114,25 @@ __device__ __forceinline__ void load_pars(const EvalArgs& a, long long e, double
 __device__ __forceinline__ long long source_of(const EvalArgs& a, long long e) {
   if (a.src_index) return (long long)__ldg(a.src_index + e);
   const unsigned long long g = (unsigned long long)(a.e0 + e);
-  // 32-bit division whenever it is exact (64-bit integer division costs ~100 instructions)
-  if (((g | (unsigned long long)a.wps) >> 32) == 0) return (long long)((unsigned)g / (unsigned)a.wps);
+  if ((g >> 32) == 0 && a.wps_mul != 0) {
+    const unsigned g32 = (unsigned)g;
+    const unsigned t = __umulhi(a.wps_mul, g32);
+    return (long long)((t + ((g32 - t) >> a.wps_sh1)) >> a.wps_sh2);
+  }
   return (long long)(g / (unsigned long long)a.wps);
 }
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
-// ---------------------------------------------------------------------------
-// thread-per-evaluation kernel
-// ---------------------------------------------------------------------------
-template <bool THIN, bool ALPHA, bool FAST>
-__global__ void __launch_bounds__(256)
-loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
-                      const SmallTab t) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.n) return;
-  double p[5];
-  load_pars(a, e, p);
-  const long long src = source_of(a, e);
-  int st;
-  const double lnl = loglike_one<THIN, ALPHA, FAST>(
-      p, m.wavenorm, m.nu_norm, pr, t, d.flux + src * d.nb, d.ivar ? d.ivar + src * d.nb : nullptr,
-      d.cinv ? d.cinv + src * (long long)d.nb * d.nb : nullptr, st);
-  a.out[e] = lnl;
-  if (a.status) a.status[e] = st;
+// Stage the exp table into shared memory, replicated 16x (8 KB): entry i, copy c
+// at double index i*16 + c.  Lane l then reads copy l & 15 (lane_exp_table), so
+// the 16 lanes of a half-warp always hit 16 different bank pairs.
+__device__ __forceinline__ void stage_exp_table(double* s_tab) {
+  const double* g = reinterpret_cast<const double*>(kExp2Tab_dev);
+  for (int i = threadIdx.x; i < kTabRepDoubles; i += blockDim.x) s_tab[i] = __ldg(g + (i >> kTabRepShift));
 }
-
-// ---------------------------------------------------------------------------
-// Delta-band specialisation of the thread kernel: every band is one node (the
-// reference's default, non-response mode -- likelihood.py:817 -- and the
-// BASELINE cfg1/cfg5 workloads), FAST arithmetic, band count known at compile
-// time.  Fully unrolled: the polynomial coefficients and node constants stay
-// in (uniform) registers for the whole evaluation and the NB independent
-// exp/expm1 chains interleave, which is what lifts FP64-pipe utilisation.
-// ---------------------------------------------------------------------------
-#ifndef MBB_DELTA_MINB
-#define MBB_DELTA_MINB 3
-#endif
-#ifndef MBB_DELTA_BLOCK
-#define MBB_DELTA_BLOCK 256
-#endif
-// one evaluation, all bands single-node, FAST arithmetic, NB compile-time
-template <bool THIN, bool ALPHA, int NB>
-__device__ __forceinline__ double delta_eval(const double p[5], long long src, const ModelP& m,
-                                             const Priors& pr, const DataRef& d, const SmallTab& t,
-                                             int& st) {
-  const double* __restrict__ fl = d.flux + src * NB;
-  const double* __restrict__ ivp = d.ivar + src * NB;
-  double diff[NB], iv[NB];
-  {
-    // data loads issued next to the parameter loads: one exposed global latency
-#pragma unroll
-    for (int b = 0; b < NB; ++b) diff[b] = __ldg(fl + b);
-    if (!d.cinv) {
-#pragma unroll
-      for (int b = 0; b < NB; ++b) iv[b] = __ldg(ivp + b);
-    }
-  }
-  st = ST_OK;
-  if (below_lowlim(pr, p)) {
-    st = ST_BELOW_LOWLIM;
-    return -kInf;
-  }
-  FastSed s;
-  fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm, m.nu_norm);
-  st = s.status;
-  if (st != ST_OK) return qnan();
-  double chi = 0.0;
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const double f = node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[b], t.lhi[b], t.llo[b], t.rcube[b]);
-    diff[b] = fma(-f, t.w[b], diff[b]);
-  }
-  if (d.cinv) {
-    const double* __restrict__ ci = d.cinv + src * (NB * NB);
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      double row = 0.0;
-#pragma unroll
-      for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
-      chi = fma(diff[r], row, chi);
-    }
-  } else {
-#pragma unroll
-    for (int b = 0; b < NB; ++b) chi = fma(diff[b] * diff[b], iv[b], chi);
-  }
-  double pen, gp;
-  prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
-  double lnl = -0.5 * chi;
-  lnl += pen;
-  if (pr.any_gprior) lnl += gp;
-  if (st != ST_OK) return qnan();
-  if (lnl != lnl) st = ST_NONFINITE;
-  return lnl;
-}
-
-template <bool THIN, bool ALPHA, int NB>
-__global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
-loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
-                     const SmallTab t) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.n) return;
-  double p[5];
-  load_pars(a, e, p);
-  int st;
-  const double lnl = delta_eval<THIN, ALPHA, NB>(p, source_of(a, e), m, pr, d, t, st);
-  a.out[e] = lnl;
-  if (a.status) a.status[e] = st;
+__device__ __forceinline__ const double* lane_exp_table(const double* s_tab) {
+  return s_tab + (threadIdx.x & 15);
 }
 
 // ---------------------------------------------------------------------------
@@ -228,6 +157,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// one array of `bytes` (multiple of 16) in requests of <= 64 KiB
+__device__ __forceinline__ void bulk_g2s_chunked(void* dst, const void* src, unsigned bytes,
+                                                 unsigned long long* bar) {
+  unsigned done = 0;
+  while (done < bytes) {
+    unsigned chunk = bytes - done;
+    if (chunk > 65536u) chunk = 65536u;
+    bulk_g2s(reinterpret_cast<unsigned char*>(dst) + done, reinterpret_cast<const unsigned char*>(src) + done,
+             chunk, bar);
+    done += chunk;
+  }
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
   unsigned ok;
   do {
@@ -241,6 +182,221 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
   } while (!ok);
 }
 
+// ---------------------------------------------------------------------------
+// thread-per-evaluation kernel
+// ---------------------------------------------------------------------------
+template <bool THIN, bool ALPHA, bool FAST>
+__global__ void __launch_bounds__(256)
+loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
+                      const SmallTab t) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  double p[5];
+  load_pars(a, e, p);
+  const long long src = source_of(a, e);
+  int st;
+  const double lnl = loglike_one<THIN, ALPHA, FAST>(
+      p, m, pr, t, d.flux + src * d.nb, d.ivar ? d.ivar + src * d.nb : nullptr,
+      d.cinv ? d.cinv + src * (long long)d.nb * d.nb : nullptr, st);
+  a.out[e] = lnl;
+  if (a.status) a.status[e] = st;
+}
+
+// ---------------------------------------------------------------------------
+// Delta-band specialisation of the thread kernel: every band is one node (the
+// reference's default, non-response mode -- likelihood.py:817 -- and the
+// BASELINE cfg1/cfg5 workloads), FAST arithmetic, band count known at compile
+// time.  Fully unrolled: the node constants stay in uniform registers for the
+// whole evaluation and the NB independent exp/expm1 chains interleave, which
+// is what lifts FP64-pipe utilisation.  Walkers whose exponents could leave
+// the double range (`safe` == 0: never in a sane fit) and walkers with an
+// active prior term take noinline cold paths.
+// ---------------------------------------------------------------------------
+#ifndef MBB_DELTA_MINB
+#define MBB_DELTA_MINB 3
+#endif
+#ifndef MBB_DELTA_BLOCK
+#define MBB_DELTA_BLOCK 256
+#endif
+// cold paths of delta_eval (scalars by value, tables from global memory)
+template <bool THIN, bool ALPHA>
+__device__ __noinline__ double delta_eval_cold(double p0, double p1, double p2, double p3, double p4,
+                                               const ColdArgs* __restrict__ cold, const double* flux,
+                                               const double* ivar, const double* cinv, int* st) {
+  const double p[5] = {p0, p1, p2, p3, p4};
+  return loglike_one<THIN, ALPHA, true>(p, cold->m, cold->pr, cold->t, flux, ivar, cinv, *st);
+}
+
+template <bool THIN>
+__device__ __noinline__ double add_priors_cold(double lnl, double p0, double p1, double p2, double p3,
+                                               double p4, double x0, const ColdArgs* __restrict__ cold,
+                                               int* st) {
+  const double p[5] = {p0, p1, p2, p3, p4};
+  double pen, gp;
+  prior_terms<THIN>(cold->pr, p, p0, p1, x0, pen, gp, *st);
+  lnl += pen;
+  if (cold->pr.any_gprior) lnl += gp;
+  return lnl;
+}
+
+// photometry of one source into registers (issued early: independent of the parameters)
+template <int NB>
+__device__ __forceinline__ void delta_load_data(const DataRef& d, long long src, double (&diff)[NB]) {
+  const double* __restrict__ fl = d.flux + src * NB;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) diff[b] = __ldg(fl + b);
+}
+
+#ifndef MBB_DELTA_GROUP
+#define MBB_DELTA_GROUP 3
+#endif
+// grey-side bands of a delta configuration in groups of MBB_DELTA_GROUP, each group's
+// exp chains issued breadth-first (grey_nodes_n)
+template <bool THIN, int NB, int B0>
+__device__ __forceinline__ void delta_groups(const FastSed& s, const SmallTab& t, double (&diff)[NB],
+                                             const double* tab) {
+  if constexpr (B0 < NB) {
+    constexpr int N = (NB - B0) < MBB_DELTA_GROUP ? (NB - B0) : MBB_DELTA_GROUP;
+    double nu[N], lp[N], we[N], acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      nu[i] = t.freq[B0 + i];
+      lp[i] = t.lp[B0 + i];
+      we[i] = t.weff[B0 + i];
+      acc[i] = -diff[B0 + i];
+    }
+    grey_nodes_n<THIN, N, kTabRepShift>(s, nu, lp, we, acc, tab);
+#pragma unroll
+    for (int i = 0; i < N; ++i) diff[B0 + i] = -acc[i];
+    delta_groups<THIN, NB, B0 + N>(s, t, diff, tab);
+  }
+}
+
+// one evaluation, all bands single-node, FAST arithmetic, NB compile-time;
+// diff[] = the source's fluxes on entry.  The inverse variances are fetched only
+// when the chi-square needs them (L1-resident: all walkers of a source share
+// them), so they do not occupy registers during the node arithmetic.
+template <bool THIN, bool ALPHA, int NB>
+__device__ __forceinline__ double delta_eval(const double p[5], long long src, double (&diff)[NB],
+                                             const ModelP& m, const Priors& pr,
+                                             const DataRef& d, const SmallTab& t,
+                                             const ColdArgs* __restrict__ cold, const double* tab,
+                                             int& st) {
+  st = ST_OK;
+  if (below_lowlim(pr, p)) {
+    st = ST_BELOW_LOWLIM;
+    return -kInf;
+  }
+  FastSed s;
+  fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m);
+  st = s.status;
+  if (st != ST_OK) return qnan();
+  if (!s.safe)
+    return delta_eval_cold<THIN, ALPHA>(p[0], p[1], p[2], p[3], p[4], cold, d.flux + src * NB,
+                                        d.cinv ? nullptr : d.ivar + src * NB,
+                                        d.cinv ? d.cinv + src * (NB * NB) : nullptr, &st);
+  double chi = 0.0;
+  if constexpr (!ALPHA) {
+    delta_groups<THIN, NB, 0>(s, t, diff, tab);
+  } else {
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      diff[b] = -node_acc<THIN, ALPHA, false, kTabRepShift>(s, t.freq[b], t.lp[b], t.weff[b], -diff[b], tab);
+  }
+  if (d.cinv) {
+    const double* __restrict__ ci = d.cinv + src * (NB * NB);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      double row = 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
+      chi = fma(diff[r], row, chi);
+    }
+  } else {
+    const double* __restrict__ ivp = d.ivar + src * NB;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) chi = fma(diff[b] * diff[b], __ldg(ivp + b), chi);
+  }
+  double lnl = -0.5 * chi;
+  if (!priors_trivial(pr, p)) {
+    lnl = add_priors_cold<THIN>(lnl, p[0], p[1], p[2], p[3], p[4], s.x0, cold, &st);
+    if (st != ST_OK) return qnan();
+  }
+  if (lnl != lnl) st = ST_NONFINITE;
+  return lnl;
+}
+
+// Persistent, TMA-pipelined: each CTA walks tiles of MBB_DELTA_BLOCK evaluations;
+// while it computes tile k, the parameter block of its tile k+1 (10 KB, the
+// only large stream of this kernel: 40 of the 48 B/evaluation) is in flight as
+// a cp.async.bulk into the other shared-memory stage, completion signalled on
+// an mbarrier.  Global-load latency is therefore off the critical path without
+// spending registers on prefetching.  Partial tiles and buffers that are not
+// 16-byte aligned fall back to direct loads (`use_tma` = 0).
+constexpr int kDeltaTile = MBB_DELTA_BLOCK;
+
+template <bool THIN, bool ALPHA, int NB>
+__global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
+loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
+                     const SmallTab t, const ColdArgs* __restrict__ cold, const int use_tma) {
+  __shared__ __align__(16) double s_tab[kTabRepDoubles];
+  __shared__ __align__(16) double s_par[2][kDeltaTile * 5];
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  const int tid = threadIdx.x;
+  const long long ntiles = (a.n + kDeltaTile - 1) / kDeltaTile;
+  const long long sd = a.soa_stride ? a.soa_stride : a.n;
+  stage_exp_table(s_tab);
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+  }
+  __syncthreads();
+  // thread 0: start the bulk copy of a (full) tile into `stage`
+  auto issue = [&](unsigned tl, int stage) {
+    const long long e0 = (long long)tl * kDeltaTile;
+    if (!use_tma || a.n - e0 < kDeltaTile) return;
+    mbar_expect_tx(&s_bar[stage], kDeltaTile * 40u);
+    if (a.layout == 0) {
+      bulk_g2s(s_par[stage], a.pars + e0 * 5, kDeltaTile * 40u, &s_bar[stage]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+        bulk_g2s(s_par[stage] + i * kDeltaTile, a.pars + (long long)i * sd + e0, kDeltaTile * 8u, &s_bar[stage]);
+    }
+  };
+  // tile counts fit 32 bits (n < 2^31 * tile); 64-bit only when forming element indices
+  const unsigned nt = (unsigned)ntiles;
+  unsigned tile = blockIdx.x;
+  if (tid == 0 && tile < nt) issue(tile, 0);
+  for (unsigned it = 0; tile < nt; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const long long e0 = (long long)tile * kDeltaTile, e = e0 + tid;
+    const bool via_tma = use_tma && a.n - e0 >= kDeltaTile;
+    // stage^1 was consumed before the __syncthreads of the previous iteration
+    if (tid == 0 && tile + gridDim.x < nt) issue(tile + gridDim.x, stage ^ 1);
+    const bool active = e < a.n;
+    double p[5];
+    if (via_tma) {
+      mbar_wait(&s_bar[stage], (it >> 1) & 1u);
+      const double* sp = s_par[stage];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) p[i] = a.layout == 0 ? sp[tid * 5 + i] : sp[i * kDeltaTile + tid];
+    } else if (active) {
+      load_pars(a, e, p);
+    }
+    __syncthreads();
+    if (active) {
+      const long long src = source_of(a, e);
+      double diff[NB];
+      delta_load_data<NB>(d, src, diff);
+      int st;
+      const double lnl = delta_eval<THIN, ALPHA, NB>(p, src, diff, m, pr, d, t, cold, lane_exp_table(s_tab), st);
+      a.out[e] = lnl;
+      if (a.status) a.status[e] = st;
+    }
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -248,13 +404,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------
-// The warp path: a thread-per-evaluation SETUP kernel
-// writes 14 doubles + status per evaluation to a scratch array, then a lean
-// NODES kernel (64 registers -> 2 CTAs x 512 threads per SM, twice the
-// resident warps of the fused kernel) does the node loops.  The scratch costs
-// 116 B/evaluation of traffic against >= 1e5 flops of node work.
+// The warp path: a thread-per-evaluation SETUP kernel writes 14 doubles +
+// status per evaluation to a scratch array, then a lean NODES kernel (64
+// registers -> 2 CTAs x 512 threads per SM) does the node loops.  The scratch
+// costs 116 B/evaluation of traffic against >= 1e5 flops of node work.
+// Status word: bits 0-7 status code, bit 8 the FAST `safe` flag.
 // ---------------------------------------------------------------------------
 constexpr int kScratchStride = 14;   // c[0..11], pen, gp
+constexpr int kSafeBit = 0x100;
 
 template <bool THIN, bool ALPHA, bool FAST>
 __global__ void __launch_bounds__(128)
@@ -264,7 +421,7 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
   if (e >= a.n) return;
   double p[5];
   load_pars(a, e, p);
-  int st = ST_OK;
+  int st = ST_OK, safe = 0;
   double pen = 0.0, gp = 0.0;
   double c[12];
 #pragma unroll
@@ -273,11 +430,13 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
     st = ST_BELOW_LOWLIM;
   } else if (FAST) {
     FastSed s;
-    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm, m.nu_norm);
+    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m);
     st = s.status;
+    safe = s.safe;
     if (st == ST_OK) prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
-    c[0] = s.hokt9; c[2] = s.beta; c[3] = s.alpha; c[6] = s.xmerge;
-    c[8] = s.amp_grey; c[9] = s.amp_pow; c[10] = s.q_hi; c[11] = s.q_lo;
+    c[0] = s.xk_hi; c[1] = s.xk_lo; c[2] = s.nb; c[3] = s.apow;
+    c[4] = s.t0c; c[5] = s.nu_merge; c[6] = s.uq_hi; c[7] = s.uq_lo;
+    c[8] = s.amp_grey; c[9] = s.amp_pow;
   } else {
     Sed s;
     sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
@@ -290,53 +449,87 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
 #pragma unroll
   for (int i = 0; i < 6; ++i) o[i] = make_double2(c[2 * i], c[2 * i + 1]);
   o[6] = make_double2(pen, gp);
-  sst[e] = st;
+  sst[e] = st | (safe ? kSafeBit : 0);
 }
 
-__host__ __device__ inline size_t nodes_kernel_smem(int nn, bool tables_in_smem) {
-  return (tables_in_smem ? (size_t)nn * sizeof(NodeRec) : 0) + (size_t)16 * kMaxBands * 8 + 16 +
-         (size_t)(kMaxBands + 1) * 4 + kMaxBands;
+#ifndef MBB_NODES_THREADS
+#define MBB_NODES_THREADS 512
+#endif
+#ifndef MBB_NODES_MINB
+#define MBB_NODES_MINB 2
+#endif
+constexpr int kNodesThreads = MBB_NODES_THREADS;
+constexpr int kNodesWarps = kNodesThreads / 32;
+
+// dynamic shared memory of the nodes kernel:
+//   [a pairs | b (FAST)] (tables_in_smem, b padded to 16 B) | exp table 8 KB | per-warp diff | mbarrier | band_off | scalar
+__host__ __device__ inline size_t nodes_b_bytes(int nn) { return ((size_t)nn * 8 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t nodes_kernel_smem(int nn, bool tables_in_smem, bool fast) {
+  return (tables_in_smem ? (size_t)nn * 16 + (fast ? nodes_b_bytes(nn) : 0) : 0) + kTabRepDoubles * 8 +
+         (size_t)(MBB_NODES_THREADS / 32) * kMaxBands * 8 + 16 + (size_t)(kMaxBands + 1) * 4 + kMaxBands;
+}
+
+// Weighted node sum of one band over the lanes of a warp (before the shuffle
+// reduction).  (Measured and rejected: a software-pipelined body carrying the
+// reciprocal and the 1 - exp(-t) tail of the lane's previous node beside the
+// two exponentials of the current one -- ptxas re-serialises the chains under
+// the 64-register cap, 6.40 ms against 6.06 ms for cfg2; two nodes per lane per
+// iteration, 6.9 ms; 40/48-register builds for 10-12 warps per scheduler spill,
+// 6.7-7.4 ms.)
+template <bool THIN, bool ALPHA, bool CLAMP>
+__device__ __forceinline__ double band_partial_fast(const FastSed& fs, const double2* __restrict__ na,
+                                                    const double* __restrict__ nl, int i0, int i1,
+                                                    int lane, const double* tab) {
+  double acc = 0.0;
+  for (int i = i0 + lane; i < i1; i += 32) {
+    const double2 fw = na[i];
+    acc = node_acc<THIN, ALPHA, CLAMP, kTabRepShift>(fs, fw.x, nl[i], fw.y, acc, tab);
+  }
+  return acc;
 }
 
 template <bool THIN, bool ALPHA, bool FAST, bool IN_SMEM>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(MBB_NODES_THREADS, MBB_NODES_MINB)
 loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, const NodeTab t,
                      const double* __restrict__ scratch, const int* __restrict__ sst) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  NodeRec* s_nodes = reinterpret_cast<NodeRec*>(smem_raw);
-  double* s_diff = reinterpret_cast<double*>(smem_raw + (IN_SMEM ? (size_t)t.nn * sizeof(NodeRec) : 0));
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_diff + 16 * kMaxBands);
+  const size_t tab_bytes = IN_SMEM ? (size_t)t.nn * 16 + (FAST ? nodes_b_bytes(t.nn) : 0) : 0;
+  double2* s_a = reinterpret_cast<double2*>(smem_raw);
+  double* s_b = reinterpret_cast<double*>(s_a + t.nn);
+  double* s_exp = reinterpret_cast<double*>(smem_raw + tab_bytes);
+  double* s_diff = s_exp + kTabRepDoubles;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_diff + kNodesWarps * kMaxBands);
   int* s_off = reinterpret_cast<int*>(bar + 2);
   unsigned char* s_scalar = reinterpret_cast<unsigned char*>(s_off + kMaxBands + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = t.nb;
 
-  if (IN_SMEM) {                       // stage the node table once per CTA (TMA bulk copy)
+  if (IN_SMEM) {                       // stage the node table once per CTA (TMA bulk copies)
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-      const unsigned bytes = (unsigned)(t.nn * sizeof(NodeRec));
-      mbar_expect_tx(bar, bytes);
-      unsigned done = 0;
-      while (done < bytes) {           // <= 64 KiB per request
-        unsigned chunk = bytes - done;
-        if (chunk > 65536u) chunk = 65536u;
-        bulk_g2s(smem_raw + done, reinterpret_cast<const unsigned char*>(t.nodes) + done, chunk, bar);
-        done += chunk;
-      }
+      // (the device arrays are allocated padded, so the rounded-up b copy stays in bounds)
+      const unsigned bytes_a = (unsigned)t.nn * 16u, bytes_b = (unsigned)nodes_b_bytes(t.nn);
+      mbar_expect_tx(bar, FAST ? bytes_a + bytes_b : bytes_a);
+      bulk_g2s_chunked(s_a, t.a, bytes_a, bar);
+      if (FAST) bulk_g2s_chunked(s_b, t.b, bytes_b, bar);
     }
   }
+  if (FAST) stage_exp_table(s_exp);
   for (int i = tid; i <= nb; i += blockDim.x) s_off[i] = t.band_off[i];
   for (int i = tid; i < nb; i += blockDim.x) s_scalar[i] = t.scalar_path[i];
   if (IN_SMEM) mbar_wait(bar, 0);
   __syncthreads();
 
-  const NodeRec* __restrict__ nodes = IN_SMEM ? s_nodes : t.nodes;
+  const double2* __restrict__ na = IN_SMEM ? s_a : t.a;
+  const double* __restrict__ nbp = IN_SMEM ? s_b : t.b;
+  const double* ltab = lane_exp_table(s_exp);
   double* wdiff = s_diff + warp * kMaxBands;
 
-  const long long wstride = (long long)gridDim.x * 16;
-  for (long long e = (long long)blockIdx.x * 16 + warp; e < a.n; e += wstride) {
-    const int st = __ldg(sst + e);
+  const long long wstride = (long long)gridDim.x * kNodesWarps;
+  for (long long e = (long long)blockIdx.x * kNodesWarps + warp; e < a.n; e += wstride) {
+    const int stw = __ldg(sst + e);
+    const int st = stw & 0xff;
     if (st != ST_OK) {
       if (lane == 0) {
         a.out[e] = (st == ST_BELOW_LOWLIM) ? -kInf : qnan();
@@ -346,34 +539,33 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
     }
     const double2* c2 = reinterpret_cast<const double2*>(scratch + e * kScratchStride);
     const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
-    const double2 c89 = __ldg(c2 + 4), cab = __ldg(c2 + 5), cpg = __ldg(c2 + 6);
+    const double2 c89 = __ldg(c2 + 4), cpg = __ldg(c2 + 6);
     Sed s;
     FastSed fs;
     if (FAST) {
-      fs.hokt9 = c01.x; fs.beta = c23.x; fs.alpha = c23.y; fs.xmerge = c67.x;
-      fs.amp_grey = c89.x; fs.amp_pow = c89.y; fs.q_hi = cab.x; fs.q_lo = cab.y;
+      fs.xk_hi = c01.x; fs.xk_lo = c01.y; fs.nb = c23.x; fs.apow = c23.y;
+      fs.t0c = c45.x; fs.nu_merge = c45.y; fs.uq_hi = c67.x; fs.uq_lo = c67.y;
+      fs.amp_grey = c89.x; fs.amp_pow = c89.y;
     } else {
       s.hokt9 = c01.x; s.hokt_e9 = c01.y; s.beta = c23.x; s.alpha = c23.y;
       s.x0 = c45.x; s.normfac = c45.y; s.xmerge = c67.x; s.kappa = c67.y;
     }
+    const bool safe = (stw & kSafeBit) != 0;
     const long long src = source_of(a, e);
     const double* fl = d.flux + src * d.nb;
     double chi = 0.0;
     for (int b = 0; b < nb; ++b) {
-      const double hk = FAST ? fs.hokt9 : (s_scalar[b] ? s.hokt_e9 : s.hokt9);
-      const int i1 = s_off[b + 1];
+      const int i0 = s_off[b], i1 = s_off[b + 1];
       double acc = 0.0;
-      for (int i = s_off[b] + lane; i < i1; i += 32) {
-        const double2 fw = *reinterpret_cast<const double2*>(&nodes[i].freq);
-        const double cx = hk * fw.x;
-        double f;
-        if (FAST) {
-          const double2 ll = *reinterpret_cast<const double2*>(&nodes[i].lhi);
-          f = node_fnu_fast<THIN, ALPHA>(fs, cx, ll.x, ll.y, THIN ? 0.0 : nodes[i].rcube);
-        } else {
-          f = node_fnu<THIN, ALPHA>(s, cx);
+      if (FAST) {
+        if (safe) acc = band_partial_fast<THIN, ALPHA, false>(fs, na, nbp, i0, i1, lane, ltab);
+        else acc = band_partial_fast<THIN, ALPHA, true>(fs, na, nbp, i0, i1, lane, ltab);
+      } else {
+        const double hk = s_scalar[b] ? s.hokt_e9 : s.hokt9;
+        for (int i = i0 + lane; i < i1; i += 32) {
+          const double2 fw = na[i];
+          acc = fma(node_fnu<THIN, ALPHA>(s, hk * fw.x), fw.y, acc);
         }
-        acc = fma(f, fw.y, acc);
       }
       acc = warp_sum(acc);
       const double df = __ldg(fl + b) - acc;
@@ -648,7 +840,7 @@ chain_lir_qags_kernel(const double* __restrict__ chain, const int* __restrict__ 
 template <bool THIN, bool ALPHA>
 __global__ void __launch_bounds__(128)
 chain_flux_kernel(const double* __restrict__ chain, const int* __restrict__ work,
-                  const unsigned* __restrict__ nwork, double wavenorm, const NodeRec* __restrict__ nodes,
+                  const unsigned* __restrict__ nwork, double wavenorm, const double2* __restrict__ nodes,
                   int i0, int i1, int scalar_path, double* __restrict__ out, int* __restrict__ status) {
   const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= *nwork) return;
@@ -660,7 +852,10 @@ chain_flux_kernel(const double* __restrict__ chain, const int* __restrict__ work
   if (s.status == ST_OK) {
     acc = 0.0;
     const double hk = scalar_path ? s.hokt_e9 : s.hokt9;
-    for (int i = i0; i < i1; ++i) acc = fma(node_fnu<THIN, ALPHA>(s, hk * nodes[i].freq), nodes[i].w, acc);
+    for (int i = i0; i < i1; ++i) {
+      const double2 fw = __ldg(nodes + i);     // {freq, passband weight}
+      acc = fma(node_fnu<THIN, ALPHA>(s, hk * fw.x), fw.y, acc);
+    }
   }
   out[idx] = acc;
   if (status) status[idx] = s.status;

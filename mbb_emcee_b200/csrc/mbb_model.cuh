@@ -30,15 +30,55 @@ struct Sed {
 };
 
 // FAST-mode per-walker state: lives in registers, never in local memory.
-//   grey side : f = amp_grey * G_i            (see node_fnu_fast)
-//   power side: f = amp_pow  * exp(alpha * L_i),  L_i = log(wave_i / wavenorm)
+// Node tables hold L'_i = log(wave_i/wavenorm)*64/ln2 (rounded to double from the
+// 80-bit value: its 2^-53 relative rounding moves exp(b L_i) by |b L_i| 1.1e-16) and the
+// effective weight  weff_i = w_i (thin) or w_i (wavenorm/wave_i)^3 (thick);
+// a node contributes  v_i * weff_i  with
+//   grey side, thin : v = amp_grey exp(-(beta+3) L_i) / expm1(x_i)
+//   grey side, thick: v = amp_grey (1 - exp(-t_i)) / expm1(x_i),  t_i = t0 exp(-beta L_i)
+//   power side      : v = amp_pow exp(apow L_i),  apow = alpha (thin) or alpha+3 (thick)
+// and x_i*64/ln2 = nu_i * (xk_hi + xk_lo)   (see mbb_fastmath.cuh).
 struct FastSed {
   double T, beta, alpha;
   double hokt9;                 // 1e9*h/(k*T)
   double x0, xmerge;
-  double amp_grey, amp_pow, q_hi, q_lo;
+  double amp_grey, amp_pow;
+  double xk_hi, xk_lo;          // hokt9 * 64/ln2
+  double nb;                    // -(beta+3) thin, -beta thick
+  double apow;                  // alpha thin, alpha+3 thick
+  double t0;                    // thick: (lambda0/wavenorm)^beta
+  double t0c;                   // t0 * 64/ln2
+  double uq_hi, uq_lo;          // thick: beta*log(lambda0/wavenorm)*64/ln2 (CLAMP path)
+  double nu_merge;              // xmerge / hokt9 [GHz]; +inf without alpha
   int status;
+  int safe;                     // every exponent of the node loop provably inside the double range
 };
+
+// Model constants shared by every evaluation of a launch.
+struct ModelP {
+  double wavenorm;
+  double nu_norm;     // 299792.458 / wavenorm [GHz]
+  double nu_max;      // largest node frequency of the band table [GHz]
+  double lmax;        // largest |log(wave_i/wavenorm)| of the band table
+};
+
+// Host-side construction of one FAST node record (mbb_set_bands and the test
+// emulation use the same code): frequency exactly as the reference forms it
+// (modified_blackbody.py:551-554), L' from the x87 80-bit logl (64-bit mantissa).
+struct FastNode {
+  double freq, weff, lp, labs;
+};
+inline FastNode fast_node(double wave_um, double weight, double wavenorm, bool thin) {
+  FastNode n;
+  n.freq = kUmToGHz / wave_um;
+  const long double l = logl((long double)wave_um) - logl((long double)wavenorm);
+  const long double lp = l * (64.0L / logl(2.0L));
+  n.lp = (double)lp;
+  n.labs = fabs((double)l);
+  const long double r = (long double)wavenorm / (long double)wave_um;
+  n.weff = thin ? weight : (double)((long double)weight * (r * r * r));
+  return n;
+}
 
 // ---------------------------------------------------------------------------
 // small math helpers
@@ -212,16 +252,17 @@ MBB_HD_NOINLINE void sed_setup(Sed& s, double T, double beta, double lambda0, do
 // FAST-mode per-walker setup.  Same quantities as sed_setup, but
 //   * only what the FAST node formulas need (no normfac / kappa: the
 //     normalisation is carried as ratios, so nothing over/underflows);
-//   * one IEEE division (hokt9, formed exactly as fnu.pyx:16 does) -- every
-//     other quotient goes through div_fast, every exp/expm1 through
+//   * every quotient goes through div_fast (<= 1 ulp), every exp/expm1 through
 //     mbb_fastmath.cuh;
 //   * xnorm = hokt9 * (c/wavenorm) instead of (h c / k T) / wavenorm: the same
 //     number to 1-2 ulp.
-// `nu_norm` = 299792.458 / wavenorm [GHz], precomputed on the host.
+// Also decides `safe`: with m.nu_max / m.lmax bounding the node table, every
+// exponent the node loop forms stays below kSafeExp in magnitude, so the loop
+// may run the CLAMP=false instantiations.
 // ---------------------------------------------------------------------------
 MBB_HD double merge_residual_fast(double x, double alpha, double beta, double inv_x0) {
   const double t = exp_tau(beta * log(x * inv_x0));
-  // t/expm1(t): -> 1 as t -> 0, -> 0 as t -> inf (saturating expm1_fast)
+  // t/expm1(t): -> 1 as t -> 0, -> 0 as t -> inf (saturating expm1)
   const double bterm = t < 1e-280 ? 1.0 : t * rcp_fast(expm1_l(t));
   return x + expm1_l(-x) * (3.0 + alpha + beta * bterm);
 }
@@ -237,40 +278,65 @@ MBB_HD double thin_merge_root_fast(double a) {
   return x;
 }
 
+// finite and not NaN, by the exponent field (2 integer instructions)
+MBB_HD bool finite_bits(double x) {
+#if defined(__CUDA_ARCH__)
+  return (unsigned)(__double2hiint(x) & 0x7fffffff) < 0x7ff00000u;
+#else
+  return finite_d(x);
+#endif
+}
+
 template <bool THIN, bool ALPHA>
 MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double alpha, double fnorm,
-                       double wavenorm, double nu_norm) {
+                       const ModelP& m) {
+  const double* tab = exp2_tab_default();   // per-walker work: the plain table
   f.T = T; f.beta = beta; f.alpha = alpha;
   f.status = ST_OK;
-  f.x0 = 0.0; f.xmerge = kInf; f.amp_grey = f.amp_pow = f.q_hi = f.q_lo = 0.0;
+  f.safe = 0;
+  f.x0 = 0.0; f.xmerge = kInf; f.nu_merge = kInf;
+  f.amp_grey = f.amp_pow = f.t0 = f.t0c = f.uq_hi = f.uq_lo = f.apow = 0.0;
   if (ALPHA && !(alpha > 0.0)) f.status = ST_BAD_ALPHA;
   if (!(beta >= 0.0)) f.status = ST_BAD_BETA;
-  if (!finite_d(T) || !finite_d(fnorm) || (!THIN && !finite_d(lambda0)) || (ALPHA && !finite_d(alpha)) ||
-      !finite_d(beta))
+  if (!finite_bits(T) || !finite_bits(fnorm) || (!THIN && !finite_bits(lambda0)) ||
+      (ALPHA && !finite_bits(alpha)) || !finite_bits(beta))
     f.status = ST_NONFINITE;
   // range of validity of the lean exp family (mbb_fastmath.cuh)
   if (f.status == ST_OK && (!(T >= kFastMinT) || beta > kFastMaxIndex || (ALPHA && alpha > kFastMaxIndex)))
     f.status = ST_OVERFLOW;
-  f.hokt9 = 1e9 * kH / (kK * T);
+  f.hokt9 = div_fast(1e9 * kH, kK * T);
+  f.xk_hi = f.hokt9 * kC64Hi;
+  f.xk_lo = fma(f.hokt9, kC64Lo, fma(f.hokt9, kC64Hi, -f.xk_hi));
+  f.nb = THIN ? -(beta + 3.0) : -beta;
   if (f.status != ST_OK) return;
-  const double xn = f.hokt9 * nu_norm;
-  double inv_x0 = 0.0, tn_fac = 1.0;
+  const double xn = f.hokt9 * m.nu_norm;
+  bool safe = f.hokt9 * m.nu_max <= kSafeExp && -f.nb * m.lmax <= kSafeExp;
+  double inv_x0 = 0.0, tn_fac = 1.0, q = 0.0;
   if (!THIN) {
     // q = log(xnorm/x0) = log(lambda0/wavenorm)
-    const double r = lambda0 / wavenorm;
+    const double r = div_fast(lambda0, m.wavenorm);
     f.x0 = div_fast(xn, r);
     inv_x0 = rcp_fast(f.x0);
-    f.q_hi = log(r);
-    f.q_lo = 0.0;
-    tn_fac = -expm1_l(-exp_prod_tau(beta, f.q_hi, f.q_lo));     // 1 - exp(-(xn/x0)^beta)
+    q = log(r);
+    const double qc_hi = q * kC64Hi;
+    const double qc_lo = fma(q, kC64Lo, fma(q, kC64Hi, -qc_hi));
+    f.uq_hi = beta * qc_hi;
+    f.uq_lo = fma(beta, qc_lo, fma(beta, qc_hi, -f.uq_hi));
+    f.t0 = exp_red<0, true>(red_prod(beta, qc_hi, qc_lo), tab);             // (lambda0/wavenorm)^beta
+    tn_fac = one_minus_exp_red<0, true>(red_x(-clamp_pos<kHi700>(f.t0)), tab);   // 1 - exp(-(xn/x0)^beta)
+    f.t0c = f.t0 * kC64Hi;
+    safe = safe && fabs(beta * q) <= kSafeExp;
   }
-  const double em_n = expm1_l(xn);
+  const double em_n = expm1_red<0, true>(red_prod(m.nu_norm, f.xk_hi, f.xk_lo), tab);
   const double grey_at_norm = THIN ? fnorm * em_n : div_fast(fnorm * em_n, tn_fac);
   if (!ALPHA) {
     f.amp_grey = grey_at_norm;
-    if (!finite_d(f.amp_grey)) f.status = ST_OVERFLOW;
+    f.safe = safe;
+    if (!finite_bits(f.amp_grey)) f.status = ST_OVERFLOW;
     return;
   }
+  f.apow = THIN ? alpha : alpha + 3.0;
+  safe = safe && f.apow * m.lmax <= kSafeExp;
   if (THIN) {
     f.xmerge = thin_merge_root_fast(3.0 + alpha + beta);               // modified_blackbody.py:253-254
   } else {
@@ -300,6 +366,7 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
   }
   // R = grey(xmerge) xmerge^alpha / (grey(xnorm) xnorm^alpha), built from ratios
   const double xm = f.xmerge;
+  f.nu_merge = div_fast(xm, f.hokt9);
   const double lmn = log(div_fast(xm, xn));
   const double inv_em_m = rcp_fast(expm1_l(xm));
   double R;
@@ -307,7 +374,7 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
     R = exp_l((3.0 + beta + alpha) * lmn) * inv_em_m * em_n;        // times grey_at_norm/fnorm
     // (amp_grey = fnorm*em_n when xn <= xm) -> amp_pow = fnorm * R
   } else {
-    const double tm = exp_tau(beta * (lmn + f.q_hi));
+    const double tm = exp_tau(beta * (lmn + q));
     R = -expm1_l(-tm) * exp_l((3.0 + alpha) * lmn) * inv_em_m * div_fast(em_n, tn_fac);
   }
   // here R = amp_pow / fnorm when the normalisation wavelength sits on the grey side
@@ -318,7 +385,8 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
     f.amp_grey = grey_at_norm;
     f.amp_pow = fnorm * R;
   }
-  if (!finite_d(f.amp_grey) || !finite_d(f.amp_pow)) f.status = ST_OVERFLOW;
+  f.safe = safe;
+  if (!finite_bits(f.amp_grey) || !finite_bits(f.amp_pow)) f.status = ST_OVERFLOW;
 }
 
 // ---------------------------------------------------------------------------
@@ -348,16 +416,114 @@ MBB_HD double node_fnu(const Sed& s, double cx) {
   return s.normfac * v;
 }
 
-// One node, FAST arithmetic.  l_hi/l_lo = log(wave_i/wavenorm) (double-double),
-// rcube = (wavenorm/wave_i)^3, cx = hokt9 * freq_i.
-template <bool THIN, bool ALPHA>
-MBB_HD double node_fnu_fast(const FastSed& s, double cx, double l_hi, double l_lo, double rcube) {
-  if (ALPHA && cx > s.xmerge) return s.amp_pow * exp_prod_l(s.alpha, l_hi, l_lo);
-  const double em = expm1_l(cx);
-  if (THIN) return div_fast(s.amp_grey * exp_prod_l(-(s.beta + 3.0), l_hi, l_lo), em);
-  // t = (cx/x0)^beta = exp(beta * (q - L_i))
-  const double t = exp_prod_tau(s.beta, s.q_hi - l_hi, s.q_lo - l_lo);
-  return div_fast(s.amp_grey * (-expm1_l(-t)) * rcube, em);
+// a > b for non-negative doubles (and +inf) on the integer pipe
+MBB_HD bool gt_pos(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(a) > __double_as_longlong(b);
+#else
+  return a > b;
+#endif
+}
+
+// One node, FAST arithmetic: acc + f_nu(nu_i) w_i  (see FastSed for the
+// formulas).  nu = node frequency [GHz], lp = L'_i, weff = effective weight.
+// The reciprocal of expm1(x_i) is folded into the weight so that it runs
+// beside the other exp chains; the last dependent step is a single FMA.
+// TS: index-stride shift of `tab` (see scaled_T).
+template <bool THIN, bool ALPHA, bool CLAMP, int TS>
+MBB_HD double node_acc(const FastSed& s, double nu, double lp, double weff, double acc, const double* tab) {
+  if (ALPHA && gt_pos(nu, s.nu_merge))
+    return fma(exp_red<TS, CLAMP>(red_prod1(s.apow, lp), tab), s.amp_pow * weff, acc);
+  const double em = expm1_red<TS, CLAMP>(red_prod(nu, s.xk_hi, s.xk_lo), tab);
+  const double wr = (s.amp_grey * weff) * rcp_cubic(em);
+  if (THIN) return fma(exp_red<TS, CLAMP>(red_prod1(s.nb, lp), tab), wr, acc);
+  // tc = t_i*64/ln2, t_i = (x_i/x0)^beta = t0 exp(-beta L_i); beyond ~700 only 1 - exp(-t) = 1 matters
+  double tc;
+  if (CLAMP) tc = exp_red_times<TS, true>(red_sum_prod(s.uq_hi, s.uq_lo, s.nb, lp), tab, kC64Hi);
+  else tc = exp_red_times<TS, false>(red_prod1(s.nb, lp), tab, s.t0c);
+  const double g = one_minus_exp_red<TS, CLAMP>(red_neg_scaled(clamp_pos<kHi700C>(tc)), tab);
+  return fma(g, wr, acc);
+}
+
+// ---------------------------------------------------------------------------
+// N grey-side nodes at once, `safe` walkers only (CLAMP=false).  Exactly the
+// operations node_acc performs per node -- results are bit-identical -- but
+// written breadth-first: step s of all 2N (thin) or 3N (thick) exp chains
+// before step s+1 of any.  A warp issues in order and a dependent DFMA waits
+// ~8 cycles (tools/fp64_probe.cu), so a thread must carry >= 4 independent
+// chains to keep the half-rate FP64 pipe fed without relying on other warps;
+// left to itself the compiler emits each chain serially under the register cap.
+//   acc[i] += f_nu(nu_i) w_i   for i < N
+// ---------------------------------------------------------------------------
+template <int N>
+MBB_HD void lean_p_n(const double (&f)[N], double (&p)[N]) {
+  double g[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) g[i] = lean_g_coef(4);
+#pragma unroll
+  for (int j = 3; j >= 0; --j) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = fma(g[i], f[i], lean_g_coef(j));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = g[i] * f[i];
+}
+
+template <bool THIN, int N, int TS>
+MBB_HD void grey_nodes_n(const FastSed& s, const double (&nu)[N], const double (&lp)[N],
+                         const double (&weff)[N], double (&acc)[N], const double* tab) {
+  // chains A: x_i = nu_i * xk, chains B: -b L_i
+  double t[2 * N], f[2 * N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    t[i] = fma(nu[i], s.xk_hi, kMagic);
+    t[N + i] = fma(s.nb, lp[i], kMagic);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    f[i] = fma(nu[i], s.xk_hi, -(t[i] - kMagic));
+    f[N + i] = fma(s.nb, lp[i], -(t[N + i] - kMagic));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) f[i] = fma(nu[i], s.xk_lo, f[i]);
+  double sT[2 * N];
+#pragma unroll
+  for (int i = 0; i < 2 * N; ++i) sT[i] = scaled_T<TS, false>(tab, lo32_of(t[i]));
+  double p[2 * N];
+  lean_p_n<2 * N>(f, p);
+  double em[N], aw[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    em[i] = fma(sT[i], p[i], sT[i] - 1.0);
+    aw[i] = s.amp_grey * weff[i];
+  }
+  if (THIN) {
+    double E[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) E[i] = fma(sT[N + i], p[N + i], sT[N + i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = fma(E[i], aw[i] * rcp_cubic(em[i]), acc[i]);
+    return;
+  }
+  // thick: third chain on tc = t0c * exp(-beta L), beside the reciprocals
+  double tc[N], f3[N], sT3[N], p3[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double s2 = sT[N + i] * s.t0c;
+    tc[i] = clamp_pos<kHi700C>(fma(s2, p[N + i], s2));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const Red r = red_neg_scaled(tc[i]);
+    f3[i] = r.f;
+    sT3[i] = scaled_T<TS, false>(tab, r.k);
+  }
+  lean_p_n<N>(f3, p3);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double g = fma(-sT3[i], p3[i], 1.0 - sT3[i]);
+    acc[i] = fma(g, aw[i] * rcp_cubic(em[i]), acc[i]);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -490,12 +656,13 @@ MBB_HD double lir_node(const LirSpan& sp, int node, double beta, double x0) {
 // ---------------------------------------------------------------------------
 struct Priors {
   double lowlim[5];
-  double uplim[6];
+  double uplim[6];       // +inf where has_uplim is 0 (mbb_set_priors enforces it)
   double gmean[6];
   double givar[6];
   unsigned char has_uplim[6];
   unsigned char has_gprior[6];
   int any_gprior;
+  int always_terms;      // lambda_peak limit/prior or any Gaussian prior set: prior_terms must run
 };
 
 MBB_HD bool below_lowlim(const Priors& pr, const double p[5]) {
@@ -503,6 +670,15 @@ MBB_HD bool below_lowlim(const Priors& pr, const double p[5]) {
 #pragma unroll
   for (int i = 0; i < 5; ++i) bad = bad || (p[i] < pr.lowlim[i]);
   return bad;
+}
+
+// true when no soft upper limit is exceeded and no other prior term is active:
+// the common case, in which prior_terms() would return pen = gp = 0
+MBB_HD bool priors_trivial(const Priors& pr, const double p[5]) {
+  bool over = false;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) over = over || (p[i] > pr.uplim[i]);
+  return !over && !pr.always_terms;
 }
 
 // Returns the soft-upper-limit penalty in `pen` and the Gaussian-prior term in
@@ -553,16 +729,16 @@ MBB_HD void prior_terms(const Priors& pr, const double p[5], double T, double be
 // One complete evaluation of likelihood.__call__ (likelihood.py:790-834) by a
 // single thread: limits gate -> per-walker setup -> band fluxes (node loop) ->
 // chi-square (diagonal or full inverse covariance) -> soft upper limits ->
-// Gaussian priors.  `Tab` is any type with freq/w/lhi/llo/rcube/band_off/
+// Gaussian priors.  `Tab` is any type with freq/w/weff/lp/band_off/
 // scalar_path members indexable by node / band (SmallTab in the kernel
-// parameter block, TabView over plain arrays).
+// parameter block, TabView over plain arrays): w = passband weight (FAITHFUL),
+// weff / lp = the FAST node constants (see FastSed).
 // ---------------------------------------------------------------------------
 struct TabView {
   const double* freq;
   const double* w;
-  const double* lhi;
-  const double* llo;
-  const double* rcube;
+  const double* weff;
+  const double* lp;
   const int* band_off;
   const unsigned char* scalar_path;
   int nb;
@@ -570,7 +746,7 @@ struct TabView {
 
 constexpr int kMaxBandsPerThread = 64;
 
-// chi-square of one evaluation given a callable returning f_nu at node i
+// chi-square of one evaluation given a callable returning the weighted node term
 template <class Tab, class NodeFn>
 MBB_HD double chi_square(const Tab& t, const double* flux, const double* ivar, const double* cinv,
                          NodeFn node) {
@@ -579,7 +755,7 @@ MBB_HD double chi_square(const Tab& t, const double* flux, const double* ivar, c
   if (!cinv) {
     for (int b = 0; b < nb; ++b) {
       double acc = 0.0;
-      for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i) acc = fma(node(b, i), t.w[i], acc);
+      for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i) acc = node(b, i, acc);
       const double df = flux[b] - acc;
       chi = fma(df * df, ivar[b], chi);
     }
@@ -588,7 +764,7 @@ MBB_HD double chi_square(const Tab& t, const double* flux, const double* ivar, c
   double diff[kMaxBandsPerThread];
   for (int b = 0; b < nb; ++b) {
     double acc = 0.0;
-    for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i) acc = fma(node(b, i), t.w[i], acc);
+    for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i) acc = node(b, i, acc);
     diff[b] = flux[b] - acc;
   }
   for (int r = 0; r < nb; ++r) {
@@ -599,10 +775,12 @@ MBB_HD double chi_square(const Tab& t, const double* flux, const double* ivar, c
   return chi;
 }
 
+// FAST evaluations here always run the saturating (CLAMP) node code: this is
+// the generic path (few-node tables that are not all-delta, out-of-range
+// walkers handed over by the specialised kernels).
 template <bool THIN, bool ALPHA, bool FAST, class Tab>
-MBB_HD double loglike_one(const double p[5], double wavenorm, double nu_norm, const Priors& pr,
-                          const Tab& t, const double* flux, const double* ivar, const double* cinv,
-                          int& st) {
+MBB_HD double loglike_one(const double p[5], const ModelP& m, const Priors& pr, const Tab& t,
+                          const double* flux, const double* ivar, const double* cinv, int& st) {
   st = ST_OK;
   if (below_lowlim(pr, p)) {
     st = ST_BELOW_LOWLIM;
@@ -611,21 +789,22 @@ MBB_HD double loglike_one(const double p[5], double wavenorm, double nu_norm, co
   const double nan = kInf - kInf;
   double chi, pen, gp;
   if (FAST) {
+    const double* tab = exp2_tab_default();
     FastSed s;
-    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm, nu_norm);
+    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m);
     st = s.status;
     if (st != ST_OK) return nan;
-    chi = chi_square(t, flux, ivar, cinv, [&](int, int i) {
-      return node_fnu_fast<THIN, ALPHA>(s, s.hokt9 * t.freq[i], t.lhi[i], t.llo[i], t.rcube[i]);
+    chi = chi_square(t, flux, ivar, cinv, [&](int, int i, double acc) {
+      return node_acc<THIN, ALPHA, true, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
     });
     prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
   } else {
     Sed s;
-    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
+    sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
     st = s.status;
     if (st != ST_OK) return nan;
-    chi = chi_square(t, flux, ivar, cinv, [&](int b, int i) {
-      return node_fnu<THIN, ALPHA>(s, (t.scalar_path[b] ? s.hokt_e9 : s.hokt9) * t.freq[i]);
+    chi = chi_square(t, flux, ivar, cinv, [&](int b, int i, double acc) {
+      return fma(node_fnu<THIN, ALPHA>(s, (t.scalar_path[b] ? s.hokt_e9 : s.hokt9) * t.freq[i]), t.w[i], acc);
     });
     prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
   }

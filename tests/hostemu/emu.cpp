@@ -19,16 +19,44 @@ using namespace mbb;
 
 namespace {
 template <bool THIN, bool ALPHA, bool FAST>
-void run_loglike(long long n, const double* pars, double wavenorm, const Priors& pr, const TabView& t,
-                 const double* flux, const double* ivar, const double* cinv, long long wps, double* out,
-                 int* status) {
+void run_loglike(long long n, const double* pars, const ModelP& m, const Priors& pr, const TabView& t,
+                 const double* flux, const double* ivar, const double* cinv, long long wps, int unclamped,
+                 double* out, int* status) {
   const int nb = t.nb;
   for (long long e = 0; e < n; ++e) {
     const long long src = e / wps;
+    const double* fl = flux + src * nb;
+    const double* iv = ivar ? ivar + src * nb : nullptr;
+    const double* ci = cinv ? cinv + src * nb * nb : nullptr;
     int st;
-    out[e] = loglike_one<THIN, ALPHA, FAST>(pars + 5 * e, wavenorm, kUmToGHz / wavenorm, pr, t, flux + src * nb,
-                                             ivar ? ivar + src * nb : nullptr,
-                                             cinv ? cinv + src * nb * nb : nullptr, st);
+    if (FAST && unclamped) {
+      // the arithmetic of the specialised kernels (loglike_delta_kernel / nodes kernel):
+      // CLAMP=false node code for `safe` walkers, the generic path otherwise
+      const double* p = pars + 5 * e;
+      const double* tab = exp2_tab_default();
+      FastSed s;
+      st = ST_OK;
+      if (below_lowlim(pr, p)) { out[e] = -kInf; status[e] = ST_BELOW_LOWLIM; continue; }
+      fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m);
+      if (s.status == ST_OK && s.safe) {
+        const double chi = chi_square(t, fl, iv, ci, [&](int, int i, double acc) {
+          return node_acc<THIN, ALPHA, false, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
+        });
+        double lnl = -0.5 * chi;
+        if (!priors_trivial(pr, p)) {
+          double pen, gp;
+          prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+          lnl += pen;
+          if (pr.any_gprior) lnl += gp;
+        }
+        if (st != ST_OK) lnl = kInf - kInf;
+        else if (lnl != lnl) st = ST_NONFINITE;
+        out[e] = lnl;
+        status[e] = st;
+        continue;
+      }
+    }
+    out[e] = loglike_one<THIN, ALPHA, FAST>(pars + 5 * e, m, pr, t, fl, iv, ci, st);
     status[e] = st;
   }
 }
@@ -51,13 +79,23 @@ void run_consts(long long n, const double* pars, double wavenorm, int want_peak,
 template <bool THIN, bool ALPHA>
 void run_fnu(long long n, const double* pars, double wavenorm, int nfreq, const double* freq, int scalar_path,
              int fast, double* out) {
+  // fast: 1 = CLAMP node code, 2 = CLAMP=false node code where the walker is `safe`
+  std::vector<FastNode> nodes(nfreq);
+  ModelP m{wavenorm, kUmToGHz / wavenorm, 0.0, 0.0};
+  for (int i = 0; i < nfreq; ++i) {
+    nodes[i] = fast_node(kUmToGHz / freq[i], 1.0, wavenorm, THIN);
+    nodes[i].freq = freq[i];
+    if (freq[i] > m.nu_max) m.nu_max = freq[i];
+    if (nodes[i].labs > m.lmax) m.lmax = nodes[i].labs;
+  }
+  const double* tab = exp2_tab_default();
   for (long long e = 0; e < n; ++e) {
     const double* p = pars + 5 * e;
     Sed s;
     FastSed fs;
     int status;
     if (fast) {
-      fast_setup<THIN, ALPHA>(fs, p[0], p[1], p[2], p[3], p[4], wavenorm, kUmToGHz / wavenorm);
+      fast_setup<THIN, ALPHA>(fs, p[0], p[1], p[2], p[3], p[4], m);
       status = fs.status;
     } else {
       sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], wavenorm);
@@ -68,11 +106,9 @@ void run_fnu(long long n, const double* pars, double wavenorm, int nfreq, const 
       if (status != ST_OK) {
         v = kInf - kInf;
       } else if (fast) {
-        const double wave = kUmToGHz / freq[i];
-        long double l = logl((long double)wave) - logl((long double)wavenorm);
-        const double hi = (double)l, lo = (double)(l - (long double)hi);
-        long double r = (long double)wavenorm / (long double)wave;
-        v = node_fnu_fast<THIN, ALPHA>(fs, fs.hokt9 * freq[i], hi, lo, (double)(r * r * r));
+        const FastNode& nd = nodes[i];
+        if (fast == 2 && fs.safe) v = node_acc<THIN, ALPHA, false, 0>(fs, nd.freq, nd.lp, nd.weff, 0.0, tab);
+        else v = node_acc<THIN, ALPHA, true, 0>(fs, nd.freq, nd.lp, nd.weff, 0.0, tab);
       } else {
         v = node_fnu<THIN, ALPHA>(s, (scalar_path ? s.hokt_e9 : s.hokt9) * freq[i]);
       }
@@ -119,6 +155,36 @@ void run_qags(long long n, const double* pars, double wavenorm, double fmin, dou
     else { if (alpha) fn<false, true>(__VA_ARGS__); else fn<false, false>(__VA_ARGS__); }    \
   } while (0)
 
+// grey_nodes_n (the breadth-first N-node form the delta kernel uses) against node_acc, node by
+// node: both return acc = 0 + f_nu(nu_i) w_i for 6 nodes per parameter vector (two groups of 3).
+template <bool THIN>
+static void run_grey(long long n, const double* pars, double wavenorm, const double* wave, const double* weight,
+                     double* out_single, double* out_group, int* safe) {
+  FastNode nd[6];
+  ModelP m{wavenorm, kUmToGHz / wavenorm, 0.0, 0.0};
+  for (int i = 0; i < 6; ++i) {
+    nd[i] = fast_node(wave[i], weight[i], wavenorm, THIN);
+    if (nd[i].freq > m.nu_max) m.nu_max = nd[i].freq;
+    if (nd[i].labs > m.lmax) m.lmax = nd[i].labs;
+  }
+  const double* tab = exp2_tab_default();
+  for (long long e = 0; e < n; ++e) {
+    const double* p = pars + 5 * e;
+    FastSed s;
+    fast_setup<THIN, false>(s, p[0], p[1], p[2], p[3], p[4], m);
+    safe[e] = (s.status == ST_OK && s.safe) ? 1 : 0;
+    if (!safe[e]) continue;
+    for (int i = 0; i < 6; ++i)
+      out_single[e * 6 + i] = node_acc<THIN, false, false, 0>(s, nd[i].freq, nd[i].lp, nd[i].weff, 0.0, tab);
+    for (int g0 = 0; g0 < 6; g0 += 3) {
+      double nu[3], lp[3], we[3], acc[3] = {0.0, 0.0, 0.0};
+      for (int i = 0; i < 3; ++i) { nu[i] = nd[g0 + i].freq; lp[i] = nd[g0 + i].lp; we[i] = nd[g0 + i].weff; }
+      grey_nodes_n<THIN, 3, 0>(s, nu, lp, we, acc, tab);
+      for (int i = 0; i < 3; ++i) out_group[e * 6 + g0 + i] = acc[i];
+    }
+  }
+}
+
 extern "C" {
 
 struct EmuPriors {
@@ -139,17 +205,20 @@ void emu_loglike(int thin, int alpha, int fast, long long n, const double* pars,
     if (ep->has_gprior[i]) pr.any_gprior = 1;
   }
   const int nn = band_off[nb];
-  std::vector<double> freq(nn), lhi(nn), llo(nn), rc(nn);
+  std::vector<double> freq(nn), lp(nn), weff(nn);
+  ModelP m{wavenorm, kUmToGHz / wavenorm, 0.0, 0.0};
   for (int i = 0; i < nn; ++i) {       // same table construction as mbb_set_bands (mbb_capi.cu)
-    freq[i] = kUmToGHz / wave[i];
-    long double l = logl((long double)wave[i]) - logl((long double)wavenorm);
-    lhi[i] = (double)l;
-    llo[i] = (double)(l - (long double)lhi[i]);
-    long double r = (long double)wavenorm / (long double)wave[i];
-    rc[i] = (double)(r * r * r);
+    const FastNode nd = fast_node(wave[i], weight[i], wavenorm, thin != 0);
+    freq[i] = nd.freq; lp[i] = nd.lp; weff[i] = nd.weff;
+    if (nd.freq > m.nu_max) m.nu_max = nd.freq;
+    if (nd.labs > m.lmax) m.lmax = nd.labs;
   }
-  TabView t{freq.data(), weight, lhi.data(), llo.data(), rc.data(), band_off, scalar_path, nb};
-#define GO(T, A, F) run_loglike<T, A, F>(n, pars, wavenorm, pr, t, flux, ivar, cinv, wps, out, status)
+  for (int i = 0; i < 6; ++i)
+    if (!pr.has_uplim[i]) pr.uplim[i] = kInf;
+  pr.always_terms = (pr.any_gprior || pr.has_uplim[5]) ? 1 : 0;
+  TabView t{freq.data(), weight, weff.data(), lp.data(), band_off, scalar_path, nb};
+  const int unclamped = fast == 2;
+#define GO(T, A, F) run_loglike<T, A, F>(n, pars, m, pr, t, flux, ivar, cinv, wps, unclamped, out, status)
   if (thin) {
     if (alpha) { if (fast) GO(true, true, true); else GO(true, true, false); }
     else { if (fast) GO(true, false, true); else GO(true, false, false); }
@@ -170,16 +239,32 @@ void emu_lir(int thin, int alpha, long long n, const double* pars, double waveno
   DISPATCH2(run_lir, thin, alpha, n, pars, wavenorm, fmin, fmax, prefac, out, status);
 }
 
-// element-wise checks of the lean math (mode 0 exp, 1 expm1, 2 reciprocal, 3 a/b with b = x+1, 4/5 table-driven exp/expm1)
+// element-wise checks of the lean math: mode 0 exp (CLAMP), 1 expm1 (CLAMP), 2 reciprocal,
+// 3 a/b with b = x+1, 4 exp (no clamp), 5 expm1 (no clamp), 6 1-exp(-x) through the scaled path,
+// 7 exp(x*y) as a product reduction with y = 0.7 (double-double of 0.7*64/ln2 formed here),
+// 8 1/x by rcp_cubic
 void emu_fastmath(int mode, long long n, const double* x, double* out) {
+  const double* tab = exp2_tab_default();
   for (long long i = 0; i < n; ++i) {
-    if (mode == 0) out[i] = exp_fast(x[i]);
-    else if (mode == 1) out[i] = expm1_fast(x[i]);
+    if (mode == 0) out[i] = exp_l(x[i]);
+    else if (mode == 1) out[i] = expm1_l(x[i]);
     else if (mode == 2) out[i] = rcp_fast(x[i]);
-    else if (mode == 4) out[i] = exp_tab(x[i]);
-    else if (mode == 5) out[i] = expm1_tab(x[i]);
+    else if (mode == 4) out[i] = exp_red<0, false>(red_x(x[i]), tab);
+    else if (mode == 5) out[i] = expm1_red<0, false>(red_x(x[i]), tab);
+    else if (mode == 6) out[i] = one_minus_exp_red<0, false>(red_neg_scaled(clamp_pos<kHi700C>(x[i] * kC64Hi)), tab);
+    else if (mode == 7) {
+      const long double b = 0.7L * (64.0L / logl(2.0L));
+      const double bh = (double)b, bl = (double)(b - (long double)bh);
+      out[i] = exp_red<0, false>(red_prod(x[i], bh, bl), tab);
+    } else if (mode == 8) out[i] = rcp_cubic(x[i]);
     else out[i] = div_fast(x[i], x[i] + 1.0);
   }
+}
+
+void emu_grey_nodes(int thin, long long n, const double* pars, double wavenorm, const double* wave,
+                    const double* weight, double* out_single, double* out_group, int* safe) {
+  if (thin) run_grey<true>(n, pars, wavenorm, wave, weight, out_single, out_group, safe);
+  else run_grey<false>(n, pars, wavenorm, wave, weight, out_single, out_group, safe);
 }
 
 void emu_qags(int thin, int alpha, long long n, const double* pars, double wavenorm, double fmin, double fmax,

@@ -101,6 +101,20 @@ def fastmath(mode, x):
     return out
 
 
+def grey_nodes(opthin, pars, wavenorm, wave, weight):
+    """(node_acc values, grey_nodes_n values, safe flags) for 6 nodes per parameter vector."""
+    P = _c(pars).reshape(-1, 5)
+    n = P.shape[0]
+    wv, wt = _c(wave), _c(weight)
+    assert wv.size == 6 and wt.size == 6
+    a = np.zeros((n, 6))
+    b = np.zeros((n, 6))
+    safe = np.zeros(n, dtype=np.int32)
+    lib().emu_grey_nodes(int(opthin), ctypes.c_longlong(n), _p(P), ctypes.c_double(wavenorm), _p(wv), _p(wt),
+                         _p(a), _p(b), _p(safe))
+    return a, b, safe.astype(bool)
+
+
 def philox(ctr, key):
     c = np.ascontiguousarray(ctr, dtype=np.uint32)
     k = np.ascontiguousarray(key, dtype=np.uint32)

@@ -227,6 +227,68 @@ def test_multi_source_batch(oracle):
         assert abs(got2[i] - oracle.loglike(spec, P[i])) <= TOL * abs(got2[i])
 
 
+def test_delta_kernel_launch_paths(oracle):
+    """The persistent delta kernel: TMA-fed full tiles, the direct-load fallback
+    (partial tail tile, buffer not 16-byte aligned, odd SoA stride), walkers-per-source
+    values that exercise the multiply-shift division, the cold paths (soft upper limit
+    exceeded; exponents outside the double range -> saturating code) -- all against
+    the oracle, and bitwise against each other where the arithmetic is the same."""
+    import torch
+    from mbb_emcee_b200 import _native, synthetic
+    rng = np.random.RandomState(21)
+    dev = torch.device("cuda:0")
+    waves = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0]
+    low = np.array([0.01, 0.1, 1, 0.1, 1e-3])
+    for opthin in (True, False):
+        for wps in (1, 37, 256, 1000):
+            n = 3 * 256 + 77                      # three full tiles + a partial one
+            nsrc = (n + wps - 1) // wps
+            flux = rng.uniform(5, 80, (nsrc, 6))
+            unc = rng.uniform(1, 6, (nsrc, 6))
+            ctx = _native.Context(0)
+            ctx.set_model(500.0, opthin, True)
+            ctx.set_bands(np.arange(7, dtype=np.int32), waves, np.ones(6))
+            ctx.set_data(flux, ivar=1.0 / unc**2)
+            has_up = [0, 1, 1, 1, 0, 0]
+            up = [np.inf, 2.2, 1500.0, 20.0, np.inf, np.inf]
+            ctx.set_priors(low, has_up, up, [0] * 6, [0.0] * 6, [1.0] * 6)
+            P = synthetic.walker_cloud((12.0, 1.8, 400.0, 4.0, 30.0), n, rng, low)
+            P[5, 1] = 2.5                          # beta above its soft upper limit -> penalty term
+            P[6, 0] = 0.05                         # h nu / k T ~ 4000: exponent outside the double range
+            P[7, 0] = 0.005                        # below the T limit -> -inf
+            Pd = torch.as_tensor(P, device=dev)
+            out = torch.empty(n, dtype=torch.float64, device=dev)
+            st = torch.empty(n, dtype=torch.int32, device=dev)
+            ctx.loglike_device(n, Pd.data_ptr(), out.data_ptr(), st.data_ptr(), walkers_per_source=wps)
+            ctx.sync()
+            got, stat = out.cpu().numpy(), st.cpu().numpy()
+            want = np.empty(n)
+            for s0 in range(nsrc):
+                spec = oracle.LikeSpec(500.0, True, opthin)
+                spec.set_phot(waves, flux[s0], unc[s0])
+                spec.lowlim = low.copy()
+                spec.has_uplim = [bool(x) for x in has_up]
+                spec.uplim = np.array(up)
+                sl = slice(s0 * wps, min((s0 + 1) * wps, n))
+                with np.errstate(all="ignore"):
+                    want[sl] = oracle.loglike_batch(spec, P[sl])
+            assert np.isneginf(got[7]) and np.isneginf(want[7]) and stat[7] == 1
+            assert stat[6] == 0 and np.isfinite(got[6])
+            fin = np.isfinite(want)
+            assert relerr(got[fin], want[fin]).max() < TOL, (opthin, wps)
+            # same rows through a buffer that is only 8-byte aligned (direct loads, no TMA)
+            buf = torch.empty(n * 5 + 1, dtype=torch.float64, device=dev)
+            buf[1:] = Pd.reshape(-1)
+            out2 = torch.empty_like(out)
+            ctx.loglike_device(n, buf.data_ptr() + 8, out2.data_ptr(), 0, walkers_per_source=wps)
+            # SoA (odd row stride n -> direct loads as well)
+            Pt = Pd.t().contiguous()
+            out3 = torch.empty_like(out)
+            ctx.loglike_device(n, Pt.data_ptr(), out3.data_ptr(), 0, walkers_per_source=wps, layout=_native.SOA)
+            ctx.sync()
+            assert bool(torch.equal(out, out2)) and bool(torch.equal(out, out3))
+
+
 def test_error_statuses():
     """Failures that make the reference raise surface as the same exception types."""
     from mbb_emcee_b200 import likelihood
