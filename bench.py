@@ -46,6 +46,16 @@ FLOP_PER_EVAL = {"cfg5": 6 * 182 + 225 + 18 + 40,            # = 1375 (cfg1 band
 BYTES_PER_EVAL = 48                                          # 40 B parameters in + 8 B out
 
 
+def ncu_fact(workload, key):
+    """Figures taken from the committed `ncu --set full` capture of the dominant kernel
+    (profiles/ncu_facts.json, written by tools/ncu_summary.py facts): not measured live."""
+    try:
+        facts = json.load(open(os.path.join(ROOT, "profiles", "ncu_facts.json")))[workload]
+    except Exception:
+        return None
+    return facts if key is None else facts.get(key)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -287,7 +297,13 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: stay on the GPU's NUMA node (pinned host buffers next to its PCIe port)
+    all_cpus = sorted(os.sched_getaffinity(0))
+    bound = None
     if world > 1:
+        from mbb_emcee_b200.sharding import bind_to_gpu_numa_node
+        pr = torch.cuda.get_device_properties(local)
+        bound = bind_to_gpu_numa_node("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
         dist.init_process_group("nccl", device_id=dev)
     name = args.workload
     W = build_workload(name, rank, args.nsrc)
@@ -303,44 +319,51 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        ctx.loglike_device(n, P.data_ptr(), out.data_ptr(), st.data_ptr(), walkers_per_source=nw)
+    def device_leg(ctx, n, nw, P, out, st, flush, steps, warmup):
+        """K timed likelihood passes with inputs resident in HBM; CUDA events on the stream the
+        library launches on (torch only sees its own current stream, so wrap the handle)."""
+        lstream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+
+        def step():
+            ctx.loglike_device(n, P.data_ptr(), out.data_ptr(), st.data_ptr(), walkers_per_source=nw)
+
+        for _ in range(warmup):
+            step()
+        ctx.sync()
+        barrier()
+        launches0 = ctx.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            if flush is not None:
+                with torch.cuda.stream(lstream):
+                    flush.fill_(1.0)
+            ev[k][0].record(lstream)
+            step()
+            ev[k][1].record(lstream)
+        ctx.sync()
+        barrier()
+        wall = time.perf_counter() - t0
+        launches = ctx.launch_count() - launches0
+        kernel_ms = [a.elapsed_time(b) for a, b in ev]
+        step_ms = float(np.mean(kernel_ms))
+        t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(step_ms=step_ms, step_ms_max=float(t.item()), kernel_ms=kernel_ms, wall=wall,
+                    launches=launches, lstream=lstream)
 
     # ---- device-resident throughput ------------------------------------------
-    # CUDA events recorded on the stream the library launches on (torch only sees
-    # its own current stream, so wrap the library's stream handle).
-    lstream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
-    for _ in range(args.warmup):
-        step_device()
-    ctx.sync()
     peak_tf = ctx.fp64_peak(20000)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    launches0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        if flush is not None:
-            with torch.cuda.stream(lstream):
-                flush.fill_(1.0)
-        ev[k][0].record(lstream)
-        step_device()
-        ev[k][1].record(lstream)
-    ctx.sync()
-    barrier()
-    wall = time.perf_counter() - t0
-    launches = ctx.launch_count() - launches0
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    # timed quantity: device time of the K steps (events on the launching stream), max over ranks
-    step_ms = float(np.mean(kernel_ms))
-    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms_max = float(t.item())
+    leg = device_leg(ctx, n, nw, P, out, st, flush, args.steps, args.warmup)
+    lstream, launches, wall = leg["lstream"], leg["launches"], leg["wall"]
+    kernel_ms, step_ms, step_ms_max = leg["kernel_ms"], leg["step_ms"], leg["step_ms_max"]
     nbad = int((st > 1).sum().item())
     nneg = int(torch.isneginf(out).sum().item())
 
@@ -441,6 +464,28 @@ def run_b200(args):
                          "note": "host call: walker positions uploaded, initial log-probability + K "
                                  "iterations, positions and log-probabilities downloaded"},
                  "mean_acceptance_fraction": acc_frac}
+    # ---- the same batch shape on the tabulated passband set (BASELINE configs[1] bands) ----
+    passband = None
+    per_worker = 20000 if name == "cfg5" else 1500
+    cores = len(all_cpus)
+    Pc = P[:cores * per_worker].cpu().numpy() if rank == 0 else None
+    if name == "cfg5" and not args.no_passband:
+        del P, out, st
+        torch.cuda.empty_cache()
+        W2 = build_workload("cfg2", rank, None)
+        ctx2, n2, P2 = W2["ctx"], W2["n"], W2["P"]
+        ctx2.set_math_mode(0 if args.math == "faithful" else 1)
+        out2 = torch.empty(n2, dtype=torch.float64, device=dev)
+        st2 = torch.empty(n2, dtype=torch.int32, device=dev)
+        flush2 = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+        leg2 = device_leg(ctx2, n2, W2["nw"], P2, out2, st2, flush2, max(3, min(args.steps, 5)), 3)
+        f2 = FLOP_PER_EVAL["cfg2"]
+        passband = {"workload": main_config("cfg2", W2["nsrc"])["workload"],
+                    "value": n2 * world / (leg2["step_ms_max"] * 1e-3), "unit": UNIT,
+                    "ms_per_step": leg2["step_ms_max"], "evals_per_step_per_gpu": int(n2),
+                    "roofline_frac": n2 * f2 / (leg2["step_ms"] * 1e-3) / 1e12 / peak_tf,
+                    "flop_per_eval": f2, "status_errors": int((st2 > 1).sum().item()),
+                    "l2_policy": "L2 flushed between timed steps by writing a 256 MB buffer"}
     clocks = sampler.stop()
 
     if rank == 0:
@@ -458,9 +503,7 @@ def run_b200(args):
         try:
             if args.no_cpu_baseline:
                 raise RuntimeError("skipped (--no-cpu-baseline)")
-            per_worker = 20000 if name == "cfg5" else 1500
-            cores = len(os.sched_getaffinity(0))
-            Pc = P[:cores * per_worker].cpu().numpy()
+            os.sched_setaffinity(0, all_cpus)      # the CPU leg uses every host core again
             cb = cpu_baseline(name, W["flux"][0], W["unc"][0], Pc, per_worker)
         except Exception as exc:           # the baseline is informational; never hide the GPU line
             cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
@@ -471,9 +514,12 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(main_config(name, W["nsrc"]), parallelism="sources sharded, "
                            "%d rank(s), no data-path collective" % world,
+                           numa_binding=("rank 0 bound to %d CPUs of its GPU's NUMA node" % len(bound))
+                           if bound else "none",
                            math_mode=args.math),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "frac": achieved_tf / peak_tf, "traffic": ncu_fact(name, "dram_bytes_per_launch"),
+                         "ncu": ncu_fact(name, None),
                          "note": "achieved = %d algorithmic FP64 flop/eval (reference formulation, "
                                  "SURVEY 8d) x evals per launch / CUDA-event kernel time; peak = DFMA "
                                  "rate measured live by mbb_fp64_peak on this GPU (no tensor cores: "
@@ -485,6 +531,7 @@ def run_b200(args):
             "cpu_baseline": cb,
             "e2e": e2e,
             "batch_fit": batch,
+            "passband": passband,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"status_errors": nbad, "neg_inf": nneg, "wall_s_timed_region": wall,
@@ -506,6 +553,7 @@ def main():
     ap.add_argument("--nsrc", type=int, default=None, help="sources per GPU (default: workload's)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg")
+    ap.add_argument("--no-passband", action="store_true", help="skip the tabulated-passband leg")
     ap.add_argument("--math", default="fast", choices=["fast", "faithful"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -11,12 +11,47 @@ import os
 
 import numpy as np
 
-__all__ = ["rank_world", "shard_range", "shard_sources", "gather_concat"]
+__all__ = ["rank_world", "shard_range", "shard_sources", "gather_concat", "bind_to_gpu_numa_node",
+           "parse_cpulist"]
 
 
 def rank_world():
     """(rank, world_size) from the torchrun environment (0, 1 when absent)."""
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def parse_cpulist(text):
+    """'0-15,32-47' -> [0, ..., 15, 32, ..., 47]  (sysfs cpulist format)."""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(pci_bus_id, sysfs="/sys"):
+    """Restrict this process to the CPUs of the NUMA node the GPU hangs off, so that the
+    pinned host buffers of the host-memory (MBB_HOST) calls are allocated next to the GPU's
+    PCIe root port.  With one process per GPU on a multi-socket box this keeps every rank's
+    H2D/D2H traffic off the inter-socket link.  `pci_bus_id` as CUDA reports it
+    ('00000000:1B:00.0'); returns the CPU list it bound to, or None when the topology is not
+    exposed (single-node hosts, containers without sysfs) -- never raises."""
+    try:
+        dom, bus, rest = pci_bus_id.lower().split(":")
+        dev = "%s:%s:%s" % (dom[-4:], bus, rest)
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", dev, "numa_node")).read())
+        if node < 0:
+            return None
+        cpus = parse_cpulist(open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)).read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
 
 
 def shard_range(n, rank, world):

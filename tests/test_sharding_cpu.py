@@ -75,3 +75,26 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     got = np.load(tmp_path / "gathered.npz")
     assert np.array_equal(got["ll"], want)
     assert np.array_equal(got["both"][:, 0], want) and np.array_equal(got["both"][:, 1], st)
+
+
+def test_numa_binding_helper(tmp_path):
+    """bind_to_gpu_numa_node reads the GPU's NUMA node and that node's CPU list from sysfs
+    and never raises when the topology is not exposed."""
+    import os
+    from mbb_emcee_b200.sharding import bind_to_gpu_numa_node, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert bind_to_gpu_numa_node("00000000:1b:00.0", sysfs=str(tmp_path)) is None      # nothing there
+    before = sorted(os.sched_getaffinity(0))
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text("%d\n" % before[0])
+    try:
+        assert bind_to_gpu_numa_node("00000000:1B:00.0", sysfs=str(tmp_path)) == [before[0]]
+        assert sorted(os.sched_getaffinity(0)) == [before[0]]
+    finally:
+        os.sched_setaffinity(0, before)
+    (dev / "numa_node").write_text("-1\n")
+    assert bind_to_gpu_numa_node("00000000:1b:00.0", sysfs=str(tmp_path)) is None

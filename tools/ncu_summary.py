@@ -93,5 +93,35 @@ def _gb(uv):
     return v * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[u]
 
 
+def facts(path):
+    """One JSON object per captured kernel: the figures bench.py attaches to its `roofline`
+    (profiles/ncu_facts.json is assembled from these, keyed by workload)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader([l for l in out.splitlines() if l.startswith('"')]))
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        d = dict(zip(hdr, zip(units, vals)))
+        f = lambda k: float(d[k][1].replace(",", ""))
+        print(json.dumps({
+            "kernel": short(d["Kernel Name"][1]),
+            "source": "ncu --set full --clock-control none, one launch (profiles/)",
+            "dram_bytes_per_launch": (_gb(d["dram__bytes_read.sum"]) + _gb(d["dram__bytes_write.sum"])) * 1e9,
+            "gpu_time_ms": _ms(d["gpu__time_duration.sum"]),
+            "fp64_pipe_pct": f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "issue_slot_pct": f("sm__inst_issued.avg.pct_of_peak_sustained_active"),
+            "dram_pct": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "warp_instructions": f("smsp__inst_executed.sum"),
+            "registers": f("launch__registers_per_thread"),
+            "smem_bank_conflicts": f("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")}))
+
+
+def _ms(uv):
+    u, v = uv
+    v = float(v.replace(",", ""))
+    return v * {"s": 1e3, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "msecond": 1.0, "usecond": 1e-3, "nsecond": 1e-6,
+                "second": 1e3}[u]
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "facts": facts}[sys.argv[1]](sys.argv[2])
