@@ -306,9 +306,13 @@ struct DeltaLauncher {
       const long long sd = a.soa_stride ? a.soa_stride : a.n;
       static const bool no_tma = getenv("MBB_B200_NO_TMA") != nullptr;
       const int use_tma = !no_tma && ((uintptr_t)a.pars % 16 == 0) && (a.layout == MBB_AOS || sd % 2 == 0);
+      // photometry rows of a tile travel with it when sources are implicit (walkers_per_source)
+      // and the errors are diagonal; d_flux / d_ivar are cudaMalloc'ed (256-byte aligned) and padded
+      static const bool no_stage = getenv("MBB_B200_NO_STAGE_DATA") != nullptr;
+      const int stage_data = use_tma && !no_stage && !a.src_index && d.ivar && !d.cinv;
       const ModelP m = model_of(c);
       loglike_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, st>>>(a, m, c->pri, d, c->small,
-                                                                           c->d_cold.p, use_tma);
+                                                                           c->d_cold.p, use_tma, stage_data);
     } else {
       DeltaLauncher<THIN, ALPHA, NB - 1>::go(c, st, a, d, nb);
     }
@@ -580,11 +584,11 @@ int mbb_set_data(mbb_ctx* c, int nsrc, int nbands, const double* flux, const dou
   Use u(c);
   CK(cudaStreamSynchronize(c->stream));
   const size_t n1 = (size_t)nsrc * nbands;
-  CK(c->d_flux.reserve(n1));
+  CK(c->d_flux.reserve(n1 + 2));      // +2: the delta kernel's bulk copies round up to 16 bytes
   CK(cudaMemcpy(c->d_flux.p, flux, n1 * sizeof(double), cudaMemcpyHostToDevice));
   c->has_ivar = c->has_cinv = false;
   if (ivar) {
-    CK(c->d_ivar.reserve(n1));
+    CK(c->d_ivar.reserve(n1 + 2));
     CK(cudaMemcpy(c->d_ivar.p, ivar, n1 * sizeof(double), cudaMemcpyHostToDevice));
     c->has_ivar = true;
   } else {

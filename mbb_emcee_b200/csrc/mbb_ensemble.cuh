@@ -129,7 +129,7 @@ ens_delta_kernel(const EnsArgs g, const ModelP m, const Priors pr, const DataRef
   double diff[NB];
   delta_load_data<NB>(d, src, diff);
   int st;
-  const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, diff, m, pr, d, t, cold, lane_exp_table(s_tab), st);
+  const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, diff, m, pr, d, t, cold, lane_exp_table(s_tab), nullptr, st);
   if (st > ST_BELOW_LOWLIM) {
     if (g.status[w] <= ST_BELOW_LOWLIM) g.status[w] = st;
     return;

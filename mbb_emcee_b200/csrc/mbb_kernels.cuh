@@ -281,7 +281,7 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
                                              const ModelP& m, const Priors& pr,
                                              const DataRef& d, const SmallTab& t,
                                              const ColdArgs* __restrict__ cold, const double* tab,
-                                             int& st) {
+                                             const double* iv_smem, int& st) {
   st = ST_OK;
   if (below_lowlim(pr, p)) {
     st = ST_BELOW_LOWLIM;
@@ -312,6 +312,9 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
       for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
       chi = fma(diff[r], row, chi);
     }
+  } else if (iv_smem) {          // the tile's photometry rows were staged by TMA
+#pragma unroll
+    for (int b = 0; b < NB; ++b) chi = fma(diff[b] * diff[b], iv_smem[b], chi);
   } else {
     const double* __restrict__ ivp = d.ivar + src * NB;
 #pragma unroll
@@ -326,40 +329,71 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
   return lnl;
 }
 
-// Persistent, TMA-pipelined: each CTA walks tiles of MBB_DELTA_BLOCK evaluations;
-// while it computes tile k, the parameter block of its tile k+1 (10 KB, the
-// only large stream of this kernel: 40 of the 48 B/evaluation) is in flight as
-// a cp.async.bulk into the other shared-memory stage, completion signalled on
-// an mbarrier.  Global-load latency is therefore off the critical path without
-// spending registers on prefetching.  Partial tiles and buffers that are not
-// 16-byte aligned fall back to direct loads (`use_tma` = 0).
-// (Measured and rejected: a 3-stage ring that also stages the tile's flux /
-// inverse-variance rows and replaces the CTA barrier by per-stage release
-// mbarriers -- 1.35 ms against 1.21 ms for cfg5: the extra index arithmetic per
-// thread costs more than the L1-resident photometry loads it removes.)
+// Persistent, TMA-pipelined: each CTA walks tiles of MBB_DELTA_BLOCK evaluations
+// through a 3-stage shared-memory ring.  While the CTA computes tile k, thread 0
+// has tile k+1 in flight as cp.async.bulk copies that complete on the stage's
+// mbarrier: the parameter block (10 KB -- 40 of the kernel's 48 B/evaluation)
+// and, when the tile spans at most kDeltaMaxSrc sources, their flux and
+// inverse-variance rows (ncu: the late, L2-latency-exposed inverse-variance
+// loads were 18 % of the warp-time of the version that fetched them with LDG).
+// Global-load latency is therefore off the critical path without spending
+// registers on prefetching.  The one CTA barrier per tile sits right after the
+// parameter read; with three stages the slot refilled in iteration k was last
+// used by tile k-2, which every thread finished before that barrier.
+// Partial tiles, buffers that are not 16-byte aligned, explicit source indices
+// and full covariances fall back to direct loads.
+// (Measured and rejected: per-stage release mbarriers, one arrive per warp,
+// instead of the CTA barrier -- thread 0 waiting for the slowest warp serialises
+// the refill, 1.35 ms against 1.20 ms for cfg5; 4 CTAs/SM at 64 registers: spills,
+// 1.29 ms.)
 constexpr int kDeltaTile = MBB_DELTA_BLOCK;
+constexpr int kDeltaStages = 3;
+constexpr int kDeltaMaxSrc = 8;
+
+struct DeltaStageHdr {
+  long long d0;       // first staged double of the flux / ivar arrays (even index)
+  int with_data;
+  int pad;
+};
 
 template <bool THIN, bool ALPHA, int NB>
 __global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
 loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
-                     const SmallTab t, const ColdArgs* __restrict__ cold, const int use_tma) {
+                     const SmallTab t, const ColdArgs* __restrict__ cold, const int use_tma,
+                     const int stage_data) {
+  constexpr int kRow = kDeltaMaxSrc * NB + 2;             // doubles per staged data array (+2: alignment slack)
   __shared__ __align__(16) double s_tab[kTabRepDoubles];
-  __shared__ __align__(16) double s_par[2][kDeltaTile * 5];
-  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ __align__(16) double s_par[kDeltaStages][kDeltaTile * 5];
+  __shared__ __align__(16) double s_dat[kDeltaStages][2][kRow];
+  __shared__ __align__(16) DeltaStageHdr s_hdr[kDeltaStages];
+  __shared__ __align__(8) unsigned long long s_bar[kDeltaStages];
   const int tid = threadIdx.x;
-  const long long ntiles = (a.n + kDeltaTile - 1) / kDeltaTile;
   const long long sd = a.soa_stride ? a.soa_stride : a.n;
   stage_exp_table(s_tab);
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < kDeltaStages; ++i) mbar_init(&s_bar[i], 1);
   }
   __syncthreads();
-  // thread 0: start the bulk copy of a (full) tile into `stage`
+  // thread 0: start the bulk copies of a (full) tile into `stage`
   auto issue = [&](unsigned tl, int stage) {
     const long long e0 = (long long)tl * kDeltaTile;
     if (!use_tma || a.n - e0 < kDeltaTile) return;
-    mbar_expect_tx(&s_bar[stage], kDeltaTile * 40u);
+    long long d0 = 0;
+    unsigned cnt = 0;
+    if (stage_data) {
+      const long long s_first = source_of(a, e0);
+      const long long s_end = source_of(a, e0 + kDeltaTile - 1) + 1;
+      if (s_end - s_first <= kDeltaMaxSrc) {
+        // doubles [d0, d0 + cnt), d0 rounded down and cnt rounded up to even (16 bytes);
+        // the library pads its flux / ivar buffers so the round-up stays in bounds
+        d0 = (s_first * NB) & ~1LL;
+        cnt = (unsigned)((s_end * NB - d0 + 1) & ~1LL);
+      }
+    }
+    s_hdr[stage].d0 = d0;
+    s_hdr[stage].with_data = cnt != 0;
+    mbar_expect_tx(&s_bar[stage], kDeltaTile * 40u + 2u * cnt * 8u);
     if (a.layout == 0) {
       bulk_g2s(s_par[stage], a.pars + e0 * 5, kDeltaTile * 40u, &s_bar[stage]);
     } else {
@@ -367,21 +401,25 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
       for (int i = 0; i < 5; ++i)
         bulk_g2s(s_par[stage] + i * kDeltaTile, a.pars + (long long)i * sd + e0, kDeltaTile * 8u, &s_bar[stage]);
     }
+    if (cnt) {
+      bulk_g2s(s_dat[stage][0], d.flux + d0, cnt * 8u, &s_bar[stage]);
+      bulk_g2s(s_dat[stage][1], d.ivar + d0, cnt * 8u, &s_bar[stage]);
+    }
   };
   // tile counts fit 32 bits (n < 2^31 * tile); 64-bit only when forming element indices
-  const unsigned nt = (unsigned)ntiles;
+  const unsigned nt = (unsigned)((a.n + kDeltaTile - 1) / kDeltaTile);
   unsigned tile = blockIdx.x;
   if (tid == 0 && tile < nt) issue(tile, 0);
-  for (unsigned it = 0; tile < nt; tile += gridDim.x, ++it) {
-    const int stage = it & 1;
+  int stage = 0;            // ring position of the current tile
+  unsigned par = 0;         // parity of this use of the stage's barrier
+  for (; tile < nt; tile += gridDim.x) {
     const long long e0 = (long long)tile * kDeltaTile, e = e0 + tid;
     const bool via_tma = use_tma && a.n - e0 >= kDeltaTile;
-    // stage^1 was consumed before the __syncthreads of the previous iteration
-    if (tid == 0 && tile + gridDim.x < nt) issue(tile + gridDim.x, stage ^ 1);
+    if (tid == 0 && tile + gridDim.x < nt) issue(tile + gridDim.x, stage + 1 == kDeltaStages ? 0 : stage + 1);
     const bool active = e < a.n;
     double p[5];
     if (via_tma) {
-      mbar_wait(&s_bar[stage], (it >> 1) & 1u);
+      mbar_wait(&s_bar[stage], par);
       const double* sp = s_par[stage];
 #pragma unroll
       for (int i = 0; i < 5; ++i) p[i] = a.layout == 0 ? sp[tid * 5 + i] : sp[i * kDeltaTile + tid];
@@ -392,11 +430,25 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
     if (active) {
       const long long src = source_of(a, e);
       double diff[NB];
-      delta_load_data<NB>(d, src, diff);
+      const double* iv_smem = nullptr;
+      if (via_tma && s_hdr[stage].with_data) {
+        // (the slot stays valid for the whole tile: it is refilled two iterations from now)
+        const int off = (int)(src * NB - s_hdr[stage].d0);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) diff[b] = s_dat[stage][0][off + b];
+        iv_smem = &s_dat[stage][1][off];
+      } else {
+        delta_load_data<NB>(d, src, diff);
+      }
       int st;
-      const double lnl = delta_eval<THIN, ALPHA, NB>(p, src, diff, m, pr, d, t, cold, lane_exp_table(s_tab), st);
+      const double lnl = delta_eval<THIN, ALPHA, NB>(p, src, diff, m, pr, d, t, cold, lane_exp_table(s_tab),
+                                                     iv_smem, st);
       a.out[e] = lnl;
       if (a.status) a.status[e] = st;
+    }
+    if (++stage == kDeltaStages) {
+      stage = 0;
+      par ^= 1u;
     }
   }
 }
