@@ -19,7 +19,7 @@ _LIBNAME = os.environ.get("MBB_B200_LIB") or os.path.join(_HERE, "csrc", "libmbb
 
 AOS, SOA = 0, 1
 HOST, DEVICE = 0, 1
-MATH_FAITHFUL, MATH_FAST = 0, 1
+MATH_FAITHFUL, MATH_FAST, MATH_FAST_GAUSS = 0, 1, 2
 LIR_QUADPACK, LIR_GAUSS = 0, 1
 
 STATUS_NAMES = {0: "ok", 1: "below lower limit", 2: "bad alpha", 3: "bad beta",

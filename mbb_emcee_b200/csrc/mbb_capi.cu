@@ -10,6 +10,7 @@
 
 #include "../../include/mbb_b200.h"
 #include "mbb_ensemble.cuh"
+#include "mbb_gaussrule.h"
 #include "mbb_kernels.cuh"
 
 using namespace mbb;
@@ -95,6 +96,12 @@ struct mbb_ctx {
   DevBuf<double2> d_node_fw;      // {freq, passband weight}: FAITHFUL kernels, chain_flux
   DevBuf<double2> d_node_fast_a;  // {freq, weff}  FAST (depends on opthin)
   DevBuf<double> d_node_fast_b;   // L' = log(wave/wavenorm)*64/ln2, FAST (depends on wavenorm)
+  // MBB_MATH_FAST_GAUSS: 32-point Gauss rules of the tabulated bands
+  DevBuf<double2> d_comp_a;
+  DevBuf<double> d_comp_b;
+  DevBuf<int> d_comp_off;
+  DevBuf<BandMeta> d_band_meta;
+  int nc = 0;                     // compressed nodes in total (0: no band has a rule)
   double nu_max = 0.0, lmax = 0.0;
   bool fast_tables_ok = false;    // FAST tables match the current (wavenorm, opthin)
   DevBuf<ColdArgs> d_cold;        // SmallTab + priors + model for the kernels' cold paths
@@ -240,6 +247,32 @@ cudaError_t ensure_tables(mbb_ctx* c) {
   if ((e = cudaMemcpy(c->d_node_fast_a.p, fa.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
   if ((e = cudaMemcpy(c->d_node_fast_b.p, fb.data(), ((size_t)nn + 1) * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
     return e;
+  // compressed rules (MBB_MATH_FAST_GAUSS), see mbb_gaussrule.h
+  {
+    const GaussTables g = build_gauss_tables(c->nb, c->h_off.data(), c->h_wave.data(), c->h_weight.data(),
+                                             c->h_scalar.data(), c->wavenorm, thin);
+    c->nc = (int)g.freq.size();
+    std::vector<double2> ca((size_t)c->nc + 1, make_double2(0.0, 0.0));
+    std::vector<double> cb((size_t)c->nc + 2, 0.0);       // padded to a multiple of 16 bytes
+    for (int k = 0; k < c->nc; ++k) {
+      ca[k] = make_double2(g.freq[k], g.weff[k]);
+      cb[k] = g.lp[k];
+    }
+    if ((e = c->d_comp_a.reserve(ca.size())) != cudaSuccess) return e;
+    if ((e = c->d_comp_b.reserve(cb.size())) != cudaSuccess) return e;
+    if ((e = c->d_comp_off.reserve(g.off.size())) != cudaSuccess) return e;
+    if ((e = c->d_band_meta.reserve(g.meta.size())) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(c->d_comp_a.p, ca.data(), ca.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return e;
+    if ((e = cudaMemcpy(c->d_comp_b.p, cb.data(), cb.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return e;
+    if ((e = cudaMemcpy(c->d_comp_off.p, g.off.data(), g.off.size() * sizeof(int), cudaMemcpyHostToDevice)) !=
+        cudaSuccess)
+      return e;
+    if ((e = cudaMemcpy(c->d_band_meta.p, g.meta.data(), g.meta.size() * sizeof(BandMeta),
+                        cudaMemcpyHostToDevice)) != cudaSuccess)
+      return e;
+  }
   c->fast_tables_ok = true;
   return upload_cold(c);
 }
@@ -370,9 +403,14 @@ struct LaunchSplit {
     t.scalar_path = c->d_scalar.p;
     t.nb = c->nb;
     t.nn = c->nn;
-    size_t smem = nodes_kernel_smem(c->nn, true, FAST);
+    const bool gauss = FAST && c->math_mode == MBB_MATH_FAST_GAUSS && c->nc > 0;
+    t.ca = c->d_comp_a.p;
+    t.cb = c->d_comp_b.p;
+    t.comp_off = c->d_comp_off.p;
+    t.nc = gauss ? c->nc : 0;
+    size_t smem = nodes_kernel_smem(c->nn, true, FAST, t.nc);
     const bool in_smem = smem <= c->smem_optin;
-    if (!in_smem) smem = nodes_kernel_smem(c->nn, false, FAST);
+    if (!in_smem) smem = nodes_kernel_smem(c->nn, false, FAST, t.nc);
     auto nodes = in_smem ? loglike_nodes_kernel<THIN, ALPHA, FAST, true>
                          : loglike_nodes_kernel<THIN, ALPHA, FAST, false>;
     *err = cudaFuncSetAttribute(nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -395,7 +433,7 @@ struct LaunchSplit {
       *err = c->scratch_for(st, (size_t)cap, &scratch, &sst);
       if (*err != cudaSuccess) return;
       loglike_setup_kernel<THIN, ALPHA, FAST><<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(
-          a, m, c->pri, scratch, sst);
+          a, m, c->pri, scratch, sst, c->d_band_meta.p, gauss ? c->nb : 0);
       const long long want = (a.n + kNodesWarps - 1) / kNodesWarps;
       const long long resident = (long long)c->sm_count * per_sm;
       const unsigned grid = (unsigned)(want < resident ? want : resident);
@@ -474,7 +512,8 @@ int mbb_ctx_destroy(mbb_ctx* c) {
   if (!c) return 0;
   Use u(c);
   cudaStreamSynchronize(c->stream);
-  c->d_cold.release(); c->d_node_fw.release(); c->d_node_fast_a.release(); c->d_node_fast_b.release(); c->d_off.release(); c->d_scalar.release();
+  c->d_cold.release(); c->d_comp_a.release(); c->d_comp_b.release(); c->d_comp_off.release();
+  c->d_band_meta.release(); c->d_node_fw.release(); c->d_node_fast_a.release(); c->d_node_fast_b.release(); c->d_off.release(); c->d_scalar.release();
   c->d_flux.release(); c->d_ivar.release(); c->d_cinv.release();
   c->h_in.release(); c->h_out.release(); c->h_st.release(); c->h_src.release();
   c->d_in.release(); c->d_out.release(); c->d_aux0.release(); c->d_aux1.release();
@@ -530,7 +569,8 @@ int mbb_set_model(mbb_ctx* c, double wavenorm, int opthin, int noalpha) {
 
 int mbb_set_math_mode(mbb_ctx* c, int mode) {
   if (!c) return fail("null context");
-  if (mode != MBB_MATH_FAITHFUL && mode != MBB_MATH_FAST) return fail("unknown math mode");
+  if (mode != MBB_MATH_FAITHFUL && mode != MBB_MATH_FAST && mode != MBB_MATH_FAST_GAUSS)
+    return fail("unknown math mode");
   c->math_mode = mode;
   return 0;
 }
@@ -644,7 +684,7 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a_in) {
   d.cinv = c->has_cinv ? c->d_cinv.p : nullptr;
   d.nsrc = c->nsrc;
   d.nb = c->nb;
-  const bool thin = c->opthin != 0, alpha = c->noalpha == 0, fast = c->math_mode == MBB_MATH_FAST;
+  const bool thin = c->opthin != 0, alpha = c->noalpha == 0, fast = c->math_mode != MBB_MATH_FAITHFUL;
   CK(ensure_tables(c));
   cudaError_t err = cudaSuccess;
   if (fast && c->nn == c->nb && c->nb <= kMaxDeltaNB) dispatch3<LaunchDelta>(thin, alpha, true, c, st, a, d, &err);
@@ -1084,7 +1124,7 @@ int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, dou
   const unsigned grid = (unsigned)((nh + 255) / 256);
   // delta-band FAST configurations take the fused one-kernel half-step
   static const bool no_fuse = getenv("MBB_B200_NO_FUSED_SAMPLER") != nullptr;
-  const bool fused = !no_fuse && c->math_mode == MBB_MATH_FAST && c->nn == c->nb && c->nb <= kMaxDeltaNB;
+  const bool fused = !no_fuse && c->math_mode != MBB_MATH_FAITHFUL && c->nn == c->nb && c->nb <= kMaxDeltaNB;
   DataRef dref;
   dref.flux = c->d_flux.p;
   dref.ivar = c->has_ivar ? c->d_ivar.p : nullptr;

@@ -97,6 +97,12 @@ struct NodeTab {
   const unsigned char* scalar_path;
   int nb;
   int nn;
+  // MBB_MATH_FAST_GAUSS: per band the 32-point Gauss rule of its discrete measure
+  // (mbb_gaussrule.h), same record layout; nc = 0 when the mode is off
+  const double2* ca;
+  const double* cb;
+  const int* comp_off;    // nb + 1 (a band without a rule has an empty range)
+  int nc;
 };
 
 __device__ __forceinline__ void load_pars(const EvalArgs& a, long long e, double p[5]) {
@@ -472,7 +478,7 @@ constexpr int kSafeBit = 0x100;
 template <bool THIN, bool ALPHA, bool FAST>
 __global__ void __launch_bounds__(128)
 loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* __restrict__ scratch,
-                     int* __restrict__ sst) {
+                     int* __restrict__ sst, const BandMeta* __restrict__ band_meta, const int nb_gauss) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n) return;
   double p[5];
@@ -493,6 +499,8 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
     c[0] = s.xk_hi; c[1] = s.xk_lo; c[2] = s.nb; c[3] = s.apow;
     c[4] = s.t0c; c[5] = s.nu_merge; c[6] = s.uq_hi; c[7] = s.uq_lo;
     c[8] = s.amp_grey; c[9] = s.amp_pow;
+    if (nb_gauss > 0 && st == ST_OK && safe)
+      c[10] = __longlong_as_double((long long)gauss_band_mask<THIN, ALPHA>(s, band_meta, nb_gauss));
   } else {
     Sed s;
     sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
@@ -520,8 +528,9 @@ constexpr int kNodesWarps = kNodesThreads / 32;
 // dynamic shared memory of the nodes kernel:
 //   [a pairs | b (FAST)] (tables_in_smem, b padded to 16 B) | exp table 8 KB | per-warp diff | mbarrier | band_off | scalar
 __host__ __device__ inline size_t nodes_b_bytes(int nn) { return ((size_t)nn * 8 + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t nodes_kernel_smem(int nn, bool tables_in_smem, bool fast) {
-  return (tables_in_smem ? (size_t)nn * 16 + (fast ? nodes_b_bytes(nn) : 0) : 0) + kTabRepDoubles * 8 +
+__host__ __device__ inline size_t nodes_kernel_smem(int nn, bool tables_in_smem, bool fast, int nc = 0) {
+  return (tables_in_smem ? (size_t)nn * 16 + (fast ? nodes_b_bytes(nn) : 0) : 0) +
+         (nc ? (size_t)nc * 16 + nodes_b_bytes(nc) + (size_t)(kMaxBands + 1) * 4 + 12 : 0) + kTabRepDoubles * 8 +
          (size_t)(MBB_NODES_THREADS / 32) * kMaxBands * 8 + 16 + (size_t)(kMaxBands + 1) * 4 + kMaxBands;
 }
 
@@ -550,9 +559,14 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
                      const double* __restrict__ scratch, const int* __restrict__ sst) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t tab_bytes = IN_SMEM ? (size_t)t.nn * 16 + (FAST ? nodes_b_bytes(t.nn) : 0) : 0;
+  // compressed rules (always in shared memory: nb * 32 nodes): [ca | cb | comp_off]
+  const size_t comp_bytes = t.nc ? (size_t)t.nc * 16 + nodes_b_bytes(t.nc) + (size_t)(kMaxBands + 1) * 4 + 12 : 0;
   double2* s_a = reinterpret_cast<double2*>(smem_raw);
   double* s_b = reinterpret_cast<double*>(s_a + t.nn);
-  double* s_exp = reinterpret_cast<double*>(smem_raw + tab_bytes);
+  double2* s_ca = reinterpret_cast<double2*>(smem_raw + tab_bytes);
+  double* s_cb = reinterpret_cast<double*>(s_ca + t.nc);
+  int* s_coff = reinterpret_cast<int*>(smem_raw + tab_bytes + (size_t)t.nc * 16 + nodes_b_bytes(t.nc));
+  double* s_exp = reinterpret_cast<double*>(smem_raw + tab_bytes + comp_bytes);
   double* s_diff = s_exp + kTabRepDoubles;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_diff + kNodesWarps * kMaxBands);
   int* s_off = reinterpret_cast<int*>(bar + 2);
@@ -572,6 +586,13 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
     }
   }
   if (FAST) stage_exp_table(s_exp);
+  if (FAST && t.nc) {
+    for (int i = tid; i < t.nc; i += blockDim.x) {
+      s_ca[i] = t.ca[i];
+      s_cb[i] = t.cb[i];
+    }
+    for (int i = tid; i <= nb; i += blockDim.x) s_coff[i] = t.comp_off[i];
+  }
   for (int i = tid; i <= nb; i += blockDim.x) s_off[i] = t.band_off[i];
   for (int i = tid; i < nb; i += blockDim.x) s_scalar[i] = t.scalar_path[i];
   if (IN_SMEM) mbar_wait(bar, 0);
@@ -596,6 +617,8 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
     const double2* c2 = reinterpret_cast<const double2*>(scratch + e * kScratchStride);
     const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
     const double2 c89 = __ldg(c2 + 4), cpg = __ldg(c2 + 6);
+    unsigned long long gmask = 0;
+    if (FAST && t.nc) gmask = (unsigned long long)__double_as_longlong(__ldg(c2 + 5).x);
     Sed s;
     FastSed fs;
     if (FAST) {
@@ -614,7 +637,9 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
       const int i0 = s_off[b], i1 = s_off[b + 1];
       double acc = 0.0;
       if (FAST) {
-        if (safe) acc = band_partial_fast<THIN, ALPHA, false>(fs, na, nbp, i0, i1, lane, ltab);
+        if (t.nc && ((gmask >> b) & 1ull))         // this walker may use the band's 32-point rule
+          acc = band_partial_fast<THIN, ALPHA, false>(fs, s_ca, s_cb, s_coff[b], s_coff[b + 1], lane, ltab);
+        else if (safe) acc = band_partial_fast<THIN, ALPHA, false>(fs, na, nbp, i0, i1, lane, ltab);
         else acc = band_partial_fast<THIN, ALPHA, true>(fs, na, nbp, i0, i1, lane, ltab);
       } else {
         const double hk = s_scalar[b] ? s.hokt_e9 : s.hokt9;

@@ -527,6 +527,52 @@ MBB_HD void grey_nodes_n(const FastSed& s, const double (&nu)[N], const double (
 }
 
 // ---------------------------------------------------------------------------
+// MBB_MATH_FAST_GAUSS support (rules built on the host: mbb_gaussrule.h)
+// ---------------------------------------------------------------------------
+// Per band: hull of its node frequencies, for the per-walker test whether the
+// compressed rule is exact to rounding for this (walker, band) pair.
+struct BandMeta {
+  double nu_lo, nu_hi;    // [GHz]
+  double dl;              // log(nu_hi / nu_lo)
+  double has_rule;        // 1 when a compressed rule exists for the band
+};
+constexpr double kGaussMaxType = 10.0;   // bound on the integrand's exponential type over the half-band
+constexpr double kGaussMaxBetaDl = 4.0;  // thick: bound on beta * log(nu_hi/nu_lo), see gauss_band_mask
+constexpr int kGaussPoints = 32;
+
+// bit b set: band b of this walker may use its compressed rule.  Over the
+// half-band the factors nu^(3+beta) e^-x / (1 - e^-x) of the integrand are of
+// exponential type <= tau = (x-range + (3+beta) dL)/2 (power-law side: alpha dL/2);
+// the 32-point rule's error for such a function is ~ tau^64/64! (5e-26 at
+// tau = 10), and the Planck poles at x = 2 pi i k stay > 1.2 half-bands away.
+// The optically thick factor 1 - exp(-t), t ~ nu^beta, is the delicate one: as a
+// function of u = log nu it grows doubly exponentially beyond |Im u| = pi/(2 beta),
+// so the rule converges like rho^-64 with rho = y + sqrt(y^2+1), y ~ pi/(beta dL);
+// beta dL <= 4 gives rho >= 1.9, rho^-64 < 1e-17.  A band containing the merge
+// point is never compressed (kink), nor is anything for a walker that is not `safe`.
+template <bool THIN, bool ALPHA>
+MBB_HD unsigned long long gauss_band_mask(const FastSed& s, const BandMeta* bm, int nb) {
+  unsigned long long mask = 0;
+  for (int b = 0; b < nb; ++b) {
+    const double lo = bm[b].nu_lo, hi = bm[b].nu_hi, dl = bm[b].dl;
+    if (bm[b].has_rule == 0.0) continue;
+    bool ok;
+    if (ALPHA && lo > s.nu_merge) {
+      ok = 0.5 * s.alpha * dl <= kGaussMaxType;                       // all power law
+    } else if (ALPHA && hi > s.nu_merge) {
+      ok = false;                                                      // the kink is inside
+    } else {
+      ok = 0.5 * (s.hokt9 * (hi - lo) + (3.0 + s.beta) * dl) <= kGaussMaxType &&
+           (THIN || s.beta * dl <= kGaussMaxBetaDl);
+    }
+    if (ok) mask |= 1ull << b;
+  }
+  return mask;
+}
+
+
+
+// ---------------------------------------------------------------------------
 // Peak wavelength: modified_blackbody._snudev / max_wave (:556-637)
 // ---------------------------------------------------------------------------
 template <bool THIN>

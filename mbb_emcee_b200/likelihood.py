@@ -107,7 +107,10 @@ class likelihood(object):
     @property
     def math_mode(self):
         """0 = reference evaluation order (pow per node), 1 = restructured
-        exp-only node arithmetic (default; see csrc/mbb_model.cuh)."""
+        exp-only node arithmetic (default; see csrc/mbb_model.cuh), 2 = 1 plus
+        the 32-point Gauss rules of the tabulated passbands wherever a
+        per-walker bound shows they reproduce the full node sum to rounding
+        (csrc/mbb_gaussrule.h; 4-9x fewer nodes per evaluation)."""
         return self._math_mode
 
     @math_mode.setter

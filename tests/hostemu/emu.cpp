@@ -14,6 +14,7 @@
 #include "../../mbb_emcee_b200/csrc/mbb_model.cuh"
 #include "../../mbb_emcee_b200/csrc/mbb_philox.cuh"
 #include "../../mbb_emcee_b200/csrc/mbb_quadpack.cuh"
+#include "../../mbb_emcee_b200/csrc/mbb_gaussrule.h"
 
 using namespace mbb;
 
@@ -21,7 +22,7 @@ namespace {
 template <bool THIN, bool ALPHA, bool FAST>
 void run_loglike(long long n, const double* pars, const ModelP& m, const Priors& pr, const TabView& t,
                  const double* flux, const double* ivar, const double* cinv, long long wps, int unclamped,
-                 double* out, int* status) {
+                 double* out, int* status, const GaussTables* gt = nullptr, long long* ncompressed = nullptr) {
   const int nb = t.nb;
   for (long long e = 0; e < n; ++e) {
     const long long src = e / wps;
@@ -39,7 +40,35 @@ void run_loglike(long long n, const double* pars, const ModelP& m, const Priors&
       if (below_lowlim(pr, p)) { out[e] = -kInf; status[e] = ST_BELOW_LOWLIM; continue; }
       fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m);
       if (s.status == ST_OK && s.safe) {
-        const double chi = chi_square(t, fl, iv, ci, [&](int, int i, double acc) {
+        double chi;
+        if (gt) {
+          // MBB_MATH_FAST_GAUSS: the band's 32-point rule where gauss_band_mask allows it
+          const unsigned long long mask = gauss_band_mask<THIN, ALPHA>(s, gt->meta.data(), nb);
+          double diff[kMaxBandsPerThread];
+          for (int b = 0; b < nb; ++b) {
+            double acc = 0.0;
+            if ((mask >> b) & 1ull) {
+              if (ncompressed) ++*ncompressed;
+              for (int i = gt->off[b]; i < gt->off[b + 1]; ++i)
+                acc = node_acc<THIN, ALPHA, false, 0>(s, gt->freq[i], gt->lp[i], gt->weff[i], acc, tab);
+            } else {
+              for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i)
+                acc = node_acc<THIN, ALPHA, false, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
+            }
+            diff[b] = fl[b] - acc;
+          }
+          chi = 0.0;
+          if (!ci) {
+            for (int b = 0; b < nb; ++b) chi = fma(diff[b] * diff[b], iv[b], chi);
+          } else {
+            for (int r = 0; r < nb; ++r) {
+              double row = 0.0;
+              for (int c = 0; c < nb; ++c) row = fma(ci[r * nb + c], diff[c], row);
+              chi = fma(diff[r], row, chi);
+            }
+          }
+        } else
+        chi = chi_square(t, fl, iv, ci, [&](int, int i, double acc) {
           return node_acc<THIN, ALPHA, false, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
         });
         double lnl = -0.5 * chi;
@@ -185,6 +214,8 @@ static void run_grey(long long n, const double* pars, double wavenorm, const dou
   }
 }
 
+static long long g_last_compressed = 0;
+
 extern "C" {
 
 struct EmuPriors {
@@ -217,8 +248,14 @@ void emu_loglike(int thin, int alpha, int fast, long long n, const double* pars,
     if (!pr.has_uplim[i]) pr.uplim[i] = kInf;
   pr.always_terms = (pr.any_gprior || pr.has_uplim[5]) ? 1 : 0;
   TabView t{freq.data(), weight, weff.data(), lp.data(), band_off, scalar_path, nb};
-  const int unclamped = fast == 2;
-#define GO(T, A, F) run_loglike<T, A, F>(n, pars, m, pr, t, flux, ivar, cinv, wps, unclamped, out, status)
+  // fast: 1 = saturating node code, 2 = unclamped node code for `safe` walkers (the specialised
+  // kernels' arithmetic), 3 = 2 + compressed Gauss rules (MBB_MATH_FAST_GAUSS)
+  const int unclamped = fast >= 2;
+  GaussTables gtab;
+  if (fast == 3) gtab = build_gauss_tables(nb, band_off, wave, weight, scalar_path, wavenorm, thin != 0);
+  const GaussTables* gt = fast == 3 ? &gtab : nullptr;
+  long long ncomp = 0;
+#define GO(T, A, F) run_loglike<T, A, F>(n, pars, m, pr, t, flux, ivar, cinv, wps, unclamped, out, status, gt, &ncomp)
   if (thin) {
     if (alpha) { if (fast) GO(true, true, true); else GO(true, true, false); }
     else { if (fast) GO(true, false, true); else GO(true, false, false); }
@@ -227,7 +264,11 @@ void emu_loglike(int thin, int alpha, int fast, long long n, const double* pars,
     else { if (fast) GO(false, false, true); else GO(false, false, false); }
   }
 #undef GO
+  g_last_compressed = ncomp;
 }
+
+// number of (walker, band) pairs the last fast=3 call took through a compressed rule
+long long emu_last_compressed() { return g_last_compressed; }
 
 void emu_consts(int thin, int alpha, long long n, const double* pars, double wavenorm, int want_peak,
                 double* out, int* status) {
@@ -265,6 +306,14 @@ void emu_grey_nodes(int thin, long long n, const double* pars, double wavenorm, 
                     const double* weight, double* out_single, double* out_group, int* safe) {
   if (thin) run_grey<true>(n, pars, wavenorm, wave, weight, out_single, out_group, safe);
   else run_grey<false>(n, pars, wavenorm, wave, weight, out_single, out_group, safe);
+}
+
+// n-point Gauss rule of the discrete measure {x, w}; returns 1 on success
+int emu_gauss_rule(int N, const double* x, const double* w, int n, double* xs, double* ws) {
+  std::vector<double> xv(x, x + N), wv(w, w + N), xo, wo;
+  if (!discrete_gauss_rule(xv, wv, n, xo, wo)) return 0;
+  for (int k = 0; k < n; ++k) { xs[k] = xo[k]; ws[k] = wo[k]; }
+  return 1;
 }
 
 void emu_qags(int thin, int alpha, long long n, const double* pars, double wavenorm, double fmin, double fmax,

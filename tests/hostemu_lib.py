@@ -63,6 +63,13 @@ def loglike(opthin, noalpha, fast, pars, wavenorm, ep, band_off, wave, weight, s
     return out, st
 
 
+def last_compressed():
+    """(walker, band) pairs the last loglike(fast=3) call evaluated with a compressed rule."""
+    f = lib().emu_last_compressed
+    f.restype = ctypes.c_longlong
+    return int(f())
+
+
 def consts(opthin, noalpha, pars, wavenorm, want_peak=True):
     P = _c(pars).reshape(-1, 5)
     n = P.shape[0]
@@ -113,6 +120,14 @@ def grey_nodes(opthin, pars, wavenorm, wave, weight):
     lib().emu_grey_nodes(int(opthin), ctypes.c_longlong(n), _p(P), ctypes.c_double(wavenorm), _p(wv), _p(wt),
                          _p(a), _p(b), _p(safe))
     return a, b, safe.astype(bool)
+
+
+def gauss_rule(x, w, n):
+    """n-point Gauss rule of the discrete measure {x, w} (csrc/mbb_gaussrule.h), or None."""
+    x, w = _c(x), _c(w)
+    xs, ws = np.empty(n), np.empty(n)
+    ok = lib().emu_gauss_rule(int(x.size), _p(x), _p(w), int(n), _p(xs), _p(ws))
+    return (xs, ws) if ok else None
 
 
 def philox(ctr, key):

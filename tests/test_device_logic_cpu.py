@@ -240,6 +240,66 @@ def test_grouped_nodes_bit_identical(opthin):
     assert np.isfinite(a[safe]).all() and (a[safe] > 0).all()
 
 
+def test_gauss_rule_of_passbands():
+    """csrc/mbb_gaussrule.h: the 32-point Gauss rule of a passband's discrete measure
+    reproduces the moments of the full table (exactness degree 63) and Planck-like sums
+    to rounding; measures it cannot handle are refused."""
+    import mpmath as mp
+    from mbb_emcee_b200.response import response_set
+    mp.mp.dps = 40
+    wheel = response_set()
+    for name in ("PACS_100um", "SPIRE_350um", "SCUBA2_850um"):
+        wv, wt, _ = wheel[name].node_table()
+        nu = 299792.458 / np.asarray(wv)
+        wt = np.asarray(wt)
+        xs, ws = emu.gauss_rule(nu, wt, 32)
+        assert (ws > 0).all() and xs.min() >= nu.min() and xs.max() <= nu.max()
+        mid, half = (nu.max() + nu.min()) / 2, (nu.max() - nu.min()) / 2
+        mass = float(wt.sum())
+        for j in (0, 1, 2, 17, 40, 63):
+            a = sum(mp.mpf(float(w)) * ((mp.mpf(float(x)) - mid) / half)**j for x, w in zip(nu, wt))
+            b = sum(mp.mpf(float(w)) * ((mp.mpf(float(x)) - mid) / half)**j for x, w in zip(xs, ws))
+            assert abs(float(a - b)) <= 2e-16 * mass, (name, j)
+        for T in (6.0, 14.0, 40.0):
+            f = lambda v: v**4.8 / np.expm1(0.0479924 * v / T)
+            assert abs(np.sum(ws * f(xs)) / np.sum(wt * f(nu)) - 1.0) < 1e-15
+    assert emu.gauss_rule(np.linspace(1, 2, 100), -np.ones(100), 32) is None          # not positive
+    assert emu.gauss_rule(np.linspace(1, 2, 40), np.ones(40), 32) is None             # too few points
+
+
+@pytest.mark.parametrize("cfgname", ["cfg2", "cfg3"])
+@pytest.mark.parametrize("opthin,noalpha", [(False, False), (True, True), (False, True), (True, False)])
+def test_gauss_mode_matches_full_tables(cfgname, opthin, noalpha):
+    """MBB_MATH_FAST_GAUSS (emulated): over a very wide parameter cloud the compressed
+    rules change lnlike by < 1e-13 relative, most (walker, band) pairs use them, and the
+    gate sends the delicate ones (merge point in the band, cold or steep walkers) to the
+    full table."""
+    from mbb_emcee_b200 import likelihood, synthetic
+    cfg = synthetic.CONFIGS[cfgname]
+    rng = np.random.RandomState(5)
+    like = likelihood(wavenorm=500.0, noalpha=noalpha, opthin=opthin, response=True)
+    nb = len(cfg["bands"])
+    like.set_phot(cfg["bands"], np.full(nb, 1e3), np.full(nb, 1.0))
+    n = 1500
+    P = np.stack([10**rng.uniform(np.log10(3), np.log10(80), n), rng.uniform(0.1, 9, n),
+                  10**rng.uniform(1, 3.17, n), rng.uniform(0.5, 10, n), 10**rng.uniform(0, 2.5, n)], axis=1)
+    P[0] = [13.74, 21.5, 419.25, 3.49, 23.06]        # steep beta: 1 - exp(-t) switches inside a band
+    P[1] = [2.0, 1.8, 400.0, 3.0, 30.0]              # cold: x-range over PACS_100 ~ 50
+    full, st2 = _emu_like(like, P, 2)
+    comp, st3 = _emu_like(like, P, 3)
+    ncomp = emu.last_compressed()
+    assert np.array_equal(st2, st3)
+    ok = np.isfinite(full)
+    assert ok.sum() > 0.9 * n
+    assert relerr(comp[ok], full[ok]).max() < 1e-13
+    frac = ncomp / (ok.sum() * nb)
+    assert frac > (0.7 if cfgname == "cfg2" else 0.4), frac
+    if cfgname == "cfg2" and not opthin:
+        # the two delicate walkers alone: most of their bands must go through the full table
+        _emu_like(like, P[:2], 3)
+        assert emu.last_compressed() < 2 * nb - 3
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for Philox4x32-10, for the C++ generator
     the device sampler uses and for the numpy twin the replay tests use."""

@@ -289,6 +289,39 @@ def test_delta_kernel_launch_paths(oracle):
             assert bool(torch.equal(out, out2)) and bool(torch.equal(out, out3))
 
 
+@pytest.mark.parametrize("cfgname", ["cfg2", "cfg3"])
+def test_gauss_mode_golden_and_oracle(golden, oracle, cfgname):
+    """MBB_MATH_FAST_GAUSS (tabulated passbands through their 32-point Gauss rules where the
+    per-walker bound allows): the reference's golden lnlike values and the oracle on a random
+    cloud, at the same 1e-12 bar; and agreement with the full-table FAST mode to 1e-13 over a
+    much wider cloud that exercises the fallback (cold, steep, merge point inside a band)."""
+    from mbb_emcee_b200 import _native, synthetic
+    cfg, like = _make_like(golden, cfgname, _native.MATH_FAST_GAUSS)
+    g = golden.like
+    P, ref = g[cfgname + "_P"], g[cfgname + "_lnlike"]
+    ll, st = like.evaluate(P)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+    assert relerr(ll[fin], ref[fin]).max() < TOL
+    rng = np.random.RandomState(77)
+    Pr = synthetic.walker_cloud(cfg["truth"], 600, rng, like.lowlims)
+    want = oracle.loglike_batch(_oracle_spec(oracle, like), Pr)
+    got, st = like.evaluate(Pr)
+    fin = np.isfinite(want)
+    assert relerr(got[fin], want[fin]).max() < TOL
+    n = 20000
+    Pw = np.stack([10**rng.uniform(np.log10(3), np.log10(80), n), rng.uniform(0.1, 9, n),
+                   10**rng.uniform(1, 3.17, n), rng.uniform(0.5, 10, n), 10**rng.uniform(0, 2.5, n)], axis=1)
+    comp, st3 = like.evaluate(Pw)
+    like.math_mode = _native.MATH_FAST
+    full, st1 = like.evaluate(Pw)
+    assert np.array_equal(st1, st3)
+    ok = np.isfinite(full) & (st1 == 0)
+    assert ok.sum() > 0.5 * n
+    assert relerr(comp[ok], full[ok]).max() < 1e-13
+    assert not np.array_equal(comp[ok], full[ok])          # the compressed rules were actually used
+
+
 def test_error_statuses():
     """Failures that make the reference raise surface as the same exception types."""
     from mbb_emcee_b200 import likelihood
