@@ -126,3 +126,40 @@ def test_sampler_matches_emcee2_schedule(oracle):
     s2.random_state = np.random.RandomState(7).get_state()
     s2.run_mcmc(p0, 30)
     assert np.allclose(s2.chain, chain, rtol=0, atol=0)
+
+
+def test_cli_flags_and_wiring():
+    """run_mbb_emcee front end: the reference's flags and defaults
+    (run_mbb_emcee.py:66-185) and the fix/limit/prior wiring (:222-287), against a
+    recording stand-in for the fitter (no device needed)."""
+    from mbb_emcee_b200 import run_mbb_emcee as cli
+    args = cli.build_parser().parse_args(["phot.txt", "out.npz"])
+    assert (args.burn, args.nsteps, args.nwalkers, args.wavenorm) == (50, 250, 250, 500.0)
+    assert (args.initT, args.initBeta, args.initLambda0, args.initAlpha, args.initFnorm) == \
+        (10.0, 2.0, 2500.0, 4.0, 40.0)
+    assert tuple(args.kappa) == (2.64, 125.0) and tuple(args.lir_range) == (8.0, 1000.0)
+    assert args.threads == 1 and args.covextn == 0 and args.cosmotype == "WMAP9"
+
+    class Rec(object):
+        def __init__(self):
+            self.calls = []
+
+        def __getattr__(self, name):
+            return lambda *a: self.calls.append((name,) + a)
+
+    args = cli.build_parser().parse_args(
+        ["phot.txt", "out.npz", "--opthin", "--noalpha", "--fixBeta", "--lowT", "2", "--upT", "60",
+         "--upLambda0", "900", "--lowAlpha", "1", "--priorBeta", "1.8", "0.3", "--priorLambda0", "300", "50",
+         "--upLambdaPeak", "400", "--priorLambdaPeak", "250", "40", "-n", "64", "-N", "10", "-b", "5"])
+    rec = Rec()
+    cli.configure_fit(rec, args)
+    assert rec.calls == [
+        ("fix_param", "beta"), ("fix_param", "alpha"),                     # --noalpha fixes alpha
+        ("set_lowlim", "T", 2.0),                                         # alpha / lambda0 flags are skipped
+        ("set_uplim", "T", 60.0), ("set_uplim", "lambda_peak", 400.0),
+        ("set_gaussian_prior", "beta", 1.8, 0.3), ("set_gaussian_prior", "lambda_peak", 250.0, 40.0)]
+    import pytest
+    with pytest.raises(ValueError):
+        cli.main(["phot.txt", "out.npz", "-n", "0"])
+    with pytest.raises(ValueError):
+        cli.main(["phot.txt", "out.npz", "--maxidx", "10"])

@@ -179,7 +179,7 @@ def test_all_variants_tabulated_vs_oracle(oracle):
         like.set_phot(bands, [40.0, 90.0, 50.0, 3.0, 28.0], [4.0, 9.0, 5.0, 1.0, 3.0])
         P = synthetic.walker_cloud((14.0, 1.8, 300.0, 3.0, 30.0), 300, rng, like.lowlims)
         want = oracle.loglike_batch(_oracle_spec(oracle, like), P)
-        for mode in (0, 1):
+        for mode in (0, 1, 2):                 # FAITHFUL, FAST, FAST_GAUSS (wavenorm 350: other L' tables)
             like.math_mode = mode
             assert relerr(like(P), want).max() < TOL, (name, mode)
 
@@ -194,6 +194,8 @@ def test_whole_wheel_global_table_path(oracle):
     like.set_phot(names, rng.uniform(5, 50, len(names)), rng.uniform(1, 5, len(names)))
     P = synthetic.walker_cloud((20.0, 1.6, 200.0, 2.5, 30.0), 96, rng, like.lowlims)
     want = oracle.loglike_batch(_oracle_spec(oracle, like), P)
+    assert relerr(like(P), want).max() < TOL
+    like.math_mode = 2                          # 18 compressed rules in shared memory, full tables in global
     assert relerr(like(P), want).max() < TOL
 
 
@@ -466,6 +468,22 @@ def test_fitter_run_end_to_end(golden):
 
 
 # ------------------------------------------------------------- chain post-processing
+def test_cli_end_to_end(tmp_path):
+    """The command line front end on a small photometry file: fit, ancillaries, save/load."""
+    from mbb_emcee_b200 import mbb_results, run_mbb_emcee as cli
+    phot = tmp_path / "phot.txt"
+    phot.write_text("# wave flux err\n100 20 3\n160 60 6\n250 80 6\n350 55 5\n500 30 4\n850 6 1.5\n")
+    out = tmp_path / "res.npz"
+    res = cli.main([str(phot), str(out), "-n", "60", "-N", "30", "-b", "10", "--initT", "12", "--initLambda0", "300",
+                    "--initFnorm", "30", "--seed", "3", "-z", "2.0", "--lumdist", "16000", "--get_peaklambda",
+                    "--get_lir", "--get_dustmass", "--priorBeta", "1.8", "0.3"])
+    assert res.chain.shape == (60, 30, 5) and np.isfinite(res.lnprobability).all()
+    assert res.has_peaklambda and res.has_lir and res.has_dustmass
+    back = mbb_results.load(str(out), device=0)
+    assert np.array_equal(back.chain, res.chain)
+    assert np.array_equal(back.lir_chain, res.lir_chain)
+
+
 @pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
 def test_chain_post_golden(golden, name, opthin, noalpha):
     from mbb_emcee_b200 import mbb_results, synthetic
