@@ -181,7 +181,9 @@ inline GaussTables build_gauss_tables(int nb, const int* band_off, const double*
     g.meta[b].has_rule = 0.0;
     if (i1 - i0 > 2 * kGaussPoints && !(scalar_path && scalar_path[b]) &&
         discrete_gauss_rule(x, w, kGaussPoints, xs, ws)) {
-      g.meta[b].has_rule = 1.0;
+      bool descending = true;
+      for (int i = i0 + 1; i < i1; ++i) descending = descending && x[i - i0] < x[i - i0 - 1];
+      g.meta[b].has_rule = descending ? 2.0 : 1.0;
       for (int k = 0; k < kGaussPoints; ++k) {
         const FastNode n = fast_node(kUmToGHz / xs[k], ws[k], wavenorm, thin);
         g.freq.push_back(xs[k]);

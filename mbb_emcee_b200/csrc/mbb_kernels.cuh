@@ -500,7 +500,11 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
     c[4] = s.t0c; c[5] = s.nu_merge; c[6] = s.uq_hi; c[7] = s.uq_lo;
     c[8] = s.amp_grey; c[9] = s.amp_pow;
     if (nb_gauss > 0 && st == ST_OK && safe)
-      c[10] = __longlong_as_double((long long)gauss_band_mask<THIN, ALPHA>(s, band_meta, nb_gauss));
+    {
+      const GaussMasks gm = gauss_band_masks<THIN, ALPHA>(s, band_meta, nb_gauss);
+      c[10] = __longlong_as_double((long long)gm.plain);
+      c[11] = __longlong_as_double((long long)gm.kink);
+    }
   } else {
     Sed s;
     sed_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m.wavenorm);
@@ -549,6 +553,51 @@ __device__ __forceinline__ double band_partial_fast(const FastSed& fs, const dou
   for (int i = i0 + lane; i < i1; i += 32) {
     const double2 fw = na[i];
     acc = node_acc<THIN, ALPHA, CLAMP, kTabRepShift>(fs, fw.x, nl[i], fw.y, acc, tab);
+  }
+  return acc;
+}
+
+// MBB_MATH_FAST_GAUSS, band with the walker's merge point inside (GaussMasks::kink): one
+// branch over the whole band by the band's 32-point rule, plus the difference of the two
+// branches over the table nodes on the other side of the merge point -- whichever side
+// has fewer nodes.  The table's frequencies descend, so the power-law side is [i0, k).
+template <bool THIN>
+__device__ __forceinline__ double band_partial_kink(const FastSed& fs, const double2* __restrict__ na,
+                                                    const double* __restrict__ nl, int i0, int i1,
+                                                    const double2* __restrict__ ca,
+                                                    const double* __restrict__ cl, int c0, int c1,
+                                                    int lane, const double* tab) {
+  constexpr int TS = kTabRepShift;
+  int lo = i0, hi = i1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (gt_pos(na[mid].x, fs.nu_merge)) lo = mid + 1;
+    else hi = mid;
+  }
+  const int k = lo;
+  double acc = 0.0;
+  if (k - i0 <= i1 - k) {
+    for (int i = c0 + lane; i < c1; i += 32) {
+      const double2 fw = ca[i];
+      acc = node_grey<THIN, false, TS>(fs, fw.x, cl[i], fw.y, acc, tab);
+    }
+    for (int i = i0 + lane; i < k; i += 32) {
+      const double2 fw = na[i];
+      const double lp = nl[i];
+      acc = node_pow<false, TS>(fs, lp, fw.y, acc, tab);
+      acc = node_grey<THIN, false, TS>(fs, fw.x, lp, -fw.y, acc, tab);
+    }
+  } else {
+    for (int i = c0 + lane; i < c1; i += 32) {
+      const double2 fw = ca[i];
+      acc = node_pow<false, TS>(fs, cl[i], fw.y, acc, tab);
+    }
+    for (int i = k + lane; i < i1; i += 32) {
+      const double2 fw = na[i];
+      const double lp = nl[i];
+      acc = node_grey<THIN, false, TS>(fs, fw.x, lp, fw.y, acc, tab);
+      acc = node_pow<false, TS>(fs, lp, -fw.y, acc, tab);
+    }
   }
   return acc;
 }
@@ -617,8 +666,12 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
     const double2* c2 = reinterpret_cast<const double2*>(scratch + e * kScratchStride);
     const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
     const double2 c89 = __ldg(c2 + 4), cpg = __ldg(c2 + 6);
-    unsigned long long gmask = 0;
-    if (FAST && t.nc) gmask = (unsigned long long)__double_as_longlong(__ldg(c2 + 5).x);
+    unsigned long long gmask = 0, kmask = 0;
+    if (FAST && t.nc) {
+      const double2 cm = __ldg(c2 + 5);
+      gmask = (unsigned long long)__double_as_longlong(cm.x);
+      kmask = (unsigned long long)__double_as_longlong(cm.y);
+    }
     Sed s;
     FastSed fs;
     if (FAST) {
@@ -639,6 +692,8 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
       if (FAST) {
         if (t.nc && ((gmask >> b) & 1ull))         // this walker may use the band's 32-point rule
           acc = band_partial_fast<THIN, ALPHA, false>(fs, s_ca, s_cb, s_coff[b], s_coff[b + 1], lane, ltab);
+        else if (ALPHA && t.nc && ((kmask >> b) & 1ull))   // ... with the merge point inside the band
+          acc = band_partial_kink<THIN>(fs, na, nbp, i0, i1, s_ca, s_cb, s_coff[b], s_coff[b + 1], lane, ltab);
         else if (safe) acc = band_partial_fast<THIN, ALPHA, false>(fs, na, nbp, i0, i1, lane, ltab);
         else acc = band_partial_fast<THIN, ALPHA, true>(fs, na, nbp, i0, i1, lane, ltab);
       } else {

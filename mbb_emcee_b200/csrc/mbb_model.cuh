@@ -430,10 +430,16 @@ MBB_HD bool gt_pos(double a, double b) {
 // The reciprocal of expm1(x_i) is folded into the weight so that it runs
 // beside the other exp chains; the last dependent step is a single FMA.
 // TS: index-stride shift of `tab` (see scaled_T).
-template <bool THIN, bool ALPHA, bool CLAMP, int TS>
-MBB_HD double node_acc(const FastSed& s, double nu, double lp, double weff, double acc, const double* tab) {
-  if (ALPHA && gt_pos(nu, s.nu_merge))
-    return fma(exp_red<TS, CLAMP>(red_prod1(s.apow, lp), tab), s.amp_pow * weff, acc);
+// node_pow / node_grey evaluate ONE branch regardless of the merge point (the
+// Gauss-rule mode needs each branch's analytic continuation, see
+// gauss_band_masks); node_acc picks the branch the reference picks.
+template <bool CLAMP, int TS>
+MBB_HD double node_pow(const FastSed& s, double lp, double weff, double acc, const double* tab) {
+  return fma(exp_red<TS, CLAMP>(red_prod1(s.apow, lp), tab), s.amp_pow * weff, acc);
+}
+
+template <bool THIN, bool CLAMP, int TS>
+MBB_HD double node_grey(const FastSed& s, double nu, double lp, double weff, double acc, const double* tab) {
   const double em = expm1_red<TS, CLAMP>(red_prod(nu, s.xk_hi, s.xk_lo), tab);
   const double wr = (s.amp_grey * weff) * rcp_cubic(em);
   if (THIN) return fma(exp_red<TS, CLAMP>(red_prod1(s.nb, lp), tab), wr, acc);
@@ -443,6 +449,12 @@ MBB_HD double node_acc(const FastSed& s, double nu, double lp, double weff, doub
   else tc = exp_red_times<TS, false>(red_prod1(s.nb, lp), tab, s.t0c);
   const double g = one_minus_exp_red<TS, CLAMP>(red_neg_scaled(clamp_pos<kHi700C>(tc)), tab);
   return fma(g, wr, acc);
+}
+
+template <bool THIN, bool ALPHA, bool CLAMP, int TS>
+MBB_HD double node_acc(const FastSed& s, double nu, double lp, double weff, double acc, const double* tab) {
+  if (ALPHA && gt_pos(nu, s.nu_merge)) return node_pow<CLAMP, TS>(s, lp, weff, acc, tab);
+  return node_grey<THIN, CLAMP, TS>(s, nu, lp, weff, acc, tab);
 }
 
 // ---------------------------------------------------------------------------
@@ -534,43 +546,53 @@ MBB_HD void grey_nodes_n(const FastSed& s, const double (&nu)[N], const double (
 struct BandMeta {
   double nu_lo, nu_hi;    // [GHz]
   double dl;              // log(nu_hi / nu_lo)
-  double has_rule;        // 1 when a compressed rule exists for the band
+  double has_rule;        // 0: no compressed rule; 1: rule; 2: rule, and the table's frequencies descend
+                          // strictly (what the kink split's binary search needs)
 };
 constexpr double kGaussMaxType = 10.0;   // bound on the integrand's exponential type over the half-band
-constexpr double kGaussMaxBetaDl = 4.0;  // thick: bound on beta * log(nu_hi/nu_lo), see gauss_band_mask
+constexpr double kGaussMaxBetaDl = 4.0;  // thick: bound on beta * log(nu_hi/nu_lo), see gauss_band_masks
 constexpr int kGaussPoints = 32;
 
-// bit b set: band b of this walker may use its compressed rule.  Over the
-// half-band the factors nu^(3+beta) e^-x / (1 - e^-x) of the integrand are of
-// exponential type <= tau = (x-range + (3+beta) dL)/2 (power-law side: alpha dL/2);
-// the 32-point rule's error for such a function is ~ tau^64/64! (5e-26 at
-// tau = 10), and the Planck poles at x = 2 pi i k stay > 1.2 half-bands away.
-// The optically thick factor 1 - exp(-t), t ~ nu^beta, is the delicate one: as a
-// function of u = log nu it grows doubly exponentially beyond |Im u| = pi/(2 beta),
-// so the rule converges like rho^-64 with rho = y + sqrt(y^2+1), y ~ pi/(beta dL);
-// beta dL <= 4 gives rho >= 1.9, rho^-64 < 1e-17.  A band containing the merge
-// point is never compressed (kink), nor is anything for a walker that is not `safe`.
+// Which bands of this walker may use their compressed rule.
+//   plain bit b: the band lies entirely on one side of the merge point.  Over the
+//     half-band the factors nu^(3+beta) e^-x / (1 - e^-x) of the integrand are of
+//     exponential type <= tau = (x-range + (3+beta) dL)/2 (power-law side: alpha dL/2);
+//     the 32-point rule's error for such a function is ~ tau^64/64! (5e-26 at
+//     tau = 10), and the Planck poles at x = 2 pi i k stay > 1.2 half-bands away.
+//     The optically thick factor 1 - exp(-t), t ~ nu^beta, is the delicate one: as a
+//     function of u = log nu it grows doubly exponentially beyond |Im u| = pi/(2 beta),
+//     so the rule converges like rho^-64 with rho = y + sqrt(y^2+1), y ~ pi/(beta dL);
+//     beta dL <= 4 gives rho >= 1.9, rho^-64 < 1e-17.
+//   kink bit b: the merge point lies inside the band (f_nu has a kink there, the
+//     rule cannot be applied to f_nu itself), but BOTH branches pass their bound over
+//     the whole band.  Then  sum_i w_i f(nu_i) = sum_i w_i A(nu_i) + sum_{i in S} w_i
+//     (B - A)(nu_i)  with A one branch continued analytically over the band (rule) and
+//     S the table nodes on the other branch's side (full table, but only those).
+// Nothing is compressed for a walker that is not `safe`.
+struct GaussMasks {
+  unsigned long long plain, kink;
+};
+
 template <bool THIN, bool ALPHA>
-MBB_HD unsigned long long gauss_band_mask(const FastSed& s, const BandMeta* bm, int nb) {
-  unsigned long long mask = 0;
+MBB_HD GaussMasks gauss_band_masks(const FastSed& s, const BandMeta* bm, int nb) {
+  GaussMasks m;
+  m.plain = m.kink = 0;
   for (int b = 0; b < nb; ++b) {
     const double lo = bm[b].nu_lo, hi = bm[b].nu_hi, dl = bm[b].dl;
     if (bm[b].has_rule == 0.0) continue;
-    bool ok;
+    const bool grey_ok = 0.5 * (s.hokt9 * (hi - lo) + (3.0 + s.beta) * dl) <= kGaussMaxType &&
+                         (THIN || s.beta * dl <= kGaussMaxBetaDl);
+    const bool pow_ok = ALPHA && 0.5 * s.alpha * dl <= kGaussMaxType;
     if (ALPHA && lo > s.nu_merge) {
-      ok = 0.5 * s.alpha * dl <= kGaussMaxType;                       // all power law
+      if (pow_ok) m.plain |= 1ull << b;                                  // all power law
     } else if (ALPHA && hi > s.nu_merge) {
-      ok = false;                                                      // the kink is inside
-    } else {
-      ok = 0.5 * (s.hokt9 * (hi - lo) + (3.0 + s.beta) * dl) <= kGaussMaxType &&
-           (THIN || s.beta * dl <= kGaussMaxBetaDl);
+      if (pow_ok && grey_ok && bm[b].has_rule == 2.0) m.kink |= 1ull << b;   // the kink is inside
+    } else if (grey_ok) {
+      m.plain |= 1ull << b;
     }
-    if (ok) mask |= 1ull << b;
   }
-  return mask;
+  return m;
 }
-
-
 
 // ---------------------------------------------------------------------------
 // Peak wavelength: modified_blackbody._snudev / max_wave (:556-637)

@@ -42,15 +42,36 @@ void run_loglike(long long n, const double* pars, const ModelP& m, const Priors&
       if (s.status == ST_OK && s.safe) {
         double chi;
         if (gt) {
-          // MBB_MATH_FAST_GAUSS: the band's 32-point rule where gauss_band_mask allows it
-          const unsigned long long mask = gauss_band_mask<THIN, ALPHA>(s, gt->meta.data(), nb);
+          // MBB_MATH_FAST_GAUSS: the band's 32-point rule where gauss_band_masks allows it
+          // (serial mirror of band_partial_fast / band_partial_kink of the nodes kernel)
+          const GaussMasks gm = gauss_band_masks<THIN, ALPHA>(s, gt->meta.data(), nb);
           double diff[kMaxBandsPerThread];
           for (int b = 0; b < nb; ++b) {
             double acc = 0.0;
-            if ((mask >> b) & 1ull) {
+            const int i0 = t.band_off[b], i1 = t.band_off[b + 1];
+            if ((gm.plain >> b) & 1ull) {
               if (ncompressed) ++*ncompressed;
               for (int i = gt->off[b]; i < gt->off[b + 1]; ++i)
                 acc = node_acc<THIN, ALPHA, false, 0>(s, gt->freq[i], gt->lp[i], gt->weff[i], acc, tab);
+            } else if (ALPHA && ((gm.kink >> b) & 1ull)) {
+              if (ncompressed) ++*ncompressed;
+              int k = i0;
+              while (k < i1 && t.freq[k] > s.nu_merge) ++k;
+              const bool grey_rule = k - i0 <= i1 - k;
+              for (int i = gt->off[b]; i < gt->off[b + 1]; ++i)
+                acc = grey_rule ? node_grey<THIN, false, 0>(s, gt->freq[i], gt->lp[i], gt->weff[i], acc, tab)
+                                : node_pow<false, 0>(s, gt->lp[i], gt->weff[i], acc, tab);
+              if (grey_rule) {
+                for (int i = i0; i < k; ++i) {
+                  acc = node_pow<false, 0>(s, t.lp[i], t.weff[i], acc, tab);
+                  acc = node_grey<THIN, false, 0>(s, t.freq[i], t.lp[i], -t.weff[i], acc, tab);
+                }
+              } else {
+                for (int i = k; i < i1; ++i) {
+                  acc = node_grey<THIN, false, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
+                  acc = node_pow<false, 0>(s, t.lp[i], -t.weff[i], acc, tab);
+                }
+              }
             } else {
               for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i)
                 acc = node_acc<THIN, ALPHA, false, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
