@@ -411,8 +411,10 @@ struct LaunchSplit {
     size_t smem = nodes_kernel_smem(c->nn, true, FAST, t.nc);
     const bool in_smem = smem <= c->smem_optin;
     if (!in_smem) smem = nodes_kernel_smem(c->nn, false, FAST, t.nc);
-    auto nodes = in_smem ? loglike_nodes_kernel<THIN, ALPHA, FAST, true>
-                         : loglike_nodes_kernel<THIN, ALPHA, FAST, false>;
+    auto nodes = gauss ? (in_smem ? loglike_nodes_kernel<THIN, ALPHA, FAST, true, FAST>
+                                  : loglike_nodes_kernel<THIN, ALPHA, FAST, false, FAST>)
+                       : (in_smem ? loglike_nodes_kernel<THIN, ALPHA, FAST, true, false>
+                                  : loglike_nodes_kernel<THIN, ALPHA, FAST, false, false>);
     *err = cudaFuncSetAttribute(nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (*err != cudaSuccess) return;
     int per_sm = 1;

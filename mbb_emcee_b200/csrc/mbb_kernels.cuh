@@ -602,14 +602,16 @@ __device__ __forceinline__ double band_partial_kink(const FastSed& fs, const dou
   return acc;
 }
 
-template <bool THIN, bool ALPHA, bool FAST, bool IN_SMEM>
+// GAUSS: compiled-in support for MBB_MATH_FAST_GAUSS (a separate instantiation, so that the
+// plain FAST kernel keeps its register allocation)
+template <bool THIN, bool ALPHA, bool FAST, bool IN_SMEM, bool GAUSS>
 __global__ void __launch_bounds__(MBB_NODES_THREADS, MBB_NODES_MINB)
 loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, const NodeTab t,
                      const double* __restrict__ scratch, const int* __restrict__ sst) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t tab_bytes = IN_SMEM ? (size_t)t.nn * 16 + (FAST ? nodes_b_bytes(t.nn) : 0) : 0;
   // compressed rules (always in shared memory: nb * 32 nodes): [ca | cb | comp_off]
-  const size_t comp_bytes = t.nc ? (size_t)t.nc * 16 + nodes_b_bytes(t.nc) + (size_t)(kMaxBands + 1) * 4 + 12 : 0;
+  const size_t comp_bytes = (GAUSS && t.nc) ? (size_t)t.nc * 16 + nodes_b_bytes(t.nc) + (size_t)(kMaxBands + 1) * 4 + 12 : 0;
   double2* s_a = reinterpret_cast<double2*>(smem_raw);
   double* s_b = reinterpret_cast<double*>(s_a + t.nn);
   double2* s_ca = reinterpret_cast<double2*>(smem_raw + tab_bytes);
@@ -635,7 +637,7 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
     }
   }
   if (FAST) stage_exp_table(s_exp);
-  if (FAST && t.nc) {
+  if (GAUSS && t.nc) {
     for (int i = tid; i < t.nc; i += blockDim.x) {
       s_ca[i] = t.ca[i];
       s_cb[i] = t.cb[i];
@@ -667,7 +669,7 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
     const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
     const double2 c89 = __ldg(c2 + 4), cpg = __ldg(c2 + 6);
     unsigned long long gmask = 0, kmask = 0;
-    if (FAST && t.nc) {
+    if (GAUSS && t.nc) {
       const double2 cm = __ldg(c2 + 5);
       gmask = (unsigned long long)__double_as_longlong(cm.x);
       kmask = (unsigned long long)__double_as_longlong(cm.y);
@@ -690,9 +692,9 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
       const int i0 = s_off[b], i1 = s_off[b + 1];
       double acc = 0.0;
       if (FAST) {
-        if (t.nc && ((gmask >> b) & 1ull))         // this walker may use the band's 32-point rule
+        if (GAUSS && t.nc && ((gmask >> b) & 1ull))   // this walker may use the band's 32-point rule
           acc = band_partial_fast<THIN, ALPHA, false>(fs, s_ca, s_cb, s_coff[b], s_coff[b + 1], lane, ltab);
-        else if (ALPHA && t.nc && ((kmask >> b) & 1ull))   // ... with the merge point inside the band
+        else if (GAUSS && ALPHA && t.nc && ((kmask >> b) & 1ull))   // ... with the merge point inside the band
           acc = band_partial_kink<THIN>(fs, na, nbp, i0, i1, s_ca, s_cb, s_coff[b], s_coff[b + 1], lane, ltab);
         else if (safe) acc = band_partial_fast<THIN, ALPHA, false>(fs, na, nbp, i0, i1, lane, ltab);
         else acc = band_partial_fast<THIN, ALPHA, true>(fs, na, nbp, i0, i1, lane, ltab);
