@@ -754,7 +754,15 @@ int mbb_loglike(mbb_ctx* c, int64_t n, const double* pars, int layout, const int
   }
   const bool pin_in = is_pinned(pars) && is_pinned(src_index);
   const bool pin_out = is_pinned(out_lnlike) && is_pinned(out_status);
-  const int64_t CH = n < host_chunk() ? n : host_chunk();
+  // chunk = at most host_chunk() evaluations, but at least ~8 chunks per call once the batch is
+  // worth pipelining (>= 2^17), so that copies and kernels of neighbouring chunks overlap also for
+  // node-heavy configurations with few evaluations; a multiple of the 256-evaluation tile
+  int64_t CH = host_chunk();
+  if (n < CH * 8 && n >= ((int64_t)1 << 17)) {
+    CH = ((n + 7) / 8 + 255) & ~(int64_t)255;
+    if (CH < ((int64_t)1 << 14)) CH = (int64_t)1 << 14;
+  }
+  if (CH > n) CH = n;
   const int64_t nchunks = (n + CH - 1) / CH;
   for (auto& sl : c->slots) sl.pend_e0 = -1;
   auto drain = [&](mbb_ctx::Slot& sl) -> int {
