@@ -7,7 +7,8 @@
 //                          delta / few-node bands.
 //   loglike_delta_kernel   every band a single node (BASELINE cfg1/cfg5), FAST,
 //                          band count a template parameter (fully unrolled);
-//                          the 1 KB exp table is staged into shared memory.
+//                          persistent CTAs, parameter tiles and photometry rows
+//                          by TMA, the exp table replicated in shared memory.
 //   loglike_setup_kernel + loglike_nodes_kernel   tabulated passbands:
 //                          (1) thread-per-evaluation setup (limits, per-walker
 //                          constants incl. the merge-point root solve, prior

@@ -5,16 +5,19 @@
 // host-side emulation library the CPU test-suite uses to check the *logic*
 // (tests/hostemu, never shipped, never a fallback).
 //
-// Two arithmetic modes, selected per context (mbb_set_math_mode):
-//   FAITHFUL  - the reference's formulas in the reference's evaluation order
-//               (fnu.pyx:9-108, modified_blackbody.py:228-337, 441-491):
-//               pow / expm1 / exp per node.
-//   FAST      - algebraically identical, restructured so that no pow() is
-//               evaluated per node: every power becomes exp(b * L) with
-//               L = log(wave_i / wavenorm) precomputed on the host in
-//               double-double, and the normalisation is applied as ratios
-//               (f/fnorm near 1).  ~2.5x fewer FP64 instructions per node;
-//               agrees with FAITHFUL to a few 1e-16 (tests/test_parity_gpu.py).
+// Arithmetic modes, selected per context (mbb_set_math_mode):
+//   FAITHFUL   - the reference's formulas in the reference's evaluation order
+//                (fnu.pyx:9-108, modified_blackbody.py:228-337, 441-491):
+//                pow / expm1 / exp per node.
+//   FAST       - algebraically identical, restructured so that no pow() is
+//                evaluated per node: every power becomes exp(b * L) with
+//                L' = log(wave_i / wavenorm) * 64/ln2 precomputed on the host
+//                from the 80-bit logarithm, the normalisation is applied as
+//                ratios (f/fnorm near 1), and exp/expm1/reciprocal come from
+//                mbb_fastmath.cuh.  ~3.5x fewer FP64 instructions per node;
+//                agrees with FAITHFUL to ~1e-14 (tests/test_parity_gpu.py).
+//   FAST_GAUSS - FAST over the 32-point Gauss rules of the tabulated bands
+//                where gauss_band_masks() allows it (mbb_gaussrule.h).
 #pragma once
 #include "mbb_model_defs.cuh"
 #include "mbb_fastmath.cuh"
