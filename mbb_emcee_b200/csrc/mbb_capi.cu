@@ -435,7 +435,7 @@ struct LaunchSplit {
       *err = c->scratch_for(st, (size_t)cap, &scratch, &sst);
       if (*err != cudaSuccess) return;
       loglike_setup_kernel<THIN, ALPHA, FAST><<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(
-          a, m, c->pri, scratch, sst, c->d_band_meta.p, gauss ? c->nb : 0);
+          a, m, c->pri, scratch, sst, c->d_band_meta.p, gauss ? c->nb : 0, c->d_node_fast_a.p, c->d_off.p);
       const long long want = (a.n + kNodesWarps - 1) / kNodesWarps;
       const long long resident = (long long)c->sm_count * per_sm;
       const unsigned grid = (unsigned)(want < resident ? want : resident);

@@ -470,25 +470,27 @@ __device__ __forceinline__ double warp_sum(double v) {
 // The warp path: a thread-per-evaluation SETUP kernel writes 14 doubles +
 // status per evaluation to a scratch array, then a lean NODES kernel (64
 // registers -> 2 CTAs x 512 threads per SM) does the node loops.  The scratch
-// costs 116 B/evaluation of traffic against >= 1e5 flops of node work.
+// costs 132 B/evaluation of traffic against >= 1e5 flops of node work.
 // Status word: bits 0-7 status code, bit 8 the FAST `safe` flag.
 // ---------------------------------------------------------------------------
-constexpr int kScratchStride = 14;   // c[0..11], pen, gp
+constexpr int kScratchStride = 16;   // c[0..13], pen, gp
+constexpr int kMaxKinkBands = 4;     // split indices of the kink bands: 16 bits each in c[12]
 constexpr int kSafeBit = 0x100;
 
 template <bool THIN, bool ALPHA, bool FAST>
 __global__ void __launch_bounds__(128)
 loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* __restrict__ scratch,
-                     int* __restrict__ sst, const BandMeta* __restrict__ band_meta, const int nb_gauss) {
+                     int* __restrict__ sst, const BandMeta* __restrict__ band_meta, const int nb_gauss,
+                     const double2* __restrict__ node_a, const int* __restrict__ band_off) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n) return;
   double p[5];
   load_pars(a, e, p);
   int st = ST_OK, safe = 0;
   double pen = 0.0, gp = 0.0;
-  double c[12];
+  double c[14];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) c[i] = 0.0;
+  for (int i = 0; i < 14; ++i) c[i] = 0.0;
   if (below_lowlim(pr, p)) {
     st = ST_BELOW_LOWLIM;
   } else if (FAST) {
@@ -502,9 +504,30 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
     c[8] = s.amp_grey; c[9] = s.amp_pow;
     if (nb_gauss > 0 && st == ST_OK && safe)
     {
-      const GaussMasks gm = gauss_band_masks<THIN, ALPHA>(s, band_meta, nb_gauss);
+      GaussMasks gm = gauss_band_masks<THIN, ALPHA>(s, band_meta, nb_gauss);
+      // kink bands: where the band's table (frequencies descending) crosses the merge point --
+      // found once here by one thread instead of by every lane of the evaluation's warp
+      unsigned long long splits = 0;
+      int nk = 0;
+      for (int b = 0; ALPHA && b < nb_gauss; ++b) {
+        if (!((gm.kink >> b) & 1ull)) continue;
+        const int i0 = __ldg(band_off + b), i1 = __ldg(band_off + b + 1);
+        if (nk == kMaxKinkBands || i1 - i0 > 0xffff) {      // no room: this band takes the full table
+          gm.kink &= ~(1ull << b);
+          continue;
+        }
+        int lo = i0, hi = i1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (gt_pos(__ldg(&node_a[mid].x), s.nu_merge)) lo = mid + 1;
+          else hi = mid;
+        }
+        splits |= (unsigned long long)(lo - i0) << (16 * nk);
+        ++nk;
+      }
       c[10] = __longlong_as_double((long long)gm.plain);
       c[11] = __longlong_as_double((long long)gm.kink);
+      c[12] = __longlong_as_double((long long)splits);
     }
   } else {
     Sed s;
@@ -516,8 +539,8 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
   }
   double2* o = reinterpret_cast<double2*>(scratch + e * kScratchStride);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) o[i] = make_double2(c[2 * i], c[2 * i + 1]);
-  o[6] = make_double2(pen, gp);
+  for (int i = 0; i < 7; ++i) o[i] = make_double2(c[2 * i], c[2 * i + 1]);
+  o[7] = make_double2(pen, gp);
   sst[e] = st | (safe ? kSafeBit : 0);
 }
 
@@ -531,12 +554,13 @@ constexpr int kNodesThreads = MBB_NODES_THREADS;
 constexpr int kNodesWarps = kNodesThreads / 32;
 
 // dynamic shared memory of the nodes kernel:
-//   [a pairs | b (FAST)] (tables_in_smem, b padded to 16 B) | exp table 8 KB | per-warp diff | mbarrier | band_off | scalar
+//   [a pairs | b (FAST)] (tables_in_smem, b padded to 16 B) | [compressed a | b] (GAUSS) | exp table 8 KB |
+//   per-warp diff | mbarrier | band_off | comp_off | scalar
 __host__ __device__ inline size_t nodes_b_bytes(int nn) { return ((size_t)nn * 8 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t nodes_kernel_smem(int nn, bool tables_in_smem, bool fast, int nc = 0) {
   return (tables_in_smem ? (size_t)nn * 16 + (fast ? nodes_b_bytes(nn) : 0) : 0) +
-         (nc ? (size_t)nc * 16 + nodes_b_bytes(nc) + (size_t)(kMaxBands + 1) * 4 + 12 : 0) + kTabRepDoubles * 8 +
-         (size_t)(MBB_NODES_THREADS / 32) * kMaxBands * 8 + 16 + (size_t)(kMaxBands + 1) * 4 + kMaxBands;
+         (nc ? (size_t)nc * 16 + nodes_b_bytes(nc) : 0) + kTabRepDoubles * 8 +
+         (size_t)(MBB_NODES_THREADS / 32) * kMaxBands * 8 + 16 + (size_t)(kMaxBands + 1) * 8 + kMaxBands;
 }
 
 // Weighted node sum of one band over the lanes of a warp (before the shuffle
@@ -561,21 +585,15 @@ __device__ __forceinline__ double band_partial_fast(const FastSed& fs, const dou
 // MBB_MATH_FAST_GAUSS, band with the walker's merge point inside (GaussMasks::kink): one
 // branch over the whole band by the band's 32-point rule, plus the difference of the two
 // branches over the table nodes on the other side of the merge point -- whichever side
-// has fewer nodes.  The table's frequencies descend, so the power-law side is [i0, k).
+// has fewer nodes.  The table's frequencies descend, so the power-law side is [i0, k); the
+// setup kernel found k.
 template <bool THIN>
 __device__ __forceinline__ double band_partial_kink(const FastSed& fs, const double2* __restrict__ na,
                                                     const double* __restrict__ nl, int i0, int i1,
                                                     const double2* __restrict__ ca,
                                                     const double* __restrict__ cl, int c0, int c1,
-                                                    int lane, const double* tab) {
+                                                    int k, int lane, const double* tab) {
   constexpr int TS = kTabRepShift;
-  int lo = i0, hi = i1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (gt_pos(na[mid].x, fs.nu_merge)) lo = mid + 1;
-    else hi = mid;
-  }
-  const int k = lo;
   double acc = 0.0;
   if (k - i0 <= i1 - k) {
     for (int i = c0 + lane; i < c1; i += 32) {
@@ -611,18 +629,18 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
                      const double* __restrict__ scratch, const int* __restrict__ sst) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t tab_bytes = IN_SMEM ? (size_t)t.nn * 16 + (FAST ? nodes_b_bytes(t.nn) : 0) : 0;
-  // compressed rules (always in shared memory: nb * 32 nodes): [ca | cb | comp_off]
-  const size_t comp_bytes = (GAUSS && t.nc) ? (size_t)t.nc * 16 + nodes_b_bytes(t.nc) + (size_t)(kMaxBands + 1) * 4 + 12 : 0;
+  // compressed rules (always in shared memory: nb * 32 nodes): [ca | cb]
+  const size_t comp_bytes = (GAUSS && t.nc) ? (size_t)t.nc * 16 + nodes_b_bytes(t.nc) : 0;
   double2* s_a = reinterpret_cast<double2*>(smem_raw);
   double* s_b = reinterpret_cast<double*>(s_a + t.nn);
   double2* s_ca = reinterpret_cast<double2*>(smem_raw + tab_bytes);
   double* s_cb = reinterpret_cast<double*>(s_ca + t.nc);
-  int* s_coff = reinterpret_cast<int*>(smem_raw + tab_bytes + (size_t)t.nc * 16 + nodes_b_bytes(t.nc));
   double* s_exp = reinterpret_cast<double*>(smem_raw + tab_bytes + comp_bytes);
   double* s_diff = s_exp + kTabRepDoubles;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_diff + kNodesWarps * kMaxBands);
   int* s_off = reinterpret_cast<int*>(bar + 2);
-  unsigned char* s_scalar = reinterpret_cast<unsigned char*>(s_off + kMaxBands + 1);
+  int* s_coff = s_off + kMaxBands + 1;          // a constant offset from s_off: no address arithmetic of its own
+  unsigned char* s_scalar = reinterpret_cast<unsigned char*>(s_coff + kMaxBands + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = t.nb;
 
@@ -668,12 +686,13 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
     }
     const double2* c2 = reinterpret_cast<const double2*>(scratch + e * kScratchStride);
     const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
-    const double2 c89 = __ldg(c2 + 4), cpg = __ldg(c2 + 6);
-    unsigned long long gmask = 0, kmask = 0;
+    const double2 c89 = __ldg(c2 + 4), cpg = __ldg(c2 + 7);
+    unsigned long long gmask = 0, kmask = 0, splits = 0;
     if (GAUSS && t.nc) {
       const double2 cm = __ldg(c2 + 5);
       gmask = (unsigned long long)__double_as_longlong(cm.x);
       kmask = (unsigned long long)__double_as_longlong(cm.y);
+      if (ALPHA && kmask) splits = (unsigned long long)__double_as_longlong(__ldg(c2 + 6).x);
     }
     Sed s;
     FastSed fs;
@@ -688,6 +707,7 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
     const bool safe = (stw & kSafeBit) != 0;
     const long long src = source_of(a, e);
     const double* fl = d.flux + src * d.nb;
+    const double* ivp = d.cinv ? nullptr : d.ivar + src * d.nb;
     double chi = 0.0;
     for (int b = 0; b < nb; ++b) {
       const int i0 = s_off[b], i1 = s_off[b + 1];
@@ -695,8 +715,11 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
       if (FAST) {
         if (GAUSS && t.nc && ((gmask >> b) & 1ull))   // this walker may use the band's 32-point rule
           acc = band_partial_fast<THIN, ALPHA, false>(fs, s_ca, s_cb, s_coff[b], s_coff[b + 1], lane, ltab);
-        else if (GAUSS && ALPHA && t.nc && ((kmask >> b) & 1ull))   // ... with the merge point inside the band
-          acc = band_partial_kink<THIN>(fs, na, nbp, i0, i1, s_ca, s_cb, s_coff[b], s_coff[b + 1], lane, ltab);
+        else if (GAUSS && ALPHA && t.nc && ((kmask >> b) & 1ull)) {   // ... with the merge point inside the band
+          acc = band_partial_kink<THIN>(fs, na, nbp, i0, i1, s_ca, s_cb, s_coff[b], s_coff[b + 1],
+                                        i0 + (int)(splits & 0xffffull), lane, ltab);
+          splits >>= 16;
+        }
         else if (safe) acc = band_partial_fast<THIN, ALPHA, false>(fs, na, nbp, i0, i1, lane, ltab);
         else acc = band_partial_fast<THIN, ALPHA, true>(fs, na, nbp, i0, i1, lane, ltab);
       } else {
@@ -711,7 +734,7 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
       if (d.cinv) {
         if (lane == 0) wdiff[b] = df;
       } else {
-        chi = fma(df * df, __ldg(d.ivar + src * d.nb + b), chi);
+        chi = fma(df * df, __ldg(ivp + b), chi);
       }
     }
     if (d.cinv) {
