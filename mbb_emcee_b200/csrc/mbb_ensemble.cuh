@@ -113,28 +113,48 @@ ens_delta_kernel(const EnsArgs g, const ModelP m, const Priors pr, const DataRef
   const unsigned ih = (unsigned)g.h;
   const long long src = (g.nsrc * g.h < (1LL << 32)) ? (long long)((unsigned)i / ih) : i / g.h;
   const int k = (int)(i - src * g.h);
-  const Draw dr = stretch_draw(g.seed, (unsigned long long)i, g.hstep, g.a, g.h);
+  // Same draws as stretch_draw(), issued in the order that hides the gathers: the first Philox
+  // block gives the partner index, the loads (own row, partner row, old log-probability,
+  // photometry) go out, and the second block, the logarithms and the division run under them.
+  const unsigned k0 = (unsigned)g.seed, k1 = (unsigned)(g.seed >> 32);
+  const unsigned long long widx = (unsigned long long)i;
+  const Philox r = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)g.hstep,
+                                 (unsigned)(g.hstep >> 32) << 1, k0, k1);
+  const int partner = (int)(((unsigned long long)r.c[2] * (unsigned long long)g.h) >> 32);
   const int own = g.half == 0 ? k : g.h + k;
-  const int oth = (g.half == 0 ? g.h : 0) + dr.partner;
+  const int oth = (g.half == 0 ? g.h : 0) + partner;
   const long long w = src * g.nw + own;
   const double* __restrict__ s = g.pos + w * 5;
   const double* __restrict__ c = g.pos + (src * g.nw + oth) * 5;
-  double q[5];
+  double sj[5], cj[5];
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    const double cj = c[j];
-    q[j] = __dsub_rn(cj, __dmul_rn(dr.z, __dsub_rn(cj, s[j])));
+    sj[j] = s[j];
+    cj[j] = c[j];
   }
   const double old = g.lnp[w];
   double diff[NB];
   delta_load_data<NB>(d, src, diff);
+  const Philox r2 = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)g.hstep,
+                                  ((unsigned)(g.hstep >> 32) << 1) | 1u, k0, k1);
+  Draw dr;
+  {
+    const double t1 = __dadd_rn(__dmul_rn(g.a - 1.0, u53(r.c[0], r.c[1])), 1.0);
+    dr.z = __ddiv_rn(__dmul_rn(t1, t1), g.a);
+    dr.partner = partner;
+    dr.lnu = log(u53(r2.c[0], r2.c[1]));
+  }
+  const double lnz4 = 4.0 * log(dr.z);
+  double q[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) q[j] = __dsub_rn(cj[j], __dmul_rn(dr.z, __dsub_rn(cj[j], sj[j])));
   int st;
   const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, diff, m, pr, d, t, cold, lane_exp_table(s_tab), nullptr, st);
   if (st > ST_BELOW_LOWLIM) {
     if (g.status[w] <= ST_BELOW_LOWLIM) g.status[w] = st;
     return;
   }
-  const double lnpdiff = 4.0 * log(dr.z) + newlnp - old;
+  const double lnpdiff = lnz4 + newlnp - old;
   if (lnpdiff > dr.lnu) {
     double* p = g.pos + w * 5;
 #pragma unroll
