@@ -42,7 +42,8 @@ UNIT = "evals/s"
 # REFERENCE formulation with CUDA-12.9 libdevice on sm_100a (pow 125, expm1 35,
 # exp 31, log 47, div 20, FMA = 2 flops).
 FLOP_PER_EVAL = {"cfg5": 6 * 182 + 225 + 18 + 40,            # = 1375 (cfg1 band set)
-                 "cfg2": 1688 * 366 + 3600 + 58}             # = 621466
+                 "cfg2": 1688 * 366 + 3600 + 58,             # = 621466
+                 "cfg5p": 1688 * 184 + 225 + 18 + 40}        # = 310875 (thin, no alpha, cfg2 band set)
 BYTES_PER_EVAL = 48                                          # 40 B parameters in + 8 B out
 
 
@@ -126,6 +127,11 @@ def build_workload(name, rank, nsrc_override=None):
         nsrc = nsrc_override or cfg["nsources"]
         nw = cfg["nwalkers"]
         truth = np.array([12.0, 1.8, 1300.0, 4.0, 30.0])
+    elif name == "cfg5p":
+        cfg = synthetic.CONFIGS["cfg5p"]
+        nsrc = nsrc_override or cfg["nsources"]
+        nw = cfg["nwalkers"]
+        truth = np.array(cfg["truth"])
     else:
         cfg = synthetic.CONFIGS["cfg2"]
         nsrc = nsrc_override or 2048
@@ -185,7 +191,7 @@ def _cpu_worker(args):
     import mbb_oracle as oracle
     from mbb_emcee_b200 import synthetic
     from mbb_emcee_b200.response import response_set
-    cfg = synthetic.CONFIGS["cfg5" if cfgname == "cfg5" else "cfg2"]
+    cfg = synthetic.CONFIGS[cfgname if cfgname in synthetic.CONFIGS else "cfg2"]
     spec = oracle.LikeSpec(cfg["wavenorm"], cfg["noalpha"], cfg["opthin"])
     if cfg["response"]:
         wheel = response_set()
@@ -232,7 +238,7 @@ def run_reference(args):
         return
     from mbb_emcee_b200 import synthetic
     name = args.workload
-    cfg = synthetic.CONFIGS["cfg5" if name == "cfg5" else "cfg2"]
+    cfg = synthetic.CONFIGS[name]
     rng = np.random.RandomState(cfg["seed"])
     nb = len(cfg["bands"])
     truth = np.array([12.0, 1.8, 1300.0, 4.0, 30.0]) if name == "cfg5" else np.array(cfg["truth"])
@@ -270,6 +276,12 @@ def workload_config(name, n_per_rank, nsrc, nw):
                 "evals_per_step_per_gpu": int(n_per_rank), "bands": 6, "nodes": 6,
                 "l2_policy": "inputs (%.2f GB of parameters per step) exceed the 126 MB L2"
                              % (n_per_rank * 40 / 1e9)}
+    if name == "cfg5p":
+        return {"workload": "BASELINE configs[4] on the tabulated band set: %d sources x %d walkers per GPU, "
+                            "passband integration over PACS_100/160, SPIRE_250/350/500, SCUBA2_850 (1688 "
+                            "nodes), optically thin, no alpha" % (nsrc, nw),
+                "evals_per_step_per_gpu": int(n_per_rank), "bands": 6, "nodes": 1688,
+                "l2_policy": "L2 flushed between timed steps by writing a 256 MB buffer"}
     return {"workload": "BASELINE configs[1]-style: %d sources x %d walkers per GPU, passband "
                         "integration over PACS_100/160, SPIRE_250/350/500, SCUBA2_850 (1688 nodes), "
                         "optically thick + alpha join" % (nsrc, nw),
@@ -283,6 +295,9 @@ def main_config(name, nsrc=None):
     if name == "cfg5":
         nsrc = nsrc or synthetic.CONFIGS["cfg5"]["nsources"]
         nw = synthetic.CONFIGS["cfg5"]["nwalkers"]
+    elif name == "cfg5p":
+        nsrc = nsrc or synthetic.CONFIGS["cfg5p"]["nsources"]
+        nw = synthetic.CONFIGS["cfg5p"]["nwalkers"]
     else:
         nsrc, nw = nsrc or 2048, 512
     return workload_config(name, nsrc * nw, nsrc, nw)
@@ -465,28 +480,23 @@ def run_b200(args):
                          "note": "host call: walker positions uploaded, initial log-probability + K "
                                  "iterations, positions and log-probabilities downloaded"},
                  "mean_acceptance_fraction": acc_frac}
-    # ---- the same batch shape on the tabulated passband set (BASELINE configs[1] bands) ----
-    passband = None
-    per_worker = 20000 if name == "cfg5" else 1500
-    cores = len(all_cpus)
-    Pc = P[:cores * per_worker].cpu().numpy() if rank == 0 else None
-    if name == "cfg5" and not args.no_passband:
-        del P, out, st
-        torch.cuda.empty_cache()
-        W2 = build_workload("cfg2", rank, None)
+    # ---- tabulated passband sets: configs[1] (thick + alpha) and configs[4]-secondary (thin) ----
+    def passband_leg(wname):
+        W2 = build_workload(wname, rank, None)
         ctx2, n2, P2 = W2["ctx"], W2["n"], W2["P"]
         ctx2.set_math_mode(MODES[args.math])
         out2 = torch.empty(n2, dtype=torch.float64, device=dev)
         st2 = torch.empty(n2, dtype=torch.int32, device=dev)
         flush2 = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
-        leg2 = device_leg(ctx2, n2, W2["nw"], P2, out2, st2, flush2, max(3, min(args.steps, 5)), 3)
-        f2 = FLOP_PER_EVAL["cfg2"]
+        k = max(3, min(args.steps, 5))
+        leg2 = device_leg(ctx2, n2, W2["nw"], P2, out2, st2, flush2, k, 3)
+        f2 = FLOP_PER_EVAL[wname]
         # the same launches with the tabulated bands' 32-point Gauss rules (MBB_MATH_FAST_GAUSS)
         gauss = None
         if args.math == "fast":
             ref_out = out2.clone()
             ctx2.set_math_mode(MODES["gauss"])
-            leg3 = device_leg(ctx2, n2, W2["nw"], P2, out2, st2, flush2, max(3, min(args.steps, 5)), 3)
+            leg3 = device_leg(ctx2, n2, W2["nw"], P2, out2, st2, flush2, k, 3)
             fin = torch.isfinite(ref_out)
             rel = ((out2[fin] - ref_out[fin]).abs() / ref_out[fin].abs()).max().item()
             gauss = {"value": n2 * world / (leg3["step_ms_max"] * 1e-3), "unit": UNIT,
@@ -494,14 +504,26 @@ def run_b200(args):
                      "max_rel_diff_vs_full_tables": rel,
                      "note": "math mode gauss: per (walker, band) the band's 32-point Gauss rule where a "
                              "per-walker bound shows it agrees with the full table to rounding"}
-            ctx2.set_math_mode(MODES["fast"])
-        passband = {"workload": main_config("cfg2", W2["nsrc"])["workload"],
-                    "value": n2 * world / (leg2["step_ms_max"] * 1e-3), "unit": UNIT,
-                    "ms_per_step": leg2["step_ms_max"], "evals_per_step_per_gpu": int(n2),
-                    "roofline_frac": n2 * f2 / (leg2["step_ms"] * 1e-3) / 1e12 / peak_tf,
-                    "flop_per_eval": f2, "status_errors": int((st2 > 1).sum().item()),
-                    "gauss_rules": gauss,
-                    "l2_policy": "L2 flushed between timed steps by writing a 256 MB buffer"}
+        res = {"workload": main_config(wname, W2["nsrc"])["workload"],
+               "value": n2 * world / (leg2["step_ms_max"] * 1e-3), "unit": UNIT,
+               "ms_per_step": leg2["step_ms_max"], "evals_per_step_per_gpu": int(n2),
+               "roofline_frac": n2 * f2 / (leg2["step_ms"] * 1e-3) / 1e12 / peak_tf,
+               "flop_per_eval": f2, "status_errors": int((st2 > 1).sum().item()),
+               "gauss_rules": gauss,
+               "l2_policy": "L2 flushed between timed steps by writing a 256 MB buffer"}
+        del W2, ctx2, P2, out2, st2, flush2
+        torch.cuda.empty_cache()
+        return res
+
+    passband = passband_batch = None
+    per_worker = 20000 if name == "cfg5" else 1500
+    cores = len(all_cpus)
+    Pc = P[:cores * per_worker].cpu().numpy() if rank == 0 else None
+    if name == "cfg5" and not args.no_passband:
+        del P, out, st
+        torch.cuda.empty_cache()
+        passband = passband_leg("cfg2")
+        passband_batch = passband_leg("cfg5p")
     clocks = sampler.stop()
 
     if rank == 0:
@@ -548,6 +570,7 @@ def run_b200(args):
             "e2e": e2e,
             "batch_fit": batch,
             "passband": passband,
+            "passband_batch": passband_batch,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"status_errors": nbad, "neg_inf": nneg, "wall_s_timed_region": wall,
@@ -565,7 +588,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg5p"])
     ap.add_argument("--nsrc", type=int, default=None, help="sources per GPU (default: workload's)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg")

@@ -11,6 +11,7 @@
 #include "../../include/mbb_b200.h"
 #include "mbb_ensemble.cuh"
 #include "mbb_gaussrule.h"
+#include "mbb_gausskernel.cuh"
 #include "mbb_kernels.cuh"
 
 using namespace mbb;
@@ -445,6 +446,38 @@ struct LaunchSplit {
   }
 };
 
+// MBB_MATH_FAST_GAUSS with diagonal errors: thread-per-evaluation kernel (mbb_gausskernel.cuh)
+template <bool THIN, bool ALPHA, bool UNUSED>
+struct LaunchGaussThread {
+  static void run(mbb_ctx* c, cudaStream_t st, const EvalArgs& a, const DataRef& d, cudaError_t* err) {
+    GaussThreadTab t;
+    t.a = c->d_node_fast_a.p;
+    t.b = c->d_node_fast_b.p;
+    t.band_off = c->d_off.p;
+    t.ca = c->d_comp_a.p;
+    t.cb = c->d_comp_b.p;
+    t.comp_off = c->d_comp_off.p;
+    t.meta = c->d_band_meta.p;
+    t.nb = c->nb;
+    t.nc = c->nc;
+    const size_t smem = gauss_thread_smem(c->nb, c->nc);
+    auto kern = loglike_gauss_thread_kernel<THIN>;
+    *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (*err != cudaSuccess) return;
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MBB_DELTA_BLOCK, smem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    const long long ntiles = (a.n + kDeltaTile - 1) / kDeltaTile;
+    const long long resident = (long long)c->sm_count * per_sm;
+    const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
+    const long long sd = a.soa_stride ? a.soa_stride : a.n;
+    static const bool no_tma = getenv("MBB_B200_NO_TMA") != nullptr;
+    const int use_tma = !no_tma && ((uintptr_t)a.pars % 16 == 0) && (a.layout == MBB_AOS || sd % 2 == 0);
+    const ModelP m = model_of(c);
+    kern<<<grid, MBB_DELTA_BLOCK, smem, st>>>(a, m, c->pri, d, t, c->d_cold.p, use_tma);
+  }
+};
+
 template <bool THIN, bool ALPHA, bool UNUSED>
 struct LaunchFnu {
   static void run(mbb_ctx* c, const EvalArgs& a, const double* freq, int nfreq, int scalar_path) {
@@ -691,7 +724,18 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a_in) {
   cudaError_t err = cudaSuccess;
   if (fast && c->nn == c->nb && c->nb <= kMaxDeltaNB) dispatch3<LaunchDelta>(thin, alpha, true, c, st, a, d, &err);
   else if (c->nn <= kSmallMaxNodes) dispatch3<LaunchThread>(thin, alpha, fast, c, st, a, d, &err);
-  else dispatch3<LaunchSplit>(thin, alpha, fast, c, st, a, d, &err);
+  else {
+    // Gauss rules, no power-law join, diagonal errors: one thread per evaluation (every band is a
+    // fixed 32-node loop, nothing diverges: 2.65 vs 5.29 ms on the cfg5p workload).  With the join
+    // a band that contains the walker's merge point needs table corrections of walker-dependent
+    // length, which a warp shares out over its lanes but a thread serialises (2.88 vs 2.11 ms for
+    // cfg2): those configurations, and full covariances, keep the warp path.
+    static const bool gauss_warp = getenv("MBB_B200_GAUSS_WARP") != nullptr;
+    const bool gthread = c->math_mode == MBB_MATH_FAST_GAUSS && c->nc > 0 && !d.cinv && !gauss_warp && !alpha &&
+                         gauss_thread_smem(c->nb, c->nc) <= c->smem_optin;
+    if (gthread) dispatch3<LaunchGaussThread>(thin, alpha, true, c, st, a, d, &err);
+    else dispatch3<LaunchSplit>(thin, alpha, fast, c, st, a, d, &err);
+  }
   CK(err);
   c->launches += 1;
   CK(cudaGetLastError());

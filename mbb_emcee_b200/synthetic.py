@@ -45,6 +45,12 @@ CONFIGS = {
                  bands=[70.0, 100.0, 160.0, 250.0, 350.0, 500.0],
                  opthin=True, noalpha=True, wavenorm=500.0,
                  nsources=100000, nwalkers=512),
+    # the same batch on cfg2's tabulated band set (cfg5 "secondary")
+    "cfg5p": dict(seed=106, response=True,
+                  bands=["PACS_100um", "PACS_160um", "SPIRE_250um", "SPIRE_350um",
+                         "SPIRE_500um", "SCUBA2_850um"],
+                  truth=(12.0, 1.8, 1300.0, 4.0, 30.0), opthin=True, noalpha=True,
+                  wavenorm=500.0, nsources=8192, nwalkers=512),
 }
 
 

@@ -324,6 +324,55 @@ def test_gauss_mode_golden_and_oracle(golden, oracle, cfgname):
     assert not np.array_equal(comp[ok], full[ok])          # the compressed rules were actually used
 
 
+@pytest.mark.parametrize("opthin", [True, False])
+def test_gauss_thread_kernel_paths(oracle, opthin):
+    """MBB_MATH_FAST_GAUSS without the power-law join runs one thread per evaluation
+    (mbb_gausskernel.cuh): rule bands, bands that fail the per-walker bound (cold walker ->
+    full table from global memory), exponents outside the double range (saturating code),
+    the -inf gate, several sources, a partial last tile, soft-limit penalties -- all
+    against the oracle; SoA input bitwise equal to AoS."""
+    import torch
+    from mbb_emcee_b200 import _native, likelihood, synthetic
+    cfg = synthetic.CONFIGS["cfg2"]
+    rng = np.random.RandomState(31)
+    like = likelihood(wavenorm=500.0, opthin=opthin, noalpha=True, response=True, device=0)
+    nb = len(cfg["bands"])
+    nsrc, wps = 21, 37
+    n = nsrc * wps
+    like.set_phot(cfg["bands"], np.full(nb, 30.0), np.full(nb, 3.0))
+    like.set_lowlim('T', 0.01)
+    flux = rng.uniform(5, 80, (nsrc, nb))
+    unc = rng.uniform(1, 6, (nsrc, nb))
+    P = synthetic.walker_cloud((14.0, 1.8, 400.0, 3.0, 30.0), n, rng, like.lowlims)
+    P[3] = [2.0, 1.8, 400.0, 3.0, 30.0]            # cold: PACS bands fail the bound -> full tables
+    P[4] = [0.05, 1.8, 400.0, 3.0, 30.0]           # h nu / k T ~ 4000 -> saturating path
+    P[5] = [0.001, 1.8, 400.0, 3.0, 30.0]          # below the T limit -> -inf
+    P[6, 1] = 25.0                                 # beta above its soft limit (and a steep thick factor)
+    like._stage()
+    ctx = like.context
+    ctx.set_math_mode(_native.MATH_FAST_GAUSS)
+    ctx.set_data(flux, ivar=1.0 / unc**2)
+    got, st = ctx.loglike(P, walkers_per_source=wps)
+    spec0 = _oracle_spec(oracle, like)
+    want = np.empty(n)
+    for s0 in range(nsrc):
+        spec = oracle.LikeSpec(500.0, True, opthin)
+        spec.set_phot(spec0.bands, flux[s0], unc[s0])
+        spec.lowlim, spec.has_uplim, spec.uplim = spec0.lowlim, spec0.has_uplim, spec0.uplim
+        with np.errstate(all="ignore"):
+            want[s0 * wps:(s0 + 1) * wps] = oracle.loglike_batch(spec, P[s0 * wps:(s0 + 1) * wps])
+    assert np.isneginf(got[5]) and np.isneginf(want[5]) and st[5] == 1
+    assert st[3] == 0 and st[4] == 0 and st[6] == 0
+    fin = np.isfinite(want)
+    assert relerr(got[fin], want[fin]).max() < TOL
+    dev = torch.device("cuda:0")
+    Pt = torch.as_tensor(P, device=dev).t().contiguous()
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    ctx.loglike_device(n, Pt.data_ptr(), out.data_ptr(), 0, walkers_per_source=wps, layout=_native.SOA)
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy(), got)
+
+
 def test_error_statuses():
     """Failures that make the reference raise surface as the same exception types."""
     from mbb_emcee_b200 import likelihood
