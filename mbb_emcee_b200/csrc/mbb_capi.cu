@@ -461,7 +461,7 @@ struct LaunchGaussThread {
     t.nb = c->nb;
     t.nc = c->nc;
     const size_t smem = gauss_thread_smem(c->nb, c->nc);
-    auto kern = loglike_gauss_thread_kernel<THIN>;
+    auto kern = loglike_gauss_thread_kernel<THIN, ALPHA>;
     *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (*err != cudaSuccess) return;
     int per_sm = 1;
@@ -725,13 +725,11 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a_in) {
   if (fast && c->nn == c->nb && c->nb <= kMaxDeltaNB) dispatch3<LaunchDelta>(thin, alpha, true, c, st, a, d, &err);
   else if (c->nn <= kSmallMaxNodes) dispatch3<LaunchThread>(thin, alpha, fast, c, st, a, d, &err);
   else {
-    // Gauss rules, no power-law join, diagonal errors: one thread per evaluation (every band is a
-    // fixed 32-node loop, nothing diverges: 2.65 vs 5.29 ms on the cfg5p workload).  With the join
-    // a band that contains the walker's merge point needs table corrections of walker-dependent
-    // length, which a warp shares out over its lanes but a thread serialises (2.88 vs 2.11 ms for
-    // cfg2): those configurations, and full covariances, keep the warp path.
+    // Gauss rules + diagonal errors: one thread per evaluation, kink bands by the warp
+    // (mbb_gausskernel.cuh: cfg5p 5.29 -> 2.64 ms, cfg2 2.11 -> 1.53 ms against the warp path);
+    // full covariances keep the warp path.
     static const bool gauss_warp = getenv("MBB_B200_GAUSS_WARP") != nullptr;
-    const bool gthread = c->math_mode == MBB_MATH_FAST_GAUSS && c->nc > 0 && !d.cinv && !gauss_warp && !alpha &&
+    const bool gthread = c->math_mode == MBB_MATH_FAST_GAUSS && c->nc > 0 && !d.cinv && !gauss_warp &&
                          gauss_thread_smem(c->nb, c->nc) <= c->smem_optin;
     if (gthread) dispatch3<LaunchGaussThread>(thin, alpha, true, c, st, a, d, &err);
     else dispatch3<LaunchSplit>(thin, alpha, fast, c, st, a, d, &err);

@@ -20,11 +20,12 @@
 //     the independent work the 8-cycle DFMA latency asks for;
 //   * the full tables stay in global memory (read-only path): only bands that
 //     fail the per-walker bound touch them, at warp-uniform addresses;
-//   * models WITHOUT the power-law join only: with it, a band containing the
-//     walker's merge point needs table corrections of walker-dependent length
-//     (band_partial_kink), which a warp shares out over its lanes but a thread
-//     would serialise and its neighbours would wait for (measured: 2.88 vs
-//     2.11 ms for cfg2) -- those configurations keep the warp kernel;
+//   * with the power-law join a band that contains the walker's merge point needs
+//     table corrections of walker-dependent length (band_partial_kink).  A thread
+//     doing them serially makes its 31 neighbours wait (measured: 2.88 ms for cfg2
+//     against 2.11 ms in the warp kernel), so they are done by the WARP: after the
+//     per-thread bands, each lane with a kink band broadcasts its eight per-walker
+//     constants by shuffle and all 32 lanes stride that band's table nodes;
 //   * diagonal errors only (a full covariance needs all band residuals at once:
 //     warp kernel as well).
 #pragma once
@@ -49,14 +50,14 @@ __host__ __device__ inline size_t gauss_thread_smem(int nb, int nc) {
 }
 
 // full-table band for one thread
-template <bool THIN, bool CLAMP>
+template <bool THIN, bool ALPHA, bool CLAMP>
 __device__ __forceinline__ double band_table_thread(const FastSed& fs, const double2* __restrict__ ga,
                                                     const double* __restrict__ gb, int i0, int i1,
                                                     const double* tab) {
   double acc = 0.0;
   for (int i = i0; i < i1; ++i) {
     const double2 fw = __ldg(ga + i);
-    acc = node_grey<THIN, CLAMP, kTabRepShift>(fs, fw.x, __ldg(gb + i), fw.y, acc, tab);
+    acc = node_acc<THIN, ALPHA, CLAMP, kTabRepShift>(fs, fw.x, __ldg(gb + i), fw.y, acc, tab);
   }
   return acc;
 }
@@ -81,7 +82,21 @@ __device__ __forceinline__ double rule_grey_thread(const FastSed& fs, const doub
   return acc;
 }
 
-template <bool THIN>
+__device__ __forceinline__ double rule_pow_thread(const FastSed& fs, const double2* __restrict__ ca,
+                                                  const double* __restrict__ cb, int c0, int c1,
+                                                  const double* tab) {
+  double acc = 0.0;
+  for (int i = c0; i < c1; ++i) acc = node_pow<false, kTabRepShift>(fs, cb[i], ca[i].y, acc, tab);
+  return acc;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src_lane) {
+  return __shfl_sync(0xffffffffu, v, src_lane);
+}
+
+constexpr int kThreadKinkSlots = 2;   // kink bands one evaluation can hand to the warp phase
+
+template <bool THIN, bool ALPHA>
 __global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
 loglike_gauss_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const DataRef d,
                             const GaussThreadTab t, const ColdArgs* __restrict__ cold, const int use_tma) {
@@ -145,41 +160,93 @@ loglike_gauss_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, c
       load_pars(a, e, p);
     }
     __syncthreads();
+    // ---- per-thread part: setup, masks, every band that needs no warp cooperation ----
+    int st = ST_OK;
+    double lnl = qnan(), chi = 0.0;
+    bool live = false;                     // this lane carries an evaluation through to the chi-square
+    FastSed fs;
+    int kband[kThreadKinkSlots], ksplit[kThreadKinkSlots], nkink = 0;
+    const double* __restrict__ fl = nullptr;
+    const double* __restrict__ ivp = nullptr;
     if (active) {
-      int st = ST_OK;
-      double lnl;
       if (below_lowlim(pr, p)) {
         st = ST_BELOW_LOWLIM;
         lnl = -kInf;
       } else {
-        FastSed fs;
-        fast_setup<THIN, false>(fs, p[0], p[1], p[2], p[3], p[4], m);
+        fast_setup<THIN, ALPHA>(fs, p[0], p[1], p[2], p[3], p[4], m);
         st = fs.status;
-        lnl = qnan();
-        if (st == ST_OK) {
-          GaussMasks gm;
-          gm.plain = gm.kink = 0;
-          if (fs.safe) gm = gauss_band_masks<THIN, false>(fs, s_meta, nb);
-          const long long src = source_of(a, e);
-          const double* __restrict__ fl = d.flux + src * nb;
-          const double* __restrict__ ivp = d.ivar + src * nb;
-          double chi = 0.0;
-          for (int b = 0; b < nb; ++b) {
-            const int i0 = s_off[b], i1 = s_off[b + 1], c0 = s_coff[b], c1 = s_coff[b + 1];
-            double acc;
-            if ((gm.plain >> b) & 1ull) acc = rule_grey_thread<THIN>(fs, s_ca, s_cb, c0, c1, tab);
-            else if (fs.safe) acc = band_table_thread<THIN, false>(fs, t.a, t.b, i0, i1, tab);
-            else acc = band_table_thread<THIN, true>(fs, t.a, t.b, i0, i1, tab);
+        live = st == ST_OK;
+      }
+    }
+    if (live) {
+      GaussMasks gm;
+      gm.plain = gm.kink = 0;
+      if (fs.safe) gm = gauss_band_masks<THIN, ALPHA>(fs, s_meta, nb);
+      const long long src = source_of(a, e);
+      fl = d.flux + src * nb;
+      ivp = d.ivar + src * nb;
+      for (int b = 0; b < nb; ++b) {
+        const int i0 = s_off[b], i1 = s_off[b + 1], c0 = s_coff[b], c1 = s_coff[b + 1];
+        double acc;
+        if ((gm.plain >> b) & 1ull) {
+          if (ALPHA && gt_pos(s_meta[b].nu_lo, fs.nu_merge)) acc = rule_pow_thread(fs, s_ca, s_cb, c0, c1, tab);
+          else acc = rule_grey_thread<THIN>(fs, s_ca, s_cb, c0, c1, tab);
+        } else if (ALPHA && ((gm.kink >> b) & 1ull) && nkink < kThreadKinkSlots) {
+          // split index of the (frequency-descending) table at the merge point; the band itself
+          // is evaluated by the whole warp below
+          int lo = i0, hi = i1;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (gt_pos(__ldg(&t.a[mid].x), fs.nu_merge)) lo = mid + 1;
+            else hi = mid;
+          }
+          kband[nkink] = b;
+          ksplit[nkink] = lo;
+          ++nkink;
+          continue;
+        } else if (fs.safe) {
+          acc = band_table_thread<THIN, ALPHA, false>(fs, t.a, t.b, i0, i1, tab);
+        } else {
+          acc = band_table_thread<THIN, ALPHA, true>(fs, t.a, t.b, i0, i1, tab);
+        }
+        const double df = __ldg(fl + b) - acc;
+        chi = fma(df * df, __ldg(ivp + b), chi);
+      }
+    }
+    // ---- warp part: the kink bands, one (evaluation, band) at a time, nodes over the lanes ----
+    if (ALPHA) {
+      const int lane = tid & 31;
+#pragma unroll
+      for (int slot = 0; slot < kThreadKinkSlots; ++slot) {
+        unsigned pending = __ballot_sync(0xffffffffu, live && nkink > slot);
+        while (pending) {
+          const int L = __ffs(pending) - 1;
+          pending &= pending - 1;
+          FastSed g;
+          g.xk_hi = shfl_d(fs.xk_hi, L); g.xk_lo = shfl_d(fs.xk_lo, L);
+          g.nb = shfl_d(fs.nb, L); g.apow = shfl_d(fs.apow, L);
+          g.t0c = shfl_d(fs.t0c, L); g.nu_merge = shfl_d(fs.nu_merge, L);
+          g.amp_grey = shfl_d(fs.amp_grey, L); g.amp_pow = shfl_d(fs.amp_pow, L);
+          const int b = __shfl_sync(0xffffffffu, kband[slot], L);
+          const int k = __shfl_sync(0xffffffffu, ksplit[slot], L);
+          double acc = band_partial_kink<THIN>(g, t.a, t.b, s_off[b], s_off[b + 1], s_ca, s_cb, s_coff[b],
+                                               s_coff[b + 1], k, lane, tab);
+          acc = warp_sum(acc);
+          if (lane == L) {
             const double df = __ldg(fl + b) - acc;
             chi = fma(df * df, __ldg(ivp + b), chi);
           }
-          lnl = -0.5 * chi;
-          if (!priors_trivial(pr, p)) {
-            lnl = add_priors_cold<THIN>(lnl, p[0], p[1], p[2], p[3], p[4], fs.x0, cold, &st);
-            if (st != ST_OK) lnl = qnan();
-          }
-          if (st == ST_OK && lnl != lnl) st = ST_NONFINITE;
         }
+      }
+    }
+    if (active) {
+      if (live) {
+        lnl = -0.5 * chi;
+        if (!priors_trivial(pr, p)) {
+          lnl = add_priors_cold<THIN>(lnl, p[0], p[1], p[2], p[3], p[4], fs.x0, cold, &st);
+          if (st != ST_OK) lnl = qnan();
+        }
+        if (st == ST_OK && lnl != lnl) st = ST_NONFINITE;
       }
       a.out[e] = lnl;
       if (a.status) a.status[e] = st;
