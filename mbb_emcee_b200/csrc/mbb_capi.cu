@@ -729,7 +729,10 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a_in) {
     // (mbb_gausskernel.cuh: cfg5p 5.29 -> 2.64 ms, cfg2 2.11 -> 1.53 ms against the warp path);
     // full covariances keep the warp path.
     static const bool gauss_warp = getenv("MBB_B200_GAUSS_WARP") != nullptr;
+    // (a small batch -- e.g. the 125 walkers of one emcee half-step -- cannot fill the GPU with one
+    // thread per evaluation; there the warp path's 32 lanes per evaluation give the lower latency)
     const bool gthread = c->math_mode == MBB_MATH_FAST_GAUSS && c->nc > 0 && !d.cinv && !gauss_warp &&
+                         a.n >= (long long)c->sm_count * 384 &&
                          gauss_thread_smem(c->nb, c->nc) <= c->smem_optin;
     if (gthread) dispatch3<LaunchGaussThread>(thin, alpha, true, c, st, a, d, &err);
     else dispatch3<LaunchSplit>(thin, alpha, fast, c, st, a, d, &err);
