@@ -13,6 +13,7 @@ python bench.py --workload cfg2 --steps 5 --warmup 3 > $O/${T}_bench_cfg2.json 2
 python tools/bench_chain.py > $O/${T}_chain_cfg4.json 2> $O/${T}_chain_cfg4.err
 tools/_build/fp64_probe > $O/${T}_fp64_probe.json 2>&1
 tools/_build/rcp_probe > $O/${T}_rcp_probe.json 2>&1
+tools/_build/exp_probe > $O/${T}_exp_probe.json 2>&1
 B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-passband"
 for w in cfg5 cfg2; do
   $B --workload $w > $O/${T}_plain_$w.log 2>&1 || continue      # the program must exit 0 without ncu first
