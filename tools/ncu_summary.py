@@ -103,6 +103,12 @@ def facts(path):
     for vals in rows[2:]:
         d = dict(zip(hdr, zip(units, vals)))
         f = lambda k: float(d[k][1].replace(",", ""))
+        nsm = 148
+        cyc = f("smsp__cycles_active.avg")
+        n_all = f("smsp__inst_executed.sum")
+        n_fp64 = f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") / 100.0 * cyc / 2.0 * 4 * nsm
+        # issue model measured by tools/exp_probe.cu: an FP64 warp instruction takes two issue cycles
+        bound_cyc = (2.0 * n_fp64 + (n_all - n_fp64)) / (4 * nsm)
         print(json.dumps({
             "kernel": short(d["Kernel Name"][1]),
             "source": "ncu --set full --clock-control none, one launch (profiles/)",
@@ -111,7 +117,10 @@ def facts(path):
             "fp64_pipe_pct": f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
             "issue_slot_pct": f("sm__inst_issued.avg.pct_of_peak_sustained_active"),
             "dram_pct": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
-            "warp_instructions": f("smsp__inst_executed.sum"),
+            "warp_instructions": n_all,
+            "fp64_warp_instructions": n_fp64,
+            "issue_bound_frac": bound_cyc / cyc,
+            "issue_bound_note": "(2*N_fp64 + N_other) issue cycles per scheduler / active cycles; see DESIGN.md 7",
             "registers": f("launch__registers_per_thread"),
             "smem_bank_conflicts": f("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")}))
 
