@@ -31,7 +31,7 @@ def u53(hi, lo):
 
 
 def stretch_draw(seed, widx, hstep, a, ncomp):
-    """(z, ln u, partner) for walker indices ``widx`` at half-step ``hstep``."""
+    """(z, u, partner) for walker indices ``widx`` at half-step ``hstep``."""
     widx = np.asarray(widx, dtype=np.uint64)
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     lo, hi = widx & MASK, widx >> np.uint64(32)
@@ -42,7 +42,7 @@ def stretch_draw(seed, widx, hstep, a, ncomp):
     t = (a - 1.0) * u53(r[0], r[1]) + 1.0
     z = (t * t) / a
     partner = ((r[2] * np.uint64(ncomp)) >> np.uint64(32)).astype(np.int64)
-    return z, np.log(u53(s[0], s[1])), partner
+    return z, u53(s[0], s[1]), partner
 
 
 def replay(lnprob_rows, p0, nsteps, seed, a=2.0, step0=0, lnp0=None):
@@ -57,14 +57,16 @@ def replay(lnprob_rows, p0, nsteps, seed, a=2.0, step0=0, lnp0=None):
             hstep = 2 * (step0 + it) + half
             for s in range(nsrc):
                 widx = s * h + np.arange(h)
-                z, lnu, partner = stretch_draw(seed, widx, hstep, a, h)
+                z, u, partner = stretch_draw(seed, widx, hstep, a, h)
                 own = np.arange(h) + (0 if half == 0 else h)
                 oth = partner + (h if half == 0 else 0)
                 c = pos[s, oth]
                 q = c - z[:, None] * (c - pos[s, own])
                 newlnp = np.asarray(lnprob_rows(s, q))
-                with np.errstate(invalid="ignore"):
-                    acc = (4.0 * np.log(z) + newlnp - lnp[s, own]) > lnu
+                # the device's log-free form of emcee's test (csrc/mbb_ensemble.cuh stretch_accept)
+                with np.errstate(invalid="ignore", over="ignore"):
+                    dl = np.fmin(np.fmax(newlnp - lnp[s, own], -745.0), 700.0)
+                    acc = u < (z * z) * (z * z) * np.exp(dl)
                 pos[s, own[acc]] = q[acc]
                 lnp[s, own[acc]] = newlnp[acc]
                 nacc[s, own[acc]] += 1
