@@ -111,8 +111,14 @@ __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
 // Fused half-step for delta-band configurations: draw, propose, evaluate and
 // accept in one kernel; the proposal never leaves registers.  Same draws, same
 // arithmetic, hence the same chain as the three-kernel pipeline above.
+// this kernel waits on gathers (ncu: long_scoreboard 3.9 of ~9 stalled warps per issue), so a
+// fourth resident CTA at 64 registers pays for its spills: 2.55 vs 2.60 ms per iteration (2 CTAs
+// at 116 registers: 3.20 ms)
+#ifndef MBB_ENS_MINB
+#define MBB_ENS_MINB 4
+#endif
 template <bool THIN, bool ALPHA, int NB>
-__global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_DELTA_MINB)
+__global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_ENS_MINB)
 ens_delta_kernel(const EnsArgs g, const ModelP m, const Priors pr, const DataRef d, const SmallTab t,
                  const ColdArgs* __restrict__ cold) {
   __shared__ __align__(16) double s_tab[kTabRepDoubles];
