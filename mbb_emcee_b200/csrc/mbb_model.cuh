@@ -263,13 +263,6 @@ MBB_HD_NOINLINE void sed_setup(Sed& s, double T, double beta, double lambda0, do
 // exponent the node loop forms stays below kSafeExp in magnitude, so the loop
 // may run the CLAMP=false instantiations.
 // ---------------------------------------------------------------------------
-MBB_HD double merge_residual_fast(double x, double alpha, double beta, double inv_x0) {
-  const double t = exp_tau(beta * log(x * inv_x0));
-  // t/expm1(t): -> 1 as t -> 0, -> 0 as t -> inf (saturating expm1)
-  const double bterm = t < 1e-280 ? 1.0 : t * rcp_fast(expm1_l(t));
-  return x + expm1_l(-x) * (3.0 + alpha + beta * bterm);
-}
-
 MBB_HD double thin_merge_root_fast(double a) {
   double x = a;
   for (int it = 0; it < 12; ++it) {
@@ -278,6 +271,67 @@ MBB_HD double thin_merge_root_fast(double a) {
     x -= dx;
     if (fabs(dx) <= 1.2e-16 * x) break;
   }
+  return x;
+}
+
+// The thick merge equation in u = log x:  G(u) = g(e^u),  g(x) = x - (1 - e^-x)(3 + alpha +
+// beta B(t)),  B(t) = t/(e^t - 1),  t = (x/x0)^beta = exp(beta (u - u0)).  In this variable a
+// residual evaluation is four lean exponentials and no logarithm.  Returns x = e^u.
+MBB_HD double merge_G_fast(double u, double alpha, double beta, double u0, double& G, double& dG) {
+  const double x = exp_l(u);
+  const double t = exp_tau(beta * (u - u0));
+  double B, dB;                       // B(t), B'(t)
+  if (t < 1e-3) {
+    B = 1.0 - t * (0.5 - t * (1.0 / 12.0));
+    dB = -0.5 + t * (1.0 / 6.0);
+  } else {
+    const double em1t = expm1_l(t);
+    const double r = rcp_cubic(em1t);
+    B = t * r;
+    dB = (em1t - t * (em1t + 1.0)) * r * r;
+  }
+  const double E = -expm1_l(-x);      // 1 - e^-x
+  const double S = 3.0 + alpha + beta * B;
+  G = x - E * S;
+  dG = x * (1.0 - (1.0 - E) * S) - E * (beta * beta) * dB * t;     // dG/du = x g'(x)
+  return x;
+}
+
+// Root of the thick merge equation; also returns u = log(root).
+//   bracket: g <= x - (3+alpha)(1 - e^-x) =: gL, whose root a + W(-a e^-a) >= a (1 - e^(1-a))
+//   (W concave on [-1/e, 0]), so g(xl) <= 0 at xl = a (1 - e^(1-a)), a = 3 + alpha; and
+//   g >= x - (3+alpha+beta)(1 - e^-x), which is positive at x = 3 + alpha + beta =: xh.
+//   iteration: Newton in u, bisecting (in u) whenever a step would leave the bracket or fails to
+//   halve the previous one -- for steep t(x) (large beta) g is nearly a step and plain Newton
+//   cycles between its flat sides.
+MBB_HD double thick_merge_root_fast(double alpha, double beta, double u0, int& status, double& u_root) {
+  const double a_lo = 3.0 + alpha;
+  double ul = log(a_lo * (-expm1_l(1.0 - a_lo)));
+  double uh = log(a_lo + beta);
+  double dxold = uh - ul, dx = dxold;
+  double u = 0.5 * (ul + uh), G, dG;
+  double x = merge_G_fast(u, alpha, beta, u0, G, dG);
+  for (int it = 0; it < 100; ++it) {
+    if (!(G == G)) { status = ST_NONFINITE; break; }
+    if (G == 0.0) break;
+    if (G < 0.0) ul = u; else uh = u;
+    if (((u - uh) * dG - G) * ((u - ul) * dG - G) > 0.0 || fabs(2.0 * G) > fabs(dxold * dG)) {
+      dxold = dx;
+      dx = 0.5 * (uh - ul);
+      u = ul + dx;
+    } else {
+      dxold = dx;
+      dx = G * rcp_fast(dG);
+      u -= dx;
+    }
+    if (fabs(dx) <= 3.0e-16) {            // du = dx/x: relative accuracy of the root
+      x = exp_l(u);
+      break;
+    }
+    x = merge_G_fast(u, alpha, beta, u0, G, dG);
+    if (it == 99) status = ST_NO_CONVERGE;
+  }
+  u_root = u;
   return x;
 }
 
@@ -314,12 +368,11 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
   if (f.status != ST_OK) return;
   const double xn = f.hokt9 * m.nu_norm;
   bool safe = f.hokt9 * m.nu_max <= kSafeExp && -f.nb * m.lmax <= kSafeExp;
-  double inv_x0 = 0.0, tn_fac = 1.0, q = 0.0;
+  double tn_fac = 1.0, q = 0.0, lnxn = 0.0, u_m = 0.0;
   if (!THIN) {
     // q = log(xnorm/x0) = log(lambda0/wavenorm)
     const double r = div_fast(lambda0, m.wavenorm);
     f.x0 = div_fast(xn, r);
-    inv_x0 = rcp_fast(f.x0);
     q = log(r);
     const double qc_hi = q * kC64Hi;
     const double qc_lo = fma(q, kC64Lo, fma(q, kC64Hi, -qc_hi));
@@ -343,34 +396,19 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
   if (THIN) {
     f.xmerge = thin_merge_root_fast(3.0 + alpha + beta);               // modified_blackbody.py:253-254
   } else {
-    // bracket + Brent exactly as sed_setup (modified_blackbody.py:286-321)
-    double a = 0.1, av = merge_residual_fast(a, alpha, beta, inv_x0);
-    int it = 0;
-    while (av >= 0.0) {
-      a /= 2.0;
-      av = merge_residual_fast(a, alpha, beta, inv_x0);
-      if (it > 100) { f.status = ST_BRACKET_LOW; break; }
-      ++it;
-    }
-    double b = 15.0, bv = merge_residual_fast(b, alpha, beta, inv_x0);
-    it = 0;
-    while (f.status == ST_OK && bv <= 0.0) {
-      b *= 2.0;
-      bv = merge_residual_fast(b, alpha, beta, inv_x0);
-      if (it > 100) { f.status = ST_BRACKET_HIGH; break; }
-      ++it;
-    }
-    if (f.status == ST_OK && (!(av < 0.0) || !(bv > 0.0))) f.status = ST_NONFINITE;
+    // Root of the merge equation (modified_blackbody.py:122-151, 286-321).  The reference
+    // brackets it by halving/doubling from [0.1, 15] and runs brentq (~14 residual
+    // evaluations, each a log and three exponentials: three quarters of this setup); here a
+    // closed-form bracket and a safeguarded Newton iteration in log x (thick_merge_root_fast),
+    // 4-6 log-free residual evaluations, root to ~3e-16.
+    lnxn = log(xn);
+    f.xmerge = thick_merge_root_fast(alpha, beta, lnxn - q, f.status, u_m);
     if (f.status != ST_OK) return;
-    int st = ST_OK;
-    f.xmerge = brent_root([=](double x) { return merge_residual_fast(x, alpha, beta, inv_x0); }, a, b,
-                          av, bv, st);
-    if (st != ST_OK) { f.status = st; return; }
   }
   // R = grey(xmerge) xmerge^alpha / (grey(xnorm) xnorm^alpha), built from ratios
   const double xm = f.xmerge;
   f.nu_merge = div_fast(xm, f.hokt9);
-  const double lmn = log(div_fast(xm, xn));
+  const double lmn = THIN ? log(div_fast(xm, xn)) : u_m - lnxn;      // log(xmerge/xnorm)
   const double inv_em_m = rcp_fast(expm1_l(xm));
   double R;
   if (THIN) {
