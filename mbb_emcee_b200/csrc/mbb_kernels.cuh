@@ -23,6 +23,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "mbb_hostutil.h"
 #include "mbb_model.cuh"
 #include "mbb_quadpack.cuh"
 
@@ -47,16 +48,12 @@ struct EvalArgs {
   int wps_sh1, wps_sh2;
 };
 
-// fills the division constants from a.wps (host side)
+// fills the division constants from a.wps (host side; mbb_hostutil.h)
 inline void set_wps_division(EvalArgs& a) {
-  a.wps_mul = 0; a.wps_sh1 = 0; a.wps_sh2 = 0;
-  const unsigned long long d = (unsigned long long)(a.wps > 0 ? a.wps : 1);
-  if (d >> 32) return;                       // device falls back to 64-bit division
-  int l = 0;
-  while ((1ull << l) < d) ++l;               // ceil(log2 d)
-  a.wps_mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-  a.wps_sh1 = l < 1 ? l : 1;
-  a.wps_sh2 = l > 1 ? l - 1 : 0;
+  const WpsDivision d = wps_division((unsigned long long)(a.wps > 0 ? a.wps : 1));
+  a.wps_mul = d.mul;
+  a.wps_sh1 = d.sh1;
+  a.wps_sh2 = d.sh2;
 }
 
 struct DataRef {

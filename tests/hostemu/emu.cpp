@@ -15,6 +15,7 @@
 #include "../../mbb_emcee_b200/csrc/mbb_philox.cuh"
 #include "../../mbb_emcee_b200/csrc/mbb_quadpack.cuh"
 #include "../../mbb_emcee_b200/csrc/mbb_gaussrule.h"
+#include "../../mbb_emcee_b200/csrc/mbb_hostutil.h"
 
 using namespace mbb;
 
@@ -335,6 +336,26 @@ int emu_gauss_rule(int N, const double* x, const double* w, int n, double* xs, d
   if (!discrete_gauss_rule(xv, wv, n, xo, wo)) return 0;
   for (int k = 0; k < n; ++k) { xs[k] = xo[k]; ws[k] = wo[k]; }
   return 1;
+}
+
+// floor(g / wps) by the multiply-shift constants the launcher computes (mbb_hostutil.h)
+void emu_wps_division(long long n, const unsigned* g, unsigned wps, unsigned* q) {
+  const WpsDivision d = wps_division(wps);
+  for (long long i = 0; i < n; ++i) q[i] = d.mul ? wps_divide(d, g[i]) : g[i] / wps;
+}
+
+// FAST per-walker setup: xmerge, amp_grey, amp_pow, safe, status (thin = 0/1, alpha = 0/1)
+void emu_fast_setup(int thin, int alpha, long long n, const double* pars, double wavenorm, double* out,
+                    int* status) {
+  ModelP m{wavenorm, kUmToGHz / wavenorm, kUmToGHz / 50.0, 3.0};
+  for (long long e = 0; e < n; ++e) {
+    const double* p = pars + 5 * e;
+    FastSed s;
+    if (thin) { if (alpha) fast_setup<true, true>(s, p[0], p[1], p[2], p[3], p[4], m); else fast_setup<true, false>(s, p[0], p[1], p[2], p[3], p[4], m); }
+    else { if (alpha) fast_setup<false, true>(s, p[0], p[1], p[2], p[3], p[4], m); else fast_setup<false, false>(s, p[0], p[1], p[2], p[3], p[4], m); }
+    out[4 * e] = s.xmerge; out[4 * e + 1] = s.amp_grey; out[4 * e + 2] = s.amp_pow; out[4 * e + 3] = s.safe;
+    status[e] = s.status;
+  }
 }
 
 void emu_qags(int thin, int alpha, long long n, const double* pars, double wavenorm, double fmin, double fmax,

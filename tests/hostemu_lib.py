@@ -130,6 +130,24 @@ def gauss_rule(x, w, n):
     return (xs, ws) if ok else None
 
 
+def wps_division(g, wps):
+    """floor(g / wps) through the launcher's multiply-shift constants (csrc/mbb_hostutil.h)."""
+    g = np.ascontiguousarray(g, dtype=np.uint32)
+    q = np.empty_like(g)
+    lib().emu_wps_division(ctypes.c_longlong(g.size), _p(g), ctypes.c_uint(int(wps)), _p(q))
+    return q
+
+
+def fast_setup(opthin, noalpha, pars, wavenorm):
+    """(xmerge, amp_grey, amp_pow, safe)[n, 4] and status[n] of the FAST per-walker setup."""
+    P = _c(pars).reshape(-1, 5)
+    out = np.empty((P.shape[0], 4))
+    st = np.empty(P.shape[0], dtype=np.int32)
+    lib().emu_fast_setup(int(opthin), int(not noalpha), ctypes.c_longlong(P.shape[0]), _p(P),
+                         ctypes.c_double(wavenorm), _p(out), _p(st))
+    return out, st
+
+
 def philox(ctr, key):
     c = np.ascontiguousarray(ctr, dtype=np.uint32)
     k = np.ascontiguousarray(key, dtype=np.uint32)

@@ -300,6 +300,37 @@ def test_gauss_mode_matches_full_tables(cfgname, opthin, noalpha):
         assert emu.last_compressed() < 2 * nb - 3
 
 
+def test_walkers_per_source_division():
+    """The multiply-shift division the kernels use for evaluation index -> source index is
+    exact for every 32-bit dividend, for small, large, power-of-two and odd divisors."""
+    rng = np.random.RandomState(4)
+    g = np.concatenate([rng.randint(0, 2**32, 20000, dtype=np.uint64), [0, 1, 2**32 - 1, 2**31, 2**31 - 1],
+                        np.arange(0, 5000)]).astype(np.uint32)
+    for wps in (1, 2, 3, 7, 37, 125, 250, 256, 512, 1000, 4096, 65537, 2**31 - 1, 2**31, 2**32 - 1):
+        assert np.array_equal(emu.wps_division(g, wps), (g.astype(np.uint64) // wps).astype(np.uint32)), wps
+
+
+@pytest.mark.parametrize("name,opthin,noalpha", [v for v in VARIANTS if not v[2]])
+def test_fast_merge_point_matches_reference(golden, name, opthin, noalpha):
+    """FAST setup: the merge point from the safeguarded Newton iteration in log x (thick) or on
+    the Lambert-W equation (thin) equals the reference's brentq / lambertw value far inside
+    brentq's own 2e-12 tolerance; extreme slopes converge too."""
+    g = golden.sed
+    tag = name + "_wn500"
+    out, st = emu.fast_setup(opthin, noalpha, g[tag + "_P"], 500.0)
+    assert (st == 0).all()
+    assert relerr(out[:, 0], g[tag + "_xmerge"]).max() < 5e-13      # brentq itself stops at ~1e-13
+    rng = np.random.RandomState(12)
+    n = 20000
+    P = np.stack([10**rng.uniform(0.2, 2.3, n), rng.uniform(0.1, 19.9, n), 10**rng.uniform(0.1, 3.17, n),
+                  rng.uniform(0.11, 19.9, n), 10**rng.uniform(-2, 3, n)], axis=1)
+    out, st = emu.fast_setup(opthin, noalpha, P, 500.0)
+    assert (st == 0).all() and np.isfinite(out[:, :3]).all()
+    ref, st0 = emu.consts(opthin, noalpha, P, 500.0, want_peak=False)      # FAITHFUL: scipy-identical Brent
+    assert (st0 == 0).all()
+    assert relerr(out[:, 0], ref[:, 1]).max() < 5e-13
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for Philox4x32-10, for the C++ generator
     the device sampler uses and for the numpy twin the replay tests use."""
