@@ -272,9 +272,6 @@ MBB_HD double rcp_cubic(double b) {
 #endif
 }
 
-// a / b = a * rcp_cubic(b)  (<= 2 ulp)
-MBB_HD double div_lean(double a, double b) { return a * rcp_cubic(b); }
-
 // generic saturating forms (per-walker setup code)
 MBB_HD double exp_l(double x) { return exp_red<0, true>(red_x(x), exp2_tab_default()); }
 MBB_HD double expm1_l(double x) { return expm1_red<0, true>(red_x(x), exp2_tab_default()); }

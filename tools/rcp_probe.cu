@@ -1,7 +1,7 @@
 // Measures the seed accuracy of MUFU.RCP64H (PTX rcp.approx.ftz.f64) on the
 // GPU at hand: max |1 - b*r0| over a dense sample of mantissas and a range of
-// exponents, plus the resulting error of div_lean (mbb_fastmath.cuh) against
-// IEEE division.  Justifies the single cubic correction step of div_lean.
+// exponents, plus the resulting error of a * rcp_cubic(b) (mbb_fastmath.cuh)
+// against IEEE division.  Justifies the single cubic correction step of rcp_cubic.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_build/rcp_probe tools/rcp_probe.cu
 #include <cstdio>
 #include <cmath>
@@ -22,7 +22,7 @@ __global__ void probe(double* out_seed, double* out_div, int n_per_thread) {
     const double e = fabs(fma(-b, r0, 1.0));
     if (e > worst_seed) worst_seed = e;
     const double a = 1.0 + (double)(s >> 40) * 1e-7;
-    const double q = mbb::div_lean(a, b), qt = a / b;
+    const double q = a * mbb::rcp_cubic(b), qt = a / b;
     const double de = fabs(q - qt) / fabs(qt);
     if (de > worst_div) worst_div = de;
   }
