@@ -223,6 +223,22 @@ class Context(object):
                                        _ptr(out), _ptr(st), HOST))
         return out, st
 
+    def loglike_into(self, pars, out, status=None, src_index=None, walkers_per_source=None, layout=AOS):
+        """Host path with caller-owned buffers, used as they are (no copies on the Python
+        side): when they are page-locked (``torch.Tensor.pin_memory().numpy()``,
+        ``cudaHostRegister``) the library copies from / to them directly."""
+        for name, a, dt in (("pars", pars, np.float64), ("out", out, np.float64), ("status", status, np.int32),
+                            ("src_index", src_index, np.int32)):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous):
+                raise TypeError("%s must be a C-contiguous %s array" % (name, np.dtype(dt).name))
+        n = pars.size // 5
+        if pars.size != 5 * n or out.size != n or (status is not None and status.size != n) or \
+                (src_index is not None and src_index.size != n):
+            raise ValueError("pars[5n] / out[n] / status[n] / src_index[n] sizes disagree")
+        wps = n if walkers_per_source is None else int(walkers_per_source)
+        self._ck(self._lib.mbb_loglike(self._h, n, _ptr(pars), layout, _ptr(src_index), max(wps, 1),
+                                       _ptr(out), _ptr(status), HOST))
+
     def loglike_device(self, n, pars_ptr, out_ptr, status_ptr=0, src_index_ptr=0,
                        walkers_per_source=None, layout=AOS):
         """Raw device pointers (e.g. torch.Tensor.data_ptr()); asynchronous."""

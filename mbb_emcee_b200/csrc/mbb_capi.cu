@@ -894,6 +894,7 @@ int mbb_fnu(mbb_ctx* c, int64_t n, const double* pars, int layout, int nfreq, co
   if (n <= 0 || nfreq <= 0) return fail("n and nfreq must be positive");
   if (n > 65535) return fail("mbb_fnu: at most 65535 parameter vectors per call");
   if (!pars || !freq_ghz || !out) return fail("null pointer");
+  if (layout != MBB_AOS && layout != MBB_SOA) return fail("bad layout");
   Use u(c);
   EvalArgs a{};
   a.n = n;
@@ -942,6 +943,7 @@ int mbb_sed_consts(mbb_ctx* c, int64_t n, const double* pars, int layout, int wa
   if (!c) return fail("null context");
   if (n <= 0) return fail("n must be positive");
   if (!pars || !out_consts) return fail("null pointer");
+  if (layout != MBB_AOS && layout != MBB_SOA) return fail("bad layout");
   Use u(c);
   EvalArgs a{};
   a.n = n;
@@ -1139,6 +1141,8 @@ int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, dou
   if (!c->bands_set || (!c->has_ivar && !c->has_cinv)) return fail("bands/data not set");
   if (nsrc > c->nsrc) return fail("more sources than mbb_set_data provided");
   if (thin < 1) thin = 1;
+  if (mem != MBB_DEVICE && (chain || chain_lnprob))
+    return fail("chain output needs MBB_DEVICE buffers (it is large); keep it on the device");
   Use u(c);
   const int h = nwalkers / 2;
   const long long nwk = nsrc * nwalkers, nh = nsrc * h;
@@ -1155,7 +1159,6 @@ int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, dou
     dlnp = c->d_elnp.p;
     dnacc = nullptr;
     dst = nullptr;
-    if (chain || chain_lnprob) return fail("chain output needs MBB_DEVICE buffers (it is large); keep it on the device");
   }
   if (!dnacc) { CK(c->d_enacc.reserve((size_t)nwk)); dnacc = c->d_enacc.p; }
   if (!dst) { CK(c->d_est.reserve((size_t)nwk)); dst = c->d_est.p; }

@@ -291,6 +291,106 @@ def test_delta_kernel_launch_paths(oracle):
             assert bool(torch.equal(out, out2)) and bool(torch.equal(out, out3))
 
 
+def test_host_pipeline_pinned_and_pageable():
+    """mbb_loglike(MBB_HOST): the chunked three-slot pipeline gives the bits of one
+    device-resident launch -- pageable and page-locked caller buffers, AoS and SoA,
+    implicit and explicit source indices, a batch just past the pipelining threshold
+    (8 chunks of a multiple of 256 + a ragged tail) and a small env-forced chunk."""
+    import torch
+    from mbb_emcee_b200 import _native, synthetic
+    rng = np.random.RandomState(33)
+    nw = 125
+    n = (1 << 17) + 1000 - ((1 << 17) + 1000) % nw + nw      # whole sources, not a multiple of 256
+    nsrc = n // nw
+    waves = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0]
+    flux = rng.uniform(5, 80, (nsrc, 6))
+    unc = rng.uniform(1, 6, (nsrc, 6))
+    ctx = _native.Context(0)
+    ctx.set_model(500.0, True, True)
+    ctx.set_bands(np.arange(7, dtype=np.int32), waves, np.ones(6))
+    ctx.set_data(flux, ivar=1.0 / unc**2)
+    low = np.array([1, 0.1, 1, 0.1, 1e-3])
+    P = synthetic.walker_cloud((12.0, 1.8, 1300.0, 4.0, 30.0), n, rng, low)
+    P[::997, 0] = 0.5
+    dev = torch.device("cuda:0")
+    Pd = torch.as_tensor(P, device=dev)
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    ctx.loglike_device(n, Pd.data_ptr(), out.data_ptr(), st.data_ptr(), walkers_per_source=nw)
+    ctx.sync()
+    want, wst = out.cpu().numpy(), st.cpu().numpy()
+    assert np.isneginf(want[::997]).all() and np.isfinite(want).sum() == n - len(want[::997])
+    # pageable
+    got, gst = ctx.loglike(P, walkers_per_source=nw)
+    assert np.array_equal(got, want) and np.array_equal(gst, wst)
+    # page-locked, used in place
+    Pp = torch.empty((n, 5), dtype=torch.float64).pin_memory()
+    Op = torch.empty(n, dtype=torch.float64).pin_memory()
+    Sp = torch.empty(n, dtype=torch.int32).pin_memory()
+    Pp.numpy()[...] = P
+    Op.fill_(7.0)
+    ctx.loglike_into(Pp.numpy(), Op.numpy(), Sp.numpy(), walkers_per_source=nw)
+    assert np.array_equal(Op.numpy(), want) and np.array_equal(Sp.numpy(), wst)
+    # SoA + explicit (shuffled) source indices, pageable and page-locked
+    idx = rng.randint(0, nsrc, n).astype(np.int32)
+    src = torch.as_tensor(idx, device=dev)
+    ctx.loglike_device(n, Pd.data_ptr(), out.data_ptr(), 0, src_index_ptr=src.data_ptr())
+    ctx.sync()
+    want2 = out.cpu().numpy()
+    assert not np.array_equal(want2, want)
+    Pt = np.ascontiguousarray(P.T)
+    got2, _ = ctx.loglike(Pt, src_index=idx, layout=_native.SOA)
+    assert np.array_equal(got2, want2)
+    Tp = torch.empty((5, n), dtype=torch.float64).pin_memory()
+    Ip = torch.empty(n, dtype=torch.int32).pin_memory()
+    Tp.numpy()[...] = Pt
+    Ip.numpy()[...] = idx
+    ctx.loglike_into(Tp.numpy(), Op.numpy(), None, src_index=Ip.numpy(), layout=_native.SOA)
+    assert np.array_equal(Op.numpy(), want2)
+    with pytest.raises(RuntimeError):
+        bad = idx.copy()
+        bad[12345] = nsrc
+        ctx.loglike(P, src_index=bad)
+    with pytest.raises(TypeError):
+        ctx.loglike_into(P.astype(np.float32), Op.numpy())
+
+
+def test_contexts_in_concurrent_threads():
+    """SURVEY 8b threading contract: a context serialises its own calls, separate contexts
+    may be driven from separate threads (ctypes drops the GIL for the call).  Two
+    contexts with different models and band tables run host-path batches at the same
+    time; each reproduces its single-threaded bits."""
+    import threading
+    from mbb_emcee_b200 import _native, likelihood, synthetic
+    rng = np.random.RandomState(8)
+    low = np.array([1, 0.1, 1, 0.1, 1e-3])
+    a = _native.Context(0)
+    a.set_model(500.0, True, True)
+    a.set_bands(np.arange(7, dtype=np.int32), [70.0, 100.0, 160.0, 250.0, 350.0, 500.0], np.ones(6))
+    a.set_data(rng.uniform(5, 80, (1, 6)), ivar=1.0 / rng.uniform(1, 6, (1, 6))**2)
+    Pa = synthetic.walker_cloud((12.0, 1.8, 1300.0, 4.0, 30.0), 400_000, rng, low)
+    cfg = synthetic.CONFIGS["cfg2"]
+    like = likelihood(wavenorm=500.0, response=True)
+    like.set_phot(cfg["bands"], [40.0, 70.0, 75.0, 50.0, 28.0, 6.0], [4.0, 7.0, 6.0, 5.0, 4.0, 1.5])
+    Pb = synthetic.walker_cloud(cfg["truth"], 4000, rng, low)
+    wa, _ = a.loglike(Pa)
+    wb = like(Pb)
+    got = {}
+    errs = []
+
+    def run(name, fn, reps):
+        try:
+            for _ in range(reps):
+                got[name] = fn()
+        except Exception as e:              # surfaced below: a thread must not fail silently
+            errs.append((name, e))
+    ta = threading.Thread(target=run, args=("a", lambda: a.loglike(Pa)[0], 6))
+    tb = threading.Thread(target=run, args=("b", lambda: like(Pb), 6))
+    ta.start(); tb.start(); ta.join(); tb.join()
+    assert not errs, errs
+    assert np.array_equal(got["a"], wa) and np.array_equal(got["b"], wb)
+
+
 @pytest.mark.parametrize("cfgname", ["cfg2", "cfg3"])
 def test_gauss_mode_golden_and_oracle(golden, oracle, cfgname):
     """MBB_MATH_FAST_GAUSS (tabulated passbands through their 32-point Gauss rules where the
