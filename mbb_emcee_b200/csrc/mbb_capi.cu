@@ -1167,6 +1167,7 @@ int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, dou
   CK(c->d_eq.reserve((size_t)nh * 5));
   CK(c->d_eqlnp.reserve((size_t)nh));
   CK(c->d_eqst.reserve((size_t)nh));
+  CK(ensure_tables(c));      // node tables and the cold-path block match the current model / priors
   begin_timing(c);
   if (!have_lnprob) {
     // log-probability of the starting ensemble (emcee computes it once up front)
@@ -1181,7 +1182,8 @@ int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, dou
   g.nsrc = nsrc; g.nw = nwalkers; g.h = h; g.seed = seed; g.a = a;
   const unsigned grid = (unsigned)((nh + 255) / 256);
   // delta-band FAST configurations take the fused one-kernel half-step
-  static const bool no_fuse = getenv("MBB_B200_NO_FUSED_SAMPLER") != nullptr;
+  // (the switch is read per call so that tests can compare the paths in one process)
+  const bool no_fuse = getenv("MBB_B200_NO_FUSED_SAMPLER") != nullptr;
   const bool fused = !no_fuse && c->math_mode != MBB_MATH_FAITHFUL && c->nn == c->nb && c->nb <= kMaxDeltaNB;
   DataRef dref;
   dref.flux = c->d_flux.p;

@@ -113,7 +113,15 @@ __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
 // arithmetic, hence the same chain as the three-kernel pipeline above.
 // this kernel waits on gathers (ncu: long_scoreboard 3.9 of ~9 stalled warps per issue), so a
 // fourth resident CTA at 64 registers pays for its spills: 2.55 vs 2.60 ms per iteration (2 CTAs
-// at 116 registers: 3.20 ms)
+// at 116 registers: 3.20 ms).
+// Measured and rejected: a persistent form that stages whole source ensembles (20 KB of
+// positions + log-probabilities + photometry rows per tile) by cp.async.bulk two tiles ahead,
+// so that the partner gather becomes a shared-memory read -- bit-identical chains, but 2.57-2.61
+// ms per iteration: the 60 KB of staging allow 3 CTAs/SM, 80 registers still spill (q, z, u and
+// the old log-probability stay live across the evaluation), and the CTA barrier per tile costs
+// what the gathers did (17 % of the stall samples; the accept/reject branch makes the warps
+// uneven).  Releasing the ring stage with a per-warp count instead of that barrier ("last warp
+// refills") was slower again, here (2.62 ms) and in loglike_delta_kernel (1.29 vs 1.20 ms).
 #ifndef MBB_ENS_MINB
 #define MBB_ENS_MINB 4
 #endif

@@ -44,7 +44,11 @@ def _problem(oracle, response, nsrc, nw, seed):
     return bf, p0, specs
 
 
-@pytest.mark.parametrize("response,nsrc,nw,nsteps", [(False, 5, 16, 25), (True, 2, 12, 8)])
+# (False, ...): delta bands -> fused one-kernel half-step, for walker counts where a CTA covers
+# several sources, part of one and a ragged tail; (True, ...): tabulated bands -> propose /
+# evaluate / accept kernels
+@pytest.mark.parametrize("response,nsrc,nw,nsteps", [(False, 5, 16, 25), (False, 11, 64, 12), (False, 5, 250, 6),
+                                                     (True, 2, 12, 8)])
 def test_device_sampler_replays_on_host(oracle, response, nsrc, nw, nsteps):
     bf, p0, specs = _problem(oracle, response, nsrc, nw, 11)
     bf._stage()
@@ -89,3 +93,35 @@ def test_batch_fitter_recovers_truth():
     Tfit = out["pos"][:, :, 0].mean(axis=1)
     assert np.median(np.abs(Tfit - T) / T) < 0.05
     assert np.isfinite(out["lnprob"]).all()
+
+
+@pytest.mark.parametrize("opthin,noalpha", [(True, True), (False, False)])
+@pytest.mark.parametrize("nsrc,nw", [(1500, 512), (1001, 250), (700, 64), (37, 1024)])
+def test_sampler_kernels_agree_bitwise(monkeypatch, opthin, noalpha, nsrc, nw):
+    """The two device forms of a half-step -- the fused kernel and propose / evaluate /
+    accept -- draw the same numbers and do the same arithmetic: identical positions,
+    log-probabilities and acceptance counts over many sources."""
+    from mbb_emcee_b200 import batch_fitter
+    rng = np.random.RandomState(nsrc)
+    bands = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0]
+    bf = batch_fitter(nwalkers=nw, opthin=opthin, noalpha=noalpha, device=0)
+    if noalpha:
+        bf.fix_param('alpha')
+    flux = rng.uniform(10, 80, (nsrc, 6))
+    bf.set_data(bands, flux, np.maximum(0.1 * flux, 1.0))
+    truth = (12.0, 1.8, 1300.0, 4.0, 30.0) if opthin else (14.0, 1.8, 400.0, 3.0, 30.0)
+    p0 = bf.generate_initial_values(truth, [2, 0.2, 100, 0.3, 5.0], seed=5)
+    bf._stage()
+    ctx = bf.like.context
+    runs = []
+    for env in ({}, {"MBB_B200_NO_FUSED_SAMPLER": "1"}):
+        monkeypatch.delenv("MBB_B200_NO_FUSED_SAMPLER", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        n0 = ctx.launch_count()
+        runs.append(ctx.ensemble_run(p0, 5, seed=77) + (ctx.launch_count() - n0,))
+    a, b = runs
+    assert a[4] == 11 and b[4] > 11                     # 1 + 2 launches per iteration when fused
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert 0 < a[2].sum() < nsrc * nw * 5
