@@ -348,8 +348,12 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
 // and full covariances fall back to direct loads.
 // (Measured and rejected: per-stage release mbarriers, one arrive per warp,
 // instead of the CTA barrier -- thread 0 waiting for the slowest warp serialises
-// the refill, 1.35 ms against 1.20 ms for cfg5; 4 CTAs/SM at 64 registers: spills,
-// 1.29 ms.)
+// the refill, 1.35 ms against 1.20 ms for cfg5; a wait-free release -- each warp
+// counts itself out of the stage with a shared-memory atomic at the end of the tile
+// and the last one refills it three tiles ahead, no barrier in the loop -- 1.28 ms
+// (1.29 with block-scope fences), although ncu attributes 19 % of the stall samples
+// to the barrier: its lock-step is worth more than it costs; 4 CTAs/SM at 64
+// registers: spills, 1.29 ms.)
 constexpr int kDeltaTile = MBB_DELTA_BLOCK;
 constexpr int kDeltaStages = 3;
 constexpr int kDeltaMaxSrc = 8;

@@ -43,7 +43,7 @@ int main() {
   double ws = 0, wd = 0;
   for (int i = 0; i < n; ++i) { if (h[i] > ws) ws = h[i]; if (h[n + i] > wd) wd = h[n + i]; }
   printf("{\"samples\": %.3g, \"rcp64h_max_rel_err\": %.6g, \"rcp64h_log2\": %.3f, "
-         "\"div_lean_max_rel_err\": %.6g, \"div_lean_ulps\": %.3f}\n",
+         "\"mul_rcp_cubic_max_rel_err\": %.6g, \"mul_rcp_cubic_ulps\": %.3f}\n",
          (double)n * 20000, ws, log2(ws), wd, wd / 1.1102230246251565e-16);
   return 0;
 }
