@@ -105,6 +105,7 @@ struct mbb_ctx {
   int nc = 0;                     // compressed nodes in total (0: no band has a rule)
   double nu_max = 0.0, lmax = 0.0;
   bool fast_tables_ok = false;    // FAST tables match the current (wavenorm, opthin)
+  uint64_t delta_attr_set = 0;    // delta-kernel instantiations whose shared-memory attribute is set
   DevBuf<ColdArgs> d_cold;        // SmallTab + priors + model for the kernels' cold paths
   bool cold_ok = false;
   DevBuf<int> d_off;
@@ -345,8 +346,16 @@ struct DeltaLauncher {
       static const bool no_stage = getenv("MBB_B200_NO_STAGE_DATA") != nullptr;
       const int stage_data = use_tma && !no_stage && !a.src_index && d.ivar && !d.cinv;
       const ModelP m = model_of(c);
-      loglike_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, st>>>(a, m, c->pri, d, c->small,
-                                                                           c->d_cold.p, use_tma, stage_data);
+      // the replicated exp table is the kernel's dynamic shared memory (beside ~33 KB static)
+      constexpr size_t kTabBytes = sizeof(double) * kTabRepDoubles;
+      const uint64_t bit = 1ull << ((THIN ? 1 : 0) | (ALPHA ? 2 : 0) | (NB << 2));
+      if (!(c->delta_attr_set & bit)) {      // once per context (the attribute is per device)
+        cudaFuncSetAttribute(loglike_delta_kernel<THIN, ALPHA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kTabBytes);
+        c->delta_attr_set |= bit;
+      }
+      loglike_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, kTabBytes, st>>>(a, m, c->pri, d, c->small,
+                                                                                   c->d_cold.p, use_tma, stage_data);
     } else {
       DeltaLauncher<THIN, ALPHA, NB - 1>::go(c, st, a, d, nb);
     }

@@ -45,25 +45,55 @@
 namespace mbb {
 
 constexpr double kMagic = 6755399441055744.0;            // 1.5*2^52: low word of x+kMagic = round(x)
-constexpr double kC64Hi = 92.332482616893657;            // 64/ln2 as a double-double
-constexpr double kC64Lo = 1.3027375194195861e-15;
 
-// Table entry i serves the exponent residue i = k & 63: T_j with j = (i + 32) & 63,
-// as a bit pattern whose high word is pre-adjusted by 0x80000 - (j << 14), so that
-// hi + (k << 14) is the high word of 2^m T_j, m = (k + 32) >> 6.
+// Table size: 64 entries with a degree-4 polynomial (default), or -DMBB_TAB_BITS=8:
+// 256 entries with a degree-3 polynomial -- one DFMA less per exponential for a
+// 32 KB instead of 8 KB shared-memory table; "64" in the comments of this file
+// and of mbb_model.cuh stands for kTabN.  Measured on B200 (make EXTRA=-DMBB_TAB_BITS=8,
+// all GPU tests green): loglike_nodes_kernel cfg2 6.00 -> 5.75 ms, Gauss-rule thread
+// kernel cfg2 1.44 -> 1.39 ms, but loglike_delta_kernel cfg5 1.196 -> 1.223 ms (66 KB of
+// shared memory per CTA).  The headline workload is the delta kernel, so 64 stays the
+// default until the table size is a per-kernel template parameter (the scaled per-walker
+// constants and node tables of the two sizes differ by an exact factor 4).  Accuracy with
+// 256 entries: exp unchanged (<= 1.5 ulp); expm1 near 0 <= 20 ulp (g is good to 4.8e-18
+// absolute = 3.5e-15 of f g(f)) and <= 8.4e-14 in the |x| ~ 0.0014-0.09 band.
+#ifndef MBB_TAB_BITS
+#define MBB_TAB_BITS 6
+#endif
+static_assert(MBB_TAB_BITS == 6 || MBB_TAB_BITS == 8, "MBB_TAB_BITS must be 6 or 8");
+constexpr int kTabBits = MBB_TAB_BITS;
+constexpr int kTabN = 1 << kTabBits;
+constexpr int kTabMask = kTabN - 1;
+constexpr int kTabHalf = kTabN / 2;
+constexpr int kTabHiShift = 20 - kTabBits;               // entry index -> exponent-field units
+constexpr int kLeanDeg = kTabBits == 6 ? 4 : 3;          // degree of g, 2^(f/N) - 1 = f g(f)
+// N/ln2 as a double-double (the 256 pair is the 64 pair times 4, exactly)
+constexpr double kC64Hi = (kTabBits == 6 ? 1.0 : 4.0) * 92.332482616893657;
+constexpr double kC64Lo = (kTabBits == 6 ? 1.0 : 4.0) * 1.3027375194195861e-15;
+
+// Table entry i serves the exponent residue i = k & (N-1): T_j with j = (i + N/2) & (N-1),
+// as a bit pattern whose high word is pre-adjusted by 0x80000 - (j << kTabHiShift), so that
+// hi + (k << kTabHiShift) is the high word of 2^m T_j, m = (k + N/2) >> kTabBits.
+// f*g(f) = 2^(f/N) - 1 on |f| <= 0.5005: max abs error 2.4e-18 (N = 64), 4.8e-18 (N = 256).
+#if MBB_TAB_BITS == 6
+#define MBB_EXPTAB_INC "mbb_exptab.inc"
+#define MBB_LEAN_G {0.010830424696249145, 5.8649049550517742e-05, 2.1173137155457974e-07, \
+                    5.7328587073751599e-10, 1.2417854561126839e-12}
+#else
+#define MBB_EXPTAB_INC "mbb_exptab256.inc"
+#define MBB_LEAN_G {0.0027076061740622767, 3.665565596910102e-06, 3.3083029843180382e-09, \
+                    2.2393953279597525e-12}
+#endif
 #if defined(__CUDACC__)
-__device__ const unsigned long long kExp2Tab_dev[64] = {
-#include "mbb_exptab.inc"
+__device__ const unsigned long long kExp2Tab_dev[kTabN] = {
+#include MBB_EXPTAB_INC
 };
-// f*g(f) = 2^(f/64) - 1 on |f| <= 0.5005, max abs error 2.4e-18
-__device__ __constant__ double kLeanG_dev[5] = {0.010830424696249145, 5.8649049550517742e-05,
-                                               2.1173137155457974e-07, 5.7328587073751599e-10,
-                                               1.2417854561126839e-12};
+__device__ __constant__ double kLeanG_dev[kLeanDeg + 1] = MBB_LEAN_G;
 #endif
 
 inline const double* exp2_tab_host() {
-  static const unsigned long long tab[64] = {
-#include "mbb_exptab.inc"
+  static const unsigned long long tab[kTabN] = {
+#include MBB_EXPTAB_INC
   };
   return reinterpret_cast<const double*>(tab);
 }
@@ -79,14 +109,13 @@ MBB_HD const double* exp2_tab_default() {
 }
 // shared-memory copy: entry i, copy c at double index i*16 + c  (TS = 4)
 constexpr int kTabRepShift = 4;
-constexpr int kTabRepDoubles = 64 << kTabRepShift;
+constexpr int kTabRepDoubles = kTabN << kTabRepShift;
 
 MBB_HD double lean_g_coef(int i) {
 #if defined(__CUDA_ARCH__)
   return kLeanG_dev[i];
 #else
-  const double c[5] = {0.010830424696249145, 5.8649049550517742e-05, 2.1173137155457974e-07,
-                       5.7328587073751599e-10, 1.2417854561126839e-12};
+  const double c[kLeanDeg + 1] = MBB_LEAN_G;
   return c[i];
 #endif
 }
@@ -129,7 +158,7 @@ MBB_HD double clamp_pos(double x) {
   return from_hilo(h < CAP_HI_WORD ? h : CAP_HI_WORD, lo32_of(x));
 }
 constexpr int kHi700 = 0x4085e000;      // high word of 700.0
-constexpr int kHi700C = 0x40ef8e00;     // high word of 64624.0 ~ 700*64/ln2
+constexpr int kHi700C = kTabBits == 6 ? 0x40ef8e00 : 0x410f8e00;   // high word of 64624.0 (x4) ~ 700*N/ln2
 
 // Reduced exponent: y = k + f in units of 1/64 octave, k = round(y), |f| <= 1/2.
 // Valid while |y| < 2^31 (callers gate their parameters).
@@ -193,20 +222,20 @@ MBB_HD Red red_sum_prod(double a_hi, double a_lo, double b, double c) {
 // guarantees m in [-1022, 1023]); CLAMP=true saturates m.
 template <int TS, bool CLAMP>
 MBB_HD double scaled_T(const double* tab, int k) {
-  const double tb = tab[(k & 63) << TS];
-  if (!CLAMP) return from_hilo(hi32_of(tb) + (int)((unsigned)k << 14), lo32_of(tb));
-  const int j = (k + 32) & 63;
-  int m = (k + 32) >> 6;
+  const double tb = tab[(k & kTabMask) << TS];
+  if (!CLAMP) return from_hilo(hi32_of(tb) + (int)((unsigned)k << kTabHiShift), lo32_of(tb));
+  const int j = (k + kTabHalf) & kTabMask;
+  int m = (k + kTabHalf) >> kTabBits;
   m = m > 1023 ? 1023 : m;
   m = m < -1022 ? -1022 : m;
-  return from_hilo(hi32_of(tb) - 0x80000 + (j << 14) + (int)((unsigned)m << 20), lo32_of(tb));
+  return from_hilo(hi32_of(tb) - 0x80000 + (j << kTabHiShift) + (int)((unsigned)m << 20), lo32_of(tb));
 }
 
 // p = 2^(f/64) - 1
 MBB_HD double lean_p(double f) {
-  double g = lean_g_coef(4);
+  double g = lean_g_coef(kLeanDeg);
 #pragma unroll
-  for (int i = 3; i >= 0; --i) g = fma(g, f, lean_g_coef(i));
+  for (int i = kLeanDeg - 1; i >= 0; --i) g = fma(g, f, lean_g_coef(i));
   return g * f;
 }
 

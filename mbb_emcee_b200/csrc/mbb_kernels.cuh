@@ -370,7 +370,7 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
                      const SmallTab t, const ColdArgs* __restrict__ cold, const int use_tma,
                      const int stage_data) {
   constexpr int kRow = kDeltaMaxSrc * NB + 2;             // doubles per staged data array (+2: alignment slack)
-  __shared__ __align__(16) double s_tab[kTabRepDoubles];
+  extern __shared__ __align__(16) double s_tab[];         // kTabRepDoubles (dynamic: 32 KB with MBB_TAB_BITS=8)
   __shared__ __align__(16) double s_par[kDeltaStages][kDeltaTile * 5];
   __shared__ __align__(16) double s_dat[kDeltaStages][2][kRow];
   __shared__ __align__(16) DeltaStageHdr s_hdr[kDeltaStages];

@@ -75,7 +75,7 @@ inline FastNode fast_node(double wave_um, double weight, double wavenorm, bool t
   FastNode n;
   n.freq = kUmToGHz / wave_um;
   const long double l = logl((long double)wave_um) - logl((long double)wavenorm);
-  const long double lp = l * (64.0L / logl(2.0L));
+  const long double lp = l * ((long double)kTabN / logl(2.0L));
   n.lp = (double)lp;
   n.labs = fabs((double)l);
   const long double r = (long double)wavenorm / (long double)wave_um;
@@ -512,9 +512,9 @@ template <int N>
 MBB_HD void lean_p_n(const double (&f)[N], double (&p)[N]) {
   double g[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) g[i] = lean_g_coef(4);
+  for (int i = 0; i < N; ++i) g[i] = lean_g_coef(kLeanDeg);
 #pragma unroll
-  for (int j = 3; j >= 0; --j) {
+  for (int j = kLeanDeg - 1; j >= 0; --j) {
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = fma(g[i], f[i], lean_g_coef(j));
   }

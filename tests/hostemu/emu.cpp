@@ -306,6 +306,10 @@ void emu_lir(int thin, int alpha, long long n, const double* pars, double waveno
 // 3 a/b with b = x+1, 4 exp (no clamp), 5 expm1 (no clamp), 6 1-exp(-x) through the scaled path,
 // 7 exp(x*y) as a product reduction with y = 0.7 (double-double of 0.7*64/ln2 formed here),
 // 8 1/x by rcp_cubic
+// table size of this build (MBB_TAB_BITS) and the double N/ln2 the scaled paths use
+int emu_tab_bits() { return kTabBits; }
+double emu_c64_hi() { return kC64Hi; }
+
 void emu_fastmath(int mode, long long n, const double* x, double* out) {
   const double* tab = exp2_tab_default();
   for (long long i = 0; i < n; ++i) {
@@ -316,7 +320,7 @@ void emu_fastmath(int mode, long long n, const double* x, double* out) {
     else if (mode == 5) out[i] = expm1_red<0, false>(red_x(x[i]), tab);
     else if (mode == 6) out[i] = one_minus_exp_red<0, false>(red_neg_scaled(clamp_pos<kHi700C>(x[i] * kC64Hi)), tab);
     else if (mode == 7) {
-      const long double b = 0.7L * (64.0L / logl(2.0L));
+      const long double b = 0.7L * ((long double)kTabN / logl(2.0L));
       const double bh = (double)b, bl = (double)(b - (long double)bh);
       out[i] = exp_red<0, false>(red_prod(x[i], bh, bl), tab);
     } else if (mode == 8) out[i] = rcp_cubic(x[i]);

@@ -7,7 +7,10 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(HERE, "_hostemu", "libmbb_hostemu.so")
+# MBB_TAB_BITS=8 in the environment tests the 256-entry-table variant of the lean math
+# (the library must then be built with EXTRA=-DMBB_TAB_BITS=8 as well)
+_BITS = os.environ.get("MBB_TAB_BITS", "6")
+_SO = os.path.join(HERE, "_hostemu", "libmbb_hostemu%s.so" % ("_b8" if _BITS == "8" else ""))
 _lib = None
 
 
@@ -20,9 +23,18 @@ class EmuPriors(ctypes.Structure):
 def lib():
     global _lib
     if _lib is None:
-        subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s"])
+        subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s", "TAB_BITS=" + _BITS])
         _lib = ctypes.CDLL(_SO)
+        _lib.emu_c64_hi.restype = ctypes.c_double
     return _lib
+
+
+def tab_bits():
+    return int(lib().emu_tab_bits())
+
+
+def c64_hi():
+    return float(lib().emu_c64_hi())
 
 
 def _p(a):
