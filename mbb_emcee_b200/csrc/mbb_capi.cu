@@ -96,7 +96,7 @@ struct mbb_ctx {
   std::vector<double> h_wave, h_weight;   // as given to mbb_set_bands
   DevBuf<double2> d_node_fw;      // {freq, passband weight}: FAITHFUL kernels, chain_flux
   DevBuf<double2> d_node_fast_a;  // {freq, weff}  FAST (depends on opthin)
-  DevBuf<double> d_node_fast_b;   // L' = log(wave/wavenorm)*64/ln2, FAST (depends on wavenorm)
+  DevBuf<double> d_node_fast_b;   // L' = log(wave/wavenorm)*256/ln2, FAST (depends on wavenorm)
   // MBB_MATH_FAST_GAUSS: 32-point Gauss rules of the tabulated bands
   DevBuf<double2> d_comp_a;
   DevBuf<double> d_comp_b;
@@ -228,7 +228,7 @@ cudaError_t ensure_tables(mbb_ctx* c) {
     const FastNode n = fast_node(c->h_wave[i], c->h_weight[i], c->wavenorm, thin);
     fw[i] = make_double2(n.freq, c->h_weight[i]);
     fa[i] = make_double2(n.freq, n.weff);
-    fb[i] = n.lp;
+    fb[i] = 4.0 * n.lp;          // the nodes / Gauss-rule kernels work in 1/256-octave units (kNodesTS)
     if (n.freq > c->nu_max) c->nu_max = n.freq;
     if (n.labs > c->lmax) c->lmax = n.labs;
     if (nn <= kSmallMaxNodes) {
@@ -258,7 +258,7 @@ cudaError_t ensure_tables(mbb_ctx* c) {
     std::vector<double> cb((size_t)c->nc + 2, 0.0);       // padded to a multiple of 16 bytes
     for (int k = 0; k < c->nc; ++k) {
       ca[k] = make_double2(g.freq[k], g.weff[k]);
-      cb[k] = g.lp[k];
+      cb[k] = 4.0 * g.lp[k];
     }
     if ((e = c->d_comp_a.reserve(ca.size())) != cudaSuccess) return e;
     if ((e = c->d_comp_b.reserve(cb.size())) != cudaSuccess) return e;

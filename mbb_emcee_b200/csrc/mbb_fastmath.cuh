@@ -46,60 +46,68 @@ namespace mbb {
 
 constexpr double kMagic = 6755399441055744.0;            // 1.5*2^52: low word of x+kMagic = round(x)
 
-// Table size: 64 entries with a degree-4 polynomial (default), or -DMBB_TAB_BITS=8:
-// 256 entries with a degree-3 polynomial -- one DFMA less per exponential for a
-// 32 KB instead of 8 KB shared-memory table; "64" in the comments of this file
-// and of mbb_model.cuh stands for kTabN.  Measured on B200 (make EXTRA=-DMBB_TAB_BITS=8,
-// all GPU tests green): loglike_nodes_kernel cfg2 6.00 -> 5.75 ms, Gauss-rule thread
-// kernel cfg2 1.44 -> 1.39 ms, but loglike_delta_kernel cfg5 1.196 -> 1.223 ms (66 KB of
-// shared memory per CTA).  The headline workload is the delta kernel, so 64 stays the
-// default until the table size is a per-kernel template parameter (the scaled per-walker
-// constants and node tables of the two sizes differ by an exact factor 4).  Accuracy with
-// 256 entries: exp unchanged (<= 1.5 ulp); expm1 near 0 <= 20 ulp (g is good to 4.8e-18
-// absolute = 3.5e-15 of f g(f)) and <= 8.4e-14 in the |x| ~ 0.0014-0.09 band.
-#ifndef MBB_TAB_BITS
-#define MBB_TAB_BITS 6
-#endif
-static_assert(MBB_TAB_BITS == 6 || MBB_TAB_BITS == 8, "MBB_TAB_BITS must be 6 or 8");
-constexpr int kTabBits = MBB_TAB_BITS;
-constexpr int kTabN = 1 << kTabBits;
-constexpr int kTabMask = kTabN - 1;
-constexpr int kTabHalf = kTabN / 2;
-constexpr int kTabHiShift = 20 - kTabBits;               // entry index -> exponent-field units
-constexpr int kLeanDeg = kTabBits == 6 ? 4 : 3;          // degree of g, 2^(f/N) - 1 = f g(f)
-// N/ln2 as a double-double (the 256 pair is the 64 pair times 4, exactly)
-constexpr double kC64Hi = (kTabBits == 6 ? 1.0 : 4.0) * 92.332482616893657;
-constexpr double kC64Lo = (kTabBits == 6 ? 1.0 : 4.0) * 1.3027375194195861e-15;
+// Two table sizes, chosen per kernel through the TS template parameter of the
+// functions below (bit 4 of TS set = 256 entries):
+//   64 entries, g of degree 4   -- per-walker setup code and the delta-band kernels;
+//   256 entries, g of degree 3  -- one DFMA less per exponential for a 32 KB instead of
+//                                  8 KB replicated table: the node loops of the passband kernels.
+// Measured on B200 (whole-library builds of either size, all GPU tests green):
+// loglike_nodes_kernel cfg2 6.00 -> 5.75 ms and the Gauss-rule thread kernel 1.44 -> 1.39 ms
+// with 256 entries, but loglike_delta_kernel cfg5 1.196 -> 1.223 ms (66 instead of 41 KB of
+// shared memory per CTA).  "64" in the comments of this file and of mbb_model.cuh stands
+// for the table size N in use; quantities "in 1/64-octave units" of the 256 flavour are the
+// 64 ones times 4, exactly (fast_sed_rescale256, node tables built with that factor).
+// Accuracy with 256 entries: exp unchanged (<= 1.5 ulp); expm1 near 0 <= 20 ulp (g is
+// good to 4.8e-18 absolute = 3.5e-15 of f g(f)) and <= 8.4e-14 in the |x| ~ 0.0014-0.09 band.
+constexpr int kTab256 = 16;                              // TS flag: the 256-entry table
+template <int TS>
+struct TabCfg {
+  static constexpr int bits = (TS & kTab256) ? 8 : 6;
+  static constexpr int n = 1 << bits;
+  static constexpr int mask = n - 1;
+  static constexpr int half = n / 2;
+  static constexpr int hishift = 20 - bits;              // entry index -> exponent-field units
+  static constexpr int stride = TS & 15;                 // log2 of the index stride (replication)
+  static constexpr int deg = bits == 6 ? 4 : 3;          // degree of g, 2^(f/N) - 1 = f g(f)
+  static constexpr double cscale = bits == 6 ? 1.0 : 4.0;   // N/ln2 relative to 64/ln2
+};
+constexpr double kC64Hi = 92.332482616893657;            // 64/ln2 as a double-double
+constexpr double kC64Lo = 1.3027375194195861e-15;
 
 // Table entry i serves the exponent residue i = k & (N-1): T_j with j = (i + N/2) & (N-1),
-// as a bit pattern whose high word is pre-adjusted by 0x80000 - (j << kTabHiShift), so that
-// hi + (k << kTabHiShift) is the high word of 2^m T_j, m = (k + N/2) >> kTabBits.
+// as a bit pattern whose high word is pre-adjusted by 0x80000 - (j << hishift), so that
+// hi + (k << hishift) is the high word of 2^m T_j, m = (k + N/2) >> bits.
 // f*g(f) = 2^(f/N) - 1 on |f| <= 0.5005: max abs error 2.4e-18 (N = 64), 4.8e-18 (N = 256).
-#if MBB_TAB_BITS == 6
-#define MBB_EXPTAB_INC "mbb_exptab.inc"
-#define MBB_LEAN_G {0.010830424696249145, 5.8649049550517742e-05, 2.1173137155457974e-07, \
-                    5.7328587073751599e-10, 1.2417854561126839e-12}
-#else
-#define MBB_EXPTAB_INC "mbb_exptab256.inc"
-#define MBB_LEAN_G {0.0027076061740622767, 3.665565596910102e-06, 3.3083029843180382e-09, \
-                    2.2393953279597525e-12}
-#endif
+#define MBB_LEAN_G64 {0.010830424696249145, 5.8649049550517742e-05, 2.1173137155457974e-07, \
+                      5.7328587073751599e-10, 1.2417854561126839e-12}
+#define MBB_LEAN_G256 {0.0027076061740622767, 3.665565596910102e-06, 3.3083029843180382e-09, \
+                       2.2393953279597525e-12}
 #if defined(__CUDACC__)
-__device__ const unsigned long long kExp2Tab_dev[kTabN] = {
-#include MBB_EXPTAB_INC
+__device__ const unsigned long long kExp2Tab_dev[64] = {
+#include "mbb_exptab.inc"
 };
-__device__ __constant__ double kLeanG_dev[kLeanDeg + 1] = MBB_LEAN_G;
+__device__ const unsigned long long kExp2Tab256_dev[256] = {
+#include "mbb_exptab256.inc"
+};
+__device__ __constant__ double kLeanG_dev[5] = MBB_LEAN_G64;
+__device__ __constant__ double kLeanG256_dev[4] = MBB_LEAN_G256;
 #endif
 
 inline const double* exp2_tab_host() {
-  static const unsigned long long tab[kTabN] = {
-#include MBB_EXPTAB_INC
+  static const unsigned long long tab[64] = {
+#include "mbb_exptab.inc"
+  };
+  return reinterpret_cast<const double*>(tab);
+}
+inline const double* exp2_tab256_host() {
+  static const unsigned long long tab[256] = {
+#include "mbb_exptab256.inc"
   };
   return reinterpret_cast<const double*>(tab);
 }
 
-// The plain (unreplicated) table: global memory (L1-resident) on the device, a
-// static array on the host.  Index stride 1 (TS = 0 below).
+// The plain (unreplicated) tables: global memory (L1-resident) on the device, a
+// static array on the host.  Index stride 1 (TS = 0, or kTab256 for the 256-entry one).
 MBB_HD const double* exp2_tab_default() {
 #if defined(__CUDA_ARCH__)
   return reinterpret_cast<const double*>(kExp2Tab_dev);
@@ -107,16 +115,27 @@ MBB_HD const double* exp2_tab_default() {
   return exp2_tab_host();
 #endif
 }
-// shared-memory copy: entry i, copy c at double index i*16 + c  (TS = 4)
-constexpr int kTabRepShift = 4;
-constexpr int kTabRepDoubles = kTabN << kTabRepShift;
+MBB_HD const double* exp2_tab256_default() {
+#if defined(__CUDA_ARCH__)
+  return reinterpret_cast<const double*>(kExp2Tab256_dev);
+#else
+  return exp2_tab256_host();
+#endif
+}
+// shared-memory copies: entry i, copy c at double index i*16 + c
+constexpr int kTabRepShift = 4;                          // TS of the replicated 64-entry table
+constexpr int kTabRepDoubles = 64 << kTabRepShift;
+constexpr int kTabRep256 = kTabRepShift | kTab256;       // TS of the replicated 256-entry table
+constexpr int kTabRep256Doubles = 256 << kTabRepShift;
 
+template <int TS>
 MBB_HD double lean_g_coef(int i) {
 #if defined(__CUDA_ARCH__)
-  return kLeanG_dev[i];
+  return TabCfg<TS>::bits == 6 ? kLeanG_dev[i] : kLeanG256_dev[i];
 #else
-  const double c[kLeanDeg + 1] = MBB_LEAN_G;
-  return c[i];
+  const double c64[5] = MBB_LEAN_G64;
+  const double c256[4] = MBB_LEAN_G256;
+  return TabCfg<TS>::bits == 6 ? c64[i] : c256[i];
 #endif
 }
 
@@ -158,7 +177,9 @@ MBB_HD double clamp_pos(double x) {
   return from_hilo(h < CAP_HI_WORD ? h : CAP_HI_WORD, lo32_of(x));
 }
 constexpr int kHi700 = 0x4085e000;      // high word of 700.0
-constexpr int kHi700C = kTabBits == 6 ? 0x40ef8e00 : 0x410f8e00;   // high word of 64624.0 (x4) ~ 700*N/ln2
+// high word of 64624.0 (x4 for the 256-entry flavour) ~ 700*N/ln2
+template <int TS>
+constexpr int hi700c() { return TabCfg<TS>::bits == 6 ? 0x40ef8e00 : 0x410f8e00; }
 
 // Reduced exponent: y = k + f in units of 1/64 octave, k = round(y), |f| <= 1/2.
 // Valid while |y| < 2^31 (callers gate their parameters).
@@ -222,47 +243,49 @@ MBB_HD Red red_sum_prod(double a_hi, double a_lo, double b, double c) {
 // guarantees m in [-1022, 1023]); CLAMP=true saturates m.
 template <int TS, bool CLAMP>
 MBB_HD double scaled_T(const double* tab, int k) {
-  const double tb = tab[(k & kTabMask) << TS];
-  if (!CLAMP) return from_hilo(hi32_of(tb) + (int)((unsigned)k << kTabHiShift), lo32_of(tb));
-  const int j = (k + kTabHalf) & kTabMask;
-  int m = (k + kTabHalf) >> kTabBits;
+  using C = TabCfg<TS>;
+  const double tb = tab[(k & C::mask) << C::stride];
+  if (!CLAMP) return from_hilo(hi32_of(tb) + (int)((unsigned)k << C::hishift), lo32_of(tb));
+  const int j = (k + C::half) & C::mask;
+  int m = (k + C::half) >> C::bits;
   m = m > 1023 ? 1023 : m;
   m = m < -1022 ? -1022 : m;
-  return from_hilo(hi32_of(tb) - 0x80000 + (j << kTabHiShift) + (int)((unsigned)m << 20), lo32_of(tb));
+  return from_hilo(hi32_of(tb) - 0x80000 + (j << C::hishift) + (int)((unsigned)m << 20), lo32_of(tb));
 }
 
-// p = 2^(f/64) - 1
+// p = 2^(f/N) - 1
+template <int TS>
 MBB_HD double lean_p(double f) {
-  double g = lean_g_coef(kLeanDeg);
+  double g = lean_g_coef<TS>(TabCfg<TS>::deg);
 #pragma unroll
-  for (int i = kLeanDeg - 1; i >= 0; --i) g = fma(g, f, lean_g_coef(i));
+  for (int i = TabCfg<TS>::deg - 1; i >= 0; --i) g = fma(g, f, lean_g_coef<TS>(i));
   return g * f;
 }
 
 template <int TS, bool CLAMP>
 MBB_HD double exp_red(const Red r, const double* tab) {
   const double sT = scaled_T<TS, CLAMP>(tab, r.k);
-  return fma(sT, lean_p(r.f), sT);
+  return fma(sT, lean_p<TS>(r.f), sT);
 }
 
 // scale * exp(y): the product scale*sT runs beside the polynomial, not after it
 template <int TS, bool CLAMP>
 MBB_HD double exp_red_times(const Red r, const double* tab, double scale) {
   const double sT = scaled_T<TS, CLAMP>(tab, r.k) * scale;
-  return fma(sT, lean_p(r.f), sT);
+  return fma(sT, lean_p<TS>(r.f), sT);
 }
 
 template <int TS, bool CLAMP>
 MBB_HD double expm1_red(const Red r, const double* tab) {
   const double sT = scaled_T<TS, CLAMP>(tab, r.k);
-  return fma(sT, lean_p(r.f), sT - 1.0);
+  return fma(sT, lean_p<TS>(r.f), sT - 1.0);
 }
 
 // 1 - exp(y) for the reduced exponent of y (y <= 0 in every use)
 template <int TS, bool CLAMP>
 MBB_HD double one_minus_exp_red(const Red r, const double* tab) {
   const double sT = scaled_T<TS, CLAMP>(tab, r.k);
-  return fma(-sT, lean_p(r.f), 1.0 - sT);
+  return fma(-sT, lean_p<TS>(r.f), 1.0 - sT);
 }
 
 // 1/b for normal b (no subnormal / zero handling), <= 1 ulp

@@ -49,7 +49,7 @@ struct GaussThreadTab {
 };
 
 __host__ __device__ inline size_t gauss_thread_smem(int nb, int nc) {
-  return (size_t)kTabRepDoubles * 8 + (size_t)3 * kDeltaTile * 40 + 3 * 8 + 8 +
+  return (size_t)kNodesTabDoubles * 8 + (size_t)3 * kDeltaTile * 40 + 3 * 8 + 8 +
          (size_t)nc * 16 + nodes_b_bytes(nc) + (size_t)(nb + 1) * 8 + (size_t)nb * sizeof(BandMeta) + 64;
 }
 
@@ -61,7 +61,7 @@ __device__ __forceinline__ double band_table_thread(const FastSed& fs, const dou
   double acc = 0.0;
   for (int i = i0; i < i1; ++i) {
     const double2 fw = __ldg(ga + i);
-    acc = node_acc<THIN, ALPHA, CLAMP, kTabRepShift>(fs, fw.x, __ldg(gb + i), fw.y, acc, tab);
+    acc = node_acc<THIN, ALPHA, CLAMP, kNodesTS>(fs, fw.x, __ldg(gb + i), fw.y, acc, tab);
   }
   return acc;
 }
@@ -76,12 +76,12 @@ __device__ __forceinline__ double rule_grey_thread(const FastSed& fs, const doub
   for (; i + 1 < c1; i += 2) {
     const double2 f0 = ca[i], f1 = ca[i + 1];
     const double nu[2] = {f0.x, f1.x}, lp[2] = {cb[i], cb[i + 1]}, we[2] = {f0.y, f1.y};
-    grey_nodes_n<THIN, 2, kTabRepShift>(fs, nu, lp, we, acc2, tab);
+    grey_nodes_n<THIN, 2, kNodesTS>(fs, nu, lp, we, acc2, tab);
   }
   double acc = acc2[0] + acc2[1];
   if (i < c1) {
     const double2 fw = ca[i];
-    acc = node_grey<THIN, false, kTabRepShift>(fs, fw.x, cb[i], fw.y, acc, tab);
+    acc = node_grey<THIN, false, kNodesTS>(fs, fw.x, cb[i], fw.y, acc, tab);
   }
   return acc;
 }
@@ -90,7 +90,7 @@ __device__ __forceinline__ double rule_pow_thread(const FastSed& fs, const doubl
                                                   const double* __restrict__ cb, int c0, int c1,
                                                   const double* tab) {
   double acc = 0.0;
-  for (int i = c0; i < c1; ++i) acc = node_pow<false, kTabRepShift>(fs, cb[i], ca[i].y, acc, tab);
+  for (int i = c0; i < c1; ++i) acc = node_pow<false, kNodesTS>(fs, cb[i], ca[i].y, acc, tab);
   return acc;
 }
 
@@ -106,7 +106,7 @@ loglike_gauss_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, c
                             const GaussThreadTab t, const ColdArgs* __restrict__ cold, const int use_tma) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_tab = reinterpret_cast<double*>(smem_raw);
-  double* s_par = s_tab + kTabRepDoubles;                                   // [3][kDeltaTile*5]
+  double* s_par = s_tab + kNodesTabDoubles;                                   // [3][kDeltaTile*5]
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_par + 3 * kDeltaTile * 5);   // [3] (+1 pad)
   double2* s_ca = reinterpret_cast<double2*>(s_bar + 4);
   double* s_cb = reinterpret_cast<double*>(s_ca + t.nc);
@@ -115,7 +115,7 @@ loglike_gauss_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, c
   int* s_coff = s_off + t.nb + 1;
   const int tid = threadIdx.x, nb = t.nb;
   const long long sd = a.soa_stride ? a.soa_stride : a.n;
-  stage_exp_table(s_tab);
+  stage_exp_table256(s_tab);
   for (int i = tid; i < t.nc; i += blockDim.x) {
     s_ca[i] = t.ca[i];
     s_cb[i] = t.cb[i];
@@ -178,6 +178,7 @@ loglike_gauss_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, c
         lnl = -kInf;
       } else {
         fast_setup<THIN, ALPHA>(fs, p[0], p[1], p[2], p[3], p[4], m);
+        fast_sed_rescale256(fs);           // node loops below: 1/256-octave units (kNodesTS)
         st = fs.status;
         live = st == ST_OK;
       }

@@ -138,6 +138,16 @@ __device__ __forceinline__ void stage_exp_table(double* s_tab) {
 __device__ __forceinline__ const double* lane_exp_table(const double* s_tab) {
   return s_tab + (threadIdx.x & 15);
 }
+// the 256-entry table of the passband kernels (32 KB), same replication
+__device__ __forceinline__ void stage_exp_table256(double* s_tab) {
+  const double* g = reinterpret_cast<const double*>(kExp2Tab256_dev);
+  for (int i = threadIdx.x; i < kTabRep256Doubles; i += blockDim.x) s_tab[i] = __ldg(g + (i >> kTabRepShift));
+}
+// Table flavour of the node loops of the passband kernels (nodes kernel, Gauss-rule thread
+// kernel): 256 entries, degree-3 polynomial.  Their per-walker constants and node tables are
+// in 1/256-octave units: fast_sed_rescale256 in the setup, L' * 4 in the tables (mbb_capi.cu).
+constexpr int kNodesTS = kTabRep256;
+constexpr int kNodesTabDoubles = kTabRep256Doubles;
 
 // ---------------------------------------------------------------------------
 // TMA bulk copy + mbarrier helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
@@ -370,7 +380,7 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
                      const SmallTab t, const ColdArgs* __restrict__ cold, const int use_tma,
                      const int stage_data) {
   constexpr int kRow = kDeltaMaxSrc * NB + 2;             // doubles per staged data array (+2: alignment slack)
-  extern __shared__ __align__(16) double s_tab[];         // kTabRepDoubles (dynamic: 32 KB with MBB_TAB_BITS=8)
+  extern __shared__ __align__(16) double s_tab[];         // kTabRepDoubles (dynamic shared memory)
   __shared__ __align__(16) double s_par[kDeltaStages][kDeltaTile * 5];
   __shared__ __align__(16) double s_dat[kDeltaStages][2][kRow];
   __shared__ __align__(16) DeltaStageHdr s_hdr[kDeltaStages];
@@ -500,6 +510,7 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
     st = s.status;
     safe = s.safe;
     if (st == ST_OK) prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
+    fast_sed_rescale256(s);        // the nodes kernel works in 1/256-octave units (kNodesTS)
     c[0] = s.xk_hi; c[1] = s.xk_lo; c[2] = s.nb; c[3] = s.apow;
     c[4] = s.t0c; c[5] = s.nu_merge; c[6] = s.uq_hi; c[7] = s.uq_lo;
     c[8] = s.amp_grey; c[9] = s.amp_pow;
@@ -555,12 +566,12 @@ constexpr int kNodesThreads = MBB_NODES_THREADS;
 constexpr int kNodesWarps = kNodesThreads / 32;
 
 // dynamic shared memory of the nodes kernel:
-//   [a pairs | b (FAST)] (tables_in_smem, b padded to 16 B) | [compressed a | b] (GAUSS) | exp table 8 KB |
+//   [a pairs | b (FAST)] (tables_in_smem, b padded to 16 B) | [compressed a | b] (GAUSS) | exp table 32 KB |
 //   per-warp diff | mbarrier | band_off | comp_off | scalar
 __host__ __device__ inline size_t nodes_b_bytes(int nn) { return ((size_t)nn * 8 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t nodes_kernel_smem(int nn, bool tables_in_smem, bool fast, int nc = 0) {
   return (tables_in_smem ? (size_t)nn * 16 + (fast ? nodes_b_bytes(nn) : 0) : 0) +
-         (nc ? (size_t)nc * 16 + nodes_b_bytes(nc) : 0) + kTabRepDoubles * 8 +
+         (nc ? (size_t)nc * 16 + nodes_b_bytes(nc) : 0) + kNodesTabDoubles * 8 +
          (size_t)(MBB_NODES_THREADS / 32) * kMaxBands * 8 + 16 + (size_t)(kMaxBands + 1) * 8 + kMaxBands;
 }
 
@@ -578,7 +589,7 @@ __device__ __forceinline__ double band_partial_fast(const FastSed& fs, const dou
   double acc = 0.0;
   for (int i = i0 + lane; i < i1; i += 32) {
     const double2 fw = na[i];
-    acc = node_acc<THIN, ALPHA, CLAMP, kTabRepShift>(fs, fw.x, nl[i], fw.y, acc, tab);
+    acc = node_acc<THIN, ALPHA, CLAMP, kNodesTS>(fs, fw.x, nl[i], fw.y, acc, tab);
   }
   return acc;
 }
@@ -594,7 +605,7 @@ __device__ __forceinline__ double band_partial_kink(const FastSed& fs, const dou
                                                     const double2* __restrict__ ca,
                                                     const double* __restrict__ cl, int c0, int c1,
                                                     int k, int lane, const double* tab) {
-  constexpr int TS = kTabRepShift;
+  constexpr int TS = kNodesTS;
   double acc = 0.0;
   if (k - i0 <= i1 - k) {
     for (int i = c0 + lane; i < c1; i += 32) {
@@ -637,7 +648,7 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
   double2* s_ca = reinterpret_cast<double2*>(smem_raw + tab_bytes);
   double* s_cb = reinterpret_cast<double*>(s_ca + t.nc);
   double* s_exp = reinterpret_cast<double*>(smem_raw + tab_bytes + comp_bytes);
-  double* s_diff = s_exp + kTabRepDoubles;
+  double* s_diff = s_exp + kNodesTabDoubles;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_diff + kNodesWarps * kMaxBands);
   int* s_off = reinterpret_cast<int*>(bar + 2);
   int* s_coff = s_off + kMaxBands + 1;          // a constant offset from s_off: no address arithmetic of its own
@@ -656,7 +667,7 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
       if (FAST) bulk_g2s_chunked(s_b, t.b, bytes_b, bar);
     }
   }
-  if (FAST) stage_exp_table(s_exp);
+  if (FAST) stage_exp_table256(s_exp);
   if (GAUSS && t.nc) {
     for (int i = tid; i < t.nc; i += blockDim.x) {
       s_ca[i] = t.ca[i];

@@ -75,7 +75,7 @@ inline FastNode fast_node(double wave_um, double weight, double wavenorm, bool t
   FastNode n;
   n.freq = kUmToGHz / wave_um;
   const long double l = logl((long double)wave_um) - logl((long double)wavenorm);
-  const long double lp = l * ((long double)kTabN / logl(2.0L));
+  const long double lp = l * (64.0L / logl(2.0L));
   n.lp = (double)lp;
   n.labs = fabs((double)l);
   const long double r = (long double)wavenorm / (long double)wave_um;
@@ -249,6 +249,16 @@ MBB_HD_NOINLINE void sed_setup(Sed& s, double T, double beta, double lambda0, do
   }
   if (ALPHA && !finite_d(s.kappa)) s.status = ST_OVERFLOW;
   if (!finite_d(s.normfac)) s.status = ST_OVERFLOW;
+}
+
+// The per-walker constants that are "in 1/64-octave units", converted for the node
+// loops that use the 256-entry table (TS & kTab256): times 4, exact.
+MBB_HD void fast_sed_rescale256(FastSed& f) {
+  f.xk_hi *= 4.0;
+  f.xk_lo *= 4.0;
+  f.t0c *= 4.0;
+  f.uq_hi *= 4.0;
+  f.uq_lo *= 4.0;
 }
 
 // ---------------------------------------------------------------------------
@@ -486,9 +496,9 @@ MBB_HD double node_grey(const FastSed& s, double nu, double lp, double weff, dou
   if (THIN) return fma(exp_red<TS, CLAMP>(red_prod1(s.nb, lp), tab), wr, acc);
   // tc = t_i*64/ln2, t_i = (x_i/x0)^beta = t0 exp(-beta L_i); beyond ~700 only 1 - exp(-t) = 1 matters
   double tc;
-  if (CLAMP) tc = exp_red_times<TS, true>(red_sum_prod(s.uq_hi, s.uq_lo, s.nb, lp), tab, kC64Hi);
+  if (CLAMP) tc = exp_red_times<TS, true>(red_sum_prod(s.uq_hi, s.uq_lo, s.nb, lp), tab, kC64Hi * TabCfg<TS>::cscale);
   else tc = exp_red_times<TS, false>(red_prod1(s.nb, lp), tab, s.t0c);
-  const double g = one_minus_exp_red<TS, CLAMP>(red_neg_scaled(clamp_pos<kHi700C>(tc)), tab);
+  const double g = one_minus_exp_red<TS, CLAMP>(red_neg_scaled(clamp_pos<hi700c<TS>()>(tc)), tab);
   return fma(g, wr, acc);
 }
 
@@ -508,15 +518,15 @@ MBB_HD double node_acc(const FastSed& s, double nu, double lp, double weff, doub
 // left to itself the compiler emits each chain serially under the register cap.
 //   acc[i] += f_nu(nu_i) w_i   for i < N
 // ---------------------------------------------------------------------------
-template <int N>
+template <int N, int TS>
 MBB_HD void lean_p_n(const double (&f)[N], double (&p)[N]) {
   double g[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) g[i] = lean_g_coef(kLeanDeg);
+  for (int i = 0; i < N; ++i) g[i] = lean_g_coef<TS>(TabCfg<TS>::deg);
 #pragma unroll
-  for (int j = kLeanDeg - 1; j >= 0; --j) {
+  for (int j = TabCfg<TS>::deg - 1; j >= 0; --j) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = fma(g[i], f[i], lean_g_coef(j));
+    for (int i = 0; i < N; ++i) g[i] = fma(g[i], f[i], lean_g_coef<TS>(j));
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) p[i] = g[i] * f[i];
@@ -543,7 +553,7 @@ MBB_HD void grey_nodes_n(const FastSed& s, const double (&nu)[N], const double (
 #pragma unroll
   for (int i = 0; i < 2 * N; ++i) sT[i] = scaled_T<TS, false>(tab, lo32_of(t[i]));
   double p[2 * N];
-  lean_p_n<2 * N>(f, p);
+  lean_p_n<2 * N, TS>(f, p);
   double em[N], aw[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -563,7 +573,7 @@ MBB_HD void grey_nodes_n(const FastSed& s, const double (&nu)[N], const double (
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double s2 = sT[N + i] * s.t0c;
-    tc[i] = clamp_pos<kHi700C>(fma(s2, p[N + i], s2));
+    tc[i] = clamp_pos<hi700c<TS>()>(fma(s2, p[N + i], s2));
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -571,7 +581,7 @@ MBB_HD void grey_nodes_n(const FastSed& s, const double (&nu)[N], const double (
     f3[i] = r.f;
     sT3[i] = scaled_T<TS, false>(tab, r.k);
   }
-  lean_p_n<N>(f3, p3);
+  lean_p_n<N, TS>(f3, p3);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double g = fma(-sT3[i], p3[i], 1.0 - sT3[i]);

@@ -20,10 +20,34 @@
 using namespace mbb;
 
 namespace {
-template <bool THIN, bool ALPHA, bool FAST>
-void run_loglike(long long n, const double* pars, const ModelP& m, const Priors& pr, const TabView& t,
+// Table flavour of the specialised node code being emulated: 0 = 64 entries (delta kernels),
+// kTab256 = 256 entries (nodes kernel, Gauss-rule kernels: per-walker constants and L' times 4).
+int g_ts = 0;
+
+template <bool THIN, bool ALPHA, bool FAST, int TS = 0>
+void run_loglike(long long n, const double* pars, const ModelP& m, const Priors& pr, const TabView& t0,
                  const double* flux, const double* ivar, const double* cinv, long long wps, int unclamped,
-                 double* out, int* status, const GaussTables* gt = nullptr, long long* ncompressed = nullptr) {
+                 double* out, int* status, const GaussTables* gt0 = nullptr, long long* ncompressed = nullptr) {
+  if (TS == 0 && g_ts != 0 && FAST && unclamped) {
+    run_loglike<THIN, ALPHA, FAST, kTab256>(n, pars, m, pr, t0, flux, ivar, cinv, wps, unclamped, out, status, gt0,
+                                            ncompressed);
+    return;
+  }
+  // the 256 flavour reads node tables scaled like the device ones (mbb_capi.cu: L' * 4)
+  TabView t = t0;
+  std::vector<double> lp_scaled;
+  GaussTables gts;
+  const GaussTables* gt = gt0;
+  if (TS != 0) {
+    lp_scaled.assign(t0.lp, t0.lp + t0.band_off[t0.nb]);
+    for (auto& v : lp_scaled) v *= 4.0;
+    if (gt0) {
+      gts = *gt0;
+      for (auto& v : gts.lp) v *= 4.0;
+      gt = &gts;
+    }
+  }
+  const double* lpn = TS != 0 ? lp_scaled.data() : t0.lp;
   const int nb = t.nb;
   for (long long e = 0; e < n; ++e) {
     const long long src = e / wps;
@@ -35,11 +59,12 @@ void run_loglike(long long n, const double* pars, const ModelP& m, const Priors&
       // the arithmetic of the specialised kernels (loglike_delta_kernel / nodes kernel):
       // CLAMP=false node code for `safe` walkers, the generic path otherwise
       const double* p = pars + 5 * e;
-      const double* tab = exp2_tab_default();
+      const double* tab = TS != 0 ? exp2_tab256_default() : exp2_tab_default();
       FastSed s;
       st = ST_OK;
       if (below_lowlim(pr, p)) { out[e] = -kInf; status[e] = ST_BELOW_LOWLIM; continue; }
       fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m);
+      if (TS != 0) fast_sed_rescale256(s);
       if (s.status == ST_OK && s.safe) {
         double chi;
         if (gt) {
@@ -53,29 +78,29 @@ void run_loglike(long long n, const double* pars, const ModelP& m, const Priors&
             if ((gm.plain >> b) & 1ull) {
               if (ncompressed) ++*ncompressed;
               for (int i = gt->off[b]; i < gt->off[b + 1]; ++i)
-                acc = node_acc<THIN, ALPHA, false, 0>(s, gt->freq[i], gt->lp[i], gt->weff[i], acc, tab);
+                acc = node_acc<THIN, ALPHA, false, TS>(s, gt->freq[i], gt->lp[i], gt->weff[i], acc, tab);
             } else if (ALPHA && ((gm.kink >> b) & 1ull)) {
               if (ncompressed) ++*ncompressed;
               int k = i0;
               while (k < i1 && t.freq[k] > s.nu_merge) ++k;
               const bool grey_rule = k - i0 <= i1 - k;
               for (int i = gt->off[b]; i < gt->off[b + 1]; ++i)
-                acc = grey_rule ? node_grey<THIN, false, 0>(s, gt->freq[i], gt->lp[i], gt->weff[i], acc, tab)
-                                : node_pow<false, 0>(s, gt->lp[i], gt->weff[i], acc, tab);
+                acc = grey_rule ? node_grey<THIN, false, TS>(s, gt->freq[i], gt->lp[i], gt->weff[i], acc, tab)
+                                : node_pow<false, TS>(s, gt->lp[i], gt->weff[i], acc, tab);
               if (grey_rule) {
                 for (int i = i0; i < k; ++i) {
-                  acc = node_pow<false, 0>(s, t.lp[i], t.weff[i], acc, tab);
-                  acc = node_grey<THIN, false, 0>(s, t.freq[i], t.lp[i], -t.weff[i], acc, tab);
+                  acc = node_pow<false, TS>(s, lpn[i], t.weff[i], acc, tab);
+                  acc = node_grey<THIN, false, TS>(s, t.freq[i], lpn[i], -t.weff[i], acc, tab);
                 }
               } else {
                 for (int i = k; i < i1; ++i) {
-                  acc = node_grey<THIN, false, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
-                  acc = node_pow<false, 0>(s, t.lp[i], -t.weff[i], acc, tab);
+                  acc = node_grey<THIN, false, TS>(s, t.freq[i], lpn[i], t.weff[i], acc, tab);
+                  acc = node_pow<false, TS>(s, lpn[i], -t.weff[i], acc, tab);
                 }
               }
             } else {
               for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i)
-                acc = node_acc<THIN, ALPHA, false, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
+                acc = node_acc<THIN, ALPHA, false, TS>(s, t.freq[i], lpn[i], t.weff[i], acc, tab);
             }
             diff[b] = fl[b] - acc;
           }
@@ -91,7 +116,7 @@ void run_loglike(long long n, const double* pars, const ModelP& m, const Priors&
           }
         } else
         chi = chi_square(t, fl, iv, ci, [&](int, int i, double acc) {
-          return node_acc<THIN, ALPHA, false, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
+          return node_acc<THIN, ALPHA, false, TS>(s, t.freq[i], lpn[i], t.weff[i], acc, tab);
         });
         double lnl = -0.5 * chi;
         if (!priors_trivial(pr, p)) {
@@ -107,7 +132,7 @@ void run_loglike(long long n, const double* pars, const ModelP& m, const Priors&
         continue;
       }
     }
-    out[e] = loglike_one<THIN, ALPHA, FAST>(pars + 5 * e, m, pr, t, fl, iv, ci, st);
+    out[e] = loglike_one<THIN, ALPHA, FAST>(pars + 5 * e, m, pr, t0, fl, iv, ci, st);
     status[e] = st;
   }
 }
@@ -302,30 +327,44 @@ void emu_lir(int thin, int alpha, long long n, const double* pars, double waveno
   DISPATCH2(run_lir, thin, alpha, n, pars, wavenorm, fmin, fmax, prefac, out, status);
 }
 
-// element-wise checks of the lean math: mode 0 exp (CLAMP), 1 expm1 (CLAMP), 2 reciprocal,
-// 3 a/b with b = x+1, 4 exp (no clamp), 5 expm1 (no clamp), 6 1-exp(-x) through the scaled path,
-// 7 exp(x*y) as a product reduction with y = 0.7 (double-double of 0.7*64/ln2 formed here),
-// 8 1/x by rcp_cubic
-// table size of this build (MBB_TAB_BITS) and the double N/ln2 the scaled paths use
-int emu_tab_bits() { return kTabBits; }
-double emu_c64_hi() { return kC64Hi; }
+// table flavour of the emulated specialised node code (see g_ts), its size and its N/ln2
+void emu_set_tab_bits(int bits) { g_ts = bits == 8 ? kTab256 : 0; }
+int emu_tab_bits() { return g_ts ? 8 : 6; }
+double emu_c64_hi() { return kC64Hi * (g_ts ? 4.0 : 1.0); }
+}  // extern "C"
 
-void emu_fastmath(int mode, long long n, const double* x, double* out) {
-  const double* tab = exp2_tab_default();
+namespace {
+template <int TS>
+void run_fastmath(int mode, long long n, const double* x, double* out) {
+  const double* tab = TS != 0 ? exp2_tab256_default() : exp2_tab_default();
+  constexpr double cs = TabCfg<TS>::cscale;
   for (long long i = 0; i < n; ++i) {
     if (mode == 0) out[i] = exp_l(x[i]);
     else if (mode == 1) out[i] = expm1_l(x[i]);
     else if (mode == 2) out[i] = rcp_fast(x[i]);
-    else if (mode == 4) out[i] = exp_red<0, false>(red_x(x[i]), tab);
-    else if (mode == 5) out[i] = expm1_red<0, false>(red_x(x[i]), tab);
-    else if (mode == 6) out[i] = one_minus_exp_red<0, false>(red_neg_scaled(clamp_pos<kHi700C>(x[i] * kC64Hi)), tab);
+    else if (mode == 4) out[i] = exp_red<TS, false>(red_prod(x[i], kC64Hi * cs, kC64Lo * cs), tab);
+    else if (mode == 5) out[i] = expm1_red<TS, false>(red_prod(x[i], kC64Hi * cs, kC64Lo * cs), tab);
+    else if (mode == 6)
+      out[i] = one_minus_exp_red<TS, false>(red_neg_scaled(clamp_pos<hi700c<TS>()>(x[i] * (kC64Hi * cs))), tab);
     else if (mode == 7) {
-      const long double b = 0.7L * ((long double)kTabN / logl(2.0L));
+      const long double b = 0.7L * ((long double)TabCfg<TS>::n / logl(2.0L));
       const double bh = (double)b, bl = (double)(b - (long double)bh);
-      out[i] = exp_red<0, false>(red_prod(x[i], bh, bl), tab);
+      out[i] = exp_red<TS, false>(red_prod(x[i], bh, bl), tab);
     } else if (mode == 8) out[i] = rcp_cubic(x[i]);
     else out[i] = div_fast(x[i], x[i] + 1.0);
   }
+}
+}  // namespace
+
+extern "C" {
+// element-wise checks of the lean math: mode 0 exp (CLAMP), 1 expm1 (CLAMP), 2 reciprocal,
+// 3 a/b with b = x+1, 4 exp (no clamp), 5 expm1 (no clamp), 6 1-exp(-x) through the scaled path,
+// 7 exp(x*y) as a product reduction with y = 0.7 (double-double of 0.7*N/ln2 formed here),
+// 8 1/x by rcp_cubic.  Modes 4-7 use the table flavour set by emu_set_tab_bits; 0-1 are the
+// per-walker forms (always 64 entries).
+void emu_fastmath(int mode, long long n, const double* x, double* out) {
+  if (g_ts) run_fastmath<kTab256>(mode, n, x, out);
+  else run_fastmath<0>(mode, n, x, out);
 }
 
 void emu_grey_nodes(int thin, long long n, const double* pars, double wavenorm, const double* wave,

@@ -7,10 +7,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# MBB_TAB_BITS=8 in the environment tests the 256-entry-table variant of the lean math
-# (the library must then be built with EXTRA=-DMBB_TAB_BITS=8 as well)
-_BITS = os.environ.get("MBB_TAB_BITS", "6")
-_SO = os.path.join(HERE, "_hostemu", "libmbb_hostemu%s.so" % ("_b8" if _BITS == "8" else ""))
+_SO = os.path.join(HERE, "_hostemu", "libmbb_hostemu.so")
 _lib = None
 
 
@@ -23,10 +20,16 @@ class EmuPriors(ctypes.Structure):
 def lib():
     global _lib
     if _lib is None:
-        subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s", "TAB_BITS=" + _BITS])
+        subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s"])
         _lib = ctypes.CDLL(_SO)
         _lib.emu_c64_hi.restype = ctypes.c_double
     return _lib
+
+
+def set_tab_bits(bits):
+    """Table flavour of the emulated specialised node code: 6 = 64 entries (delta kernels),
+    8 = 256 entries (nodes kernel, Gauss-rule kernels)."""
+    lib().emu_set_tab_bits(int(bits))
 
 
 def tab_bits():

@@ -68,6 +68,15 @@ def _setup(golden, cfgname):
     return cfg, like
 
 
+@pytest.fixture(params=[6, 8], ids=["tab64", "tab256"])
+def tabbits(request):
+    """Table flavour of the emulated specialised node code: 64 entries (the delta kernels) or
+    256 entries (nodes kernel, Gauss-rule kernels; per-walker constants and L' times 4)."""
+    emu.set_tab_bits(request.param)
+    yield request.param
+    emu.set_tab_bits(6)
+
+
 def _emu_like(like, P, fast):
     off, wave, weight, scalar = like.band_tables()
     ep = emu.priors_struct(like.lowlims, like.has_uplims, like.uplims, like.has_gpriors,
@@ -79,7 +88,7 @@ def _emu_like(like, P, fast):
 
 @pytest.mark.parametrize("cfgname", ["cfg1", "cfg2", "cfg3"])
 @pytest.mark.parametrize("fast", [0, 1, 2])
-def test_loglike(golden, cfgname, fast):
+def test_loglike(golden, cfgname, fast, tabbits):
     cfg, like = _setup(golden, cfgname)
     g = golden.like
     assert np.array_equal(like.uplims, g[cfgname + "_uplim"])
@@ -93,7 +102,7 @@ def test_loglike(golden, cfgname, fast):
 
 
 @pytest.mark.parametrize("fast", [0, 1, 2])
-def test_loglike_extra(golden, fast):
+def test_loglike_extra(golden, fast, tabbits):
     from mbb_emcee_b200 import likelihood
     g = golden.like
     like = likelihood(wavenorm=500.0)
@@ -168,7 +177,7 @@ def test_freq_integrate(golden, oracle, name, opthin, noalpha):
         assert abs(got[i] - truth) <= 1e-13 * abs(truth)
 
 
-def test_fastmath():
+def test_fastmath(tabbits):
     """The lean exp family of csrc/mbb_fastmath.cuh against mpmath, in ulps: saturating
     (CLAMP) and unclamped instantiations, the scaled 1-exp(-t) path and the product
     reduction the node loops use."""
@@ -178,7 +187,7 @@ def test_fastmath():
     x = np.concatenate([rng.uniform(-60, 60, 3000), rng.uniform(-1, 1, 3000),
                         rng.uniform(-690, 690, 500), [0.0, 1e-300, -1e-300, 1e-17, 0.34657, -0.34658,
                                                       0.0054, -0.0054, 0.0108, -0.0109]])
-    N = 1 << emu.tab_bits()                      # 64 (default build) or 256 (MBB_TAB_BITS=8)
+    N = 1 << emu.tab_bits()                      # 64 or 256 (modes 4-7 follow the flavour)
     c64 = mp.mpf(N) / mp.log(2)
     band = 2.1e-14 * N / 64
 
@@ -273,7 +282,7 @@ def test_gauss_rule_of_passbands():
 
 @pytest.mark.parametrize("cfgname", ["cfg2", "cfg3"])
 @pytest.mark.parametrize("opthin,noalpha", [(False, False), (True, True), (False, True), (True, False)])
-def test_gauss_mode_matches_full_tables(cfgname, opthin, noalpha):
+def test_gauss_mode_matches_full_tables(cfgname, opthin, noalpha, tabbits):
     """MBB_MATH_FAST_GAUSS (emulated): over a very wide parameter cloud the compressed
     rules change lnlike by < 1e-13 relative, most (walker, band) pairs use them, and the
     gate sends the delicate ones (merge point in the band, cold or steep walkers) to the
@@ -305,7 +314,7 @@ def test_gauss_mode_matches_full_tables(cfgname, opthin, noalpha):
 
 
 @pytest.mark.parametrize("opthin,noalpha", [(False, False), (True, True), (False, True), (True, False)])
-def test_gauss_mode_every_shipped_filter(opthin, noalpha):
+def test_gauss_mode_every_shipped_filter(opthin, noalpha, tabbits):
     """MBB_MATH_FAST_GAUSS (emulated), one band at a time over the whole filter wheel:
     with the data flux at zero lnlike = -m^2/2, so the comparison measures the band flux m
     itself (no chi-square cancellation) -- the compressed rule and its gate hold for the

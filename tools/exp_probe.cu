@@ -21,11 +21,11 @@ __device__ __forceinline__ double link(double x, double c_hi, double c_lo, const
   if (MODE == 0) return exp_red<kTabRepShift, false>(red_prod(x, c_hi, c_lo), tab);
   if (MODE == 1) {
     const Red r = red_prod(x, c_hi, c_lo);
-    return fma(1.0, lean_p(r.f), 1.0 + 1e-300 * r.k);
+    return fma(1.0, lean_p<0>(r.f), 1.0 + 1e-300 * r.k);
   }
   if (MODE == 2) {
     const double f = x * 0.25;
-    return fma(0.5, lean_p(f), 0.5);
+    return fma(0.5, lean_p<0>(f), 0.5);
   }
   const Red r = red_prod(x, c_hi, c_lo);
   return 0.6 + r.f + 1e-300 * r.k;
