@@ -341,6 +341,29 @@ def test_gauss_mode_every_shipped_filter(opthin, noalpha, tabbits):
     assert used > 0.5 * 2 * 17 * n          # GISMO_2mm (53 nodes) has no rule; the rest mostly use theirs
 
 
+@pytest.mark.parametrize("opthin,noalpha", [(False, False), (True, True), (True, False), (False, True)])
+def test_fast_paths_agree_with_faithful_over_extreme_parameters(opthin, noalpha, tabbits):
+    """Log-uniform parameters over the whole range the limits allow (T 1-200 K, beta and alpha
+    0.1-20, lambda0 1-3000 um, fnorm 1e-3-1e4 mJy), bands from 12 um to 3 mm: the saturating
+    FAST code and the unclamped specialisation (either table flavour) return the FAITHFUL
+    status for every walker and the FAITHFUL value to 1e-13."""
+    from mbb_emcee_b200 import likelihood
+    rng = np.random.RandomState(77)
+    n = 1500
+    P = np.stack([10**rng.uniform(0.0, 2.3, n), 10**rng.uniform(-1, 1.3, n), 10**rng.uniform(0, 3.47, n),
+                  10**rng.uniform(-1, 1.3, n), 10**rng.uniform(-3, 4, n)], axis=1)
+    waves = [12.0, 24.0, 70.0, 160.0, 350.0, 850.0, 2000.0, 3000.0]
+    flux = rng.uniform(1, 100, len(waves))
+    like = likelihood(wavenorm=500.0, noalpha=noalpha, opthin=opthin)
+    like.set_phot(waves, flux, np.maximum(0.1 * flux, 1.0))
+    ref, st_ref = _emu_like(like, P, 0)
+    assert (st_ref == 0).all() and np.isfinite(ref).all()
+    for fast in (1, 2):
+        got, st = _emu_like(like, P, fast)
+        assert np.array_equal(st, st_ref)
+        assert relerr(got, ref).max() < 1e-13, fast
+
+
 def test_walkers_per_source_division():
     """The multiply-shift division the kernels use for evaluation index -> source index is
     exact for every 32-bit dividend, for small, large, power-of-two and odd divisors."""
