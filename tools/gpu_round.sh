@@ -20,9 +20,21 @@ for w in cfg5 cfg2; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches_$w.csv \
       $B --workload $w > $O/${T}_ncu_l_$w.log 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:loglike_delta -s 3 -c 1 -o $O/${T}_prof_cfg5 -f \
-    $B --workload cfg5 > $O/${T}_ncu_f_cfg5.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:loglike_nodes -s 3 -c 1 -o $O/${T}_prof_cfg2 -f \
-    $B --workload cfg2 > $O/${T}_ncu_f_cfg2.log 2>&1
+# full captures, summarised on the box (each .ncu-rep is 25-40 MB and gpurun_out/ may carry 64 MiB
+# back: the reports are deleted after the summaries are written; keep one by passing KEEP_REP=name)
+full() { # name  kernel-regex  command...
+  local name=$1 rx=$2; shift 2
+  ncu --set full --clock-control none --import-source on -k regex:$rx -s 3 -c 1 -o $O/${T}_prof_$name -f \
+      "$@" > $O/${T}_ncu_f_$name.log 2>&1
+  python tools/ncu_summary.py full $O/${T}_prof_$name.ncu-rep > $O/${T}_full_$name.md 2>> $O/${T}_ncu_f_$name.log
+  python tools/ncu_summary.py facts $O/${T}_prof_$name.ncu-rep > $O/${T}_facts_$name.json 2>> $O/${T}_ncu_f_$name.log
+  [ "$KEEP_REP" = "$name" ] || rm -f $O/${T}_prof_$name.ncu-rep
+}
+full cfg5 loglike_delta $B --workload cfg5
+full cfg2 loglike_nodes $B --workload cfg2
+full cfg2_gauss loglike_gauss_thread $B --workload cfg2 --math gauss
+full cfg5p_gauss loglike_gauss_thread $B --workload cfg5p --math gauss
+full ens_delta ens_delta python tools/sampler_probe.py 4
+python tools/sampler_probe.py 10 > $O/${T}_sampler.json 2> $O/${T}_sampler.err
 head -c 600 $O/${T}_bench_cfg5.json; echo
 echo DONE
