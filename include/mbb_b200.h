@@ -29,6 +29,7 @@
 #ifndef MBB_B200_H
 #define MBB_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -81,6 +82,11 @@ uint64_t mbb_stream_handle(const mbb_ctx *ctx);
  * (CUDA events on the context's stream around the launch); call after mbb_sync
  * for MBB_DEVICE calls. */
 int mbb_last_kernel_ms(mbb_ctx *ctx, float *ms);
+
+/* page-locked host memory for the MBB_HOST calls (cudaHostAlloc, portable across the
+ * contexts of all devices): buffers the library can DMA from / to directly. */
+int mbb_host_alloc(size_t bytes, void **out);
+int mbb_host_free(void *p);
 
 /* ---- model: replaces the constructor arguments the reference threads through
  *      likelihood._set_sed (likelihood.py:765-768) ------------------------- */
@@ -171,22 +177,55 @@ int mbb_chain_flux(mbb_ctx *ctx, int64_t nwalkers, int64_t nsteps,
                    const double *chain, int band, double *out_flux,
                    int32_t *out_status, int mem);
 
-/* ---- device-resident ensemble sampler for nsrc sources at once:
- * what mbb_fitter.run asks emcee for (mbb_fit.py:525-542 -> emcee 2.2 stretch
- * move, two half-ensembles per iteration), with proposal, log-probability and
- * accept/reject all on the GPU.  pos[nsrc][nwalkers][5] and
- * lnprob[nsrc][nwalkers] are updated in place (lnprob is computed first unless
- * have_lnprob != 0).  Random numbers: Philox4x32-10 keyed by `seed`, counter =
- * (source*nwalkers/2 + walker-in-half, 2*(step0+t)+half, stream): pass step0 =
- * iterations already done to continue a run (burn-in then main chain).
- * naccept/status [nsrc][nwalkers] may be NULL.  chain[nsteps/thin][nsrc][nwalkers][5]
- * and chain_lnprob[nsteps/thin][nsrc][nwalkers] (MBB_DEVICE only, may be NULL)
- * receive every thin-th ensemble. */
-int mbb_ensemble_run(mbb_ctx *ctx, int64_t nsrc, int nwalkers, int64_t nsteps,
-                     double a, uint64_t seed, uint64_t step0, double *pos,
-                     double *lnprob, int have_lnprob, int32_t *naccept,
-                     int32_t *status, double *chain, double *chain_lnprob,
+/* ---- batch fit: device-resident ensemble sampler for nsrc sources at once (SURVEY 8f
+ * row 1, BASELINE configs[4]): what mbb_fitter.run asks emcee for per source
+ * (mbb_fit.py:524-543: burn-in, sampler.reset(), main run -> emcee 2.2 stretch move, two
+ * half-ensembles per iteration) and what mbb_results derives from the chain
+ * (results.py:314-431), with proposal, log-probability, accept/reject and the
+ * posterior summaries all on the GPU.
+ *   pos[nsrc][nwalkers][5], lnprob[nsrc][nwalkers]: updated in place (lnprob is
+ *     computed first unless have_lnprob != 0).
+ *   nburn iterations are run and discarded, then nsteps iterations of the main run.
+ *   naccept[nsrc][nwalkers] (may be NULL): accepted moves of the main run.
+ *   status[nsrc][nwalkers] (may be NULL): first status > 1 a walker's proposals produced.
+ *   stats[nsrc][MBB_FIT_NSTATS] (may be NULL): summary over the recorded samples = all
+ *     walkers at every thin-th iteration of the main run; row layout MBB_FS_*.
+ *   chain[nsteps/thin][nsrc][nwalkers][5], chain_lnprob[nsteps/thin][nsrc][nwalkers]
+ *     (may be NULL): the recorded ensembles.  With MBB_HOST they are streamed to the
+ *     host in segments behind the sampler (page-locked memory recommended).
+ *   chain_nsrc: sources per record of the chain arrays (0 = nsrc).  A shard of a larger
+ *     source list passes the full count and pointers offset to its first source, so
+ *     that several GPUs fill disjoint slices of one [nrec][chain_nsrc][nwalkers] array.
+ * Random numbers: Philox4x32-10 keyed by `seed`, one block per proposal, counter =
+ * ((src0 + source)*nwalkers/2 + walker-in-half, 2*(step0 + t) + half); src0 is the global
+ * index of this call's source 0, so that shards of one source list draw independent
+ * numbers under one seed; pass step0 = iterations already done to continue a run.
+ * Delta-band configurations (every band one node, FAST modes) run source-resident:
+ * a CTA keeps whole ensembles in shared memory for all iterations of the call. */
+#define MBB_FIT_NSTATS 28
+enum {
+  MBB_FS_N = 0,        /* number of samples                                            */
+  MBB_FS_MEAN = 1,     /* [5] mean                                                     */
+  MBB_FS_M2 = 6,       /* [5] sum of squared deviations (variance = M2/(N-1))          */
+  MBB_FS_MIN = 11,     /* [5]                                                          */
+  MBB_FS_MAX = 16,     /* [5]                                                          */
+  MBB_FS_BESTLNP = 21, /* largest log-probability among the samples                    */
+  MBB_FS_BEST = 22,    /* [5] the sample that has it                                   */
+  MBB_FS_ACC = 27      /* mean acceptance fraction of the main run (emcee's             */
+                       /* acceptance_fraction averaged over walkers)                   */
+};
+int mbb_ensemble_fit(mbb_ctx *ctx, int64_t nsrc, int nwalkers, int64_t nburn, int64_t nsteps,
+                     double a, uint64_t seed, uint64_t step0, int64_t src0, double *pos,
+                     double *lnprob, int have_lnprob, int32_t *naccept, int32_t *status,
+                     double *stats, double *chain, double *chain_lnprob, int64_t chain_nsrc,
                      int thin, int mem);
+
+/* mbb_ensemble_fit without burn-in, summaries or source offset (kept for callers that
+ * drive burn-in and main run themselves through step0). */
+int mbb_ensemble_run(mbb_ctx *ctx, int64_t nsrc, int nwalkers, int64_t nsteps, double a,
+                     uint64_t seed, uint64_t step0, double *pos, double *lnprob,
+                     int have_lnprob, int32_t *naccept, int32_t *status, double *chain,
+                     double *chain_lnprob, int thin, int mem);
 
 /* ---- measurement aid: sustained DFMA rate of this device in TFLOP/s
  * (2 flops per DFMA), the FP64 roofline denominator bench.py reports. */

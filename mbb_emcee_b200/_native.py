@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 __all__ = ["MBBNativeError", "Context", "library_path", "load_library",
-           "default_context", "raise_for_status", "STATUS_NAMES"]
+           "default_context", "raise_for_status", "STATUS_NAMES", "pinned_empty"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MBB_B200_LIB: developer knob for A/B-timing alternative builds of the same library
@@ -84,6 +84,10 @@ def load_library():
             "mbb_chain_flux": (i32, [vp, i64, i64, vp, i32, vp, vp, i32]),
             "mbb_ensemble_run": (i32, [vp, i64, i32, i64, dbl, ctypes.c_uint64, ctypes.c_uint64, vp, vp,
                                        i32, vp, vp, vp, vp, i32, i32]),
+            "mbb_ensemble_fit": (i32, [vp, i64, i32, i64, i64, dbl, ctypes.c_uint64, ctypes.c_uint64, i64,
+                                       vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32]),
+            "mbb_host_alloc": (i32, [ctypes.c_size_t, ctypes.POINTER(vp)]),
+            "mbb_host_free": (i32, [vp]),
             "mbb_fp64_peak": (i32, [vp, i32, ctypes.POINTER(dbl)]),
         }
         for name, (res, args) in sig.items():
@@ -98,7 +102,11 @@ EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ct
                     "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
                     "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_lir_method", "mbb_set_bands",
                     "mbb_set_data", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
-                    "mbb_chain_post", "mbb_chain_flux", "mbb_ensemble_run", "mbb_fp64_peak"]
+                    "mbb_chain_post", "mbb_chain_flux", "mbb_ensemble_run", "mbb_ensemble_fit", "mbb_host_alloc", "mbb_host_free", "mbb_fp64_peak"]
+
+# layout of one row of mbb_ensemble_fit's per-source summary (include/mbb_b200.h MBB_FS_*)
+FIT_NSTATS = 28
+FS_N, FS_MEAN, FS_M2, FS_MIN, FS_MAX, FS_BESTLNP, FS_BEST, FS_ACC = 0, 1, 6, 11, 16, 21, 22, 27
 
 
 def _f64(a):
@@ -107,6 +115,22 @@ def _f64(a):
 
 def _ptr(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (mbb_host_alloc): the MBB_HOST calls copy from / to
+    such buffers directly, without staging.  The memory is released when the last view dies."""
+    import weakref
+    lib = load_library()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape))
+    nbytes = max(n * dt.itemsize, 1)
+    p = ctypes.c_void_p()
+    if lib.mbb_host_alloc(nbytes, ctypes.byref(p)) != 0:
+        raise MBBNativeError(lib.mbb_last_error().decode())
+    buf = (ctypes.c_char * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib.mbb_host_free, p)      # numpy views keep `buf` alive through .base
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
 
 
 def raise_for_status(status, pars=None):
@@ -290,16 +314,34 @@ class Context(object):
     def ensemble_run(self, pos, nsteps, seed=0, step0=0, a=2.0, lnprob=None):
         """Device-resident stretch-move sampler (host arrays in/out).
         pos[nsrc][nwalkers][5]; returns (pos, lnprob, naccept, status)."""
+        out = self.ensemble_fit(pos, 0, nsteps, seed=seed, step0=step0, a=a, lnprob=lnprob, stats=False)
+        return out["pos"], out["lnprob"], out["naccept"], out["status"]
+
+    def ensemble_fit(self, pos, nburn, nsteps, seed=0, step0=0, src0=0, a=2.0, lnprob=None, stats=True,
+                     chain=False, thin=1):
+        """mbb_ensemble_fit with host arrays: burn-in, main run, per-source posterior summary and
+        (optionally) the recorded chain.  Returns a dict: pos, lnprob, naccept, status, and when
+        asked for stats[nsrc][FIT_NSTATS], chain[nrec][nsrc][nw][5], chain_lnprob[nrec][nsrc][nw]."""
         pos = np.array(pos, dtype=np.float64, order="C")
         nsrc, nw = pos.shape[0], pos.shape[1]
         have = lnprob is not None
         lnp = np.array(lnprob, dtype=np.float64, order="C") if have else np.empty((nsrc, nw))
         nacc = np.zeros((nsrc, nw), dtype=np.int32)
         st = np.zeros((nsrc, nw), dtype=np.int32)
-        self._ck(self._lib.mbb_ensemble_run(self._h, nsrc, nw, int(nsteps), float(a), int(seed),
-                                            int(step0), _ptr(pos), _ptr(lnp), int(have), _ptr(nacc),
-                                            _ptr(st), None, None, 1, HOST))
-        return pos, lnp, nacc, st
+        thin = max(int(thin), 1)
+        nrec = int(nsteps) // thin
+        stt = np.zeros((nsrc, FIT_NSTATS)) if stats else None
+        ch = np.empty((nrec, nsrc, nw, 5)) if chain else None
+        chl = np.empty((nrec, nsrc, nw)) if chain else None
+        self._ck(self._lib.mbb_ensemble_fit(self._h, nsrc, nw, int(nburn), int(nsteps), float(a), int(seed),
+                                            int(step0), int(src0), _ptr(pos), _ptr(lnp), int(have), _ptr(nacc),
+                                            _ptr(st), _ptr(stt), _ptr(ch), _ptr(chl), 0, thin, HOST))
+        out = {"pos": pos, "lnprob": lnp, "naccept": nacc, "status": st}
+        if stats:
+            out["stats"] = stt
+        if chain:
+            out["chain"], out["chain_lnprob"] = ch, chl
+        return out
 
     def ensemble_run_device(self, nsrc, nwalkers, nsteps, pos_ptr, lnprob_ptr, have_lnprob=False,
                             seed=0, step0=0, a=2.0, naccept_ptr=0, status_ptr=0, chain_ptr=0,
@@ -311,6 +353,61 @@ class Context(object):
                                             int(seed), int(step0), vp(pos_ptr), vp(lnprob_ptr),
                                             int(bool(have_lnprob)), vp(naccept_ptr), vp(status_ptr),
                                             vp(chain_ptr), vp(chain_lnprob_ptr), int(thin), DEVICE))
+
+    def ensemble_fit_into(self, pos, lnprob, nburn, nsteps, naccept=None, status=None, stats=None,
+                          chain=None, chain_lnprob=None, chain_nsrc=0, have_lnprob=False, seed=0, step0=0,
+                          src0=0, a=2.0, thin=1):
+        """mbb_ensemble_fit(MBB_HOST) on caller-owned arrays, used in place: pos[nsrc][nw][5] and
+        lnprob[nsrc][nw] are updated; the optional outputs are filled.  ``chain`` / ``chain_lnprob``
+        may be views [:, lo:] of arrays holding ``chain_nsrc`` sources per record (their first
+        element is where this call's source 0 goes).  Page-locked arrays (``pinned_empty``) are
+        DMA'd directly."""
+        def chk(name, arr, dt, contiguous=True):
+            if arr is None:
+                return
+            if not isinstance(arr, np.ndarray) or arr.dtype != dt or (contiguous and not arr.flags.c_contiguous):
+                raise TypeError("%s must be a C-contiguous %s array" % (name, np.dtype(dt).name))
+        chk("pos", pos, np.float64)
+        chk("lnprob", lnprob, np.float64)
+        chk("naccept", naccept, np.int32)
+        chk("status", status, np.int32)
+        chk("stats", stats, np.float64)
+        chk("chain", chain, np.float64, False)
+        chk("chain_lnprob", chain_lnprob, np.float64, False)
+        nsrc, nw = pos.shape[0], pos.shape[1]
+        if pos.shape != (nsrc, nw, 5) or lnprob.shape != (nsrc, nw):
+            raise ValueError("pos[nsrc][nw][5] / lnprob[nsrc][nw] shapes disagree")
+        for name, arr, shp in (("naccept", naccept, (nsrc, nw)), ("status", status, (nsrc, nw)),
+                               ("stats", stats, (nsrc, FIT_NSTATS))):
+            if arr is not None and arr.shape != shp:
+                raise ValueError("%s must have shape %s" % (name, shp))
+        thin = max(int(thin), 1)
+        cn = int(chain_nsrc) if chain_nsrc else nsrc
+        for name, arr, tail in (("chain", chain, (nw, 5)), ("chain_lnprob", chain_lnprob, (nw,))):
+            if arr is None:
+                continue
+            inner = int(np.prod(tail)) * 8
+            if arr.shape[0] != int(nsteps) // thin or arr.shape[1] < nsrc or arr.shape[2:] != tail or \
+                    arr.strides[1] != inner or (arr.shape[0] > 1 and arr.strides[0] != cn * inner) or \
+                    not arr[0, 0].flags.c_contiguous:
+                raise ValueError("%s must be (a [:, lo:] view of) a C-contiguous [nsteps//thin][chain_nsrc]%s array"
+                                 % (name, list(tail)))
+        self._ck(self._lib.mbb_ensemble_fit(self._h, nsrc, nw, int(nburn), int(nsteps), float(a), int(seed),
+                                            int(step0), int(src0), _ptr(pos), _ptr(lnprob), int(bool(have_lnprob)),
+                                            _ptr(naccept), _ptr(status), _ptr(stats), _ptr(chain),
+                                            _ptr(chain_lnprob), cn, thin, HOST))
+
+    def ensemble_fit_device(self, nsrc, nwalkers, nburn, nsteps, pos_ptr, lnprob_ptr, have_lnprob=False,
+                            seed=0, step0=0, src0=0, a=2.0, naccept_ptr=0, status_ptr=0, stats_ptr=0,
+                            chain_ptr=0, chain_lnprob_ptr=0, thin=1):
+        """Raw device pointers; asynchronous (call sync())."""
+        def vp(x):
+            return ctypes.c_void_p(x) if x else None
+        self._ck(self._lib.mbb_ensemble_fit(self._h, int(nsrc), int(nwalkers), int(nburn), int(nsteps),
+                                            float(a), int(seed), int(step0), int(src0), vp(pos_ptr),
+                                            vp(lnprob_ptr), int(bool(have_lnprob)), vp(naccept_ptr),
+                                            vp(status_ptr), vp(stats_ptr), vp(chain_ptr),
+                                            vp(chain_lnprob_ptr), 0, int(thin), DEVICE))
 
     def sync(self):
         self._ck(self._lib.mbb_sync(self._h))

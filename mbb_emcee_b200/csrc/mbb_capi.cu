@@ -164,8 +164,10 @@ struct mbb_ctx {
     *s_out = sc->s.p;
     return cudaSuccess;
   }
-  DevBuf<double> d_epos, d_elnp, d_eq, d_eqlnp;
+  DevBuf<double> d_epos, d_elnp, d_eq, d_eqlnp, d_escratch, d_estats, d_echain[2], d_echainl[2];
   DevBuf<int> d_enacc, d_est, d_eqst;
+  cudaStream_t copy_stream = nullptr;          // D2H of chain segments behind the sampler (mbb_ensemble_fit)
+  cudaEvent_t seg_done[2] = {nullptr, nullptr}, seg_copied[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -366,28 +368,59 @@ struct DeltaLauncher<THIN, ALPHA, 0> {
   static void go(mbb_ctx*, cudaStream_t, const EvalArgs&, const DataRef&, int) {}
 };
 
+// source-resident sampler (mbb_ensemble.cuh): grid = one wave of CTAs, each walking groups of G sources
+struct EnsResidentPlan {
+  int G = 0;
+  size_t smem = 0;
+  bool ok = false;
+};
+
+EnsResidentPlan ens_resident_plan(const mbb_ctx* c, int nwalkers, bool stats) {
+  EnsResidentPlan p;
+  const int h = nwalkers / 2;
+  p.G = h <= kEnsThreads ? kEnsThreads / h : 1;
+  p.smem = ens_resident_smem(p.G, nwalkers, c->nb, stats);
+  // one CTA must leave room for a second one's static needs: cap at the opt-in limit
+  while (p.G > 1 && p.smem > c->smem_optin) {
+    --p.G;
+    p.smem = ens_resident_smem(p.G, nwalkers, c->nb, stats);
+  }
+  p.ok = p.smem <= c->smem_optin;
+  return p;
+}
+
 template <bool THIN, bool ALPHA, int NB>
-struct EnsDeltaLauncher {
-  static void go(mbb_ctx* c, const EnsArgs& g, const DataRef& d, int nb) {
+struct EnsResidentLauncher {
+  static void go(mbb_ctx* c, EnsFit& g, const DataRef& d, int nb, size_t smem, cudaError_t* err) {
     if (nb == NB) {
-      const long long nh = g.nsrc * g.h;
-      const unsigned grid = (unsigned)((nh + MBB_DELTA_BLOCK - 1) / MBB_DELTA_BLOCK);
+      auto kern = ens_resident_kernel<THIN, ALPHA, NB>;
+      *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (*err != cudaSuccess) return;
+      int per_sm = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEnsThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+      const long long ngroups = (g.nsrc + g.G - 1) / g.G;
+      const long long resident = (long long)c->sm_count * per_sm;
+      const unsigned grid = (unsigned)(ngroups < resident ? ngroups : resident);
+      *err = c->d_escratch.reserve((size_t)grid * 15 * kEnsThreads);
+      if (*err != cudaSuccess) return;
+      g.scratch = c->d_escratch.p;
       const ModelP m = model_of(c);
-      ens_delta_kernel<THIN, ALPHA, NB><<<grid, MBB_DELTA_BLOCK, 0, c->stream>>>(g, m, c->pri, d, c->small, c->d_cold.p);
+      kern<<<grid, kEnsThreads, smem, c->stream>>>(g, m, c->pri, d, c->small, c->d_cold.p);
     } else {
-      EnsDeltaLauncher<THIN, ALPHA, NB - 1>::go(c, g, d, nb);
+      EnsResidentLauncher<THIN, ALPHA, NB - 1>::go(c, g, d, nb, smem, err);
     }
   }
 };
 template <bool THIN, bool ALPHA>
-struct EnsDeltaLauncher<THIN, ALPHA, 0> {
-  static void go(mbb_ctx*, const EnsArgs&, const DataRef&, int) {}
+struct EnsResidentLauncher<THIN, ALPHA, 0> {
+  static void go(mbb_ctx*, EnsFit&, const DataRef&, int, size_t, cudaError_t*) {}
 };
 
 template <bool THIN, bool ALPHA, bool FAST>
-struct LaunchEnsDelta {
-  static void run(mbb_ctx* c, const EnsArgs& g, const DataRef& d) {
-    EnsDeltaLauncher<THIN, ALPHA, kMaxDeltaNB>::go(c, g, d, c->nb);
+struct LaunchEnsResident {
+  static void run(mbb_ctx* c, EnsFit& g, const DataRef& d, size_t smem, cudaError_t* err) {
+    EnsResidentLauncher<THIN, ALPHA, kMaxDeltaNB>::go(c, g, d, c->nb, smem, err);
   }
 };
 
@@ -566,6 +599,13 @@ int mbb_ctx_destroy(mbb_ctx* c) {
   for (auto& x : c->scratch) { x.c.release(); x.s.release(); }
   c->d_epos.release(); c->d_elnp.release(); c->d_eq.release(); c->d_eqlnp.release();
   c->d_enacc.release(); c->d_est.release(); c->d_eqst.release();
+  c->d_escratch.release(); c->d_estats.release();
+  for (int i = 0; i < 2; ++i) {
+    c->d_echain[i].release(); c->d_echainl[i].release();
+    if (c->seg_done[i]) cudaEventDestroy(c->seg_done[i]);
+    if (c->seg_copied[i]) cudaEventDestroy(c->seg_copied[i]);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (auto& sl : c->slots) {
     sl.hin.release(); sl.hout.release(); sl.hst.release(); sl.hsrc.release();
     sl.din.release(); sl.dout.release(); sl.dst.release(); sl.dsrc.release();
@@ -596,6 +636,18 @@ int mbb_last_kernel_ms(mbb_ctx* c, float* ms) {
   Use u(c);
   CK(cudaEventSynchronize(c->ev1));
   CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+
+int mbb_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail("mbb_host_alloc: out is NULL");
+  *out = nullptr;
+  CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return 0;
+}
+
+int mbb_host_free(void* p) {
+  if (p) CK(cudaFreeHost(p));
   return 0;
 }
 
@@ -1138,27 +1190,34 @@ int mbb_chain_flux(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
   return 0;
 }
 
-int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, double a, uint64_t seed,
-                     uint64_t step0, double* pos, double* lnprob, int have_lnprob, int32_t* naccept,
-                     int32_t* status, double* chain, double* chain_lnprob, int thin, int mem) {
+// see include/mbb_b200.h
+int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int64_t nsteps, double a,
+                     uint64_t seed, uint64_t step0, int64_t src0, double* pos, double* lnprob, int have_lnprob,
+                     int32_t* naccept, int32_t* status, double* stats, double* chain, double* chain_lnprob,
+                     int64_t chain_nsrc, int thin, int mem) {
   if (!c) return fail("null context");
-  if (nsrc <= 0 || nsteps < 0) return fail("nsrc must be positive, nsteps non-negative");
+  if (chain_nsrc <= 0) chain_nsrc = nsrc;
+  if (chain_nsrc < nsrc) return fail("chain_nsrc is smaller than nsrc");
+  if (nsrc <= 0 || nsteps < 0 || nburn < 0) return fail("nsrc must be positive, nburn / nsteps non-negative");
   if (nwalkers < 2 || (nwalkers & 1)) return fail("the number of walkers must be even");
   if (nwalkers <= 10) return fail("need more than 2*dim = 10 walkers");
   if (!(a > 1.0)) return fail("stretch scale a must be > 1");
   if (!pos || !lnprob) return fail("null pos/lnprob pointer");
+  if (src0 < 0) return fail("src0 must be non-negative");
   if (!c->bands_set || (!c->has_ivar && !c->has_cinv)) return fail("bands/data not set");
+  if (c->data_nb != c->nb) return fail("data has a different number of bands than the band table");
   if (nsrc > c->nsrc) return fail("more sources than mbb_set_data provided");
+  if (nburn + nsteps >= ((int64_t)1 << 31)) return fail("too many iterations for one call");
   if (thin < 1) thin = 1;
-  if (mem != MBB_DEVICE && (chain || chain_lnprob))
-    return fail("chain output needs MBB_DEVICE buffers (it is large); keep it on the device");
   Use u(c);
   const int h = nwalkers / 2;
   const long long nwk = nsrc * nwalkers, nh = nsrc * h;
   if (nwk >= (1LL << 31)) return fail("too many walkers for one call (>= 2^31); shard the sources");
-  double *dpos = pos, *dlnp = lnprob;
+  const bool host = mem != MBB_DEVICE;
+  const int64_t nrec_total = nsteps / thin;
+  double *dpos = pos, *dlnp = lnprob, *dstats = stats;
   int *dnacc = naccept, *dst = status;
-  if (mem != MBB_DEVICE) {
+  if (host) {
     CK(c->d_epos.reserve((size_t)nwk * 5));
     CK(c->d_elnp.reserve((size_t)nwk));
     CK(cudaMemcpyAsync(c->d_epos.p, pos, (size_t)nwk * 5 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1168,14 +1227,12 @@ int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, dou
     dlnp = c->d_elnp.p;
     dnacc = nullptr;
     dst = nullptr;
+    if (stats) { CK(c->d_estats.reserve((size_t)nsrc * kFitStats)); dstats = c->d_estats.p; }
   }
   if (!dnacc) { CK(c->d_enacc.reserve((size_t)nwk)); dnacc = c->d_enacc.p; }
   if (!dst) { CK(c->d_est.reserve((size_t)nwk)); dst = c->d_est.p; }
   CK(cudaMemsetAsync(dnacc, 0, (size_t)nwk * sizeof(int), c->stream));
   CK(cudaMemsetAsync(dst, 0, (size_t)nwk * sizeof(int), c->stream));
-  CK(c->d_eq.reserve((size_t)nh * 5));
-  CK(c->d_eqlnp.reserve((size_t)nh));
-  CK(c->d_eqst.reserve((size_t)nh));
   CK(ensure_tables(c));      // node tables and the cold-path block match the current model / priors
   begin_timing(c);
   if (!have_lnprob) {
@@ -1185,61 +1242,171 @@ int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, dou
     e.pars = dpos; e.src_index = nullptr; e.out = dlnp; e.status = dst;
     if (launch_loglike(c, c->stream, e)) return 1;
   }
-  EnsArgs g;
-  g.pos = dpos; g.lnp = dlnp; g.nacc = dnacc; g.status = dst;
-  g.q = c->d_eq.p; g.qlnp = c->d_eqlnp.p; g.qst = c->d_eqst.p;
-  g.nsrc = nsrc; g.nw = nwalkers; g.h = h; g.seed = seed; g.a = a;
-  const unsigned grid = (unsigned)((nh + 255) / 256);
-  // delta-band FAST configurations take the fused one-kernel half-step
-  // (the switch is read per call so that tests can compare the paths in one process)
-  const bool no_fuse = getenv("MBB_B200_NO_FUSED_SAMPLER") != nullptr;
-  const bool fused = !no_fuse && c->math_mode != MBB_MATH_FAITHFUL && c->nn == c->nb && c->nb <= kMaxDeltaNB;
   DataRef dref;
   dref.flux = c->d_flux.p;
   dref.ivar = c->has_ivar ? c->d_ivar.p : nullptr;
   dref.cinv = c->has_cinv ? c->d_cinv.p : nullptr;
   dref.nsrc = c->nsrc;
   dref.nb = c->nb;
-  int64_t kept = 0;
-  for (int64_t it = 0; it < nsteps; ++it) {
-    for (int half = 0; half < 2; ++half) {
-      g.half = half;
-      g.hstep = 2 * (step0 + (uint64_t)it) + (uint64_t)half;
-      if (fused) {
-        dispatch3<LaunchEnsDelta>(c->opthin != 0, c->noalpha == 0, true, c, g, dref);
-        c->launches += 1;
-        continue;
-      }
-      ens_propose_kernel<<<grid, 256, 0, c->stream>>>(g);
-      EvalArgs e{};
-      e.n = nh; e.e0 = 0; e.wps = h; e.layout = MBB_AOS;
-      e.pars = g.q; e.src_index = nullptr; e.out = g.qlnp; e.status = g.qst;
-      if (launch_loglike(c, c->stream, e)) return 1;
-      ens_accept_kernel<<<grid, 256, 0, c->stream>>>(g);
-      c->launches += 2;
+  // delta-band FAST configurations whose ensembles fit in shared memory take the source-resident kernel
+  // (the switch is read per call so that tests can compare the paths in one process)
+  const bool no_fuse = getenv("MBB_B200_NO_FUSED_SAMPLER") != nullptr;
+  const EnsResidentPlan plan = ens_resident_plan(c, nwalkers, stats != nullptr);
+  const bool aligned = ((uintptr_t)dpos % 16 == 0) && ((uintptr_t)dlnp % 16 == 0) &&
+                       (host || (((uintptr_t)chain % 16 == 0) && ((uintptr_t)chain_lnprob % 16 == 0)));
+  const bool resident = !no_fuse && c->math_mode != MBB_MATH_FAITHFUL && c->nn == c->nb && c->nb <= kMaxDeltaNB &&
+                        plan.ok && aligned;
+  if (!resident) {
+    CK(c->d_eq.reserve((size_t)nh * 5));
+    CK(c->d_eqlnp.reserve((size_t)nh));
+    CK(c->d_eqst.reserve((size_t)nh));
+  }
+  const StretchScale sc = stretch_scale(a);
+
+  // One segment = iterations [i0, i1) of the call (burn-in first); its records go to cdst / ldst.
+  auto run_segment = [&](int64_t i0, int64_t i1, double* cdst, double* ldst, int64_t cns) -> int {
+    const int64_t main_done = i0 > nburn ? i0 - nburn : 0;
+    const int64_t main_here = i1 > nburn ? i1 - (i0 > nburn ? i0 : nburn) : 0;
+    const int64_t nrec = (main_done + main_here) / thin - main_done / thin;
+    if (resident) {
+      EnsFit g{};
+      g.pos = dpos; g.lnp = dlnp; g.nacc = dnacc; g.status = dst; g.stats = dstats;
+      g.chain = cdst; g.chain_lnp = ldst;
+      g.nsrc = nsrc; g.src0 = src0; g.chain_nsrc = cns; g.nw = nwalkers; g.h = h; g.G = plan.G;
+      g.niter = (int)(i1 - i0);
+      g.main_from = (int)(nburn > i0 ? (nburn - i0 < i1 - i0 ? nburn - i0 : i1 - i0) : 0);
+      g.main_done = main_done;
+      g.thin = thin;
+      g.nrec = (int)nrec;
+      g.merge = main_done > 0;
+      g.seed = seed;
+      g.step0 = step0 + (uint64_t)i0;
+      g.sc = sc;
+      cudaError_t err = cudaSuccess;
+      dispatch3<LaunchEnsResident>(c->opthin != 0, c->noalpha == 0, true, c, g, dref, plan.smem, &err);
+      CK(err);
+      c->launches += 1;
+      CK(cudaGetLastError());
+      return 0;
     }
-    if ((chain || chain_lnprob) && ((it + 1) % thin == 0)) {
-      if (chain)
-        CK(cudaMemcpyAsync(chain + (size_t)kept * nwk * 5, dpos, (size_t)nwk * 5 * sizeof(double),
-                           cudaMemcpyDeviceToDevice, c->stream));
-      if (chain_lnprob)
-        CK(cudaMemcpyAsync(chain_lnprob + (size_t)kept * nwk, dlnp, (size_t)nwk * sizeof(double),
-                           cudaMemcpyDeviceToDevice, c->stream));
-      ++kept;
+    EnsArgs g{};
+    g.pos = dpos; g.lnp = dlnp; g.nacc = dnacc; g.status = dst;
+    g.q = c->d_eq.p; g.qlnp = c->d_eqlnp.p; g.qst = c->d_eqst.p;
+    g.nsrc = nsrc; g.src0 = src0; g.nw = nwalkers; g.h = h; g.seed = seed; g.sc = sc;
+    const unsigned grid = (unsigned)((nh + 255) / 256);
+    int64_t kept = 0;
+    for (int64_t it = i0; it < i1; ++it) {
+      const bool is_main = it >= nburn;
+      g.count = is_main ? 1 : 0;
+      for (int half = 0; half < 2; ++half) {
+        g.half = half;
+        g.hstep = 2 * (step0 + (uint64_t)it) + (uint64_t)half;
+        ens_propose_kernel<<<grid, 256, 0, c->stream>>>(g);
+        EvalArgs e{};
+        e.n = nh; e.e0 = 0; e.wps = h; e.layout = MBB_AOS;
+        e.pars = g.q; e.src_index = nullptr; e.out = g.qlnp; e.status = g.qst;
+        if (launch_loglike(c, c->stream, e)) return 1;
+        ens_accept_kernel<<<grid, 256, 0, c->stream>>>(g);
+        c->launches += 2;
+      }
+      const int64_t jm = it - nburn;
+      if (is_main && (jm + 1) % thin == 0) {
+        if (dstats) {
+          ens_stats_kernel<<<(unsigned)nsrc, kStatsThreads, 0, c->stream>>>(dpos, dlnp, dnacc, dstats, nwalkers,
+                                                                          jm + 1 > thin ? 1 : 0, (double)(jm + 1));
+          c->launches += 1;
+        }
+        if (cdst)
+          CK(cudaMemcpyAsync(cdst + (size_t)kept * cns * nwalkers * 5, dpos, (size_t)nwk * 5 * sizeof(double),
+                             cudaMemcpyDeviceToDevice, c->stream));
+        if (ldst)
+          CK(cudaMemcpyAsync(ldst + (size_t)kept * cns * nwalkers, dlnp, (size_t)nwk * sizeof(double),
+                             cudaMemcpyDeviceToDevice, c->stream));
+        ++kept;
+      }
+    }
+    CK(cudaGetLastError());
+    return 0;
+  };
+
+  const int64_t total = nburn + nsteps;
+  if (!host || (!chain && !chain_lnprob) || nrec_total == 0) {
+    if (total > 0 && run_segment(0, total, host ? nullptr : chain, host ? nullptr : chain_lnprob, chain_nsrc))
+      return 1;
+    if (total == 0 && dstats) CK(cudaMemsetAsync(dstats, 0, (size_t)nsrc * kFitStats * sizeof(double), c->stream));
+  } else {
+    // chain to host memory: segments of R records through two device buffers; the D2H copy of
+    // one segment runs on its own stream behind the sampler working on the next
+    if (!c->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&c->seg_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->seg_copied[i], cudaEventDisableTiming));
+      }
+    }
+    const size_t rec_bytes = (size_t)nwk * 48;
+    // (MBB_B200_CHAIN_SEGMENT_MB: segment budget in MiB, default 256; read per call so that tests can shrink it)
+    const char* seg_env = getenv("MBB_B200_CHAIN_SEGMENT_MB");
+    const size_t seg_mb = seg_env && atoll(seg_env) > 0 ? (size_t)atoll(seg_env) : 256;
+    int64_t R = (int64_t)((seg_mb << 20) / rec_bytes);
+    if (R < 1) R = 1;
+    if (R > nrec_total) R = nrec_total;
+    for (int i = 0; i < 2; ++i) {
+      if (chain) CK(c->d_echain[i].reserve((size_t)R * nwk * 5));
+      if (chain_lnprob) CK(c->d_echainl[i].reserve((size_t)R * nwk));
+    }
+    int64_t i0 = 0, rec0 = 0;
+    for (int seg = 0; rec0 < nrec_total || i0 < total; ++seg) {
+      const int b = seg & 1;
+      const int64_t recs = (nrec_total - rec0) < R ? (nrec_total - rec0) : R;
+      // the segment ends with its last record; the final one also takes the unrecorded tail
+      int64_t i1 = nburn + (rec0 + recs) * thin;
+      if (rec0 + recs >= nrec_total) i1 = total;
+      if (seg >= 2) CK(cudaStreamWaitEvent(c->stream, c->seg_copied[b], 0));
+      if (run_segment(i0, i1, chain ? c->d_echain[b].p : nullptr, chain_lnprob ? c->d_echainl[b].p : nullptr, nsrc))
+        return 1;
+      CK(cudaEventRecord(c->seg_done[b], c->stream));
+      CK(cudaStreamWaitEvent(c->copy_stream, c->seg_done[b], 0));
+      // one record = nsrc contiguous ensembles; the host arrays hold chain_nsrc sources per record
+      if (chain && recs > 0)
+        CK(cudaMemcpy2DAsync(chain + (size_t)rec0 * chain_nsrc * nwalkers * 5,
+                             (size_t)chain_nsrc * nwalkers * 5 * sizeof(double), c->d_echain[b].p,
+                             (size_t)nwk * 5 * sizeof(double), (size_t)nwk * 5 * sizeof(double), (size_t)recs,
+                             cudaMemcpyDeviceToHost, c->copy_stream));
+      if (chain_lnprob && recs > 0)
+        CK(cudaMemcpy2DAsync(chain_lnprob + (size_t)rec0 * chain_nsrc * nwalkers,
+                             (size_t)chain_nsrc * nwalkers * sizeof(double), c->d_echainl[b].p,
+                             (size_t)nwk * sizeof(double), (size_t)nwk * sizeof(double), (size_t)recs,
+                             cudaMemcpyDeviceToHost, c->copy_stream));
+      CK(cudaEventRecord(c->seg_copied[b], c->copy_stream));
+      i0 = i1;
+      rec0 += recs;
+      if (i0 >= total) break;
     }
   }
   end_timing(c);
   CK(cudaGetLastError());
-  if (mem != MBB_DEVICE) {
+  if (host) {
     CK(cudaMemcpyAsync(pos, dpos, (size_t)nwk * 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(lnprob, dlnp, (size_t)nwk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (naccept)
       CK(cudaMemcpyAsync(naccept, dnacc, (size_t)nwk * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (status)
       CK(cudaMemcpyAsync(status, dst, (size_t)nwk * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (stats)
+      CK(cudaMemcpyAsync(stats, dstats, (size_t)nsrc * kFitStats * sizeof(double), cudaMemcpyDeviceToHost,
+                         c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
   }
   return 0;
+}
+
+int mbb_ensemble_run(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nsteps, double a, uint64_t seed,
+                     uint64_t step0, double* pos, double* lnprob, int have_lnprob, int32_t* naccept,
+                     int32_t* status, double* chain, double* chain_lnprob, int thin, int mem) {
+  return mbb_ensemble_fit(c, nsrc, nwalkers, 0, nsteps, a, seed, step0, 0, pos, lnprob, have_lnprob, naccept,
+                          status, nullptr, chain, chain_lnprob, 0, thin, mem);
 }
 
 int mbb_fp64_peak(mbb_ctx* c, int iters, double* tflops) {

@@ -1,21 +1,49 @@
 // Device-resident affine-invariant ensemble sampler for many sources at once
-// (SURVEY.md 8f row 1).  The stretch move of Goodman & Weare (2010) with the
-// scheduling of emcee 2.2 (two half-ensembles per iteration, reference
-// mbb_fit.py:80-81, 533-542 drives exactly this through emcee), but with the
-// proposals, the log-probability and the accept/reject step all on the GPU, so
-// walker positions never cross PCIe.
+// (BASELINE configs[4]).  The stretch move of Goodman &
+// Weare (2010) with the scheduling of emcee 2.2 (two half-ensembles per
+// iteration; reference mbb_fit.py:80-81, 525-542 drives exactly this through
+// emcee), with the proposals, the log-probability, the accept/reject step AND
+// the posterior summaries on the GPU: walker positions never cross PCIe, a fit
+// returns per-source statistics (what results.py:314-431 derives from a chain)
+// and, optionally, a thinned chain.
+//
+// Two device forms, bit-identical in what they compute:
+//   ens_resident_kernel  delta-band FAST configurations.  A CTA owns whole
+//       sources: their ensembles (positions, log-probabilities, photometry) are
+//       loaded into shared memory once, ALL iterations of the launch run there
+//       -- the partner gather of the stretch move is a shared-memory read, one
+//       CTA barrier per half-step, no HBM traffic inside the loop -- and the
+//       per-thread posterior accumulators are reduced once at the end.
+//   ens_propose_kernel + likelihood kernels + ens_accept_kernel (+
+//       ens_stats_kernel per recorded iteration)  any band set / math mode.
 //
 // Randomness is counter-based (Philox4x32-10, Salmon et al. 2011): the draws
-// of walker `w` of source `s` at half-step `h` of iteration `t` depend only on
-// (seed, s*nw/2 + w, 2t+h), so results are independent of launch geometry and
-// can be replayed on the host (tests/test_ensemble_gpu.py does exactly that
-// with a numpy Philox and the CPU oracle).  Statistically equivalent to, not
-// bit-identical with, emcee's Mersenne-Twister stream.
+// of walker `k` of the updating half of GLOBAL source `s` at half-step `hs`
+// depend only on (seed, s*nw/2 + k, hs), so results are independent of launch
+// geometry and of how sources are sharded over GPUs, and can be replayed on
+// the host (tests/test_ensemble_gpu.py does exactly that with a numpy Philox
+// and the CPU oracle).  Statistically equivalent to, not bit-identical with,
+// emcee's Mersenne-Twister stream.  One Philox block per proposal: 52 bits for
+// the stretch factor, 32 for the partner, 43 for the acceptance uniform.
 #pragma once
 #include "mbb_kernels.cuh"
 #include "mbb_philox.cuh"
 
 namespace mbb {
+
+// ---- per-source posterior summary row (doubles) -----------------------------
+// over the recorded samples (every thin-th iteration of the main run, all walkers)
+constexpr int kFitStats = 28;
+enum FitStat {
+  FS_N = 0,         // number of samples
+  FS_MEAN = 1,      // [5] mean
+  FS_M2 = 6,        // [5] sum of squared deviations from the mean (variance = M2/(N-1))
+  FS_MIN = 11,      // [5]
+  FS_MAX = 16,      // [5]
+  FS_BESTLNP = 21,  // largest log-probability among the samples
+  FS_BEST = 22,     // [5] the sample that has it (first in (thread, time) order on ties)
+  FS_ACC = 27       // mean acceptance fraction of the main run so far
+};
 
 struct Draw {
   double z;      // stretch factor ((a-1)u+1)^2/a
@@ -25,28 +53,43 @@ struct Draw {
 
 // emcee 2.2 accepts where (dim-1) ln z + lnp(q) - lnp(s) > ln u.  The same test
 // without logarithms:  u < z^4 exp(lnp(q) - lnp(s))  -- one lean exp instead of two
-// libdevice logs (~240 of the fused kernel's ~1400 issue cycles per warp).  The
-// difference is clamped to [-745, 700] first: -inf (proposal below a lower limit)
-// and NaN reject, +inf accepts, exactly as the logarithmic form does.
+// libdevice logs.  The difference is clamped to [-745, 700] first: -inf (proposal
+// below a lower limit) and NaN reject, +inf accepts, exactly as the logarithmic form
+// does (tests/test_ensemble_gpu.py checks the two forms against each other).
 __device__ __forceinline__ bool stretch_accept(double z, double u, double newlnp, double oldlnp) {
   const double dl = fmin(fmax(newlnp - oldlnp, -745.0), 700.0);
   const double z2 = z * z;
   return u < (z2 * z2) * exp_l(dl);
 }
 
+// One Philox block -> (z, partner, u).  emcee: zz = ((a - 1.) * rand + 1) ** 2. / a with
+// separate roundings; for a power of two (the default a = 2) the division is an exact
+// multiplication by 1/a.
+struct StretchScale {
+  double a, am1, inv_a;
+  int pow2;
+};
+inline StretchScale stretch_scale(double a) {
+  StretchScale s;
+  s.a = a;
+  s.am1 = a - 1.0;
+  s.inv_a = 1.0 / a;
+  int e;
+  s.pow2 = frexp(a, &e) == 0.5;
+  return s;
+}
+
 __device__ __forceinline__ Draw stretch_draw(unsigned long long seed, unsigned long long widx,
-                                             unsigned long long hstep, double a, int ncomp) {
-  const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+                                             unsigned long long hstep, const StretchScale& sc, int ncomp) {
   const Philox r = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)hstep,
-                                 (unsigned)(hstep >> 32) << 1, k0, k1);
-  const Philox s = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)hstep,
-                                 ((unsigned)(hstep >> 32) << 1) | 1u, k0, k1);
+                                 (unsigned)(hstep >> 32), (unsigned)seed, (unsigned)(seed >> 32));
   Draw d;
-  // emcee: zz = ((a - 1.) * rand + 1) ** 2. / a   -- separate roundings, no FMA
-  const double t = __dadd_rn(__dmul_rn(a - 1.0, u53(r.c[0], r.c[1])), 1.0);
-  d.z = __ddiv_rn(__dmul_rn(t, t), a);
-  d.partner = (int)(((unsigned long long)r.c[2] * (unsigned long long)ncomp) >> 32);
-  d.u = u53(s.c[0], s.c[1]);
+  const double uz = u52w(r.c[0], r.c[1] >> 12);
+  const double t = __dadd_rn(__dmul_rn(sc.am1, uz), 1.0);
+  const double tt = __dmul_rn(t, t);
+  d.z = sc.pow2 ? __dmul_rn(tt, sc.inv_a) : __ddiv_rn(tt, sc.a);
+  d.partner = (int)__umulhi(r.c[2], (unsigned)ncomp);
+  d.u = u43(r.c[3], r.c[1] & 0x7ffu);
   return d;
 }
 
@@ -58,10 +101,11 @@ struct EnsArgs {
   double* q;                // [nsrc*h][5] proposal scratch
   double* qlnp;             // [nsrc*h]
   int* qst;                 // [nsrc*h]
-  long long nsrc;
+  long long nsrc, src0;     // src0: global index of source 0 (sharded runs), enters the RNG counter
   int nw, h, half;          // h = nw/2; half 0 updates walkers [0,h) against [h,nw)
+  int count;                // != 0: accepted moves are counted (main run)
   unsigned long long seed, hstep;   // hstep = 2*iteration + half
-  double a;
+  StretchScale sc;
 };
 
 // q = c[j] - z (c[j] - s), in emcee's operation order
@@ -70,7 +114,7 @@ __global__ void __launch_bounds__(256) ens_propose_kernel(const EnsArgs g) {
   if (i >= g.nsrc * g.h) return;
   const long long src = i / g.h;
   const int k = (int)(i - src * g.h);
-  const Draw d = stretch_draw(g.seed, (unsigned long long)i, g.hstep, g.a, g.h);
+  const Draw d = stretch_draw(g.seed, (unsigned long long)((g.src0 + src) * g.h + k), g.hstep, g.sc, g.h);
   const int own = g.half == 0 ? k : g.h + k;
   const int oth = (g.half == 0 ? g.h : 0) + d.partner;
   const double* s = g.pos + (src * g.nw + own) * 5;
@@ -83,13 +127,12 @@ __global__ void __launch_bounds__(256) ens_propose_kernel(const EnsArgs g) {
   }
 }
 
-// accept where (dim-1) ln z + lnp(q) - lnp(s) > ln u   (emcee 2.2 _propose_stretch), see stretch_accept
 __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nsrc * g.h) return;
   const long long src = i / g.h;
   const int k = (int)(i - src * g.h);
-  const Draw d = stretch_draw(g.seed, (unsigned long long)i, g.hstep, g.a, g.h);
+  const Draw d = stretch_draw(g.seed, (unsigned long long)((g.src0 + src) * g.h + k), g.hstep, g.sc, g.h);
   const int own = g.half == 0 ? k : g.h + k;
   const long long w = src * g.nw + own;
   const double newlnp = g.qlnp[i];
@@ -104,85 +147,377 @@ __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) p[j] = q[j];
     g.lnp[w] = newlnp;
-    g.nacc[w] += 1;
+    if (g.count) g.nacc[w] += 1;
   }
 }
 
-// Fused half-step for delta-band configurations: draw, propose, evaluate and
-// accept in one kernel; the proposal never leaves registers.  Same draws, same
-// arithmetic, hence the same chain as the three-kernel pipeline above.
-// this kernel waits on gathers (ncu: long_scoreboard 3.9 of ~9 stalled warps per issue), so a
-// fourth resident CTA at 64 registers pays for its spills: 2.55 vs 2.60 ms per iteration (2 CTAs
-// at 116 registers: 3.20 ms).
-// Measured and rejected: a persistent form that stages whole source ensembles (20 KB of
-// positions + log-probabilities + photometry rows per tile) by cp.async.bulk two tiles ahead,
-// so that the partner gather becomes a shared-memory read -- bit-identical chains, but 2.57-2.61
-// ms per iteration: the 60 KB of staging allow 3 CTAs/SM, 80 registers still spill (q, z, u and
-// the old log-probability stay live across the evaluation), and the CTA barrier per tile costs
-// what the gathers did (17 % of the stall samples; the accept/reject branch makes the warps
-// uneven).  Releasing the ring stage with a per-warp count instead of that barrier ("last warp
-// refills") was slower again, here (2.62 ms) and in loglike_delta_kernel (1.29 vs 1.20 ms).
-#ifndef MBB_ENS_MINB
-#define MBB_ENS_MINB 4
-#endif
-template <bool THIN, bool ALPHA, int NB>
-__global__ void __launch_bounds__(MBB_DELTA_BLOCK, MBB_ENS_MINB)
-ens_delta_kernel(const EnsArgs g, const ModelP m, const Priors pr, const DataRef d, const SmallTab t,
-                 const ColdArgs* __restrict__ cold) {
-  __shared__ __align__(16) double s_tab[kTabRepDoubles];
-  stage_exp_table(s_tab);
-  __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.nsrc * g.h) return;
-  const unsigned ih = (unsigned)g.h;
-  const long long src = (g.nsrc * g.h < (1LL << 32)) ? (long long)((unsigned)i / ih) : i / g.h;
-  const int k = (int)(i - src * g.h);
-  // Same draws as stretch_draw(), issued in the order that hides the gathers: the first Philox
-  // block gives the partner index, the loads (own row, partner row, old log-probability,
-  // photometry) go out, and the second block and the division run under them.
-  const unsigned k0 = (unsigned)g.seed, k1 = (unsigned)(g.seed >> 32);
-  const unsigned long long widx = (unsigned long long)i;
-  const Philox r = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)g.hstep,
-                                 (unsigned)(g.hstep >> 32) << 1, k0, k1);
-  const int partner = (int)(((unsigned long long)r.c[2] * (unsigned long long)g.h) >> 32);
-  const int own = g.half == 0 ? k : g.h + k;
-  const int oth = (g.half == 0 ? g.h : 0) + partner;
-  const long long w = src * g.nw + own;
-  const double* __restrict__ s = g.pos + w * 5;
-  const double* __restrict__ c = g.pos + (src * g.nw + oth) * 5;
-  double sj[5], cj[5];
+// ---------------------------------------------------------------------------
+// Posterior accumulators.  Per thread: shifted sums S1 = sum (x - c), S2 = sum
+// (x - c)^2 (c = the source's walker 0 when accumulation starts: of the order of
+// a posterior width away from the mean, so S2 - S1^2/n loses no digits), min, max
+// and the best sample.  fit_reduce turns the per-thread partials of one source
+// into its summary row, merging with what the row already holds (an earlier
+// segment of the same run) by the pairwise update of Chan, Golub & LeVeque (1979).
+// Deterministic: fixed serial order over the threads of the source.
+// ---------------------------------------------------------------------------
+struct FitPartials {
+  const double* sums;     // [10][stride]: S1[5], S2[5]
+  const double* minmax;   // [10][stride]: min[5], max[5]
+  const double* bestpos;  // [5][stride]
+  const double* bestlnp;  // [stride]
+  int stride;
+};
+
+// component c (0..20) of the source whose threads are [t0, t1); c = 20 returns the
+// winning thread index (as a double) of the best-sample search
+__device__ __forceinline__ double fit_reduce_component(const FitPartials& p, int c, int t0, int t1) {
+  if (c < 10) {
+    double s = 0.0;
+    for (int t = t0; t < t1; ++t) s += p.sums[c * p.stride + t];
+    return s;
+  }
+  if (c < 15) {
+    double v = kInf;
+    for (int t = t0; t < t1; ++t) v = fmin(v, p.minmax[(c - 10) * p.stride + t]);
+    return v;
+  }
+  if (c < 20) {
+    double v = -kInf;
+    for (int t = t0; t < t1; ++t) v = fmax(v, p.minmax[(c - 10) * p.stride + t]);
+    return v;
+  }
+  int win = t0;
+  double best = p.bestlnp[t0];
+  for (int t = t0 + 1; t < t1; ++t) {
+    const double v = p.bestlnp[t];
+    if (v > best) { best = v; win = t; }
+  }
+  return (double)win;
+}
+
+// red[0..20] of one source -> its row; n_seg samples in this segment, shift[5]
+__device__ __forceinline__ void fit_write_row(double* row, const double* red, const double* shift,
+                                              const FitPartials& p, double n_seg, double acc_frac, int merge) {
+  const int win = (int)red[20];
+  const double blnp = p.bestlnp[win];
+  if (n_seg > 0.0) {
+    const double nA = merge ? row[FS_N] : 0.0;
+    const double n = nA + n_seg;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const double s1 = red[j], s2 = red[5 + j];
+      double mean = shift[j] + s1 / n_seg;
+      double m2 = fmax(s2 - s1 * s1 / n_seg, 0.0);
+      double mn = red[10 + j], mx = red[15 + j];
+      if (nA > 0.0) {
+        const double meanA = row[FS_MEAN + j], dlt = mean - meanA;
+        m2 = row[FS_M2 + j] + m2 + dlt * dlt * (nA * n_seg / n);
+        mean = meanA + dlt * (n_seg / n);
+        mn = fmin(mn, row[FS_MIN + j]);
+        mx = fmax(mx, row[FS_MAX + j]);
+      }
+      row[FS_MEAN + j] = mean;
+      row[FS_M2 + j] = m2;
+      row[FS_MIN + j] = mn;
+      row[FS_MAX + j] = mx;
+    }
+    if (!(nA > 0.0) || blnp > row[FS_BESTLNP]) {
+      row[FS_BESTLNP] = blnp;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) row[FS_BEST + j] = p.bestpos[j * p.stride + win];
+    }
+    row[FS_N] = n;
+  } else if (!merge) {
+    for (int j = 0; j < kFitStats; ++j) row[j] = 0.0;
+    row[FS_BESTLNP] = -kInf;
+  }
+  row[FS_ACC] = acc_frac;
+}
+
+// one sample into a thread's accumulators (S in shared memory, the rest wherever `mm` / `bp` live)
+__device__ __forceinline__ void fit_accumulate(const double* x, double lnp, const double* shift, double* sums,
+                                               double* mm, double* bp, double& best, int stride, int t) {
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    sj[j] = s[j];
-    cj[j] = c[j];
+    const double v = x[j], dv = v - shift[j];
+    sums[j * stride + t] += dv;
+    sums[(5 + j) * stride + t] = fma(dv, dv, sums[(5 + j) * stride + t]);
+    if (v < mm[j * stride + t]) mm[j * stride + t] = v;
+    if (v > mm[(5 + j) * stride + t]) mm[(5 + j) * stride + t] = v;
   }
-  const double old = g.lnp[w];
-  double diff[NB];
-  delta_load_data<NB>(d, src, diff);
-  const Philox r2 = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)g.hstep,
-                                  ((unsigned)(g.hstep >> 32) << 1) | 1u, k0, k1);
-  Draw dr;
-  {
-    const double t1 = __dadd_rn(__dmul_rn(g.a - 1.0, u53(r.c[0], r.c[1])), 1.0);
-    dr.z = __ddiv_rn(__dmul_rn(t1, t1), g.a);
-    dr.partner = partner;
-    dr.u = u53(r2.c[0], r2.c[1]);
-  }
-  double q[5];
+  if (lnp > best) {
+    best = lnp;
 #pragma unroll
-  for (int j = 0; j < 5; ++j) q[j] = __dsub_rn(cj[j], __dmul_rn(dr.z, __dsub_rn(cj[j], sj[j])));
-  int st;
-  const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, diff, m, pr, d, t, cold, lane_exp_table(s_tab), nullptr, st);
-  if (st > ST_BELOW_LOWLIM) {
-    if (g.status[w] <= ST_BELOW_LOWLIM) g.status[w] = st;
-    return;
+    for (int j = 0; j < 5; ++j) bp[j * stride + t] = x[j];
   }
-  if (stretch_accept(dr.z, dr.u, newlnp, old)) {
-    double* p = g.pos + w * 5;
+}
+
+// Summary update from ensembles in global memory (the propose / evaluate / accept path): one
+// CTA per source, called once per recorded iteration; each call merges nw samples into the row.
+constexpr int kStatsThreads = 128;
+__global__ void __launch_bounds__(kStatsThreads)
+ens_stats_kernel(const double* __restrict__ pos, const double* __restrict__ lnp, const int* __restrict__ nacc,
+                 double* __restrict__ stats, int nw, int merge, double main_iters) {
+  __shared__ double s_part[26 * kStatsThreads];
+  __shared__ double s_red[24];
+  __shared__ double s_shift[5];
+  const int tid = threadIdx.x;
+  const long long src = blockIdx.x;
+  const double* P = pos + src * nw * 5;
+  double* sums = s_part;
+  double* mm = s_part + 10 * kStatsThreads;
+  double* bp = s_part + 20 * kStatsThreads;
+  double* bl = s_part + 25 * kStatsThreads;
+  if (tid < 5) s_shift[tid] = P[tid];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) p[j] = q[j];
-    g.lnp[w] = newlnp;
-    g.nacc[w] += 1;
+  for (int j = 0; j < 10; ++j) sums[j * kStatsThreads + tid] = 0.0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    mm[j * kStatsThreads + tid] = kInf;
+    mm[(5 + j) * kStatsThreads + tid] = -kInf;
+    bp[j * kStatsThreads + tid] = 0.0;
+  }
+  __syncthreads();
+  double best = -kInf;
+  int acc = 0;
+  for (int w = tid; w < nw; w += kStatsThreads) {
+    double x[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) x[j] = P[w * 5 + j];
+    fit_accumulate(x, lnp[src * nw + w], s_shift, sums, mm, bp, best, kStatsThreads, tid);
+    acc += nacc[src * nw + w];
+  }
+  bl[tid] = best;
+  // acceptance: integer sum through the (now free for this purpose) s_red after the barrier
+  __syncthreads();
+  FitPartials p{sums, mm, bp, bl, kStatsThreads};
+  const int t1 = nw < kStatsThreads ? nw : kStatsThreads;
+  if (tid < 21) s_red[tid] = fit_reduce_component(p, tid, 0, t1);
+  // per-thread acceptance counts -> warp sums -> total
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ int s_acc[kStatsThreads / 32];
+  if ((tid & 31) == 0) s_acc[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+    for (int i = 0; i < kStatsThreads / 32; ++i) tot += s_acc[i];
+    fit_write_row(stats + src * kFitStats, s_red, s_shift, p, (double)nw,
+                  main_iters > 0.0 ? (double)tot / ((double)nw * main_iters) : 0.0, merge);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The source-resident sampler.
+// ---------------------------------------------------------------------------
+struct EnsFit {
+  double* pos;              // [nsrc][nw][5], updated in place
+  double* lnp;              // [nsrc][nw]
+  int* nacc;                // [nsrc][nw], accepted moves of the main run (accumulated)
+  int* status;              // [nsrc][nw], sticky
+  double* stats;            // [nsrc][kFitStats] or null
+  double* chain;            // this launch's records: [nrec][nsrc][nw][5], or null
+  double* chain_lnp;        // [nrec][nsrc][nw], or null
+  double* scratch;          // [gridDim.x][15][256]: per-thread min / max / best sample
+  long long nsrc, src0;
+  long long chain_nsrc;     // sources per record of the chain arrays (>= nsrc: a shard writes into a larger array)
+  int nw, h, G;             // G sources per CTA
+  int niter;                // iterations in this launch
+  int main_from;            // iterations >= main_from belong to the main run (counted, recorded)
+  long long main_done;      // main iterations before this launch (a multiple of thin)
+  int thin;
+  int nrec;                 // recorded iterations in this launch
+  int merge;                // the stats rows already hold earlier segments of this main run
+  unsigned long long seed, step0;   // step0: global iteration index of this launch's iteration 0
+  StretchScale sc;
+};
+
+constexpr int kEnsThreads = 256;
+#ifndef MBB_ENS_MINB
+#define MBB_ENS_MINB 3
+#endif
+
+// dynamic shared memory of ens_resident_kernel, in doubles (then ints):
+//   exp table | pos [G*nw*5] | lnp [G*nw] | flux,ivar [2*G*NB (even)] | shift [G*5 (even)] |
+//   S1,S2 [10*256] + best lnp [256] + reduction [G*22]   (only with stats) | nacc ints [G*nw]
+__host__ __device__ inline size_t ens_even(size_t n) { return (n + 1) & ~(size_t)1; }
+__host__ __device__ inline size_t ens_resident_smem(int G, int nw, int nb, bool stats) {
+  size_t d = kTabRepDoubles + (size_t)G * nw * 5 + (size_t)G * nw + ens_even((size_t)2 * G * nb) +
+             ens_even((size_t)G * 5);
+  if (stats) d += 11 * kEnsThreads + ens_even((size_t)G * 22);
+  return d * 8 + (size_t)G * nw * 4;
+}
+
+template <bool THIN, bool ALPHA, int NB>
+__global__ void __launch_bounds__(kEnsThreads, MBB_ENS_MINB)
+ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataRef d, const SmallTab t,
+                    const ColdArgs* __restrict__ cold) {
+  extern __shared__ __align__(16) double smem[];
+  const int nw = g.nw, h = g.h, G = g.G;
+  const bool stats = g.stats != nullptr;
+  double* const s_tab = smem;
+  double* const s_pos = s_tab + kTabRepDoubles;
+  double* const s_lnp = s_pos + (size_t)G * nw * 5;
+  double* const s_dat = s_lnp + (size_t)G * nw;
+  double* const s_shift = s_dat + ens_even((size_t)2 * G * NB);
+  double* const s_sum = s_shift + ens_even((size_t)G * 5);
+  double* const s_bl = s_sum + 10 * kEnsThreads;
+  double* const s_red = s_bl + kEnsThreads;
+  int* const s_nacc = reinterpret_cast<int*>(stats ? s_red + ens_even((size_t)G * 22) : s_sum);
+  const int tid = threadIdx.x;
+  stage_exp_table(s_tab);
+  const double* tab = lane_exp_table(s_tab);
+  // thread -> (source of the group, first walker of the half, stride)
+  const int sg = h <= kEnsThreads ? tid / h : 0;
+  const int kfirst = h <= kEnsThreads ? tid - sg * h : tid;
+  const int kstride = h <= kEnsThreads ? h : kEnsThreads;
+  const long long ngroups = (g.nsrc + G - 1) / G;
+  double* const mm = g.scratch + (size_t)blockIdx.x * 15 * kEnsThreads;
+  double* const bp = mm + 10 * kEnsThreads;
+  const bool use_cinv = d.cinv != nullptr;
+
+  for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const long long s_first = grp * G;
+    const int ga = (int)((g.nsrc - s_first) < G ? (g.nsrc - s_first) : G);
+    const bool active = sg < ga;
+    const long long src = s_first + sg;                  // this thread's source (local index)
+    __syncthreads();      // the previous group's epilogue is done with the shared arrays (first pass: table staged)
+    {
+      const double2* gp2 = reinterpret_cast<const double2*>(g.pos + s_first * nw * 5);
+      double2* sp2 = reinterpret_cast<double2*>(s_pos);
+      for (int i = tid; i < ga * nw * 5 / 2; i += kEnsThreads) sp2[i] = gp2[i];
+      const double2* gl2 = reinterpret_cast<const double2*>(g.lnp + s_first * nw);
+      double2* sl2 = reinterpret_cast<double2*>(s_lnp);
+      for (int i = tid; i < ga * nw / 2; i += kEnsThreads) sl2[i] = gl2[i];
+      for (int i = tid; i < ga * nw; i += kEnsThreads) s_nacc[i] = g.nacc[s_first * nw + i];
+      for (int i = tid; i < ga * NB; i += kEnsThreads) {
+        s_dat[i] = d.flux[s_first * NB + i];
+        s_dat[G * NB + i] = use_cinv ? 0.0 : d.ivar[s_first * NB + i];
+      }
+    }
+    double best = -kInf;
+    if (stats) {
+#pragma unroll
+      for (int j = 0; j < 10; ++j) s_sum[j * kEnsThreads + tid] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        mm[j * kEnsThreads + tid] = kInf;
+        mm[(5 + j) * kEnsThreads + tid] = -kInf;
+        bp[j * kEnsThreads + tid] = 0.0;
+      }
+    }
+    __syncthreads();
+
+    for (int it = 0; it < g.niter; ++it) {
+      const bool is_main = it >= g.main_from;
+      if (stats && it == (g.main_from > 0 ? g.main_from : 0) && active && kfirst == 0) {
+        // this launch's shift: walker 0 of the source, read by its owner before it moves
+#pragma unroll
+        for (int j = 0; j < 5; ++j) s_shift[sg * 5 + j] = s_pos[(size_t)sg * nw * 5 + j];
+      }
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const unsigned long long hstep = 2ull * (g.step0 + (unsigned long long)it) + (unsigned long long)half;
+        if (active) {
+#pragma unroll 1
+          for (int k = kfirst; k < h; k += kstride) {
+            const Draw dr = stretch_draw(g.seed, (unsigned long long)((g.src0 + src) * h + k), hstep, g.sc, h);
+            const int own = sg * nw + (half == 0 ? k : h + k);
+            const int oth = sg * nw + (half == 0 ? h : 0) + dr.partner;
+            const double* sj = s_pos + (size_t)own * 5;
+            const double* cj = s_pos + (size_t)oth * 5;
+            double q[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const double c = cj[j];
+              q[j] = __dsub_rn(c, __dmul_rn(dr.z, __dsub_rn(c, sj[j])));
+            }
+            double diff[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) diff[b] = s_dat[sg * NB + b];
+            int st;
+            const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, diff, m, pr, d, t, cold, tab,
+                                                              use_cinv ? nullptr : s_dat + (G + sg) * NB, st);
+            if (st > ST_BELOW_LOWLIM) {
+              int* gs = g.status + (s_first * nw + own);
+              if (*gs <= ST_BELOW_LOWLIM) *gs = st;
+            } else if (stretch_accept(dr.z, dr.u, newlnp, s_lnp[own])) {
+              double* p = s_pos + (size_t)own * 5;
+#pragma unroll
+              for (int j = 0; j < 5; ++j) p[j] = q[j];
+              s_lnp[own] = newlnp;
+              if (is_main) s_nacc[own] += 1;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (is_main) {
+        const long long jm = g.main_done + (it - g.main_from);       // index within the main run
+        if ((jm + 1) % g.thin == 0) {
+          if (stats && active) {
+            for (int k = kfirst; k < h; k += kstride) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int w = sg * nw + hh * h + k;
+                fit_accumulate(s_pos + (size_t)w * 5, s_lnp[w], s_shift + sg * 5, s_sum, mm, bp, best,
+                               kEnsThreads, tid);
+              }
+            }
+          }
+          if (g.chain || g.chain_lnp) {
+            const long long rec = (jm + 1) / g.thin - 1 - g.main_done / g.thin;
+            if (g.chain) {
+              double2* dst = reinterpret_cast<double2*>(g.chain + ((size_t)rec * g.chain_nsrc + s_first) * nw * 5);
+              const double2* sp2 = reinterpret_cast<const double2*>(s_pos);
+              for (int i = tid; i < ga * nw * 5 / 2; i += kEnsThreads) dst[i] = sp2[i];
+            }
+            if (g.chain_lnp) {
+              double2* dst = reinterpret_cast<double2*>(g.chain_lnp + ((size_t)rec * g.chain_nsrc + s_first) * nw);
+              const double2* sl2 = reinterpret_cast<const double2*>(s_lnp);
+              for (int i = tid; i < ga * nw / 2; i += kEnsThreads) dst[i] = sl2[i];
+            }
+            __syncthreads();      // rows are read by other threads than their owners: before they move again
+          }
+        }
+      }
+    }
+
+    // ---- epilogue: ensembles back to HBM, per-thread partials -> summary rows
+    {
+      double2* gp2 = reinterpret_cast<double2*>(g.pos + s_first * nw * 5);
+      const double2* sp2 = reinterpret_cast<const double2*>(s_pos);
+      for (int i = tid; i < ga * nw * 5 / 2; i += kEnsThreads) gp2[i] = sp2[i];
+      double2* gl2 = reinterpret_cast<double2*>(g.lnp + s_first * nw);
+      const double2* sl2 = reinterpret_cast<const double2*>(s_lnp);
+      for (int i = tid; i < ga * nw / 2; i += kEnsThreads) gl2[i] = sl2[i];
+      for (int i = tid; i < ga * nw; i += kEnsThreads) g.nacc[s_first * nw + i] = s_nacc[i];
+    }
+    if (stats) {
+      s_bl[tid] = best;
+      __syncthreads();           // (also makes the per-thread global scratch visible CTA-wide)
+      const FitPartials p{s_sum, mm, bp, s_bl, kEnsThreads};
+      for (int pi = tid; pi < ga * 22; pi += kEnsThreads) {
+        const int s2 = pi / 22, c = pi - s2 * 22;
+        const int t0 = h <= kEnsThreads ? s2 * h : 0, t1 = h <= kEnsThreads ? t0 + h : kEnsThreads;
+        double v;
+        if (c < 21) {
+          v = fit_reduce_component(p, c, t0, t1);
+        } else {
+          int tot = 0;
+          for (int w = 0; w < nw; ++w) tot += s_nacc[s2 * nw + w];
+          v = (double)tot;
+        }
+        s_red[pi] = v;
+      }
+      __syncthreads();
+      if (tid < ga) {
+        const int main_iters_here = g.niter - (g.main_from > 0 ? g.main_from : 0);
+        const double iters = (double)(g.main_done + (main_iters_here > 0 ? main_iters_here : 0));
+        const double frac = iters > 0.0 ? s_red[tid * 22 + 21] / ((double)nw * iters) : 0.0;
+        fit_write_row(g.stats + (s_first + tid) * kFitStats, s_red + tid * 22, s_shift + tid * 5, p,
+                      (double)g.nrec * (double)nw, frac, g.merge);
+      }
+    }
   }
 }
 

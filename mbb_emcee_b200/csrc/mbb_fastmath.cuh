@@ -179,6 +179,9 @@ MBB_HD double clamp_pos(double x) {
 constexpr int kHi700 = 0x4085e000;      // high word of 700.0
 // high word of 64624.0 (x4 for the 256-entry flavour) ~ 700*N/ln2
 template <int TS>
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 constexpr int hi700c() { return TabCfg<TS>::bits == 6 ? 0x40ef8e00 : 0x410f8e00; }
 
 // Reduced exponent: y = k + f in units of 1/64 octave, k = round(y), |f| <= 1/2.

@@ -44,4 +44,16 @@ MBB_PHILOX_HD double u53(unsigned hi, unsigned lo) {
   return ((double)m + 0.5) * 1.1102230246251565e-16;   // 2^-53
 }
 
+// the three fields the sampler cuts out of ONE Philox block (mbb_ensemble.cuh): 52 bits from
+// word 0 and the top 20 bits of word 1 (m + 0.5 is exact below 2^52: strictly inside (0, 1)) ...
+MBB_PHILOX_HD double u52w(unsigned w0, unsigned w1_top20) {
+  const unsigned long long m = ((unsigned long long)w0 << 20) | (unsigned long long)w1_top20;
+  return ((double)m + 0.5) * 2.2204460492503131e-16;   // 2^-52
+}
+// ... and 43 bits from word 3 and the low 11 bits of word 1
+MBB_PHILOX_HD double u43(unsigned w3, unsigned w1_low11) {
+  const unsigned long long m = ((unsigned long long)w3 << 11) | (unsigned long long)w1_low11;
+  return ((double)m + 0.5) * 1.1368683772161603e-13;   // 2^-43
+}
+
 }  // namespace mbb

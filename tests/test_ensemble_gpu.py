@@ -1,4 +1,4 @@
-"""GPU: the device-resident ensemble sampler (mbb_ensemble_run / batch_fitter).
+"""GPU: the device-resident ensemble sampler (mbb_ensemble_fit / mbb_ensemble_run / batch_fitter).
 
 Replay: the same Philox draws regenerated in numpy (tests/philox_np.py) drive
 the emcee-2.2 stretch move on the host with the CPU oracle as log-probability;
@@ -51,8 +51,7 @@ def _problem(oracle, response, nsrc, nw, seed):
                                                      (True, 2, 12, 8)])
 def test_device_sampler_replays_on_host(oracle, response, nsrc, nw, nsteps):
     bf, p0, specs = _problem(oracle, response, nsrc, nw, 11)
-    bf._stage()
-    ctx = bf.like.context
+    ctx = bf._stage()
     pos, lnp, nacc, st = ctx.ensemble_run(p0, nsteps, seed=0x1234ABCD5678, a=2.0)
     assert (st <= 1).all()
     rpos, rlnp, rnacc = philox_np.replay(lambda s, Q: oracle.loglike_batch(specs[s], Q), p0, nsteps,
@@ -67,13 +66,127 @@ def test_device_sampler_replays_on_host(oracle, response, nsrc, nw, nsteps):
     assert np.array_equal(p2, pos) and np.array_equal(l2, lnp) and np.array_equal(n1 + n2, nacc)
     if not response:
         assert (pos[:, :, 3] == 4.0).all()            # a fixed parameter never moves
+    # a shard of a larger source list: global source offset in the RNG counter, recorded chain
+    out = ctx.ensemble_fit(p0, 0, nsteps, seed=99, src0=1000, stats=False, chain=True)
+    r = philox_np.replay(lambda s, Q: oracle.loglike_batch(specs[s], Q), p0, nsteps, 99, src0=1000, chain=True)
+    assert np.array_equal(out["pos"], r[0]) and np.array_equal(out["naccept"], r[2])
+    assert np.array_equal(out["chain"], r[3])
+    assert relerr(out["chain_lnprob"], r[4]).max() < TOL
+    assert not np.array_equal(out["pos"], pos)
 
 
-def test_batch_fitter_recovers_truth():
-    """Statistical sanity on synthetic sources with known parameters."""
+def _numpy_stats(ch, chl):
+    """Reference summaries of a recorded chain ch[nrec][nsrc][nw][5], chl[nrec][nsrc][nw]."""
+    nrec, nsrc, nw, _ = ch.shape
+    flat = np.moveaxis(ch, 1, 0).reshape(nsrc, nrec * nw, 5)
+    fl = np.moveaxis(chl, 1, 0).reshape(nsrc, nrec * nw)
+    mean = flat.mean(axis=1)
+    m2 = ((flat - mean[:, None, :])**2).sum(axis=1)
+    ibest = fl.argmax(axis=1)
+    return dict(n=np.full(nsrc, nrec * nw), mean=mean, m2=m2, min=flat.min(axis=1), max=flat.max(axis=1),
+                best_lnp=fl.max(axis=1), best=flat[np.arange(nsrc), ibest])
+
+
+# resident kernel: several sources per CTA (nw 16, 64), one per CTA (512), threads looping over
+# walkers (1024); tabulated bands: propose / evaluate / accept + the per-record summary kernel
+@pytest.mark.parametrize("response,nsrc,nw,nburn,nsteps,thin", [
+    (False, 37, 16, 5, 24, 1), (False, 21, 64, 0, 18, 3), (False, 9, 512, 4, 12, 2), (False, 3, 1024, 2, 9, 1),
+    (True, 3, 12, 3, 10, 2)])
+def test_fit_summaries_equal_numpy_over_the_chain(oracle, response, nsrc, nw, nburn, nsteps, thin):
+    from mbb_emcee_b200 import _native as nat
+    bf, p0, _ = _problem(oracle, response, nsrc, nw, 21)
+    ctx = bf._stage()
+    out = ctx.ensemble_fit(p0, nburn, nsteps, seed=31, chain=True, thin=thin)
+    assert (out["status"] <= 1).all()
+    ch, chl, S = out["chain"], out["chain_lnprob"], out["stats"]
+    assert ch.shape == (nsteps // thin, nsrc, nw, 5)
+    # the chain is what burn-in + main run through the plain sampler produce (continuation by step0)
+    pb, lb, _, _ = ctx.ensemble_run(p0, nburn, seed=31) if nburn else (p0, None, None, None)
+    full = ctx.ensemble_fit(pb, 0, nsteps, seed=31, step0=nburn, lnprob=lb, stats=False, chain=True)
+    assert np.array_equal(full["chain"][thin - 1::thin][:nsteps // thin], ch)
+    assert np.array_equal(full["pos"], out["pos"]) and np.array_equal(full["lnprob"], out["lnprob"])
+    assert np.array_equal(full["naccept"], out["naccept"])          # burn-in moves are not counted
+    assert np.array_equal(ch[-1], out["pos"]) if nsteps % thin == 0 else True
+    want = _numpy_stats(ch, chl)
+    assert np.array_equal(S[:, nat.FS_N], want["n"])
+    assert np.array_equal(S[:, nat.FS_MIN:nat.FS_MIN + 5], want["min"])
+    assert np.array_equal(S[:, nat.FS_MAX:nat.FS_MAX + 5], want["max"])
+    assert np.array_equal(S[:, nat.FS_BESTLNP], want["best_lnp"])
+    assert np.array_equal(S[:, nat.FS_BEST:nat.FS_BEST + 5], want["best"])
+    assert relerr(S[:, nat.FS_MEAN:nat.FS_MEAN + 5], want["mean"]).max() < 1e-13
+    m2 = S[:, nat.FS_M2:nat.FS_M2 + 5]
+    free = want["m2"] > 0
+    assert relerr(m2[free], want["m2"][free]).max() < 1e-10 and (m2[~free] == 0).all()
+    assert np.allclose(S[:, nat.FS_ACC], out["naccept"].sum(axis=1) / float(nw * nsteps), rtol=1e-14)
+    assert 0 < out["naccept"].sum() < nsrc * nw * nsteps
+
+
+def test_fit_chain_streams_to_host_in_segments(oracle, monkeypatch):
+    """Host chain output is cut into segments (two device buffers, D2H behind the sampler);
+    the summaries are merged across segments.  Same numbers as one device-resident pass."""
+    import torch
+    from mbb_emcee_b200 import _native as nat
+    nsrc, nw, nburn, nsteps, thin = 300, 512, 3, 14, 2
+    bf, p0, _ = _problem(oracle, False, nsrc, nw, 5)
+    ctx = bf._stage()
+    nrec = nsteps // thin
+    dev = torch.device("cuda:0")
+    P = torch.as_tensor(p0, device=dev).contiguous()
+    L = torch.empty((nsrc, nw), dtype=torch.float64, device=dev)
+    A = torch.zeros((nsrc, nw), dtype=torch.int32, device=dev)
+    S = torch.zeros((nsrc, nat.FIT_NSTATS), dtype=torch.float64, device=dev)
+    C = torch.empty((nrec, nsrc, nw, 5), dtype=torch.float64, device=dev)
+    CL = torch.empty((nrec, nsrc, nw), dtype=torch.float64, device=dev)
+    ctx.ensemble_fit_device(nsrc, nw, nburn, nsteps, P.data_ptr(), L.data_ptr(), seed=8, naccept_ptr=A.data_ptr(),
+                            stats_ptr=S.data_ptr(), chain_ptr=C.data_ptr(), chain_lnprob_ptr=CL.data_ptr(),
+                            thin=thin)
+    ctx.sync()
+    # one record of this problem is 7.4 MB: the 256 MB segment budget holds all 7; force small segments
+    monkeypatch.setenv("MBB_B200_CHAIN_SEGMENT_MB", "16")
+    out = ctx.ensemble_fit(p0, nburn, nsteps, seed=8, chain=True, thin=thin)
+    assert np.array_equal(out["chain"], C.cpu().numpy()) and np.array_equal(out["chain_lnprob"], CL.cpu().numpy())
+    assert np.array_equal(out["pos"], P.cpu().numpy()) and np.array_equal(out["naccept"], A.cpu().numpy())
+    s1, s2 = out["stats"], S.cpu().numpy()
+    exact = [nat.FS_N] + list(range(nat.FS_MIN, nat.FS_BEST + 5)) + [nat.FS_ACC]
+    assert np.array_equal(s1[:, exact], s2[:, exact])
+    assert relerr(s1[:, nat.FS_MEAN:nat.FS_MEAN + 5], s2[:, nat.FS_MEAN:nat.FS_MEAN + 5]).max() < 1e-13
+    free = s2[:, nat.FS_M2:nat.FS_M2 + 5] > 0
+    assert relerr(s1[:, nat.FS_M2:nat.FS_M2 + 5][free], s2[:, nat.FS_M2:nat.FS_M2 + 5][free]).max() < 1e-10
+
+
+def test_batch_fitter_shards_are_the_same_fit():
+    """devices=[0, 0, 0]: three shards (three contexts, three host threads) fill disjoint slices of
+    the shared page-locked outputs; bit-identical to the unsharded fit (global source index in the
+    RNG counter), chain included."""
+    from mbb_emcee_b200 import batch_fitter
+    rng = np.random.RandomState(4)
+    nsrc, nw = 101, 64
+    bands = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0]
+    flux = rng.uniform(10, 80, (nsrc, 6))
+    unc = np.maximum(0.1 * flux, 1.0)
+    res = []
+    for devices in ([0], [0, 0, 0]):
+        bf = batch_fitter(nwalkers=nw, opthin=True, noalpha=True, devices=devices)
+        bf.fix_param('alpha')
+        bf.set_data(bands, flux, unc)
+        p0 = bf.generate_initial_values((12.0, 1.8, 1300.0, 4.0, 30.0), [2, 0.2, 100, 0.3, 5.0], seed=2)
+        res.append(bf.run(6, 10, p0, seed=5, thin=2, chain=True))
+    a, b = res
+    for key in ("pos", "lnprob", "naccept", "status", "stats", "chain", "chain_lnprob"):
+        assert np.array_equal(a[key], b[key]), key
+    assert a["chain"].shape == (5, nsrc, nw, 5)
+    cen = a.par_cen("T")
+    assert cen.shape == (nsrc, 3) and (cen[:, 1:] > 0).all()
+
+
+def test_batch_fitter_posteriors_match_host_sampler(oracle):
+    """The fit a user gets: per-source posterior mean / sigma from the device summaries against
+    (a) the known truths and (b) an independent host run of the emcee-2.2 stretch move
+    (oracle.stretch_chain: Mersenne-Twister draws, original log-form acceptance, CPU oracle as
+    log-probability) on the same sources, within Monte-Carlo error."""
     from mbb_emcee_b200 import batch_fitter, modified_blackbody
     rng = np.random.RandomState(3)
-    nsrc, nw = 64, 64
+    nsrc, nw, nburn, nsteps = 64, 64, 200, 400
     waves = np.array([70.0, 100.0, 160.0, 250.0, 350.0, 500.0])
     T = rng.uniform(10, 20, nsrc)
     flux = np.empty((nsrc, 6))
@@ -83,16 +196,36 @@ def test_batch_fitter_recovers_truth():
     flux = flux + unc * rng.standard_normal(flux.shape)
     bf = batch_fitter(nwalkers=nw, opthin=True, noalpha=True, device=0)
     bf.fix_param('alpha')
+    bf.fix_param('lambda0')
     bf.set_data(waves, flux, unc)
     init = np.column_stack([T + 1.0, np.full(nsrc, 1.7), np.full(nsrc, 1300.0), np.full(nsrc, 4.0),
                             np.full(nsrc, 35.0)])
     p0 = bf.generate_initial_values(init, [2, 0.2, 100, 0.3, 5.0], seed=1)
-    out = bf.run(150, 150, p0, seed=99)
-    acc = out["acceptance_fraction"].mean()
-    assert 0.15 < acc < 0.75
-    Tfit = out["pos"][:, :, 0].mean(axis=1)
-    assert np.median(np.abs(Tfit - T) / T) < 0.05
-    assert np.isfinite(out["lnprob"]).all()
+    out = bf.run(nburn, nsteps, p0, seed=99)
+    acc = out.mean_acceptance
+    assert (0.15 < acc).all() and (acc < 0.8).all()
+    assert np.allclose(acc, out["acceptance_fraction"].mean(axis=1), rtol=1e-12)
+    assert np.isfinite(out["lnprob"]).all() and (out.nsamples == nw * nsteps).all()
+    # (a) truths: pulls of T are standard-normal-ish
+    pull = (out.mean[:, 0] - T) / out.std[:, 0]
+    assert np.abs(pull).max() < 5.0 and np.abs(pull.mean()) < 0.5 and 0.5 < pull.std() < 1.6
+    assert (out.best_lnprob >= out["lnprob"].max(axis=1)).all()
+    assert (out.std[:, 3] == 0).all() and (out.mean[:, 3] == 4.0).all()           # fixed parameters
+    # (b) host sampler on 8 of the sources
+    free = [0, 1, 4]
+    for s in range(0, nsrc, 8):
+        sp = oracle.LikeSpec(500.0, True, True)
+        sp.set_phot(list(waves), flux[s], unc[s])
+        sp.has_uplim = list(bf.like.has_uplims)
+        sp.uplim = np.array(bf.like.uplims)
+        ch, _, nacc = oracle.stretch_chain(lambda Q: oracle.loglike_batch(sp, Q), p0[s], nburn + nsteps,
+                                           np.random.RandomState(100 + s))
+        main = ch[:, nburn:, :].reshape(-1, 5)
+        hm, hs = main.mean(axis=0), main.std(axis=0, ddof=1)
+        # autocorrelation ~30 steps -> ~850 independent samples per run: error of the mean ~ sigma/29
+        assert (np.abs(out.mean[s, free] - hm[free]) < 0.25 * hs[free]).all(), (s, out.mean[s], hm, hs)
+        assert (np.abs(out.std[s, free] / hs[free] - 1.0) < 0.25).all(), (s, out.std[s], hs)
+        assert abs(acc[s] - nacc.mean() / (nburn + nsteps)) < 0.08
 
 
 @pytest.mark.parametrize("opthin,noalpha", [(True, True), (False, False)])
@@ -111,8 +244,7 @@ def test_sampler_kernels_agree_bitwise(monkeypatch, opthin, noalpha, nsrc, nw):
     bf.set_data(bands, flux, np.maximum(0.1 * flux, 1.0))
     truth = (12.0, 1.8, 1300.0, 4.0, 30.0) if opthin else (14.0, 1.8, 400.0, 3.0, 30.0)
     p0 = bf.generate_initial_values(truth, [2, 0.2, 100, 0.3, 5.0], seed=5)
-    bf._stage()
-    ctx = bf.like.context
+    ctx = bf._stage()
     runs = []
     for env in ({}, {"MBB_B200_NO_FUSED_SAMPLER": "1"}):
         monkeypatch.delenv("MBB_B200_NO_FUSED_SAMPLER", raising=False)
@@ -121,7 +253,7 @@ def test_sampler_kernels_agree_bitwise(monkeypatch, opthin, noalpha, nsrc, nw):
         n0 = ctx.launch_count()
         runs.append(ctx.ensemble_run(p0, 5, seed=77) + (ctx.launch_count() - n0,))
     a, b = runs
-    assert a[4] == 11 and b[4] > 11                     # 1 + 2 launches per iteration when fused
+    assert a[4] == 2 and b[4] > 11                      # initial log-probability + ONE resident launch
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert 0 < a[2].sum() < nsrc * nw * 5
