@@ -129,6 +129,9 @@ struct mbb_ctx {
     DevBuf<double> din, dout;
     DevBuf<int> dst, dsrc;
     int64_t pend_e0 = -1, pend_n = 0;   // chunk whose outputs still sit in hout/hst
+    // source chunks of mbb_ensemble_fit(MBB_HOST)
+    DevBuf<double> epos, elnp, estats, escratch;
+    DevBuf<int> enacc, est;
   };
   Slot slots[3];
   bool slots_ready = false;
@@ -185,8 +188,7 @@ void default_priors(Priors& p) {
   }
   p.has_uplim[1] = p.has_uplim[3] = 1;
   p.uplim[1] = p.uplim[3] = 20.0;
-  p.any_gprior = 0;
-  p.always_terms = 0;
+  priors_finalize(p);
 }
 
 struct Use {
@@ -391,7 +393,8 @@ EnsResidentPlan ens_resident_plan(const mbb_ctx* c, int nwalkers, bool stats) {
 
 template <bool THIN, bool ALPHA, int NB>
 struct EnsResidentLauncher {
-  static void go(mbb_ctx* c, EnsFit& g, const DataRef& d, int nb, size_t smem, cudaError_t* err) {
+  static void go(mbb_ctx* c, EnsFit& g, const DataRef& d, int nb, size_t smem, cudaStream_t st,
+                 DevBuf<double>* scratch, cudaError_t* err) {
     if (nb == NB) {
       auto kern = ens_resident_kernel<THIN, ALPHA, NB>;
       *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -402,25 +405,26 @@ struct EnsResidentLauncher {
       const long long ngroups = (g.nsrc + g.G - 1) / g.G;
       const long long resident = (long long)c->sm_count * per_sm;
       const unsigned grid = (unsigned)(ngroups < resident ? ngroups : resident);
-      *err = c->d_escratch.reserve((size_t)grid * 15 * kEnsThreads);
+      *err = scratch->reserve((size_t)grid * 5 * kEnsThreads);
       if (*err != cudaSuccess) return;
-      g.scratch = c->d_escratch.p;
+      g.scratch = scratch->p;
       const ModelP m = model_of(c);
-      kern<<<grid, kEnsThreads, smem, c->stream>>>(g, m, c->pri, d, c->small, c->d_cold.p);
+      kern<<<grid, kEnsThreads, smem, st>>>(g, m, c->pri, d, c->small, c->d_cold.p);
     } else {
-      EnsResidentLauncher<THIN, ALPHA, NB - 1>::go(c, g, d, nb, smem, err);
+      EnsResidentLauncher<THIN, ALPHA, NB - 1>::go(c, g, d, nb, smem, st, scratch, err);
     }
   }
 };
 template <bool THIN, bool ALPHA>
 struct EnsResidentLauncher<THIN, ALPHA, 0> {
-  static void go(mbb_ctx*, EnsFit&, const DataRef&, int, size_t, cudaError_t*) {}
+  static void go(mbb_ctx*, EnsFit&, const DataRef&, int, size_t, cudaStream_t, DevBuf<double>*, cudaError_t*) {}
 };
 
 template <bool THIN, bool ALPHA, bool FAST>
 struct LaunchEnsResident {
-  static void run(mbb_ctx* c, EnsFit& g, const DataRef& d, size_t smem, cudaError_t* err) {
-    EnsResidentLauncher<THIN, ALPHA, kMaxDeltaNB>::go(c, g, d, c->nb, smem, err);
+  static void run(mbb_ctx* c, EnsFit& g, const DataRef& d, size_t smem, cudaStream_t st, DevBuf<double>* scratch,
+                  cudaError_t* err) {
+    EnsResidentLauncher<THIN, ALPHA, kMaxDeltaNB>::go(c, g, d, c->nb, smem, st, scratch, err);
   }
 };
 
@@ -609,6 +613,8 @@ int mbb_ctx_destroy(mbb_ctx* c) {
   for (auto& sl : c->slots) {
     sl.hin.release(); sl.hout.release(); sl.hst.release(); sl.hsrc.release();
     sl.din.release(); sl.dout.release(); sl.dst.release(); sl.dsrc.release();
+    sl.epos.release(); sl.elnp.release(); sl.estats.release(); sl.escratch.release();
+    sl.enacc.release(); sl.est.release();
     if (sl.done) cudaEventDestroy(sl.done);
     if (sl.s) cudaStreamDestroy(sl.s);
   }
@@ -745,16 +751,14 @@ int mbb_set_priors(mbb_ctx* c, const double lowlim[5], const uint8_t has_uplim[6
   if (!lowlim || !has_uplim || !uplim || !has_gprior || !gmean || !givar) return fail("null argument");
   Priors& p = c->pri;
   for (int i = 0; i < 5; ++i) p.lowlim[i] = lowlim[i];
-  p.any_gprior = 0;
   for (int i = 0; i < 6; ++i) {
     p.has_uplim[i] = has_uplim[i] ? 1 : 0;
-    p.uplim[i] = has_uplim[i] ? uplim[i] : kInf;
+    p.uplim[i] = uplim[i];
     p.has_gprior[i] = has_gprior[i] ? 1 : 0;
     p.gmean[i] = gmean[i];
     p.givar[i] = givar[i];
-    if (has_gprior[i]) p.any_gprior = 1;
   }
-  p.always_terms = (p.any_gprior || p.has_uplim[5]) ? 1 : 0;
+  priors_finalize(p);
   c->cold_ok = false;
   return 0;
 }
@@ -801,6 +805,16 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a_in) {
   CK(err);
   c->launches += 1;
   CK(cudaGetLastError());
+  return 0;
+}
+
+int ensure_slots(mbb_ctx* c) {
+  if (c->slots_ready) return 0;
+  for (auto& sl : c->slots) {
+    CK(cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  c->slots_ready = true;
   return 0;
 }
 
@@ -851,13 +865,7 @@ int mbb_loglike(mbb_ctx* c, int64_t n, const double* pars, int layout, const int
   if (src_index)
     for (int64_t i = 0; i < n; ++i)
       if (src_index[i] < 0 || src_index[i] >= c->nsrc) return fail("src_index out of range");
-  if (!c->slots_ready) {
-    for (auto& sl : c->slots) {
-      CK(cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
-    }
-    c->slots_ready = true;
-  }
+  if (ensure_slots(c)) return 1;
   const bool pin_in = is_pinned(pars) && is_pinned(src_index);
   const bool pin_out = is_pinned(out_lnlike) && is_pinned(out_status);
   // chunk = at most host_chunk() evaluations, but at least ~8 chunks per call once the batch is
@@ -1215,6 +1223,97 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
   if (nwk >= (1LL << 31)) return fail("too many walkers for one call (>= 2^31); shard the sources");
   const bool host = mem != MBB_DEVICE;
   const int64_t nrec_total = nsteps / thin;
+  CK(ensure_tables(c));      // node tables and the cold-path block match the current model / priors
+  // delta-band FAST configurations whose ensembles fit in shared memory take the source-resident kernel
+  // (the switch is read per call so that tests can compare the paths in one process)
+  const bool no_fuse = getenv("MBB_B200_NO_FUSED_SAMPLER") != nullptr;
+  const EnsResidentPlan plan = ens_resident_plan(c, nwalkers, stats != nullptr);
+  const bool resident_ok = !no_fuse && c->math_mode != MBB_MATH_FAITHFUL && c->nn == c->nb &&
+                           c->nb <= kMaxDeltaNB && plan.ok;
+  const StretchScale sc = stretch_scale(a);
+  DataRef dref;
+  dref.flux = c->d_flux.p;
+  dref.ivar = c->has_ivar ? c->d_ivar.p : nullptr;
+  dref.cinv = c->has_cinv ? c->d_cinv.p : nullptr;
+  dref.nsrc = c->nsrc;
+  dref.nb = c->nb;
+
+  // ---- host buffers, no chain: chunks of sources flow through three slots, each with its own stream, so
+  // that the upload of one chunk's starting ensembles and the download of another's results run behind
+  // the sampler working on a third (the resident kernel treats sources independently)
+  {
+    static const bool no_pipe = getenv("MBB_B200_NO_FIT_PIPELINE") != nullptr;
+    const int64_t min_chunk = 2048;
+    if (host && resident_ok && !chain && !chain_lnprob && !no_pipe && nsrc >= 2 * min_chunk && nburn + nsteps > 0) {
+      if (ensure_slots(c)) return 1;
+      int64_t nchunks = 8;
+      if (nsrc / nchunks < min_chunk) nchunks = nsrc / min_chunk;
+      const int64_t CH = (nsrc + nchunks - 1) / nchunks;
+      begin_timing(c);
+      for (int64_t k = 0; k * CH < nsrc; ++k) {
+        mbb_ctx::Slot& sl = c->slots[k % 3];
+        CK(cudaStreamSynchronize(sl.s));
+        const int64_t s0 = k * CH, ns = (nsrc - s0) < CH ? (nsrc - s0) : CH;
+        const size_t nw_c = (size_t)ns * nwalkers;
+        CK(sl.epos.reserve((size_t)CH * nwalkers * 5));
+        CK(sl.elnp.reserve((size_t)CH * nwalkers));
+        CK(sl.enacc.reserve((size_t)CH * nwalkers));
+        CK(sl.est.reserve((size_t)CH * nwalkers));
+        if (stats) CK(sl.estats.reserve((size_t)CH * kFitStats));
+        if (k == 0) CK(cudaStreamWaitEvent(sl.s, c->ev0, 0));
+        CK(cudaMemcpyAsync(sl.epos.p, pos + (size_t)s0 * nwalkers * 5, nw_c * 5 * sizeof(double),
+                           cudaMemcpyHostToDevice, sl.s));
+        if (have_lnprob)
+          CK(cudaMemcpyAsync(sl.elnp.p, lnprob + (size_t)s0 * nwalkers, nw_c * sizeof(double),
+                             cudaMemcpyHostToDevice, sl.s));
+        CK(cudaMemsetAsync(sl.enacc.p, 0, nw_c * sizeof(int), sl.s));
+        CK(cudaMemsetAsync(sl.est.p, 0, nw_c * sizeof(int), sl.s));
+        if (!have_lnprob) {
+          EvalArgs e{};
+          e.n = (long long)nw_c; e.e0 = s0 * nwalkers; e.wps = nwalkers; e.layout = MBB_AOS;
+          e.pars = sl.epos.p; e.src_index = nullptr; e.out = sl.elnp.p; e.status = sl.est.p;
+          if (launch_loglike(c, sl.s, e)) return 1;
+        }
+        EnsFit g{};
+        g.pos = sl.epos.p; g.lnp = sl.elnp.p; g.nacc = sl.enacc.p; g.status = sl.est.p;
+        g.stats = stats ? sl.estats.p : nullptr;
+        g.nsrc = ns; g.src0 = src0 + s0; g.dsrc0 = s0; g.chain_nsrc = ns;
+        g.nw = nwalkers; g.h = h; g.G = plan.G;
+        g.niter = (int)(nburn + nsteps);
+        g.main_from = (int)nburn;
+        g.main_done = 0;
+        g.thin = thin;
+        g.nrec = (int)nrec_total;
+        g.merge = 0;
+        g.seed = seed;
+        g.step0 = step0;
+        g.sc = sc;
+        cudaError_t err = cudaSuccess;
+        dispatch3<LaunchEnsResident>(c->opthin != 0, c->noalpha == 0, true, c, g, dref, plan.smem, sl.s,
+                                     &sl.escratch, &err);
+        CK(err);
+        c->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(pos + (size_t)s0 * nwalkers * 5, sl.epos.p, nw_c * 5 * sizeof(double),
+                           cudaMemcpyDeviceToHost, sl.s));
+        CK(cudaMemcpyAsync(lnprob + (size_t)s0 * nwalkers, sl.elnp.p, nw_c * sizeof(double),
+                           cudaMemcpyDeviceToHost, sl.s));
+        if (naccept)
+          CK(cudaMemcpyAsync(naccept + (size_t)s0 * nwalkers, sl.enacc.p, nw_c * sizeof(int),
+                             cudaMemcpyDeviceToHost, sl.s));
+        if (status)
+          CK(cudaMemcpyAsync(status + (size_t)s0 * nwalkers, sl.est.p, nw_c * sizeof(int),
+                             cudaMemcpyDeviceToHost, sl.s));
+        if (stats)
+          CK(cudaMemcpyAsync(stats + (size_t)s0 * kFitStats, sl.estats.p, (size_t)ns * kFitStats * sizeof(double),
+                             cudaMemcpyDeviceToHost, sl.s));
+      }
+      for (auto& sl : c->slots) CK(cudaStreamSynchronize(sl.s));
+      end_timing(c);
+      return 0;
+    }
+  }
+
   double *dpos = pos, *dlnp = lnprob, *dstats = stats;
   int *dnacc = naccept, *dst = status;
   if (host) {
@@ -1233,7 +1332,6 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
   if (!dst) { CK(c->d_est.reserve((size_t)nwk)); dst = c->d_est.p; }
   CK(cudaMemsetAsync(dnacc, 0, (size_t)nwk * sizeof(int), c->stream));
   CK(cudaMemsetAsync(dst, 0, (size_t)nwk * sizeof(int), c->stream));
-  CK(ensure_tables(c));      // node tables and the cold-path block match the current model / priors
   begin_timing(c);
   if (!have_lnprob) {
     // log-probability of the starting ensemble (emcee computes it once up front)
@@ -1242,27 +1340,14 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
     e.pars = dpos; e.src_index = nullptr; e.out = dlnp; e.status = dst;
     if (launch_loglike(c, c->stream, e)) return 1;
   }
-  DataRef dref;
-  dref.flux = c->d_flux.p;
-  dref.ivar = c->has_ivar ? c->d_ivar.p : nullptr;
-  dref.cinv = c->has_cinv ? c->d_cinv.p : nullptr;
-  dref.nsrc = c->nsrc;
-  dref.nb = c->nb;
-  // delta-band FAST configurations whose ensembles fit in shared memory take the source-resident kernel
-  // (the switch is read per call so that tests can compare the paths in one process)
-  const bool no_fuse = getenv("MBB_B200_NO_FUSED_SAMPLER") != nullptr;
-  const EnsResidentPlan plan = ens_resident_plan(c, nwalkers, stats != nullptr);
   const bool aligned = ((uintptr_t)dpos % 16 == 0) && ((uintptr_t)dlnp % 16 == 0) &&
                        (host || (((uintptr_t)chain % 16 == 0) && ((uintptr_t)chain_lnprob % 16 == 0)));
-  const bool resident = !no_fuse && c->math_mode != MBB_MATH_FAITHFUL && c->nn == c->nb && c->nb <= kMaxDeltaNB &&
-                        plan.ok && aligned;
+  const bool resident = resident_ok && aligned;
   if (!resident) {
     CK(c->d_eq.reserve((size_t)nh * 5));
     CK(c->d_eqlnp.reserve((size_t)nh));
     CK(c->d_eqst.reserve((size_t)nh));
   }
-  const StretchScale sc = stretch_scale(a);
-
   // One segment = iterations [i0, i1) of the call (burn-in first); its records go to cdst / ldst.
   auto run_segment = [&](int64_t i0, int64_t i1, double* cdst, double* ldst, int64_t cns) -> int {
     const int64_t main_done = i0 > nburn ? i0 - nburn : 0;
@@ -1272,7 +1357,7 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
       EnsFit g{};
       g.pos = dpos; g.lnp = dlnp; g.nacc = dnacc; g.status = dst; g.stats = dstats;
       g.chain = cdst; g.chain_lnp = ldst;
-      g.nsrc = nsrc; g.src0 = src0; g.chain_nsrc = cns; g.nw = nwalkers; g.h = h; g.G = plan.G;
+      g.nsrc = nsrc; g.src0 = src0; g.dsrc0 = 0; g.chain_nsrc = cns; g.nw = nwalkers; g.h = h; g.G = plan.G;
       g.niter = (int)(i1 - i0);
       g.main_from = (int)(nburn > i0 ? (nburn - i0 < i1 - i0 ? nburn - i0 : i1 - i0) : 0);
       g.main_done = main_done;
@@ -1283,7 +1368,8 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
       g.step0 = step0 + (uint64_t)i0;
       g.sc = sc;
       cudaError_t err = cudaSuccess;
-      dispatch3<LaunchEnsResident>(c->opthin != 0, c->noalpha == 0, true, c, g, dref, plan.smem, &err);
+      dispatch3<LaunchEnsResident>(c->opthin != 0, c->noalpha == 0, true, c, g, dref, plan.smem, c->stream,
+                                   &c->d_escratch, &err);
       CK(err);
       c->launches += 1;
       CK(cudaGetLastError());

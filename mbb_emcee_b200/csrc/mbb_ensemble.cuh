@@ -152,47 +152,69 @@ __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
 }
 
 // ---------------------------------------------------------------------------
-// Posterior accumulators.  Per thread: shifted sums S1 = sum (x - c), S2 = sum
-// (x - c)^2 (c = the source's walker 0 when accumulation starts: of the order of
-// a posterior width away from the mean, so S2 - S1^2/n loses no digits), min, max
-// and the best sample.  fit_reduce turns the per-thread partials of one source
+// Posterior accumulators.  The hs threads that serve one source split its 5 x nw
+// sample values by COMPONENT: thread r accumulates component j = r % 5 over the
+// walkers slot, slot + nslots, ... (slot = r / 5, nslots = hs / 5), so a record is
+// one conflict-free linear sweep of the ensemble in shared memory and the running
+// S1 = sum (x - c), S2 = sum (x - c)^2, min and max of a thread are four REGISTERS
+// for the whole run -- no read-modify-write of any memory per record.  (c = the
+// source's walker 0 at the first record: a posterior width away from the mean,
+// so S2 - S1^2/n loses no digits.)  The best sample is tracked per walker owner.
+// fit_reduce_component / fit_write_row turn the per-thread partials of one source
 // into its summary row, merging with what the row already holds (an earlier
 // segment of the same run) by the pairwise update of Chan, Golub & LeVeque (1979).
 // Deterministic: fixed serial order over the threads of the source.
 // ---------------------------------------------------------------------------
+struct StatAcc {
+  double s1, s2, mn, mx, shift;
+};
+
+__device__ __forceinline__ void stat_reset(StatAcc& a) {
+  a.s1 = 0.0;
+  a.s2 = 0.0;
+  a.mn = kInf;
+  a.mx = -kInf;
+  a.shift = 0.0;
+}
+
+// one record of one source: P = its ensemble [nw][5]
+__device__ __forceinline__ void stat_record(StatAcc& a, const double* P, int nw, int cj, int slot, int nslots) {
+  for (int w = slot; w < nw; w += nslots) {
+    const double v = P[w * 5 + cj], dv = v - a.shift;
+    a.s1 += dv;
+    a.s2 = fma(dv, dv, a.s2);
+    a.mn = fmin(a.mn, v);
+    a.mx = fmax(a.mx, v);
+  }
+}
+
 struct FitPartials {
-  const double* sums;     // [10][stride]: S1[5], S2[5]
-  const double* minmax;   // [10][stride]: min[5], max[5]
+  const double* part;     // [4][stride]: S1, S2, min, max of each thread (component = thread-in-source % 5)
   const double* bestpos;  // [5][stride]
   const double* bestlnp;  // [stride]
   int stride;
 };
 
-// component c (0..20) of the source whose threads are [t0, t1); c = 20 returns the
-// winning thread index (as a double) of the best-sample search
-__device__ __forceinline__ double fit_reduce_component(const FitPartials& p, int c, int t0, int t1) {
-  if (c < 10) {
-    double s = 0.0;
-    for (int t = t0; t < t1; ++t) s += p.sums[c * p.stride + t];
-    return s;
+// component c (0..20) of the source served by threads [t0, t0 + hs): 0-4 S1, 5-9 S2, 10-14 min,
+// 15-19 max; c = 20 returns the winning thread index (as a double) of the best-sample search
+__device__ __forceinline__ double fit_reduce_component(const FitPartials& p, int c, int t0, int hs) {
+  if (c == 20) {
+    int win = t0;
+    double best = p.bestlnp[t0];
+    for (int t = t0 + 1; t < t0 + hs; ++t) {
+      const double v = p.bestlnp[t];
+      if (v > best) { best = v; win = t; }
+    }
+    return (double)win;
   }
-  if (c < 15) {
-    double v = kInf;
-    for (int t = t0; t < t1; ++t) v = fmin(v, p.minmax[(c - 10) * p.stride + t]);
-    return v;
+  const int kind = c / 5, j = c - kind * 5, nslots = hs / 5;
+  const double* q = p.part + kind * p.stride + t0 + j;
+  double v = kind < 2 ? 0.0 : (kind == 2 ? kInf : -kInf);
+  for (int sl = 0; sl < nslots; ++sl) {
+    const double x = q[sl * 5];
+    v = kind < 2 ? v + x : (kind == 2 ? fmin(v, x) : fmax(v, x));
   }
-  if (c < 20) {
-    double v = -kInf;
-    for (int t = t0; t < t1; ++t) v = fmax(v, p.minmax[(c - 10) * p.stride + t]);
-    return v;
-  }
-  int win = t0;
-  double best = p.bestlnp[t0];
-  for (int t = t0 + 1; t < t1; ++t) {
-    const double v = p.bestlnp[t];
-    if (v > best) { best = v; win = t; }
-  }
-  return (double)win;
+  return v;
 }
 
 // red[0..20] of one source -> its row; n_seg samples in this segment, shift[5]
@@ -234,69 +256,52 @@ __device__ __forceinline__ void fit_write_row(double* row, const double* red, co
   row[FS_ACC] = acc_frac;
 }
 
-// one sample into a thread's accumulators (S in shared memory, the rest wherever `mm` / `bp` live)
-__device__ __forceinline__ void fit_accumulate(const double* x, double lnp, const double* shift, double* sums,
-                                               double* mm, double* bp, double& best, int stride, int t) {
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const double v = x[j], dv = v - shift[j];
-    sums[j * stride + t] += dv;
-    sums[(5 + j) * stride + t] = fma(dv, dv, sums[(5 + j) * stride + t]);
-    if (v < mm[j * stride + t]) mm[j * stride + t] = v;
-    if (v > mm[(5 + j) * stride + t]) mm[(5 + j) * stride + t] = v;
-  }
-  if (lnp > best) {
-    best = lnp;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) bp[j * stride + t] = x[j];
-  }
-}
-
 // Summary update from ensembles in global memory (the propose / evaluate / accept path): one
 // CTA per source, called once per recorded iteration; each call merges nw samples into the row.
 constexpr int kStatsThreads = 128;
 __global__ void __launch_bounds__(kStatsThreads)
 ens_stats_kernel(const double* __restrict__ pos, const double* __restrict__ lnp, const int* __restrict__ nacc,
                  double* __restrict__ stats, int nw, int merge, double main_iters) {
-  __shared__ double s_part[26 * kStatsThreads];
+  __shared__ double s_part[4 * kStatsThreads];
+  __shared__ double s_bp[5 * kStatsThreads];
+  __shared__ double s_bl[kStatsThreads];
   __shared__ double s_red[24];
   __shared__ double s_shift[5];
+  __shared__ int s_acc[kStatsThreads / 32];
   const int tid = threadIdx.x;
   const long long src = blockIdx.x;
   const double* P = pos + src * nw * 5;
-  double* sums = s_part;
-  double* mm = s_part + 10 * kStatsThreads;
-  double* bp = s_part + 20 * kStatsThreads;
-  double* bl = s_part + 25 * kStatsThreads;
-  if (tid < 5) s_shift[tid] = P[tid];
-#pragma unroll
-  for (int j = 0; j < 10; ++j) sums[j * kStatsThreads + tid] = 0.0;
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    mm[j * kStatsThreads + tid] = kInf;
-    mm[(5 + j) * kStatsThreads + tid] = -kInf;
-    bp[j * kStatsThreads + tid] = 0.0;
+  const int hs = nw / 2 < kStatsThreads ? nw / 2 : kStatsThreads;      // >= 6
+  const int nslots = hs / 5, cj = tid % 5, slot = tid / 5;
+  StatAcc a;
+  stat_reset(a);
+  if (tid < hs && slot < nslots) {
+    a.shift = P[cj];
+    stat_record(a, P, nw, cj, slot, nslots);
   }
-  __syncthreads();
+  if (tid < 5) s_shift[tid] = P[tid];
+  s_part[tid] = a.s1;
+  s_part[kStatsThreads + tid] = a.s2;
+  s_part[2 * kStatsThreads + tid] = a.mn;
+  s_part[3 * kStatsThreads + tid] = a.mx;
   double best = -kInf;
   int acc = 0;
-  for (int w = tid; w < nw; w += kStatsThreads) {
-    double x[5];
+  for (int w = tid; w < nw; w += hs) {
+    if (tid >= hs) break;
+    const double l = lnp[src * nw + w];
+    if (l > best) {
+      best = l;
 #pragma unroll
-    for (int j = 0; j < 5; ++j) x[j] = P[w * 5 + j];
-    fit_accumulate(x, lnp[src * nw + w], s_shift, sums, mm, bp, best, kStatsThreads, tid);
+      for (int j = 0; j < 5; ++j) s_bp[j * kStatsThreads + tid] = P[w * 5 + j];
+    }
     acc += nacc[src * nw + w];
   }
-  bl[tid] = best;
-  // acceptance: integer sum through the (now free for this purpose) s_red after the barrier
-  __syncthreads();
-  FitPartials p{sums, mm, bp, bl, kStatsThreads};
-  const int t1 = nw < kStatsThreads ? nw : kStatsThreads;
-  if (tid < 21) s_red[tid] = fit_reduce_component(p, tid, 0, t1);
-  // per-thread acceptance counts -> warp sums -> total
+  s_bl[tid] = best;
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  __shared__ int s_acc[kStatsThreads / 32];
   if ((tid & 31) == 0) s_acc[tid >> 5] = acc;
+  __syncthreads();
+  const FitPartials p{s_part, s_bp, s_bl, kStatsThreads};
+  if (tid < 21) s_red[tid] = fit_reduce_component(p, tid, 0, hs);
   __syncthreads();
   if (tid == 0) {
     int tot = 0;
@@ -315,10 +320,11 @@ struct EnsFit {
   int* nacc;                // [nsrc][nw], accepted moves of the main run (accumulated)
   int* status;              // [nsrc][nw], sticky
   double* stats;            // [nsrc][kFitStats] or null
-  double* chain;            // this launch's records: [nrec][nsrc][nw][5], or null
-  double* chain_lnp;        // [nrec][nsrc][nw], or null
-  double* scratch;          // [gridDim.x][15][256]: per-thread min / max / best sample
-  long long nsrc, src0;
+  double* chain;            // this launch's records: [nrec][chain_nsrc][nw][5], or null
+  double* chain_lnp;        // [nrec][chain_nsrc][nw], or null
+  double* scratch;          // [gridDim.x][5][256]: per-thread best sample
+  long long nsrc, src0;     // src0: global index of source 0 (RNG counter)
+  long long dsrc0;          // index of source 0 in the photometry arrays of mbb_set_data
   long long chain_nsrc;     // sources per record of the chain arrays (>= nsrc: a shard writes into a larger array)
   int nw, h, G;             // G sources per CTA
   int niter;                // iterations in this launch
@@ -338,12 +344,14 @@ constexpr int kEnsThreads = 256;
 
 // dynamic shared memory of ens_resident_kernel, in doubles (then ints):
 //   exp table | pos [G*nw*5] | lnp [G*nw] | flux,ivar [2*G*NB (even)] | shift [G*5 (even)] |
-//   S1,S2 [10*256] + best lnp [256] + reduction [G*22]   (only with stats) | nacc ints [G*nw]
+//   per-thread accumulators [6][256] + reduction [G*22 (even)]  (only with stats) | nacc ints [G*nw]
+// The accumulators (S1, S2, min, max, shift, best log-probability of a thread) live in shared
+// memory between records on purpose: as long-lived registers they end up in local memory, and the
+// compiler then stores them back on every iteration of the record loop.
 __host__ __device__ inline size_t ens_even(size_t n) { return (n + 1) & ~(size_t)1; }
 __host__ __device__ inline size_t ens_resident_smem(int G, int nw, int nb, bool stats) {
-  size_t d = kTabRepDoubles + (size_t)G * nw * 5 + (size_t)G * nw + ens_even((size_t)2 * G * nb) +
-             ens_even((size_t)G * 5);
-  if (stats) d += 11 * kEnsThreads + ens_even((size_t)G * 22);
+  size_t d = kTabRepDoubles + (size_t)G * nw * 6 + ens_even((size_t)2 * G * nb) + ens_even((size_t)G * 5);
+  if (stats) d += 6 * kEnsThreads + ens_even((size_t)G * 22);
   return d * 8 + (size_t)G * nw * 4;
 }
 
@@ -359,10 +367,9 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
   double* const s_lnp = s_pos + (size_t)G * nw * 5;
   double* const s_dat = s_lnp + (size_t)G * nw;
   double* const s_shift = s_dat + ens_even((size_t)2 * G * NB);
-  double* const s_sum = s_shift + ens_even((size_t)G * 5);
-  double* const s_bl = s_sum + 10 * kEnsThreads;
-  double* const s_red = s_bl + kEnsThreads;
-  int* const s_nacc = reinterpret_cast<int*>(stats ? s_red + ens_even((size_t)G * 22) : s_sum);
+  double* const s_acc = s_shift + ens_even((size_t)G * 5);          // [6][256]: S1, S2, min, max, shift, best lnp
+  double* const s_red = s_acc + 6 * kEnsThreads;
+  int* const s_nacc = reinterpret_cast<int*>(stats ? s_red + ens_even((size_t)G * 22) : s_acc);
   const int tid = threadIdx.x;
   stage_exp_table(s_tab);
   const double* tab = lane_exp_table(s_tab);
@@ -370,16 +377,18 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
   const int sg = h <= kEnsThreads ? tid / h : 0;
   const int kfirst = h <= kEnsThreads ? tid - sg * h : tid;
   const int kstride = h <= kEnsThreads ? h : kEnsThreads;
+  // summaries: thread r of the hs threads serving a source owns component r % 5, walkers r / 5 + i * nslots
+  const int hs = h <= kEnsThreads ? h : kEnsThreads;
+  const int nslots = hs / 5, cj = kfirst % 5, slot = kfirst / 5;
   const long long ngroups = (g.nsrc + G - 1) / G;
-  double* const mm = g.scratch + (size_t)blockIdx.x * 15 * kEnsThreads;
-  double* const bp = mm + 10 * kEnsThreads;
+  double* const bp = g.scratch + (size_t)blockIdx.x * 5 * kEnsThreads;
   const bool use_cinv = d.cinv != nullptr;
 
   for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const long long s_first = grp * G;
     const int ga = (int)((g.nsrc - s_first) < G ? (g.nsrc - s_first) : G);
     const bool active = sg < ga;
-    const long long src = s_first + sg;                  // this thread's source (local index)
+    const long long src = s_first + sg;                  // this thread's source (index within the call)
     __syncthreads();      // the previous group's epilogue is done with the shared arrays (first pass: table staged)
     {
       const double2* gp2 = reinterpret_cast<const double2*>(g.pos + s_first * nw * 5);
@@ -390,30 +399,22 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
       for (int i = tid; i < ga * nw / 2; i += kEnsThreads) sl2[i] = gl2[i];
       for (int i = tid; i < ga * nw; i += kEnsThreads) s_nacc[i] = g.nacc[s_first * nw + i];
       for (int i = tid; i < ga * NB; i += kEnsThreads) {
-        s_dat[i] = d.flux[s_first * NB + i];
-        s_dat[G * NB + i] = use_cinv ? 0.0 : d.ivar[s_first * NB + i];
+        s_dat[i] = d.flux[(g.dsrc0 + s_first) * NB + i];
+        s_dat[G * NB + i] = use_cinv ? 0.0 : d.ivar[(g.dsrc0 + s_first) * NB + i];
       }
     }
-    double best = -kInf;
     if (stats) {
-#pragma unroll
-      for (int j = 0; j < 10; ++j) s_sum[j * kEnsThreads + tid] = 0.0;
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        mm[j * kEnsThreads + tid] = kInf;
-        mm[(5 + j) * kEnsThreads + tid] = -kInf;
-        bp[j * kEnsThreads + tid] = 0.0;
-      }
+      s_acc[tid] = 0.0;
+      s_acc[kEnsThreads + tid] = 0.0;
+      s_acc[2 * kEnsThreads + tid] = kInf;
+      s_acc[3 * kEnsThreads + tid] = -kInf;
+      s_acc[4 * kEnsThreads + tid] = 0.0;
+      s_acc[5 * kEnsThreads + tid] = -kInf;
     }
     __syncthreads();
 
     for (int it = 0; it < g.niter; ++it) {
       const bool is_main = it >= g.main_from;
-      if (stats && it == (g.main_from > 0 ? g.main_from : 0) && active && kfirst == 0) {
-        // this launch's shift: walker 0 of the source, read by its owner before it moves
-#pragma unroll
-        for (int j = 0; j < 5; ++j) s_shift[sg * 5 + j] = s_pos[(size_t)sg * nw * 5 + j];
-      }
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const unsigned long long hstep = 2ull * (g.step0 + (unsigned long long)it) + (unsigned long long)half;
@@ -424,18 +425,18 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
             const int own = sg * nw + (half == 0 ? k : h + k);
             const int oth = sg * nw + (half == 0 ? h : 0) + dr.partner;
             const double* sj = s_pos + (size_t)own * 5;
-            const double* cj = s_pos + (size_t)oth * 5;
+            const double* cj5 = s_pos + (size_t)oth * 5;
             double q[5];
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-              const double c = cj[j];
+              const double c = cj5[j];
               q[j] = __dsub_rn(c, __dmul_rn(dr.z, __dsub_rn(c, sj[j])));
             }
             double diff[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) diff[b] = s_dat[sg * NB + b];
             int st;
-            const double newlnp = delta_eval<THIN, ALPHA, NB>(q, src, diff, m, pr, d, t, cold, tab,
+            const double newlnp = delta_eval<THIN, ALPHA, NB>(q, g.dsrc0 + src, diff, m, pr, d, t, cold, tab,
                                                               use_cinv ? nullptr : s_dat + (G + sg) * NB, st);
             if (st > ST_BELOW_LOWLIM) {
               int* gs = g.status + (s_first * nw + own);
@@ -454,18 +455,41 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
       if (is_main) {
         const long long jm = g.main_done + (it - g.main_from);       // index within the main run
         if ((jm + 1) % g.thin == 0) {
+          const long long rec = (jm + 1) / g.thin - 1 - g.main_done / g.thin;       // record index within the launch
           if (stats && active) {
-            for (int k = kfirst; k < h; k += kstride) {
+            const double* P = s_pos + (size_t)sg * nw * 5;
+            if (slot < nslots) {
+              StatAcc a;
+              a.s1 = s_acc[tid];
+              a.s2 = s_acc[kEnsThreads + tid];
+              a.mn = s_acc[2 * kEnsThreads + tid];
+              a.mx = s_acc[3 * kEnsThreads + tid];
+              a.shift = rec == 0 ? P[cj] : s_acc[4 * kEnsThreads + tid];
+              stat_record(a, P, nw, cj, slot, nslots);
+              s_acc[tid] = a.s1;
+              s_acc[kEnsThreads + tid] = a.s2;
+              s_acc[2 * kEnsThreads + tid] = a.mn;
+              s_acc[3 * kEnsThreads + tid] = a.mx;
+              if (rec == 0) s_acc[4 * kEnsThreads + tid] = a.shift;
+            }
+            double best = s_acc[5 * kEnsThreads + tid];
+            bool better = false;
+            for (int k = kfirst; k < h; k += kstride) {           // best sample: by the walkers' owner
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
                 const int w = sg * nw + hh * h + k;
-                fit_accumulate(s_pos + (size_t)w * 5, s_lnp[w], s_shift + sg * 5, s_sum, mm, bp, best,
-                               kEnsThreads, tid);
+                const double l = s_lnp[w];
+                if (l > best) {
+                  best = l;
+                  better = true;
+#pragma unroll
+                  for (int j = 0; j < 5; ++j) bp[j * kEnsThreads + tid] = s_pos[(size_t)w * 5 + j];
+                }
               }
             }
+            if (better) s_acc[5 * kEnsThreads + tid] = best;
           }
           if (g.chain || g.chain_lnp) {
-            const long long rec = (jm + 1) / g.thin - 1 - g.main_done / g.thin;
             if (g.chain) {
               double2* dst = reinterpret_cast<double2*>(g.chain + ((size_t)rec * g.chain_nsrc + s_first) * nw * 5);
               const double2* sp2 = reinterpret_cast<const double2*>(s_pos);
@@ -476,8 +500,9 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
               const double2* sl2 = reinterpret_cast<const double2*>(s_lnp);
               for (int i = tid; i < ga * nw / 2; i += kEnsThreads) dst[i] = sl2[i];
             }
-            __syncthreads();      // rows are read by other threads than their owners: before they move again
           }
+          // a record reads rows that other threads own: they must not move before everyone has read
+          if (stats || g.chain || g.chain_lnp) __syncthreads();
         }
       }
     }
@@ -493,15 +518,15 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
       for (int i = tid; i < ga * nw; i += kEnsThreads) g.nacc[s_first * nw + i] = s_nacc[i];
     }
     if (stats) {
-      s_bl[tid] = best;
+      if (active && slot == 0) s_shift[sg * 5 + cj] = s_acc[4 * kEnsThreads + tid];
       __syncthreads();           // (also makes the per-thread global scratch visible CTA-wide)
-      const FitPartials p{s_sum, mm, bp, s_bl, kEnsThreads};
+      const FitPartials p{s_acc, bp, s_acc + 5 * kEnsThreads, kEnsThreads};
       for (int pi = tid; pi < ga * 22; pi += kEnsThreads) {
         const int s2 = pi / 22, c = pi - s2 * 22;
-        const int t0 = h <= kEnsThreads ? s2 * h : 0, t1 = h <= kEnsThreads ? t0 + h : kEnsThreads;
+        const int t0 = h <= kEnsThreads ? s2 * h : 0;
         double v;
         if (c < 21) {
-          v = fit_reduce_component(p, c, t0, t1);
+          v = fit_reduce_component(p, c, t0, hs);
         } else {
           int tot = 0;
           for (int w = 0; w < nw; ++w) tot += s_nacc[s2 * nw + w];

@@ -247,9 +247,11 @@ loglike_gauss_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, c
     if (active) {
       if (live) {
         lnl = -0.5 * chi;
-        if (!priors_trivial(pr, p)) {
+        if (pr.peak_terms) {
           lnl = add_priors_cold<THIN>(lnl, p[0], p[1], p[2], p[3], p[4], fs.x0, cold, &st);
           if (st != ST_OK) lnl = qnan();
+        } else {
+          lnl = add_simple_priors(pr, p, lnl);
         }
         if (st == ST_OK && lnl != lnl) st = ST_NONFINITE;
       }

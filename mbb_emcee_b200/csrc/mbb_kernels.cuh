@@ -335,9 +335,11 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
     for (int b = 0; b < NB; ++b) chi = fma(diff[b] * diff[b], __ldg(ivp + b), chi);
   }
   double lnl = -0.5 * chi;
-  if (!priors_trivial(pr, p)) {
+  if (pr.peak_terms) {           // lambda_peak limit / prior: needs the peak solve
     lnl = add_priors_cold<THIN>(lnl, p[0], p[1], p[2], p[3], p[4], s.x0, cold, &st);
     if (st != ST_OK) return qnan();
+  } else {
+    lnl = add_simple_priors(pr, p, lnl);
   }
   if (lnl != lnl) st = ST_NONFINITE;
   return lnl;

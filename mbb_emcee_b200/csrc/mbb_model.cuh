@@ -796,7 +796,26 @@ struct Priors {
   unsigned char has_gprior[6];
   int any_gprior;
   int always_terms;      // lambda_peak limit/prior or any Gaussian prior set: prior_terms must run
+  // derived by priors_finalize():
+  double inv_w2[5];      // 1/(0.02 (uplim - lowlim))^2 of the soft upper limits (0 where there is none)
+  int peak_terms;        // a lambda_peak limit or prior is set: the peak solve (max_wave) is needed
 };
+
+// Fills the derived members from lowlim / has_uplim / uplim / has_gprior (host side: mbb_set_priors,
+// the test emulation).  uplim becomes +inf where no limit is set.
+inline void priors_finalize(Priors& p) {
+  p.any_gprior = 0;
+  for (int i = 0; i < 6; ++i) {
+    if (!p.has_uplim[i]) p.uplim[i] = kInf;
+    if (p.has_gprior[i]) p.any_gprior = 1;
+  }
+  for (int i = 0; i < 5; ++i) {
+    const double w = 0.02 * (p.uplim[i] - p.lowlim[i]);
+    p.inv_w2[i] = p.has_uplim[i] ? 1.0 / (w * w) : 0.0;
+  }
+  p.peak_terms = (p.has_uplim[5] || p.has_gprior[5]) ? 1 : 0;
+  p.always_terms = (p.any_gprior || p.has_uplim[5]) ? 1 : 0;
+}
 
 MBB_HD bool below_lowlim(const Priors& pr, const double p[5]) {
   bool bad = false;
@@ -812,6 +831,34 @@ MBB_HD bool priors_trivial(const Priors& pr, const double p[5]) {
 #pragma unroll
   for (int i = 0; i < 5; ++i) over = over || (p[i] > pr.uplim[i]);
   return !over && !pr.always_terms;
+}
+
+// Soft upper limits and Gaussian priors of the five parameters proper (likelihood.py:672-752
+// without the lambda_peak slot), for inlining into the specialised kernels: in a real fit a
+// nuisance parameter sits above its soft limit for a good part of the walkers (an optically thin
+// fit lets lambda0 wander up to its automatic limit, likelihood.py:187-204), so this is not a cold
+// path.  Same terms as prior_terms(), added in the reference's order; the division by the limit
+// width is a multiplication by the precomputed inv_w2.  Requires !pr.peak_terms.
+MBB_HD double add_simple_priors(const Priors& pr, const double p[5], double lnl) {
+  double pen = 0.0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const double d = p[i] - pr.uplim[i];          // -inf where no limit is set
+    if (d > 0.0) pen -= (0.5 * (d * d)) * pr.inv_w2[i];
+  }
+  lnl += pen;
+  if (pr.any_gprior) {
+    double gp = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      if (pr.has_gprior[i]) {
+        const double d = p[i] - pr.gmean[i];
+        gp -= 0.5 * pr.givar[i] * (d * d);
+      }
+    }
+    lnl += gp;
+  }
+  return lnl;
 }
 
 // Returns the soft-upper-limit penalty in `pen` and the Gaussian-prior term in

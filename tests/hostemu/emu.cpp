@@ -119,11 +119,13 @@ void run_loglike(long long n, const double* pars, const ModelP& m, const Priors&
           return node_acc<THIN, ALPHA, false, TS>(s, t.freq[i], lpn[i], t.weff[i], acc, tab);
         });
         double lnl = -0.5 * chi;
-        if (!priors_trivial(pr, p)) {
+        if (pr.peak_terms) {           // as delta_eval / the Gauss-rule thread kernel do
           double pen, gp;
           prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
           lnl += pen;
           if (pr.any_gprior) lnl += gp;
+        } else {
+          lnl = add_simple_priors(pr, p, lnl);
         }
         if (st != ST_OK) lnl = kInf - kInf;
         else if (lnl != lnl) st = ST_NONFINITE;
@@ -275,13 +277,12 @@ void emu_loglike(int thin, int alpha, int fast, long long n, const double* pars,
                  const unsigned char* scalar_path, const double* flux, const double* ivar, const double* cinv,
                  long long wps, double* out, int* status) {
   Priors pr;
-  pr.any_gprior = 0;
   for (int i = 0; i < 5; ++i) pr.lowlim[i] = ep->lowlim[i];
   for (int i = 0; i < 6; ++i) {
     pr.uplim[i] = ep->uplim[i]; pr.gmean[i] = ep->gmean[i]; pr.givar[i] = ep->givar[i];
     pr.has_uplim[i] = ep->has_uplim[i]; pr.has_gprior[i] = ep->has_gprior[i];
-    if (ep->has_gprior[i]) pr.any_gprior = 1;
   }
+  priors_finalize(pr);
   const int nn = band_off[nb];
   std::vector<double> freq(nn), lp(nn), weff(nn);
   ModelP m{wavenorm, kUmToGHz / wavenorm, 0.0, 0.0};
@@ -291,9 +292,6 @@ void emu_loglike(int thin, int alpha, int fast, long long n, const double* pars,
     if (nd.freq > m.nu_max) m.nu_max = nd.freq;
     if (nd.labs > m.lmax) m.lmax = nd.labs;
   }
-  for (int i = 0; i < 6; ++i)
-    if (!pr.has_uplim[i]) pr.uplim[i] = kInf;
-  pr.always_terms = (pr.any_gprior || pr.has_uplim[5]) ? 1 : 0;
   TabView t{freq.data(), weight, weff.data(), lp.data(), band_off, scalar_path, nb};
   // fast: 1 = saturating node code, 2 = unclamped node code for `safe` walkers (the specialised
   // kernels' arithmetic), 3 = 2 + compressed Gauss rules (MBB_MATH_FAST_GAUSS)

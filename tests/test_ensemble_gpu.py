@@ -154,6 +154,36 @@ def test_fit_chain_streams_to_host_in_segments(oracle, monkeypatch):
     assert relerr(s1[:, nat.FS_M2:nat.FS_M2 + 5][free], s2[:, nat.FS_M2:nat.FS_M2 + 5][free]).max() < 1e-10
 
 
+def test_fit_host_pipeline_equals_device(oracle):
+    """Without a chain the host call cuts the sources into chunks that flow through three slots
+    (upload / sampler / download of neighbouring chunks overlap); the numbers are those of one
+    device-resident call, page-locked or pageable buffers alike."""
+    import torch
+    from mbb_emcee_b200 import _native as nat
+    nsrc, nw, nburn, nsteps = 5000, 16, 3, 8
+    bf, p0, _ = _problem(oracle, False, nsrc, nw, 6)
+    ctx = bf._stage()
+    dev = torch.device("cuda:0")
+    P = torch.as_tensor(np.ascontiguousarray(p0), device=dev).contiguous()
+    L = torch.empty((nsrc, nw), dtype=torch.float64, device=dev)
+    A = torch.zeros((nsrc, nw), dtype=torch.int32, device=dev)
+    S = torch.zeros((nsrc, nat.FIT_NSTATS), dtype=torch.float64, device=dev)
+    ctx.ensemble_fit_device(nsrc, nw, nburn, nsteps, P.data_ptr(), L.data_ptr(), seed=12, src0=7,
+                            naccept_ptr=A.data_ptr(), stats_ptr=S.data_ptr(), thin=2)
+    ctx.sync()
+    n0 = ctx.launch_count()
+    out = ctx.ensemble_fit(p0, nburn, nsteps, seed=12, src0=7, thin=2)                  # pageable arrays
+    assert ctx.launch_count() - n0 == 4                                              # 2 chunks x (lnprob + sampler)
+    pin = {k: nat.pinned_empty(v.shape, v.dtype) for k, v in out.items()}
+    pin["pos"][...] = p0
+    ctx.ensemble_fit_into(pin["pos"], pin["lnprob"], nburn, nsteps, naccept=pin["naccept"], status=pin["status"],
+                          stats=pin["stats"], seed=12, src0=7, thin=2)
+    for res in (out, pin):
+        assert np.array_equal(res["pos"], P.cpu().numpy()) and np.array_equal(res["lnprob"], L.cpu().numpy())
+        assert np.array_equal(res["naccept"], A.cpu().numpy()) and np.array_equal(res["stats"], S.cpu().numpy())
+        assert (res["status"] <= 1).all()
+
+
 def test_batch_fitter_shards_are_the_same_fit():
     """devices=[0, 0, 0]: three shards (three contexts, three host threads) fill disjoint slices of
     the shared page-locked outputs; bit-identical to the unsharded fit (global source index in the
