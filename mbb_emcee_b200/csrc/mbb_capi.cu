@@ -150,7 +150,7 @@ struct mbb_ctx {
     DevBuf<double> c;
     DevBuf<int> s;
   };
-  Scratch scratch[4];
+  Scratch scratch[5];
   cudaError_t scratch_for(cudaStream_t st, size_t cap, double** c_out, int** s_out) {
     Scratch* sc = nullptr;
     for (auto& x : scratch)
@@ -167,6 +167,26 @@ struct mbb_ctx {
     *s_out = sc->s.p;
     return cudaSuccess;
   }
+  // small host-buffer calls of mbb_loglike (the 125-walker half-steps of a single-source fit, reference
+  // mbb_fit.py:533-542): upload, kernels and downloads replayed as ONE CUDA graph launch per call
+  struct SmallGraph {
+    int64_t n = 0;
+    long long wps = 0;
+    int layout = 0, with_status = 0, seen = 0;
+    uint64_t gen = 0;
+    cudaGraphExec_t exec = nullptr;
+  };
+  static constexpr int64_t kGraphMaxN = 8192;
+  SmallGraph graphs[4];
+  int graph_next = 0;
+  uint64_t gen = 1;                      // bumped by every set_* call: what a captured graph has baked in
+  cudaStream_t gstream = nullptr;
+  PinBuf<double> g_hin, g_hout;
+  PinBuf<int> g_hst;
+  DevBuf<double> g_din, g_dout;
+  DevBuf<int> g_dst;
+  int64_t graph_launches = 0;
+
   DevBuf<double> d_epos, d_elnp, d_eq, d_eqlnp, d_escratch, d_estats, d_echain[2], d_echainl[2];
   DevBuf<int> d_enacc, d_est, d_eqst;
   cudaStream_t copy_stream = nullptr;          // D2H of chain segments behind the sampler (mbb_ensemble_fit)
@@ -610,6 +630,11 @@ int mbb_ctx_destroy(mbb_ctx* c) {
     if (c->seg_copied[i]) cudaEventDestroy(c->seg_copied[i]);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto& g : c->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (c->gstream) cudaStreamDestroy(c->gstream);
+  c->g_hin.release(); c->g_hout.release(); c->g_hst.release();
+  c->g_din.release(); c->g_dout.release(); c->g_dst.release();
   for (auto& sl : c->slots) {
     sl.hin.release(); sl.hout.release(); sl.hst.release(); sl.hsrc.release();
     sl.din.release(); sl.dout.release(); sl.dst.release(); sl.dsrc.release();
@@ -663,6 +688,7 @@ int mbb_set_model(mbb_ctx* c, double wavenorm, int opthin, int noalpha) {
   // the FAST node tables hold log(lambda/wavenorm) and (thick) weights scaled by
   // (wavenorm/lambda)^3: rebuilt lazily at the next launch
   if (wavenorm != c->wavenorm || (opthin ? 1 : 0) != c->opthin) c->fast_tables_ok = false;
+  c->gen++;
   c->wavenorm = wavenorm;
   c->opthin = opthin ? 1 : 0;
   c->noalpha = noalpha ? 1 : 0;
@@ -674,6 +700,7 @@ int mbb_set_math_mode(mbb_ctx* c, int mode) {
   if (mode != MBB_MATH_FAITHFUL && mode != MBB_MATH_FAST && mode != MBB_MATH_FAST_GAUSS)
     return fail("unknown math mode");
   c->math_mode = mode;
+  c->gen++;
   return 0;
 }
 
@@ -712,6 +739,7 @@ int mbb_set_bands(mbb_ctx* c, int nbands, const int32_t* band_off, const double*
   CK(cudaMemcpyAsync(c->d_scalar.p, c->h_scalar.data(), nbands, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->fast_tables_ok = false;
+  c->gen++;
   CK(ensure_tables(c));
   c->bands_set = true;
   return 0;
@@ -741,6 +769,7 @@ int mbb_set_data(mbb_ctx* c, int nsrc, int nbands, const double* flux, const dou
   }
   c->nsrc = nsrc;
   c->data_nb = nbands;
+  c->gen++;
   return 0;
 }
 
@@ -759,6 +788,7 @@ int mbb_set_priors(mbb_ctx* c, const double lowlim[5], const uint8_t has_uplim[6
     p.givar[i] = givar[i];
   }
   priors_finalize(p);
+  c->gen++;
   c->cold_ok = false;
   return 0;
 }
@@ -831,6 +861,88 @@ int64_t host_chunk() {
 
 }  // namespace
 
+namespace {
+
+// Small host-buffer batch through a captured graph.  Returns -1 when the call was not handled (first
+// sighting of this shape: the plain path runs once and sizes every buffer), else 0 / 1.
+int loglike_small_graph(mbb_ctx* c, int64_t n, const double* pars, int layout, long long wps, double* out_lnlike,
+                        int32_t* out_status) {
+  static const bool off = getenv("MBB_B200_NO_GRAPH") != nullptr;
+  if (off) return -1;
+  mbb_ctx::SmallGraph* g = nullptr;
+  for (auto& x : c->graphs)
+    if (x.n == n && x.layout == layout && x.wps == wps && x.with_status == (out_status ? 1 : 0)) g = &x;
+  if (!g) {
+    g = &c->graphs[c->graph_next];
+    c->graph_next = (c->graph_next + 1) % 4;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    *g = mbb_ctx::SmallGraph();
+    g->n = n; g->layout = layout; g->wps = wps; g->with_status = out_status ? 1 : 0;
+  }
+  if (g->exec && g->gen != c->gen) {
+    cudaGraphExecDestroy(g->exec);
+    g->exec = nullptr;
+  }
+  if (!g->exec) {
+    if (g->seen++ == 0) return -1;
+    // capture: fixed staging buffers, fixed scratch (sized for the largest graphed batch)
+    if (!c->gstream) CK(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
+    const size_t cap = (size_t)mbb_ctx::kGraphMaxN;
+    CK(c->g_hin.reserve(cap * 5)); CK(c->g_din.reserve(cap * 5));
+    CK(c->g_hout.reserve(cap)); CK(c->g_dout.reserve(cap));
+    CK(c->g_hst.reserve(cap)); CK(c->g_dst.reserve(cap));
+    double* sc = nullptr;
+    int* ss = nullptr;
+    CK(c->scratch_for(c->gstream, cap, &sc, &ss));
+    CK(ensure_tables(c));
+    EvalArgs a{};
+    a.n = n; a.e0 = 0; a.wps = wps; a.layout = layout;
+    a.pars = c->g_din.p; a.src_index = nullptr; a.out = c->g_dout.p; a.status = c->g_dst.p;
+    const int64_t before = c->launches;
+    // (an uncaptured run on this stream first: function attributes, lazily loaded modules)
+    if (launch_loglike(c, c->gstream, a)) return 1;
+    CK(cudaStreamSynchronize(c->gstream));
+    c->launches = before;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(c->gstream, cudaStreamCaptureModeRelaxed));
+    cudaMemcpyAsync(c->g_din.p, c->g_hin.p, (size_t)n * 5 * sizeof(double), cudaMemcpyHostToDevice, c->gstream);
+    const int rc = launch_loglike(c, c->gstream, a);
+    cudaMemcpyAsync(c->g_hout.p, c->g_dout.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->gstream);
+    if (out_status)
+      cudaMemcpyAsync(c->g_hst.p, c->g_dst.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->gstream);
+    const cudaError_t ce = cudaStreamEndCapture(c->gstream, &graph);
+    g->gen = c->gen;
+    c->graph_launches = c->launches - before;      // kernels per replay
+    c->launches = before;
+    if (rc != 0 || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      g->seen = 0;
+      return -1;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      g->exec = nullptr;
+      cudaGetLastError();
+      g->seen = 0;
+      return -1;
+    }
+  }
+  memcpy(c->g_hin.p, pars, (size_t)n * 5 * sizeof(double));
+  CK(cudaEventRecord(c->ev0, c->gstream));
+  CK(cudaGraphLaunch(g->exec, c->gstream));
+  CK(cudaEventRecord(c->ev1, c->gstream));
+  c->timed = true;
+  c->launches += c->graph_launches;
+  CK(cudaStreamSynchronize(c->gstream));
+  memcpy(out_lnlike, c->g_hout.p, (size_t)n * sizeof(double));
+  if (out_status) memcpy(out_status, c->g_hst.p, (size_t)n * sizeof(int));
+  return 0;
+}
+
+}  // namespace
+
 // Host path: the batch is cut into chunks that flow through three slots, each
 // with its own stream: H2D copy, kernel and D2H copy of consecutive chunks
 // overlap (two copy engines + SMs).  Caller memory that is already pinned
@@ -865,6 +977,10 @@ int mbb_loglike(mbb_ctx* c, int64_t n, const double* pars, int layout, const int
   if (src_index)
     for (int64_t i = 0; i < n; ++i)
       if (src_index[i] < 0 || src_index[i] >= c->nsrc) return fail("src_index out of range");
+  if (!src_index && n <= mbb_ctx::kGraphMaxN) {
+    const int rc = loglike_small_graph(c, n, pars, layout, wps, out_lnlike, out_status);
+    if (rc >= 0) return rc;
+  }
   if (ensure_slots(c)) return 1;
   const bool pin_in = is_pinned(pars) && is_pinned(src_index);
   const bool pin_out = is_pinned(out_lnlike) && is_pinned(out_status);

@@ -229,6 +229,87 @@ def test_multi_source_batch(oracle):
         assert abs(got2[i] - oracle.loglike(spec, P[i])) <= TOL * abs(got2[i])
 
 
+def test_multi_source_covariance_delta_kernel(oracle):
+    """Several sources, each with its own full covariance, delta bands: the delta kernel's
+    direct-load path with the quadratic form over Cinv rows (likelihood.py:821-825), for
+    implicit and explicit source indices and for the resident sampler's shared-memory staging."""
+    from mbb_emcee_b200 import _native, synthetic
+    rng = np.random.RandomState(23)
+    nsrc, nw = 9, 48
+    waves = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0]
+    flux = rng.uniform(5, 80, (nsrc, 6))
+    unc = rng.uniform(1, 6, (nsrc, 6))
+    cov = np.empty((nsrc, 6, 6))
+    for s in range(nsrc):
+        cov[s] = synthetic.cfg3_covariance(flux[s], unc[s], spire_idx=(3, 4, 5))
+    low = np.array([1, 0.1, 1, 0.1, 1e-3])
+    for opthin, noalpha in ((True, True), (False, False)):
+        ctx = _native.Context(0)
+        ctx.set_model(500.0, opthin, noalpha)
+        ctx.set_bands(np.arange(7, dtype=np.int32), waves, np.ones(6))
+        ctx.set_data(flux, cinv=np.linalg.inv(cov))
+        truth = (12.0, 1.8, 1300.0, 4.0, 30.0) if opthin else (14.0, 1.8, 400.0, 3.0, 30.0)
+        P = synthetic.walker_cloud(truth, nsrc * nw, rng, low)
+        want = np.empty(nsrc * nw)
+        specs = []
+        for s in range(nsrc):
+            spec = oracle.LikeSpec(500.0, noalpha, opthin)
+            spec.set_phot(waves, flux[s], unc[s])
+            spec.set_cov(cov[s])
+            specs.append(spec)
+            want[s * nw:(s + 1) * nw] = oracle.loglike_batch(spec, P[s * nw:(s + 1) * nw])
+        got, st = ctx.loglike(P, walkers_per_source=nw)
+        assert (st == 0).all() and relerr(got, want).max() < TOL
+        idx = np.repeat(np.arange(nsrc), nw).astype(np.int32)
+        got2, _ = ctx.loglike(P, src_index=idx)
+        assert np.array_equal(got2, got)
+        # the sampler keeps each source's ensemble resident and evaluates against the same Cinv
+        import philox_np
+        p0 = P.reshape(nsrc, nw, 5)
+        out = ctx.ensemble_fit(p0, 0, 5, seed=3, stats=False)
+        r = philox_np.replay(lambda s, Q: oracle.loglike_batch(specs[s], Q), p0, 5, 3)
+        assert np.array_equal(out["pos"], r[0]) and relerr(out["lnprob"], r[1]).max() < TOL
+
+
+def test_small_batch_graph_replay(golden, oracle):
+    """Host-buffer calls with <= 8192 parameter vectors (the 125-walker half-steps of a
+    single-source fit, reference mbb_fit.py:533-542) are replayed as one CUDA graph from the
+    third call of a shape on; same numbers as the plain path, and a graph never outlives the
+    data / tables / priors it was captured with."""
+    from mbb_emcee_b200 import synthetic
+    for cfgname in ("cfg1", "cfg2", "cfg3"):
+        cfg, like = _make_like(golden, cfgname, 1)
+        rng = np.random.RandomState(31)
+        P = synthetic.walker_cloud(cfg["truth"], 125, rng, like.lowlims)
+        P[3, 0] = 0.2                                   # one walker below the T limit
+        ctx = like.context
+        first = like(P)                                 # plain path (sizes the buffers)
+        n0 = ctx.launch_count()
+        second = like(P)                                # captured, then replayed
+        per_call = ctx.launch_count() - n0
+        third = like(P)
+        assert ctx.launch_count() - n0 == 2 * per_call and per_call >= 1
+        assert np.array_equal(first, second) and np.array_equal(first, third)
+        assert np.isneginf(first[3])
+        want = oracle.loglike_batch(_oracle_spec(oracle, like), P)
+        fin = np.isfinite(want)
+        assert relerr(first[fin], want[fin]).max() < TOL
+        # other rows through the same graph
+        P2 = synthetic.walker_cloud(cfg["truth"], 125, rng, like.lowlims)
+        assert relerr(like(P2), oracle.loglike_batch(_oracle_spec(oracle, like), P2)).max() < TOL
+        # new photometry / a new prior: the graph is re-captured, never replayed stale
+        cov = np.array(like.data_covmatrix) if like.has_data_covmatrix else None
+        like.set_phot(cfg["bands"], like.data_flux * 1.1, like._flux_unc)
+        if cov is not None:
+            like.set_cov(cov)
+        like.set_gaussian_prior('beta', 1.7, 0.4)
+        a = like(P2)
+        assert relerr(a, oracle.loglike_batch(_oracle_spec(oracle, like), P2)).max() < TOL
+        assert np.array_equal(a, like(P2))
+        # a single row (emcee's calling convention) has its own shape
+        assert like(P2[5]) == a[5] and like(P2[5]) == a[5] and like(P2[5]) == a[5]
+
+
 def test_delta_kernel_launch_paths(oracle):
     """The persistent delta kernel: TMA-fed full tiles, the direct-load fallback
     (partial tail tile, buffer not 16-byte aligned, odd SoA stride), walkers-per-source
