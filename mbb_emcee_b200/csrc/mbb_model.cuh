@@ -840,13 +840,18 @@ MBB_HD bool priors_trivial(const Priors& pr, const double p[5]) {
 // path.  Same terms as prior_terms(), added in the reference's order; the division by the limit
 // width is a multiplication by the precomputed inv_w2.  Requires !pr.peak_terms.
 MBB_HD double add_simple_priors(const Priors& pr, const double p[5], double lnl) {
-  double pen = 0.0;
+  bool over = false;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const double d = p[i] - pr.uplim[i];          // -inf where no limit is set
-    if (d > 0.0) pen -= (0.5 * (d * d)) * pr.inv_w2[i];
+  for (int i = 0; i < 5; ++i) over = over || (p[i] > pr.uplim[i]);      // +inf where no limit is set
+  if (over) {
+    double pen = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const double d = p[i] - pr.uplim[i];
+      if (d > 0.0) pen -= (0.5 * (d * d)) * pr.inv_w2[i];
+    }
+    lnl += pen;
   }
-  lnl += pen;
   if (pr.any_gprior) {
     double gp = 0.0;
 #pragma unroll

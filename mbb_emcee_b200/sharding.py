@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 __all__ = ["rank_world", "shard_range", "shard_sources", "gather_concat", "bind_to_gpu_numa_node",
-           "parse_cpulist"]
+           "bind_rank_cpus", "parse_cpulist"]
 
 
 def rank_world():
@@ -50,6 +50,27 @@ def bind_to_gpu_numa_node(pci_bus_id, sysfs="/sys"):
             return None
         os.sched_setaffinity(0, allowed)
         return allowed
+    except Exception:
+        return None
+
+
+def bind_rank_cpus(pci_bus_id, local_rank, local_world, sysfs="/sys"):
+    """CPU placement of one rank of a one-process-per-GPU launch: the GPU's NUMA node where the
+    topology is exposed (bind_to_gpu_numa_node); otherwise -- single-node VMs, containers that hide
+    sysfs -- the process's CPU set is cut into ``local_world`` disjoint contiguous pieces and the
+    rank takes its own, so that the staging copies and driver threads of different ranks never
+    share a core.  Returns the CPU list bound to, or None (never raises)."""
+    got = bind_to_gpu_numa_node(pci_bus_id, sysfs=sysfs)
+    if got:
+        return got
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if local_world <= 1 or len(cpus) < local_world:
+            return None
+        lo, hi = shard_range(len(cpus), local_rank, local_world)
+        mine = cpus[lo:hi]
+        os.sched_setaffinity(0, mine)
+        return mine
     except Exception:
         return None
 

@@ -10,8 +10,8 @@ across numpy versions).
 """
 import numpy as np
 
-__all__ = ["CONFIGS", "noisy_photometry", "walker_cloud", "cfg3_covariance",
-           "random_walk_chain"]
+__all__ = ["CONFIGS", "SAMPLE_PHOT", "sample_problem", "noisy_photometry", "walker_cloud",
+           "cfg3_covariance", "random_walk_chain"]
 
 P0_SIGMA = np.array([2.0, 0.2, 100.0, 0.3, 5.0])   # reference run_mbb_emcee.py:285-291
 
@@ -52,6 +52,37 @@ CONFIGS = {
                   truth=(12.0, 1.8, 1300.0, 4.0, 30.0), opthin=True, noalpha=True,
                   wavenorm=500.0, nsources=8192, nwalkers=512),
 }
+
+
+# One representative source per configuration (truth + one seeded noise draw, rounded): the
+# photometry of the bounded single-source sample that bench.py's CPU arms time and that its GPU arm
+# re-evaluates as a cross-check.  Literal numbers, so that both arms hold the same data without
+# either evaluating a model.
+SAMPLE_PHOT = {
+    "cfg1": ([2.844, 4.846, 43.249, 73.149, 59.524, 29.042], [1.0, 1.0, 3.965, 6.964, 5.589, 3.0]),
+    "cfg2": ([6.959, 23.43, 54.617, 44.904, 35.288, 8.339], [1.0, 2.144, 4.939, 4.946, 3.123, 1.0]),
+    "cfg3": ([43.221, 48.168, 32.427, 7.622, 6.647, 4.551, 2.646, 0.795],
+             [4.939, 4.946, 3.123, 1.0, 1.0, 1.0, 1.0, 1.0]),
+    "cfg5": ([-0.108, 3.605, 36.768, 70.053, 61.505, 29.616], [1.0, 1.0, 3.965, 6.964, 5.589, 3.0]),
+    "cfg5p": ([7.184, 34.353, 72.031, 60.65, 27.961, 6.771], [1.0, 3.813, 6.892, 5.687, 3.168, 1.0]),
+    # the reference's default model (optically thick + alpha) on cfg5's six delta bands
+    "default_model": ([2.1, 9.7, 38.4, 55.2, 44.9, 29.3], [1.0, 1.0, 3.84, 5.52, 4.49, 2.93]),
+}
+
+
+def sample_problem(name, n, seed=None):
+    """(cfg, flux, unc, cov-or-None, P[n][5]) of the bounded single-source sample of a workload:
+    literal photometry (SAMPLE_PHOT) and n walker positions ~ N(truth, P0_SIGMA) inside the default
+    lower limits -- a function of (name, n, seed) only, identical in every process that calls it."""
+    cfg = dict(CONFIGS["cfg5" if name == "default_model" else name])
+    if name == "default_model":
+        cfg.update(opthin=False, noalpha=False, truth=(14.0, 1.8, 400.0, 3.0, 30.0))
+    truth = np.asarray(cfg.get("truth", (12.0, 1.8, 1300.0, 4.0, 30.0)), dtype=np.float64)
+    flux, unc = (np.array(x, dtype=np.float64) for x in SAMPLE_PHOT[name])
+    cov = cfg3_covariance(flux, unc) if name == "cfg3" else None
+    rng = np.random.RandomState(cfg["seed"] + 77 if seed is None else seed)
+    P = walker_cloud(truth, n, rng, np.array([1, 0.1, 1, 0.1, 1e-3]) * 1.01)
+    return cfg, flux, unc, cov, P
 
 
 def noisy_photometry(model_flux, rng):

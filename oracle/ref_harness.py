@@ -193,6 +193,48 @@ def import_reference(refdir: str = DEFAULT_REF, apply_fixes: bool = True):
     return ref
 
 
+INSTALLED_REF = os.path.normpath(os.path.join(HERE, "..", "baseline", "_ref"))
+
+
+def installed_reference_available(path: str = INSTALLED_REF) -> bool:
+    """The reference as `pip install --target baseline/_ref` left it (package + compiled fnu)."""
+    return os.path.isfile(os.path.join(path, "mbb_emcee", "likelihood.py")) and \
+        len(glob.glob(os.path.join(path, "fnu*.so"))) > 0
+
+
+def import_installed_reference(path: str = INSTALLED_REF, apply_fixes: bool = True):
+    """Import the UNMODIFIED reference from its pip-installed copy (baseline/_ref: git-ignored,
+    travels to the GPU box, where /root/reference does not exist).  Same shims as
+    import_reference; the native module is the one the reference's own setup.py built."""
+    if not installed_reference_available(path):
+        raise RuntimeError("no installed reference at %s" % path)
+    import warnings
+
+    _install_stubs()
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = importlib.import_module("mbb_emcee")
+    if apply_fixes and not getattr(ref, "_oracle_fixes_applied", False):
+        _apply_fixes()
+        ref._oracle_fixes_applied = True
+    return ref
+
+
+def import_any_reference():
+    """(module, where) -- the reference tree when it is mounted (build container), else the
+    installed copy; (None, reason) when neither exists."""
+    try:
+        if reference_available():
+            return import_reference(), "/root/reference (fnu.pyx compiled into oracle/_ref)"
+        if installed_reference_available():
+            return import_installed_reference(), "baseline/_ref (pip install of the reference)"
+    except Exception as exc:      # pragma: no cover - reported by the caller
+        return None, "reference import failed: %r" % (exc,)
+    return None, "neither /root/reference nor baseline/_ref is present"
+
+
 def _apply_fixes():
     """Wrap (never edit) two reference methods so they run on modern numpy.
 

@@ -28,6 +28,10 @@ bench)
   timeout 1500 python bench.py --steps 10 --warmup 3 > $O/r02_bench_cfg5.json 2> $O/r02_bench_cfg5.err; head -c 3000 $O/r02_bench_cfg5.json; tail -3 $O/r02_bench_cfg5.err ;;
 bench_ref)
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_ref.json 2> $O/r02_bench_ref.err; cat $O/r02_bench_ref.json; tail -3 $O/r02_bench_ref.err ;;
+ncu_all)
+  timeout 1500 python tools/ncu_capture.py r02 2>&1 | tee $O/r02_ncu_capture.log ;;
+bench_quick)
+  timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/r02_bench_quick.json 2> $O/r02_bench_quick.err; head -c 1500 $O/r02_bench_quick.json; tail -12 $O/r02_bench_quick.err ;;
 *) echo "unknown step $step" ;;
 esac
 done
