@@ -751,7 +751,7 @@ def chain_leg(dev, rank, world, barrier, allmax, peak_tf):
     is inside the timed region."""
     import torch
     from mbb_emcee_b200 import _native, synthetic
-    from mbb_emcee_b200.sharding import gather_concat, shard_range
+    from mbb_emcee_b200.sharding import gather_concat, shard_range, shared_array
     cfg = synthetic.CONFIGS["cfg4"]
     nw, ns = 500, 20000
     chain = synthetic.random_walk_chain(cfg["truth"], nw, ns, np.random.RandomState(cfg["seed"]))
@@ -796,24 +796,42 @@ def chain_leg(dev, rank, world, barrier, allmax, peak_tf):
                 res[key]["roofline"] = {"kernel": f["kernel"], "frac_of_fp64_peak_in_kernel": f["fp64_pipe_pct"] / 100.0,
                                         "fp64_warp_instructions_per_unique_sample": per, "ncu_stale": bool(stale)}
     del ch, o, s
-    # end to end: host chain rows in, all three quantities out, gather of the shards included
-    pk, lir, dm, stt = ctx.chain_post(mine[:2, :100], 7, z=cfg["z"], dl_mpc=cfg["lumdist"])      # warm-up
+    # end to end: host chain rows in, all three quantities out; the "final gather" is every rank's
+    # device-to-host copy landing in its rows of one shared page-locked array, then a barrier
+    import torch.distributed as dist
+    bar = dist.barrier if world > 1 else None
+    shared = [shared_array(t, (nw, ns), rank, world, barrier=bar) for t in ("peak", "lir", "dust")]
+    stt = np.empty((hi - lo, ns), dtype=np.int32)
+    ctx.chain_post(mine[:2, :100], 7, z=cfg["z"], dl_mpc=cfg["lumdist"])      # warm-up
     ctx.set_model(500.0, False, False)
+    ctx.set_lir_method("quadpack")
     barrier()
     t0 = time.perf_counter()
-    pk, lir, dm, stt = ctx.chain_post(mine, 7, z=cfg["z"], dl_mpc=cfg["lumdist"], kappa=cfg["kappa"],
-                                      kappa_wave=cfg["kappa_wave"])
+    ctx.chain_post_into(mine, 7, peak=shared[0].array[lo:hi], lir=shared[1].array[lo:hi],
+                        dustmass=shared[2].array[lo:hi], status=stt, z=cfg["z"], dl_mpc=cfg["lumdist"],
+                        kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
     t_local = time.perf_counter() - t0
-    full = [gather_concat(x.reshape(hi - lo, ns)) for x in (pk, lir, dm)]
-    barrier()
+    for sh in shared:
+        sh.sync()
     t_all = allmax(time.perf_counter() - t0)[0]
+    ok = bool(all(np.isfinite(sh.array).all() for sh in shared))
+    # the same gather through the collective, for comparison (outside the e2e time)
+    t1 = time.perf_counter()
+    coll = gather_concat(np.ascontiguousarray(shared[1].array[lo:hi]))
+    t_coll = allmax(time.perf_counter() - t1)[0]
+    same = bool(np.array_equal(coll, shared[1].array))
     res["e2e"] = {"value": nw * ns / t_all, "unit": "samples/s", "s_per_chain": t_all,
                   "s_local_post_processing": allmax(t_local)[0],
                   "h2d_bytes": int(mine.nbytes), "d2h_bytes": int(3 * mine.shape[0] * ns * 8 + mine.shape[0] * ns * 4),
-                  "gathered_shape": list(full[1].shape),
-                  "what": "mbb_chain_post(MBB_HOST): peak wavelength + L_IR (QUADPACK replay) + dust mass of "
-                          "this rank's walker rows, then the one final gather over ranks (inside the time)",
-                  "all_finite": bool(all(np.isfinite(x).all() for x in full))}
+                  "gathered_shape": list(shared[1].array.shape),
+                  "what": "mbb_chain_post(MBB_HOST): peak wavelength + L_IR (QUADPACK replay) + dust mass of this "
+                          "rank's walker rows, written by the device-to-host copies straight into this rank's rows "
+                          "of arrays shared by all ranks (page-locked /dev/shm mappings), then a barrier: the final "
+                          "gather, inside the time, without a collective",
+                  "all_finite": ok,
+                  "nccl_all_gather_of_one_output_s": t_coll, "nccl_gather_matches": same}
+    for sh in shared:
+        sh.close()
     return res
 
 

@@ -87,6 +87,10 @@ int mbb_last_kernel_ms(mbb_ctx *ctx, float *ms);
  * contexts of all devices): buffers the library can DMA from / to directly. */
 int mbb_host_alloc(size_t bytes, void **out);
 int mbb_host_free(void *p);
+/* page-lock memory the caller already owns (cudaHostRegister) -- e.g. a shared-memory mapping that
+ * several one-process-per-GPU ranks fill in disjoint slices: the final gather without a collective */
+int mbb_host_register(void *p, size_t bytes);
+int mbb_host_unregister(void *p);
 
 /* ---- model: replaces the constructor arguments the reference threads through
  *      likelihood._set_sed (likelihood.py:765-768) ------------------------- */

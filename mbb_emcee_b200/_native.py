@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 __all__ = ["MBBNativeError", "Context", "library_path", "load_library",
-           "default_context", "raise_for_status", "STATUS_NAMES", "pinned_empty"]
+           "default_context", "raise_for_status", "STATUS_NAMES", "pinned_empty", "host_register"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MBB_B200_LIB: developer knob for A/B-timing alternative builds of the same library
@@ -88,6 +88,8 @@ def load_library():
                                        vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32]),
             "mbb_host_alloc": (i32, [ctypes.c_size_t, ctypes.POINTER(vp)]),
             "mbb_host_free": (i32, [vp]),
+            "mbb_host_register": (i32, [vp, ctypes.c_size_t]),
+            "mbb_host_unregister": (i32, [vp]),
             "mbb_fp64_peak": (i32, [vp, i32, ctypes.POINTER(dbl)]),
         }
         for name, (res, args) in sig.items():
@@ -102,7 +104,8 @@ EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ct
                     "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
                     "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_lir_method", "mbb_set_bands",
                     "mbb_set_data", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
-                    "mbb_chain_post", "mbb_chain_flux", "mbb_ensemble_run", "mbb_ensemble_fit", "mbb_host_alloc", "mbb_host_free", "mbb_fp64_peak"]
+                    "mbb_chain_post", "mbb_chain_flux", "mbb_ensemble_run", "mbb_ensemble_fit", "mbb_host_alloc", "mbb_host_free", "mbb_host_register",
+                    "mbb_host_unregister", "mbb_fp64_peak"]
 
 # layout of one row of mbb_ensemble_fit's per-source summary (include/mbb_b200.h MBB_FS_*)
 FIT_NSTATS = 28
@@ -131,6 +134,16 @@ def pinned_empty(shape, dtype=np.float64):
     buf = (ctypes.c_char * nbytes).from_address(p.value)
     weakref.finalize(buf, lib.mbb_host_free, p)      # numpy views keep `buf` alive through .base
     return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+
+def host_register(arr):
+    """Page-lock a numpy array in place (cudaHostRegister); returns a callable that undoes it.
+    False when registration is refused (the array then simply behaves as pageable memory)."""
+    lib = load_library()
+    if lib.mbb_host_register(ctypes.c_void_p(arr.ctypes.data), arr.nbytes) != 0:
+        return False
+    addr = ctypes.c_void_p(arr.ctypes.data)
+    return lambda: lib.mbb_host_unregister(addr)
 
 
 def raise_for_status(status, pars=None):
@@ -302,6 +315,27 @@ class Context(object):
                                           float(kappa), float(kappa_wave), _ptr(pk), _ptr(lir),
                                           _ptr(dm), _ptr(st), HOST))
         return pk, lir, dm, st
+
+    def chain_post_into(self, chain, which, peak=None, lir=None, dustmass=None, status=None, z=0.0,
+                        dl_mpc=1.0, lir_min=8.0, lir_max=1000.0, kappa=2.64, kappa_wave=125.0):
+        """mbb_chain_post(MBB_HOST) on caller-owned arrays (e.g. the rows of one shard inside shared
+        page-locked outputs): chain[nw][ns][5] C-contiguous, outputs [nw][ns] for the bits of
+        ``which`` (1 peak, 2 L_IR, 4 dust mass)."""
+        nw, ns = chain.shape[0], chain.shape[1]
+        for name, a, dt, need in (("chain", chain, np.float64, True), ("peak", peak, np.float64, which & 1),
+                                  ("lir", lir, np.float64, which & 2), ("dustmass", dustmass, np.float64, which & 4),
+                                  ("status", status, np.int32, False)):
+            if a is None:
+                if need:
+                    raise ValueError("%s is required" % name)
+                continue
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous):
+                raise TypeError("%s must be a C-contiguous %s array" % (name, np.dtype(dt).name))
+            if name != "chain" and a.shape != (nw, ns):
+                raise ValueError("%s must have shape (nwalkers, nsteps)" % name)
+        self._ck(self._lib.mbb_chain_post(self._h, nw, ns, _ptr(chain), int(which), float(z), float(dl_mpc),
+                                          float(lir_min), float(lir_max), float(kappa), float(kappa_wave),
+                                          _ptr(peak), _ptr(lir), _ptr(dustmass), _ptr(status), HOST))
 
     def chain_flux(self, chain, band=0):
         chain = _f64(chain)

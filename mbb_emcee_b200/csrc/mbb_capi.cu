@@ -677,6 +677,17 @@ int mbb_host_alloc(size_t bytes, void** out) {
   return 0;
 }
 
+int mbb_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return fail("mbb_host_register: empty range");
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+
+int mbb_host_unregister(void* p) {
+  if (p) CK(cudaHostUnregister(p));
+  return 0;
+}
+
 int mbb_host_free(void* p) {
   if (p) CK(cudaFreeHost(p));
   return 0;

@@ -39,7 +39,7 @@ class mbb_results(object):
                     'alpha': 3, 'fnorm': 4, 'f500': 4}
 
     def __init__(self, fit=None, h5file=None, redshift=None, lumdist=None,
-                 cosmo_type='WMAP9', device=None):
+                 cosmo_type='WMAP9', device=None, devices=None):
         if h5file is not None:
             raise NotImplementedError("HDF5 results files are not supported "
                                       "(h5py is not a dependency); use "
@@ -54,6 +54,12 @@ class mbb_results(object):
         self._has_peaklambda = False
         self._device = device
         self._ctx = None
+        # devices=[0, 1, ...]: the chain's walker rows are cut into one contiguous shard per GPU
+        # (the per-walker repeat scan of _map_chain stays local), each driven from its own host
+        # thread through its own context, results landing in disjoint rows of one page-locked
+        # array -- no collective
+        self._devices = None if devices is None else [int(d) for d in devices]
+        self._shard_ctx = {}
 
         self._z = None if redshift is None else float(redshift)
         if lumdist is None:
@@ -121,9 +127,9 @@ class mbb_results(object):
 
     @classmethod
     def from_chain(cls, chain, lnprobability=None, wavenorm=500.0, noalpha=False,
-                   opthin=False, redshift=None, lumdist=None, device=None):
+                   opthin=False, redshift=None, lumdist=None, device=None, devices=None):
         """Post-process a bare chain (extension; used for sharded chains)."""
-        self = cls(redshift=redshift, lumdist=lumdist, device=device)
+        self = cls(redshift=redshift, lumdist=lumdist, device=device, devices=devices)
         self._fitset = True
         self._noalpha, self._opthin = bool(noalpha), bool(opthin)
         self._wavenorm = float(wavenorm)
@@ -300,12 +306,50 @@ class mbb_results(object):
         return self._parcen_internal(self.peaklambda.flatten(), percentile,
                                      lowlim=lowlim, uplim=uplim)
 
-    def _post(self, which, wavenorm, opthin, noalpha, **kw):
-        ctx = self.context
-        ctx.set_model(wavenorm, opthin, noalpha)
-        pk, lir, dm, status = ctx.chain_post(self.chain, which, **kw)
-        _native.raise_for_status(status, self.chain)
-        return pk, lir, dm
+    def _post(self, which, wavenorm, opthin, noalpha, lir_method=None, **kw):
+        if not self._devices:
+            ctx = self.context
+            ctx.set_model(wavenorm, opthin, noalpha)
+            if lir_method is not None:
+                ctx.set_lir_method(lir_method)
+            pk, lir, dm, status = ctx.chain_post(self.chain, which, **kw)
+            _native.raise_for_status(status, self.chain)
+            return pk, lir, dm
+        import threading
+        from .sharding import shard_range
+        chain = np.ascontiguousarray(self.chain, dtype=np.float64)
+        nw, ns = chain.shape[0], chain.shape[1]
+        world = len(self._devices)
+        out = [(_native.pinned_empty((nw, ns)) if which & bit else None) for bit in (1, 2, 4)]
+        status = _native.pinned_empty((nw, ns), np.int32)
+        errors = [None] * world
+
+        def shard(r):
+            try:
+                lo, hi = shard_range(nw, r, world)
+                if hi <= lo:
+                    return
+                ctx = self._shard_ctx.get(r)
+                if ctx is None:
+                    ctx = self._shard_ctx[r] = _native.Context(self._devices[r])
+                ctx.set_model(wavenorm, opthin, noalpha)
+                if lir_method is not None:
+                    ctx.set_lir_method(lir_method)
+                ctx.chain_post_into(chain[lo:hi], which, *[None if o is None else o[lo:hi] for o in out],
+                                    status=status[lo:hi], **kw)
+            except BaseException as exc:
+                errors[r] = exc
+
+        threads = [threading.Thread(target=shard, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for exc in errors:
+            if exc is not None:
+                raise exc
+        _native.raise_for_status(status, chain)
+        return tuple(out)
 
     def compute_peaklambda(self):
         """Observer-frame wavelength of peak f_nu [um] for every chain sample."""
@@ -355,8 +399,7 @@ class mbb_results(object):
             raise ValueError("Invalid wavemax: {:f}".format(self._lir_max))
         if self._lir_min > self._lir_max:
             self._lir_min, self._lir_max = self._lir_max, self._lir_min
-        self.context.set_lir_method(method)
-        self.lir = self._post(2, 500.0, self._opthin, self._noalpha, z=self._z,
+        self.lir = self._post(2, 500.0, self._opthin, self._noalpha, lir_method=method, z=self._z,
                               dl_mpc=self.lumdist, lir_min=self._lir_min,
                               lir_max=self._lir_max)[1]
         self._has_lir = True

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-__all__ = ["rank_world", "shard_range", "shard_sources", "gather_concat", "bind_to_gpu_numa_node",
+__all__ = ["rank_world", "shard_range", "shard_sources", "gather_concat", "shared_array", "bind_to_gpu_numa_node",
            "bind_rank_cpus", "parse_cpulist"]
 
 
@@ -89,6 +89,51 @@ def shard_sources(nsrc, nwalkers, rank, world):
     of one source) are split across ranks: (src_lo, src_hi, eval_lo, eval_hi)."""
     lo, hi = shard_range(nsrc, rank, world)
     return lo, hi, lo * nwalkers, hi * nwalkers
+
+
+class shared_array(object):
+    """One array that every rank of a one-process-per-GPU launch on ONE node maps and fills in
+    disjoint slices: the "final gather" without a collective.  Rank 0 creates a file
+    in /dev/shm, everyone maps it and page-locks its mapping (cudaHostRegister), so that each GPU's
+    device-to-host copy lands directly in the shared pages; a barrier after the last copy is all the
+    synchronisation there is.  ``barrier`` is any callable that synchronises the ranks
+    (torch.distributed.barrier); without one (single process) the array is private.
+
+        sh = shared_array("lir", (nwalkers, nsteps), rank, world, barrier=dist.barrier)
+        ctx.chain_post_into(chain[lo:hi], 2, lir=sh.array[lo:hi], ...)
+        sh.sync()            # every rank's slice is complete and visible
+        ... sh.array ...     # the whole result, on every rank
+        sh.close()
+    """
+
+    def __init__(self, tag, shape, rank=0, world=1, dtype=np.float64, barrier=None, register=True,
+                 directory="/dev/shm"):
+        self._barrier = barrier if world > 1 else None
+        self._rank = rank
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._path = os.path.join(directory, "mbb_b200_%s_%s" % (os.environ.get("MASTER_PORT", str(os.getppid())), tag))
+        if rank == 0:
+            with open(self._path, "wb") as fh:
+                fh.truncate(max(nbytes, 1))
+        if self._barrier:
+            self._barrier()
+        self.array = np.memmap(self._path, dtype=dtype, mode="r+", shape=tuple(shape))
+        self._unregister = None
+        if register:
+            from . import _native
+            self._unregister = _native.host_register(self.array) or None
+
+    def sync(self):
+        if self._barrier:
+            self._barrier()
+
+    def close(self):
+        if self._unregister:
+            self._unregister()
+            self._unregister = None
+        self.sync()
+        if self._rank == 0 and os.path.exists(self._path):
+            os.unlink(self._path)
 
 
 def gather_concat(local, group=None):

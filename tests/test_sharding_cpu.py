@@ -77,6 +77,66 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     assert np.array_equal(got["both"][:, 0], want) and np.array_equal(got["both"][:, 1], st)
 
 
+def _chain_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch.distributed as dist
+    import mbb_oracle as oracle
+    from mbb_emcee_b200.sharding import gather_concat, shard_range, shared_array
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    chain = np.load(os.path.join(tmp, "chain.npy"))
+    nw, ns = chain.shape[:2]
+    lo, hi = shard_range(nw, rank, world)
+    # the final gather without a collective: every rank fills its rows of one shared mapping
+    sh = shared_array("peak", (nw, ns), rank, world, barrier=dist.barrier, register=False)
+    sh.array[lo:hi] = oracle.map_chain(chain[lo:hi], oracle.peaklambda_step)
+    sh.sync()
+    whole = np.array(sh.array)
+    # ... and the same through the collective
+    coll = gather_concat(np.ascontiguousarray(sh.array[lo:hi]))
+    assert np.array_equal(whole, coll)
+    if rank == 1:                         # any rank sees the whole result
+        np.save(os.path.join(tmp, "peak_sharded.npy"), whole)
+    sh.close()
+    dist.destroy_process_group()
+
+
+def test_chain_rows_shard_with_local_repeat_scan(tmp_path):
+    """configs[3] over ranks: walker rows are cut contiguously, so the sequential np.allclose
+    repeat scan of _map_chain (reference results.py:553-566) never crosses a shard; the shards land
+    in disjoint rows of one shared array (no collective) and equal the single-process result."""
+    import torch.multiprocessing as mp
+    import mbb_oracle as oracle
+    from mbb_emcee_b200 import synthetic
+    chain = synthetic.random_walk_chain((14.0, 1.8, 400.0, 3.0, 30.0), 7, 40, np.random.RandomState(3))
+    np.save(tmp_path / "chain.npy", chain)
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_chain_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    want = oracle.map_chain(chain, oracle.peaklambda_step)
+    got = np.load(tmp_path / "peak_sharded.npy")
+    assert np.array_equal(got, want)
+    assert (np.diff(want, axis=1) == 0).any()         # the chain does contain repeats
+
+
+def test_rank_cpu_sets_are_disjoint():
+    """Where sysfs hides the NUMA topology every rank still gets its own CPUs."""
+    from mbb_emcee_b200.sharding import bind_rank_cpus
+    before = sorted(os.sched_getaffinity(0))
+    if len(before) < 2:
+        pytest.skip("one CPU")
+    try:
+        sets = []
+        for r in range(2):
+            os.sched_setaffinity(0, before)
+            sets.append(bind_rank_cpus("00000000:ff:00.0", r, 2, sysfs="/nonexistent"))
+        assert sets[0] and sets[1] and not set(sets[0]) & set(sets[1])
+        assert sorted(sets[0] + sets[1]) == before
+    finally:
+        os.sched_setaffinity(0, before)
+
+
 def test_numa_binding_helper(tmp_path):
     """bind_to_gpu_numa_node reads the GPU's NUMA node and that node's CPU list from sysfs
     and never raises when the topology is not exposed."""
