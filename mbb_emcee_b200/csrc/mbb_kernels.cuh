@@ -302,7 +302,7 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
     return -kInf;
   }
   FastSed s;
-  fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m);
+  fast_setup<THIN, ALPHA, kTabRepShift>(s, p[0], p[1], p[2], p[3], p[4], m, tab);
   st = s.status;
   if (st != ST_OK) return qnan();
   if (!s.safe)

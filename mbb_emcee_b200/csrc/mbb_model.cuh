@@ -273,10 +273,11 @@ MBB_HD void fast_sed_rescale256(FastSed& f) {
 // exponent the node loop forms stays below kSafeExp in magnitude, so the loop
 // may run the CLAMP=false instantiations.
 // ---------------------------------------------------------------------------
-MBB_HD double thin_merge_root_fast(double a) {
-  double x = a;
+template <int TS>
+MBB_HD double thin_merge_root_fast(double a, const double* tab) {
+  double x = a;                       // a <= 603 (gates of fast_setup): the exponent needs no clamp
   for (int it = 0; it < 12; ++it) {
-    const double e = a * exp_l(-x);
+    const double e = a * exp_red<TS, false>(red_x(-x), tab);
     const double dx = div_fast((x - a) + e, 1.0 - e);
     x -= dx;
     if (fabs(dx) <= 1.2e-16 * x) break;
@@ -286,77 +287,201 @@ MBB_HD double thin_merge_root_fast(double a) {
 
 // The thick merge equation in u = log x:  G(u) = g(e^u),  g(x) = x - (1 - e^-x)(3 + alpha +
 // beta B(t)),  B(t) = t/(e^t - 1),  t = (x/x0)^beta = exp(beta (u - u0)).  In this variable a
-// residual evaluation is four lean exponentials and no logarithm.  Returns x = e^u.
-MBB_HD double merge_G_fast(double u, double alpha, double beta, double u0, double& G, double& dG) {
-  const double x = exp_l(u);
-  const double t = exp_tau(beta * (u - u0));
+// residual evaluation is four lean exponentials and no logarithm.  Every exponent is bounded
+// (u <= log(603) by the gates of fast_setup; beta (u - u0) is clamped to [-700, log 700], where
+// B(t) is 1 resp. 0 to far below rounding), so the exponentials run unclamped on whatever table
+// the caller works with (TS: the replicated shared-memory copy in the delta kernels).
+struct MergeEval {
+  double x, t, e, E, em1t;      // e^u, t, e^-x, 1 - e^-x, e^t - 1 (em1t only where t >= 1e-3)
+  double S, dB, rem;            // 3 + alpha + beta B(t), B'(t), 1/(e^t - 1)
+  double G, dG;                 // residual and dG/du = x g'(x)
+};
+constexpr double kMergeTauMax = 6.5510803350434044;       // log(700)
+
+template <int TS>
+MBB_HD void merge_eval(double u, double a_lo, double beta, double u0, const double* tab, MergeEval& v) {
+#if defined(MBB_COUNT_EVALS)
+  ++g_f64_evals;
+#endif
+  v.x = exp_red<TS, false>(red_x(u), tab);
+  double arg = beta * (u - u0);
+  arg = arg < -700.0 ? -700.0 : arg;
+  arg = arg > kMergeTauMax ? kMergeTauMax : arg;
+  v.t = exp_red<TS, false>(red_x(arg), tab);
   double B, dB;                       // B(t), B'(t)
-  if (t < 1e-3) {
-    B = 1.0 - t * (0.5 - t * (1.0 / 12.0));
-    dB = -0.5 + t * (1.0 / 6.0);
+  if (v.t < 1e-3) {
+    B = 1.0 - v.t * (0.5 - v.t * (1.0 / 12.0));
+    dB = -0.5 + v.t * (1.0 / 6.0);
+    v.em1t = v.t;
+    v.rem = 0.0;
   } else {
-    const double em1t = expm1_l(t);
-    const double r = rcp_cubic(em1t);
-    B = t * r;
-    dB = (em1t - t * (em1t + 1.0)) * r * r;
+    v.em1t = expm1_red<TS, false>(red_x(v.t), tab);
+    const double r = rcp_cubic(v.em1t);
+    B = v.t * r;
+    dB = (v.em1t - v.t * (v.em1t + 1.0)) * r * r;
+    v.rem = r;
   }
-  const double E = -expm1_l(-x);      // 1 - e^-x
-  const double S = 3.0 + alpha + beta * B;
-  G = x - E * S;
-  dG = x * (1.0 - (1.0 - E) * S) - E * (beta * beta) * dB * t;     // dG/du = x g'(x)
-  return x;
+  v.dB = dB;
+  v.e = exp_red<TS, false>(red_x(-v.x), tab);
+  v.E = 1.0 - v.e;                    // x >= ~2.6: no cancellation
+  const double S = a_lo + beta * B;
+  v.S = S;
+  v.G = v.x - v.E * S;
+  v.dG = v.x * (1.0 - v.e * S) - v.E * (beta * beta) * dB * v.t;
 }
 
-// Root of the thick merge equation; also returns u = log(root).
+// d2G/du2 at the point of `v` (for the Halley step): with B'' = e^t (t (e^t + 1) - 2 (e^t - 1)) /
+// (e^t - 1)^3, factored so that nothing overflows for t up to 700.  The cancellation in B'' for
+// small t costs ~1e-9 relative at t = 1e-3 -- immaterial, G'' only corrects a correction.
+MBB_HD double merge_d2G(const MergeEval& v, double beta) {
+  const double b2 = beta * beta;
+  double Bpp;
+  if (v.t < 1e-3) {
+    Bpp = 1.0 / 6.0;
+  } else {
+    const double et = v.em1t + 1.0;
+    Bpp = (et * v.rem) * ((v.t * (et + 1.0) - 2.0 * v.em1t) * v.rem) * v.rem;
+  }
+  const double xe = v.x * v.e;
+  return v.x - xe * v.S * (1.0 - v.x) - 2.0 * xe * b2 * v.t * v.dB - v.E * b2 * beta * v.t * (v.dB + v.t * Bpp);
+}
+
+// Single-precision approximation of the root (u = log x) to ~1e-5: the same safeguarded Newton
+// iteration on MUFU exponentials (an evaluation costs ~45 issue slots against ~300 for the
+// double-precision one).  It replaces the first 3-4 double-precision evaluations; what it
+// returns is only a starting point, so its accuracy does not enter the result.
+MBB_HD float f32_exp(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.44269504f));
+  return r;
+#elif defined(MBB_F32_NOISE)
+  static unsigned lcg = 12345u;
+  lcg = lcg * 1664525u + 1013904223u;
+  return expf(x) * (1.0f + ((lcg >> 16) & 1 ? 4e-7f : -4e-7f));
+#else
+  return expf(x);
+#endif
+}
+MBB_HD float f32_log(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.693147181f;
+#else
+  return logf(x);
+#endif
+}
+MBB_HD float f32_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+// Newton steps kept inside the bracket (a step that leaves it is replaced by the midpoint); the
+// "fails to halve" test of the double-precision iteration is left to that iteration.
+MBB_HD float thick_merge_seed(float a_lo, float beta, float u0, float ul, float uh) {
+  float u = 0.5f * (ul + uh);
+  const float bb = beta * beta;
+  for (int it = 0; it < 8; ++it) {
+#if defined(MBB_COUNT_EVALS)
+    ++g_f32_iters;
+#endif
+    const float x = f32_exp(u);
+    const float t = f32_exp(fminf(fmaxf(beta * (u - u0), -80.0f), 4.38f));     // t <= 80: e^t finite
+    float B, dB;
+    if (t < 0.03f) {
+      B = 1.0f - t * (0.5f - t * (1.0f / 12.0f));
+      dB = -0.5f + t * (1.0f / 6.0f);
+    } else {
+      const float em = f32_exp(t) - 1.0f;
+      const float r = f32_rcp(em);
+      B = t * r;
+      dB = (em - t * (em + 1.0f)) * r * r;
+    }
+    const float e = f32_exp(-x);
+    const float E = 1.0f - e;
+    const float S = a_lo + beta * B;
+    const float G = x - E * S;
+    const float dG = x * (1.0f - e * S) - E * bb * dB * t;
+    // (no bracket update inside the rounding noise of G, where its sign means nothing)
+    if (G < -1e-3f) ul = u; else if (G > 1e-3f) uh = u;
+    float un = u - G * f32_rcp(dG);
+    if (!(un > ul && un < uh)) un = 0.5f * (ul + uh);
+    const float dx = un - u;
+    u = un;
+    if (fabsf(dx) <= 3e-6f) break;
+  }
+  return u;
+}
+
+// Root of the thick merge equation.
 //   bracket: g <= x - (3+alpha)(1 - e^-x) =: gL, whose root a + W(-a e^-a) >= a (1 - e^(1-a))
 //   (W concave on [-1/e, 0]), so g(xl) <= 0 at xl = a (1 - e^(1-a)), a = 3 + alpha; and
-//   g >= x - (3+alpha+beta)(1 - e^-x), which is positive at x = 3 + alpha + beta =: xh.
-//   iteration: Newton in u, bisecting (in u) whenever a step would leave the bracket or fails to
-//   halve the previous one -- for steep t(x) (large beta) g is nearly a step and plain Newton
-//   cycles between its flat sides.
-MBB_HD double thick_merge_root_fast(double alpha, double beta, double u0, int& status, double& u_root) {
+//   g >= x - (3+alpha+beta)(1 - e^-x), which is positive at x = 3 + alpha + beta =: xh.  g < 0
+//   on (0, root) and > 0 beyond, so the ends may be moved outwards freely: they are formed in
+//   single precision (MUFU.LG2) and widened by 1e-3.
+//   iteration: the single-precision seed, then Newton in u, bisecting (in u) whenever a step
+//   would leave the bracket or fails to halve the previous one -- for steep t(x) (large beta) g is
+//   nearly a step and plain Newton cycles between its flat sides.  A Newton step |du| <= 3e-9
+//   ends it: the error left is ~ C du^2 <= 1e-17 C (host experiment over 2e5 walkers, cfg2 and
+//   wide clouds: root unchanged to 1e-15), so from a 1e-5 seed two evaluations suffice.
+//   From the seed (error <= ~3e-6) ONE evaluation is enough: its Newton step du = G/G' already
+//   leaves ~0.3 du^2 ~ 1e-13, and the Halley step du / (1 - du G''/(2 G')) (G'' in closed form,
+//   merge_d2G) is third order: root error <= 9e-16 over 2e5 walkers drawn from T 3-80 K, beta
+//   0.1-9, lambda0 10-1500 um, alpha 0.5-10, and over the cfg2 cloud (host experiment).  Taken
+//   when |du| <= 3e-6; otherwise the safeguarded iteration runs as described.
+// Returns in `v` the LAST evaluation (at u_eval = u_root + du), x_root by a second-order update
+// of v.x, and `dh`: the caller matches the power law to the grey body at u_eval, where every
+// factor is already known, and multiplies the amplitude by 1 + dh.  With h(u) = log(grey(x)
+// x^alpha): h' = -G/E (the merge equation IS h' = 0) and h'' = -G'/E + O(G), so
+// h(u_root) - h(u_eval) = du (G - G' du / 2) / E + O(du^3).
+template <int TS>
+MBB_HD double thick_merge_root_fast(double alpha, double beta, double u0, const double* tab, int& status,
+                                    double& u_eval, MergeEval& v, double& dh) {
   const double a_lo = 3.0 + alpha;
-  double ul = log(a_lo * (-expm1_l(1.0 - a_lo)));
-  double uh = log(a_lo + beta);
-  double dxold = uh - ul, dx = dxold;
-  double u = 0.5 * (ul + uh), G, dG;
-  double x = merge_G_fast(u, alpha, beta, u0, G, dG);
-  for (int it = 0; it < 100; ++it) {
-    if (!(G == G)) { status = ST_NONFINITE; break; }
-    if (G == 0.0) break;
-    if (G < 0.0) ul = u; else uh = u;
-#if defined(MBB_NEWTON_EARLY_STOP)
-    bool newton_step = false;
-#endif
-    if (((u - uh) * dG - G) * ((u - ul) * dG - G) > 0.0 || fabs(2.0 * G) > fabs(dxold * dG)) {
-      dxold = dx;
-      dx = 0.5 * (uh - ul);
-      u = ul + dx;
-    } else {
-      dxold = dx;
-      dx = G * rcp_fast(dG);
-      u -= dx;
-#if defined(MBB_NEWTON_EARLY_STOP)
-      newton_step = true;
-#endif
+  const float af = (float)a_lo, bf = (float)beta;
+  const float ulf = f32_log(af * (1.0f - f32_exp(1.0f - af))) - 1e-3f;
+  const float uhf = f32_log(af + bf) + 1e-3f;
+  double ul = (double)ulf, uh = (double)uhf;
+  double u = (double)thick_merge_seed(af, bf, (float)u0, ulf, uhf);
+  if (!(u > ul && u < uh)) u = 0.5 * (ul + uh);
+  merge_eval<TS>(u, a_lo, beta, u0, tab, v);
+  u_eval = u;
+  const double rdG = rcp_fast(v.dG);
+  double du = v.G * rdG;
+  if (fabs(du) <= 3.0e-6) {
+    du *= fma(0.5 * du, merge_d2G(v, beta) * rdG, 1.0);       // Halley, to first order in du G''/G'
+    u -= du;
+  } else {
+    double dxold = uh - ul, dx = dxold;
+    for (int it = 0; it < 100; ++it) {
+      if (!(v.G == v.G)) { status = ST_NONFINITE; break; }
+      if (v.G == 0.0) break;
+      if (v.G < 0.0) ul = u; else uh = u;
+      if (((u - uh) * v.dG - v.G) * ((u - ul) * v.dG - v.G) > 0.0 || fabs(2.0 * v.G) > fabs(dxold * v.dG)) {
+        dxold = dx;
+        dx = 0.5 * (uh - ul);
+        u = ul + dx;
+        if (fabs(dx) <= 3.0e-16) break;       // du = dx/x: relative accuracy of the root
+      } else {
+        dxold = dx;
+        dx = v.G * rcp_fast(v.dG);
+        u -= dx;
+        if (fabs(dx) <= 3.0e-9) break;
+      }
+      if (it == 99) { status = ST_NO_CONVERGE; break; }
+      merge_eval<TS>(u, a_lo, beta, u0, tab, v);
+      u_eval = u;
     }
-    if (fabs(dx) <= 3.0e-16) {            // du = dx/x: relative accuracy of the root
-      x = exp_l(u);
-      break;
-    }
-#if defined(MBB_NEWTON_EARLY_STOP)
-    // round-2 candidate (off by default): after a Newton step this small the
-    // next error is ~ C * 9e-18, so the confirming residual evaluation can go -- one of ~5 saved
-    if (newton_step && fabs(dx) <= 3.0e-9) {
-      x = exp_l(u);
-      break;
-    }
-#endif
-    x = merge_G_fast(u, alpha, beta, u0, G, dG);
-    if (it == 99) status = ST_NO_CONVERGE;
+    du = u_eval - u;
   }
-  u_root = u;
-  return x;
+  dh = du * fma(-0.5 * du, v.dG, v.G) * rcp_fast(v.E);
+  // x_root = e^(u_eval - du) = x_eval (1 - du + du^2/2)
+  return fma(v.x, -du * fma(-0.5, du, 1.0), v.x);
 }
 
 // finite and not NaN, by the exponent field (2 integer instructions)
@@ -368,10 +493,11 @@ MBB_HD bool finite_bits(double x) {
 #endif
 }
 
-template <bool THIN, bool ALPHA>
+// `tab` / TS: the exp table the caller works with -- the plain one in global memory (default), or
+// the calling lane's copy of the replicated shared-memory table (TS = kTabRepShift).
+template <bool THIN, bool ALPHA, int TS = 0>
 MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double alpha, double fnorm,
-                       const ModelP& m) {
-  const double* tab = exp2_tab_default();   // per-walker work: the plain table
+                       const ModelP& m, const double* tab = exp2_tab_default()) {
   f.T = T; f.beta = beta; f.alpha = alpha;
   f.status = ST_OK;
   f.safe = 0;
@@ -392,22 +518,22 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
   if (f.status != ST_OK) return;
   const double xn = f.hokt9 * m.nu_norm;
   bool safe = f.hokt9 * m.nu_max <= kSafeExp && -f.nb * m.lmax <= kSafeExp;
-  double tn_fac = 1.0, q = 0.0, lnxn = 0.0, u_m = 0.0;
+  double tn_fac = 1.0, q = 0.0;
   if (!THIN) {
     // q = log(xnorm/x0) = log(lambda0/wavenorm)
     const double r = div_fast(lambda0, m.wavenorm);
     f.x0 = div_fast(xn, r);
-    q = log(r);
+    q = log_l(r);
     const double qc_hi = q * kC64Hi;
     const double qc_lo = fma(q, kC64Lo, fma(q, kC64Hi, -qc_hi));
     f.uq_hi = beta * qc_hi;
     f.uq_lo = fma(beta, qc_lo, fma(beta, qc_hi, -f.uq_hi));
-    f.t0 = exp_red<0, true>(red_prod(beta, qc_hi, qc_lo), tab);             // (lambda0/wavenorm)^beta
-    tn_fac = one_minus_exp_red<0, true>(red_x(-clamp_pos<kHi700>(f.t0)), tab);   // 1 - exp(-(xn/x0)^beta)
+    f.t0 = exp_red<TS, true>(red_prod(beta, qc_hi, qc_lo), tab);             // (lambda0/wavenorm)^beta
+    tn_fac = one_minus_exp_red<TS, false>(red_x(-clamp_pos<kHi700>(f.t0)), tab);   // 1 - exp(-(xn/x0)^beta)
     f.t0c = f.t0 * kC64Hi;
     safe = safe && fabs(beta * q) <= kSafeExp;
   }
-  const double em_n = expm1_red<0, true>(red_prod(m.nu_norm, f.xk_hi, f.xk_lo), tab);
+  const double em_n = expm1_red<TS, true>(red_prod(m.nu_norm, f.xk_hi, f.xk_lo), tab);
   const double grey_at_norm = THIN ? fnorm * em_n : div_fast(fnorm * em_n, tn_fac);
   if (!ALPHA) {
     f.amp_grey = grey_at_norm;
@@ -417,31 +543,35 @@ MBB_HD void fast_setup(FastSed& f, double T, double beta, double lambda0, double
   }
   f.apow = THIN ? alpha : alpha + 3.0;
   safe = safe && f.apow * m.lmax <= kSafeExp;
+  double R;         // amp_pow / fnorm when the normalisation wavelength sits on the grey side:
+                    // grey(xmerge) xmerge^alpha / (grey(xnorm) xnorm^alpha), built from ratios
   if (THIN) {
-    f.xmerge = thin_merge_root_fast(3.0 + alpha + beta);               // modified_blackbody.py:253-254
+    f.xmerge = thin_merge_root_fast<TS>(3.0 + alpha + beta, tab);      // modified_blackbody.py:253-254
+    const double xm = f.xmerge;
+    const double lmn = log_l(div_fast(xm, xn));                        // log(xmerge/xnorm)
+    const double inv_em_m = rcp_fast(expm1_red<TS, false>(red_x(xm), tab));
+    R = exp_red<TS, true>(red_x((3.0 + beta + alpha) * lmn), tab) * inv_em_m * em_n;
   } else {
     // Root of the merge equation (modified_blackbody.py:122-151, 286-321).  The reference
     // brackets it by halving/doubling from [0.1, 15] and runs brentq (~14 residual
     // evaluations, each a log and three exponentials: three quarters of this setup); here a
-    // closed-form bracket and a safeguarded Newton iteration in log x (thick_merge_root_fast),
-    // 4-6 log-free residual evaluations, root to ~3e-16.
-    lnxn = log(xn);
-    f.xmerge = thick_merge_root_fast(alpha, beta, lnxn - q, f.status, u_m);
+    // closed-form bracket, a single-precision seed and a safeguarded Newton iteration in log x
+    // (thick_merge_root_fast): typically 2 log-free double-precision residual evaluations.
+    const double lnxn = log_l(xn);
+    MergeEval v;
+    double u_eval, dh;
+    f.xmerge = thick_merge_root_fast<TS>(alpha, beta, lnxn - q, tab, f.status, u_eval, v, dh);
     if (f.status != ST_OK) return;
+    // the power law is matched to the grey body at the last evaluation point (see above)
+    double tau_fac;                                       // 1 - exp(-t)
+    if (v.t < 1e-3) tau_fac = v.t * (1.0 - v.t * (0.5 - v.t * (1.0 / 6.0 - v.t * (1.0 / 24.0 - v.t * (1.0 / 120.0)))));
+    else tau_fac = v.em1t * rcp_fast(v.em1t + 1.0);
+    const double lmn = u_eval - lnxn;                     // log(x_eval/xnorm)
+    R = tau_fac * exp_red<TS, true>(red_x((3.0 + alpha) * lmn), tab) * (v.e * rcp_fast(v.E)) * div_fast(em_n, tn_fac);
+    R = fma(R, dh, R);
   }
-  // R = grey(xmerge) xmerge^alpha / (grey(xnorm) xnorm^alpha), built from ratios
+  f.nu_merge = div_fast(f.xmerge, f.hokt9);
   const double xm = f.xmerge;
-  f.nu_merge = div_fast(xm, f.hokt9);
-  const double lmn = THIN ? log(div_fast(xm, xn)) : u_m - lnxn;      // log(xmerge/xnorm)
-  const double inv_em_m = rcp_fast(expm1_l(xm));
-  double R;
-  if (THIN) {
-    R = exp_l((3.0 + beta + alpha) * lmn) * inv_em_m * em_n;        // times grey_at_norm/fnorm
-    // (amp_grey = fnorm*em_n when xn <= xm) -> amp_pow = fnorm * R
-  } else {
-    const double tm = exp_tau(beta * (lmn + q));
-    R = -expm1_l(-tm) * exp_l((3.0 + alpha) * lmn) * inv_em_m * div_fast(em_n, tn_fac);
-  }
   // here R = amp_pow / fnorm when the normalisation wavelength sits on the grey side
   if (xn > xm) {
     f.amp_pow = fnorm;

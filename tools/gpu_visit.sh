@@ -32,6 +32,16 @@ ncu_all)
   timeout 1500 python tools/ncu_capture.py r02 2>&1 | tee $O/r02_ncu_capture.log ;;
 bench_quick)
   timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/r02_bench_quick.json 2> $O/r02_bench_quick.err; head -c 1500 $O/r02_bench_quick.json; tail -12 $O/r02_bench_quick.err ;;
+probe)
+  for v in "1 0" "0 1" "1 1" "0 0"; do timeout 120 tools/_build/delta_probe $v 20000 20 2>&1 | tee -a $O/r02_probe.jsonl; done ;;
+probe_ncu)   # PROBE_V="0 1": per-source-line executed instruction counts of one variant
+  V=${PROBE_V:-0 1}; T=$(echo $V | tr -d ' ')
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:loglike_delta -s 3 -c 1 \
+      -o $O/r02_probe_$T -f tools/_build/delta_probe $V 4000 2 > $O/r02_probe_ncu_$T.log 2>&1
+  ncu -i $O/r02_probe_$T.ncu-rep --page source --csv --print-source cuda > $O/r02_probe_src_cuda_$T.csv 2>> $O/r02_probe_ncu_$T.log
+  ncu -i $O/r02_probe_$T.ncu-rep --page source --csv > $O/r02_probe_src_sass_$T.csv 2>> $O/r02_probe_ncu_$T.log
+  python tools/ncu_summary.py full $O/r02_probe_$T.ncu-rep > $O/r02_probe_full_$T.md 2>> $O/r02_probe_ncu_$T.log
+  rm -f $O/r02_probe_$T.ncu-rep; tail -3 $O/r02_probe_ncu_$T.log ;;
 *) echo "unknown step $step" ;;
 esac
 done
