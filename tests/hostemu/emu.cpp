@@ -349,6 +349,7 @@ void run_fastmath(int mode, long long n, const double* x, double* out) {
       const double bh = (double)b, bl = (double)(b - (long double)bh);
       out[i] = exp_red<TS, false>(red_prod(x[i], bh, bl), tab);
     } else if (mode == 8) out[i] = rcp_cubic(x[i]);
+    else if (mode == 9) out[i] = log_l(x[i]);
     else out[i] = div_fast(x[i], x[i] + 1.0);
   }
 }
@@ -358,7 +359,7 @@ extern "C" {
 // element-wise checks of the lean math: mode 0 exp (CLAMP), 1 expm1 (CLAMP), 2 reciprocal,
 // 3 a/b with b = x+1, 4 exp (no clamp), 5 expm1 (no clamp), 6 1-exp(-x) through the scaled path,
 // 7 exp(x*y) as a product reduction with y = 0.7 (double-double of 0.7*N/ln2 formed here),
-// 8 1/x by rcp_cubic.  Modes 4-7 use the table flavour set by emu_set_tab_bits; 0-1 are the
+// 8 1/x by rcp_cubic, 9 log (table + series).  Modes 4-7 use the table flavour set by emu_set_tab_bits; 0-1 are the
 // per-walker forms (always 64 entries).
 void emu_fastmath(int mode, long long n, const double* x, double* out) {
   if (g_ts) run_fastmath<kTab256>(mode, n, x, out);

@@ -235,6 +235,14 @@ def test_fastmath(tabbits):
     b = np.concatenate([rng.uniform(0.5, 2.0, 2000), 10.0**rng.uniform(-200, 200, 2000)])
     assert np.max(np.abs(emu.fastmath(2, b) * b - 1.0)) < 4e-16
     assert np.max(np.abs(emu.fastmath(8, b) * b - 1.0)) < 4e-16
+    # lean log: absolute error relative to max(1, |log x|), incl. arguments next to 1 and next to
+    # powers of two (where the table term and e*ln2 cancel)
+    xs = np.concatenate([10.0**rng.uniform(-300, 300, 3000), rng.uniform(0.5, 2.0, 3000),
+                         1.0 + rng.uniform(-1e-3, 1e-3, 1000), 2.0**rng.randint(-50, 50, 500) * (1 - 1e-9)])
+    got = emu.fastmath(9, xs)
+    err = max(abs((mp.mpf(float(g)) - mp.log(mp.mpf(float(x)))) / max(1, abs(mp.log(mp.mpf(float(x))))))
+              for g, x in zip(got, xs))
+    assert err < 2.5e-16, err       # ~1 ulp of a result in [1, 2)
 
 
 @pytest.mark.parametrize("opthin", [True, False])
