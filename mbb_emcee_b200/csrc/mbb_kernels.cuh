@@ -306,9 +306,16 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
   st = s.status;
   if (st != ST_OK) return qnan();
   if (!s.safe)
-    return delta_eval_cold<THIN, ALPHA>(p[0], p[1], p[2], p[3], p[4], cold, d.flux + src * NB,
-                                        d.cinv ? nullptr : d.ivar + src * NB,
-                                        d.cinv ? d.cinv + src * (NB * NB) : nullptr, &st);
+  {
+    // (status through a local of its own: taking the address of `st` would park it in local
+    // memory for the whole evaluation)
+    int st_cold = ST_OK;
+    const double r = delta_eval_cold<THIN, ALPHA>(p[0], p[1], p[2], p[3], p[4], cold, d.flux + src * NB,
+                                                  d.cinv ? nullptr : d.ivar + src * NB,
+                                                  d.cinv ? d.cinv + src * (NB * NB) : nullptr, &st_cold);
+    st = st_cold;
+    return r;
+  }
   double chi = 0.0;
   if constexpr (!ALPHA) {
     delta_groups<THIN, NB, 0>(s, t, diff, tab);
@@ -336,7 +343,9 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
   }
   double lnl = -0.5 * chi;
   if (pr.peak_terms) {           // lambda_peak limit / prior: needs the peak solve
-    lnl = add_priors_cold<THIN>(lnl, p[0], p[1], p[2], p[3], p[4], s.x0, cold, &st);
+    int st_cold = ST_OK;
+    lnl = add_priors_cold<THIN>(lnl, p[0], p[1], p[2], p[3], p[4], s.x0, cold, &st_cold);
+    st = st_cold;
     if (st != ST_OK) return qnan();
   } else {
     lnl = add_simple_priors(pr, p, lnl);
@@ -432,6 +441,8 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
   if (tid == 0 && tile < nt) issue(tile, 0);
   int stage = 0;            // ring position of the current tile
   unsigned par = 0;         // parity of this use of the stage's barrier
+  const int par_tid_stride = a.layout == 0 ? 5 : 1;
+  const int par_idx_stride = a.layout == 0 ? 1 : kDeltaTile;
   for (; tile < nt; tile += gridDim.x) {
     const long long e0 = (long long)tile * kDeltaTile, e = e0 + tid;
     const bool via_tma = use_tma && a.n - e0 >= kDeltaTile;
@@ -440,9 +451,9 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
     double p[5];
     if (via_tma) {
       mbar_wait(&s_bar[stage], par);
-      const double* sp = s_par[stage];
+      const double* sp = s_par[stage] + tid * par_tid_stride;       // AoS: row tid; SoA: column tid
 #pragma unroll
-      for (int i = 0; i < 5; ++i) p[i] = a.layout == 0 ? sp[tid * 5 + i] : sp[i * kDeltaTile + tid];
+      for (int i = 0; i < 5; ++i) p[i] = sp[i * par_idx_stride];
     } else if (active) {
       load_pars(a, e, p);
     }
