@@ -75,6 +75,7 @@ def load_library():
             "mbb_set_lir_method": (i32, [vp, i32]),
             "mbb_set_bands": (i32, [vp, i32, vp, vp, vp, vp]),
             "mbb_set_data": (i32, [vp, i32, i32, vp, vp, vp]),
+            "mbb_set_data_chol": (i32, [vp, i32, i32, vp, vp]),
             "mbb_set_priors": (i32, [vp, vp, vp, vp, vp, vp, vp]),
             "mbb_loglike": (i32, [vp, i64, vp, i32, vp, i64, vp, vp, i32]),
             "mbb_fnu": (i32, [vp, i64, vp, i32, i32, vp, i32, vp, vp, i32]),
@@ -103,7 +104,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ctx_create",
                     "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
                     "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_lir_method", "mbb_set_bands",
-                    "mbb_set_data", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
+                    "mbb_set_data", "mbb_set_data_chol", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
                     "mbb_chain_post", "mbb_chain_flux", "mbb_ensemble_run", "mbb_ensemble_fit", "mbb_host_alloc", "mbb_host_free", "mbb_host_register",
                     "mbb_host_unregister", "mbb_fp64_peak"]
 
@@ -228,12 +229,21 @@ class Context(object):
         self._ck(self._lib.mbb_set_bands(self._h, nb, _ptr(off), _ptr(wv), _ptr(wt), _ptr(sp)))
         self.nbands = nb
 
-    def set_data(self, flux, ivar=None, cinv=None):
+    def set_data(self, flux, ivar=None, cinv=None, chol=None):
+        """Photometry of nsrc sources with exactly one of: inverse variances ``ivar`` [nsrc, nb],
+        inverse covariances ``cinv`` [nsrc, nb, nb], or lower Cholesky factors ``chol``
+        [nsrc, nb, nb] of the covariances (mbb_set_data_chol)."""
         flux = np.atleast_2d(_f64(flux))
         nsrc, nb = flux.shape
-        iv = None if ivar is None else np.atleast_2d(_f64(ivar))
-        ci = None if cinv is None else _f64(cinv).reshape(nsrc, nb, nb)
-        self._ck(self._lib.mbb_set_data(self._h, nsrc, nb, _ptr(flux), _ptr(iv), _ptr(ci)))
+        if sum(a is not None for a in (ivar, cinv, chol)) != 1:
+            raise ValueError("give exactly one of ivar / cinv / chol")
+        if chol is not None:
+            ch = _f64(chol).reshape(nsrc, nb, nb)
+            self._ck(self._lib.mbb_set_data_chol(self._h, nsrc, nb, _ptr(flux), _ptr(ch)))
+        else:
+            iv = None if ivar is None else np.atleast_2d(_f64(ivar))
+            ci = None if cinv is None else _f64(cinv).reshape(nsrc, nb, nb)
+            self._ck(self._lib.mbb_set_data(self._h, nsrc, nb, _ptr(flux), _ptr(iv), _ptr(ci)))
         self.nsrc = nsrc
 
     def set_priors(self, lowlim, has_uplim, uplim, has_gprior, gmean, givar):

@@ -123,6 +123,7 @@ class batch_fitter(object):
         self._fixed = [False] * 5
         self._steps_done = 0
         self._flux = None
+        self._ivar = self._cinv = self._chol = None
 
     @property
     def nwalkers(self):
@@ -150,10 +151,11 @@ class batch_fitter(object):
         idx = self.like._param_order[param.lower()] if isinstance(param, str) else int(param)
         self._fixed[idx] = True
 
-    def set_data(self, bands, flux, flux_unc=None, covmatrix=None):
+    def set_data(self, bands, flux, flux_unc=None, covmatrix=None, cholesky=False):
         """bands: wavelengths [um] or response names (shared by all sources);
         flux[nsrc][nb] in mJy; exactly one of flux_unc[nsrc][nb] and
-        covmatrix[nsrc][nb][nb]."""
+        covmatrix[nsrc][nb][nb].  ``cholesky``: factor the covariances once on the host and let
+        the device form |L^-1 diff|^2 (mbb_set_data_chol) instead of using explicit inverses."""
         if (flux_unc is None) == (covmatrix is None):
             raise ValueError("give exactly one of flux_unc and covmatrix")
         flux = np.atleast_2d(np.asarray(flux, dtype=np.float64))
@@ -161,7 +163,8 @@ class batch_fitter(object):
         if covmatrix is not None:
             cov = np.asarray(covmatrix, dtype=np.float64).reshape(nsrc, nb, nb)
             unc0 = np.sqrt(np.diagonal(cov[0]))
-            self._cinv = np.linalg.inv(cov)
+            self._chol = np.linalg.cholesky(cov) if cholesky else None
+            self._cinv = None if cholesky else np.linalg.inv(cov)
             self._ivar = None
         else:
             unc = np.atleast_2d(np.asarray(flux_unc, dtype=np.float64))
@@ -169,7 +172,7 @@ class batch_fitter(object):
                 raise ValueError("flux_unc must have the shape of flux")
             unc0 = unc[0]
             self._ivar = 1.0 / unc**2
-            self._cinv = None
+            self._cinv = self._chol = None
         # the template likelihood sees source 0 (sets bands, lambda0 auto-limit)
         self.like.set_phot(bands, flux[0], unc0)
         self._flux = flux
@@ -191,7 +194,9 @@ class batch_fitter(object):
         ctx.set_model(like.wavenorm, like.opthin, like.noalpha)
         ctx.set_math_mode(like.math_mode)
         ctx.set_bands(*like.band_tables())
-        if self._cinv is not None:
+        if self._chol is not None:
+            ctx.set_data(self._flux[lo:hi], chol=self._chol[lo:hi])
+        elif self._cinv is not None:
             ctx.set_data(self._flux[lo:hi], cinv=self._cinv[lo:hi])
         else:
             ctx.set_data(self._flux[lo:hi], ivar=self._ivar[lo:hi])

@@ -117,6 +117,7 @@ struct mbb_ctx {
   int nsrc = 0, data_nb = 0;
   DevBuf<double> d_flux, d_ivar, d_cinv;
   bool has_ivar = false, has_cinv = false;
+  bool cinv_is_chol = false;      // d_cinv holds Cholesky factors (mbb_set_data_chol)
 
   Priors pri;
 
@@ -767,7 +768,7 @@ int mbb_set_data(mbb_ctx* c, int nsrc, int nbands, const double* flux, const dou
   const size_t n1 = (size_t)nsrc * nbands;
   CK(c->d_flux.reserve(n1 + 2));      // +2: the delta kernel's bulk copies round up to 16 bytes
   CK(cudaMemcpy(c->d_flux.p, flux, n1 * sizeof(double), cudaMemcpyHostToDevice));
-  c->has_ivar = c->has_cinv = false;
+  c->has_ivar = c->has_cinv = c->cinv_is_chol = false;
   if (ivar) {
     CK(c->d_ivar.reserve(n1 + 2));
     CK(cudaMemcpy(c->d_ivar.p, ivar, n1 * sizeof(double), cudaMemcpyHostToDevice));
@@ -781,6 +782,31 @@ int mbb_set_data(mbb_ctx* c, int nsrc, int nbands, const double* flux, const dou
   c->nsrc = nsrc;
   c->data_nb = nbands;
   c->gen++;
+  return 0;
+}
+
+int mbb_set_data_chol(mbb_ctx* c, int nsrc, int nbands, const double* flux, const double* chol) {
+  if (!c) return fail("null context");
+  if (nsrc <= 0 || nbands <= 0) return fail("nsrc and nbands must be positive");
+  if (!flux || !chol) return fail("flux / chol is NULL");
+  // staged form: strictly lower triangle = L, diagonal = 1/L_rr, upper triangle zero
+  const size_t nb = (size_t)nbands, n2 = (size_t)nsrc * nb * nb;
+  std::vector<double> lhat(n2, 0.0);
+  for (size_t s = 0; s < (size_t)nsrc; ++s) {
+    const double* L = chol + s * nb * nb;
+    double* H = lhat.data() + s * nb * nb;
+    for (size_t r = 0; r < nb; ++r) {
+      const double d = L[r * nb + r];
+      if (!(d > 0.0) || !std::isfinite(d)) return fail("Cholesky factor with a non-positive or non-finite diagonal");
+      H[r * nb + r] = 1.0 / d;
+      for (size_t cc = 0; cc < r; ++cc) {
+        if (!std::isfinite(L[r * nb + cc])) return fail("non-finite entry in a Cholesky factor");
+        H[r * nb + cc] = L[r * nb + cc];
+      }
+    }
+  }
+  if (mbb_set_data(c, nsrc, nbands, flux, nullptr, lhat.data()) != 0) return -1;
+  c->cinv_is_chol = true;
   return 0;
 }
 
@@ -823,6 +849,7 @@ int launch_loglike(mbb_ctx* c, cudaStream_t st, const EvalArgs& a_in) {
   d.flux = c->d_flux.p;
   d.ivar = c->has_ivar ? c->d_ivar.p : nullptr;
   d.cinv = c->has_cinv ? c->d_cinv.p : nullptr;
+  d.chol = c->has_cinv && c->cinv_is_chol ? 1 : 0;
   d.nsrc = c->nsrc;
   d.nb = c->nb;
   const bool thin = c->opthin != 0, alpha = c->noalpha == 0, fast = c->math_mode != MBB_MATH_FAITHFUL;
@@ -1362,6 +1389,7 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
   dref.flux = c->d_flux.p;
   dref.ivar = c->has_ivar ? c->d_ivar.p : nullptr;
   dref.cinv = c->has_cinv ? c->d_cinv.p : nullptr;
+  dref.chol = c->has_cinv && c->cinv_is_chol ? 1 : 0;
   dref.nsrc = c->nsrc;
   dref.nb = c->nb;
 

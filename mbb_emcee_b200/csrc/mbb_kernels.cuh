@@ -60,6 +60,7 @@ struct DataRef {
   const double* flux;   // [nsrc][nb]
   const double* ivar;   // [nsrc][nb] or null
   const double* cinv;   // [nsrc][nb][nb] or null
+  int chol;             // cinv holds Cholesky factors (strictly lower = L, diagonal = 1/L_rr)
   int nsrc;
   int nb;
 };
@@ -211,7 +212,7 @@ loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const D
   int st;
   const double lnl = loglike_one<THIN, ALPHA, FAST>(
       p, m, pr, t, d.flux + src * d.nb, d.ivar ? d.ivar + src * d.nb : nullptr,
-      d.cinv ? d.cinv + src * (long long)d.nb * d.nb : nullptr, st);
+      d.cinv ? d.cinv + src * (long long)d.nb * d.nb : nullptr, st, d.chol != 0);
   a.out[e] = lnl;
   if (a.status) a.status[e] = st;
 }
@@ -236,9 +237,9 @@ loglike_thread_kernel(const EvalArgs a, const ModelP m, const Priors pr, const D
 template <bool THIN, bool ALPHA>
 __device__ __noinline__ double delta_eval_cold(double p0, double p1, double p2, double p3, double p4,
                                                const ColdArgs* __restrict__ cold, const double* flux,
-                                               const double* ivar, const double* cinv, int* st) {
+                                               const double* ivar, const double* cinv, int chol, int* st) {
   const double p[5] = {p0, p1, p2, p3, p4};
-  return loglike_one<THIN, ALPHA, true>(p, cold->m, cold->pr, cold->t, flux, ivar, cinv, *st);
+  return loglike_one<THIN, ALPHA, true>(p, cold->m, cold->pr, cold->t, flux, ivar, cinv, *st, chol != 0);
 }
 
 template <bool THIN>
@@ -312,7 +313,7 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
     int st_cold = ST_OK;
     const double r = delta_eval_cold<THIN, ALPHA>(p[0], p[1], p[2], p[3], p[4], cold, d.flux + src * NB,
                                                   d.cinv ? nullptr : d.ivar + src * NB,
-                                                  d.cinv ? d.cinv + src * (NB * NB) : nullptr, &st_cold);
+                                                  d.cinv ? d.cinv + src * (NB * NB) : nullptr, d.chol, &st_cold);
     st = st_cold;
     return r;
   }
@@ -326,12 +327,24 @@ __device__ __forceinline__ double delta_eval(const double p[5], long long src, d
   }
   if (d.cinv) {
     const double* __restrict__ ci = d.cinv + src * (NB * NB);
+    if (d.chol) {            // |L^-1 diff|^2, forward substitution in registers
 #pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      double row = 0.0;
+      for (int r = 0; r < NB; ++r) {
+        double acc = diff[r];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
-      chi = fma(diff[r], row, chi);
+        for (int c = 0; c < r; ++c) acc = fma(-__ldg(ci + r * NB + c), diff[c], acc);
+        acc *= __ldg(ci + r * NB + r);
+        diff[r] = acc;
+        chi = fma(acc, acc, chi);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < NB; ++r) {
+        double row = 0.0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) row = fma(__ldg(ci + r * NB + c), diff[c], row);
+        chi = fma(diff[r], row, chi);
+      }
     }
   } else if (iv_smem) {          // the tile's photometry rows were staged by TMA
 #pragma unroll
@@ -766,12 +779,25 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
       __syncwarp();
       const double* ci = d.cinv + src * (long long)nb * nb;
       double part = 0.0;
-      for (int r = lane; r < nb; r += 32) {
-        double row = 0.0;
-        for (int cc = 0; cc < nb; ++cc) row = fma(__ldg(ci + r * nb + cc), wdiff[cc], row);
-        part = fma(wdiff[r], row, part);
+      if (d.chol) {          // forward substitution is serial in the rows: lane 0, in place
+        if (lane == 0) {
+          for (int r = 0; r < nb; ++r) {
+            double acc = wdiff[r];
+            for (int cc = 0; cc < r; ++cc) acc = fma(-__ldg(ci + r * nb + cc), wdiff[cc], acc);
+            acc *= __ldg(ci + r * nb + r);
+            wdiff[r] = acc;
+            part = fma(acc, acc, part);
+          }
+        }
+        chi = __shfl_sync(0xffffffffu, part, 0);
+      } else {
+        for (int r = lane; r < nb; r += 32) {
+          double row = 0.0;
+          for (int cc = 0; cc < nb; ++cc) row = fma(__ldg(ci + r * nb + cc), wdiff[cc], row);
+          part = fma(wdiff[r], row, part);
+        }
+        chi = warp_sum(part);
       }
-      chi = warp_sum(part);
       __syncwarp();
     }
     if (lane == 0) {

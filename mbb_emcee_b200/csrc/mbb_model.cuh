@@ -1062,9 +1062,33 @@ struct TabView {
 constexpr int kMaxBandsPerThread = 64;
 
 // chi-square of one evaluation given a callable returning the weighted node term
+// Quadratic form of a full covariance: diff' inv(C) diff with the explicit inverse (what the
+// reference does, likelihood.py:356, 823), or |L^-1 diff|^2 by forward substitution when the
+// caller staged the Cholesky factor C = L L' (mbb_set_data_chol: strictly lower triangle = L,
+// diagonal = 1/L_rr; `diff` is overwritten with L^-1 diff).
+MBB_HD double quad_form(const double* m, double* diff, int nb, bool chol) {
+  double chi = 0.0;
+  if (chol) {
+    for (int r = 0; r < nb; ++r) {
+      double acc = diff[r];
+      for (int c = 0; c < r; ++c) acc = fma(-m[r * nb + c], diff[c], acc);
+      acc *= m[r * nb + r];
+      diff[r] = acc;
+      chi = fma(acc, acc, chi);
+    }
+    return chi;
+  }
+  for (int r = 0; r < nb; ++r) {
+    double row = 0.0;
+    for (int c = 0; c < nb; ++c) row = fma(m[r * nb + c], diff[c], row);
+    chi = fma(diff[r], row, chi);
+  }
+  return chi;
+}
+
 template <class Tab, class NodeFn>
 MBB_HD double chi_square(const Tab& t, const double* flux, const double* ivar, const double* cinv,
-                         NodeFn node) {
+                         NodeFn node, bool chol = false) {
   const int nb = t.nb;
   double chi = 0.0;
   if (!cinv) {
@@ -1082,12 +1106,7 @@ MBB_HD double chi_square(const Tab& t, const double* flux, const double* ivar, c
     for (int i = t.band_off[b]; i < t.band_off[b + 1]; ++i) acc = node(b, i, acc);
     diff[b] = flux[b] - acc;
   }
-  for (int r = 0; r < nb; ++r) {
-    double row = 0.0;
-    for (int c = 0; c < nb; ++c) row = fma(cinv[r * nb + c], diff[c], row);
-    chi = fma(diff[r], row, chi);
-  }
-  return chi;
+  return quad_form(cinv, diff, nb, chol);
 }
 
 // FAST evaluations here always run the saturating (CLAMP) node code: this is
@@ -1095,7 +1114,8 @@ MBB_HD double chi_square(const Tab& t, const double* flux, const double* ivar, c
 // walkers handed over by the specialised kernels).
 template <bool THIN, bool ALPHA, bool FAST, class Tab>
 MBB_HD double loglike_one(const double p[5], const ModelP& m, const Priors& pr, const Tab& t,
-                          const double* flux, const double* ivar, const double* cinv, int& st) {
+                          const double* flux, const double* ivar, const double* cinv, int& st,
+                          bool chol = false) {
   st = ST_OK;
   if (below_lowlim(pr, p)) {
     st = ST_BELOW_LOWLIM;
@@ -1111,7 +1131,7 @@ MBB_HD double loglike_one(const double p[5], const ModelP& m, const Priors& pr, 
     if (st != ST_OK) return nan;
     chi = chi_square(t, flux, ivar, cinv, [&](int, int i, double acc) {
       return node_acc<THIN, ALPHA, true, 0>(s, t.freq[i], t.lp[i], t.weff[i], acc, tab);
-    });
+    }, chol);
     prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
   } else {
     Sed s;
@@ -1120,7 +1140,7 @@ MBB_HD double loglike_one(const double p[5], const ModelP& m, const Priors& pr, 
     if (st != ST_OK) return nan;
     chi = chi_square(t, flux, ivar, cinv, [&](int b, int i, double acc) {
       return fma(node_fnu<THIN, ALPHA>(s, (t.scalar_path[b] ? s.hokt_e9 : s.hokt9) * t.freq[i]), t.w[i], acc);
-    });
+    }, chol);
     prior_terms<THIN>(pr, p, s.T, s.beta, s.x0, pen, gp, st);
   }
   double lnl = -0.5 * chi;

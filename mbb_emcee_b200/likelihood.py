@@ -61,6 +61,7 @@ class likelihood(object):
         self._ctx = None
         self._dirty = True
         self._math_mode = _native.MATH_FAST
+        self._cov_solver = "inverse"
 
         self._response_integrate = False
         if response:
@@ -258,6 +259,23 @@ class likelihood(object):
         self.set_cov(hdu[extn].data)
 
     @property
+    def cov_solver(self):
+        """How the chi-square of a full covariance is formed on the device (extension):
+        ``"inverse"`` (default) -- diff . inv(C) . diff with the explicit inverse, the
+        reference's arithmetic (likelihood.py:356, 823); ``"cholesky"`` -- the covariance is
+        factored once on the host, C = L L', and the device forms |L^-1 diff|^2 by forward
+        substitution (no inverse is ever formed).  The two agree to ~cond(C) * 1e-16."""
+        return self._cov_solver
+
+    @cov_solver.setter
+    def cov_solver(self, value):
+        if value not in ("inverse", "cholesky"):
+            raise ValueError("cov_solver must be 'inverse' or 'cholesky'")
+        if value != self._cov_solver:
+            self._cov_solver = value
+            self._dirty = True
+
+    @property
     def has_data_covmatrix(self):
         return self._has_covmatrix
 
@@ -388,7 +406,9 @@ class likelihood(object):
         ctx.set_model(self._wavenorm, self._opthin, self._noalpha)
         ctx.set_math_mode(self._math_mode)
         ctx.set_bands(*self.band_tables())
-        if self._has_covmatrix:
+        if self._has_covmatrix and self._cov_solver == "cholesky":
+            ctx.set_data(self._flux, chol=np.linalg.cholesky(np.asarray(self._covmatrix, dtype=np.float64)))
+        elif self._has_covmatrix:
             ctx.set_data(self._flux, cinv=self._invcovmatrix)
         else:
             ctx.set_data(self._flux, ivar=self._ivar)

@@ -71,6 +71,9 @@ def build_parser():
     a("--responsedir", default=None, help="response specification directory")
     a("-t", "--threads", type=int, default=1, help="must be 1 on the device path")
     a("--math", default="fast", choices=["fast", "faithful", "gauss"], help="device arithmetic mode")
+    a("--covsolver", default="inverse", choices=["inverse", "cholesky"],
+      help="chi-square of a covariance matrix: explicit inverse like the reference (def), or its Cholesky factor")
+    a("--version", action="version", version="mbb_emcee_b200 " + __import__("mbb_emcee_b200").__version__)
     a("--seed", type=int, default=None, help="seed of the initial ensemble and of the sampler")
     a("-v", "--verbose", action="store_true", help="print status messages")
     a("-w", "--wavenorm", type=float, default=500.0, help="normalisation wavelength [um] (def: 500)")
@@ -126,6 +129,7 @@ def main(argv=None):
                      response=args.response, responsefile=args.responsefile, responsedir=args.responsedir)
     fit.like.math_mode = {"faithful": _native.MATH_FAITHFUL, "fast": _native.MATH_FAST,
                           "gauss": _native.MATH_FAST_GAUSS}[args.math]
+    fit.like.cov_solver = args.covsolver
     if args.seed is not None and hasattr(fit.sampler, "random_state"):
         fit.sampler.random_state = np.random.RandomState(args.seed + 1).get_state()
     configure_fit(fit, args)

@@ -366,6 +366,13 @@ void emu_fastmath(int mode, long long n, const double* x, double* out) {
   else run_fastmath<0>(mode, n, x, out);
 }
 
+// chi-square of a full covariance from the staged matrix (explicit inverse, or the Cholesky form
+// of mbb_set_data_chol: strictly lower triangle = L, diagonal = 1/L_rr) -- the device's quad_form
+double emu_quad_form(const double* m, const double* diff, int nb, int chol) {
+  std::vector<double> d(diff, diff + nb);
+  return quad_form(m, d.data(), nb, chol != 0);
+}
+
 void emu_grey_nodes(int thin, long long n, const double* pars, double wavenorm, const double* wave,
                     const double* weight, double* out_single, double* out_group, int* safe) {
   if (thin) run_grey<true>(n, pars, wavenorm, wave, weight, out_single, out_group, safe);

@@ -78,6 +78,14 @@ def loglike(opthin, noalpha, fast, pars, wavenorm, ep, band_off, wave, weight, s
     return out, st
 
 
+def quad_form(m, diff, chol):
+    """diff' inv(C) diff from the staged matrix, as the device forms it (mbb_model.cuh quad_form)."""
+    m, diff = _c(m), _c(diff)
+    f = lib().emu_quad_form
+    f.restype = ctypes.c_double
+    return float(f(_p(m), _p(diff), int(diff.size), int(bool(chol))))
+
+
 def last_compressed():
     """(walker, band) pairs the last loglike(fast=3) call evaluated with a compressed rule."""
     f = lib().emu_last_compressed

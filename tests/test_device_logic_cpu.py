@@ -445,3 +445,38 @@ def test_qags_matches_scipy(golden):
             got, nev, st = emu.qags(opthin, noalpha, g[tag + "_P"][m], wn, 24.0, 3000.0)
             assert (st == 0).all()
             assert relerr(got, ref[m]).max() < 1e-15
+
+
+def test_cholesky_quadratic_form_vs_exact():
+    """chi-square of a full covariance: the device's two forms (explicit inverse like the
+    reference's likelihood.py:356/823; forward substitution with the Cholesky factor staged by
+    mbb_set_data_chol) against the exact value from 50-digit arithmetic, on cfg3's 8x8
+    covariance and on an ill-conditioned one (cond ~1e9): either form is good to a small multiple
+    of cond(C) * 2^-53 (the factorisation / inversion of the host carries that much), far inside
+    1e-12 for covariances like cfg3's."""
+    import mpmath as mp
+    from mbb_emcee_b200 import synthetic
+    mp.mp.dps = 50
+    rng = np.random.RandomState(5)
+    covs = [np.asarray(synthetic.sample_problem("cfg3", 1)[3], dtype=np.float64)]
+    a = rng.normal(size=(8, 8))
+    covs.append(a @ np.diag(10.0 ** np.linspace(0, 9, 8)) @ a.T)
+    for cov in covs:
+        cond = np.linalg.cond(cov)
+        nb = cov.shape[0]
+        L = np.linalg.cholesky(cov)
+        staged = np.tril(L, -1) + np.diag(1.0 / np.diag(L))
+        cinv = np.linalg.inv(cov)
+        Cm = mp.matrix(cov.tolist())
+        worst_ch = worst_inv = 0.0
+        for _ in range(20):
+            diff = rng.normal(size=nb) * np.sqrt(np.diag(cov))
+            exact = (mp.matrix(diff.tolist()).T * mp.lu_solve(Cm, mp.matrix(diff.tolist())))[0]
+            ch = emu.quad_form(staged, diff, True)
+            iv = emu.quad_form(cinv, diff, False)
+            worst_ch = max(worst_ch, float(abs(ch - exact) / exact))
+            worst_inv = max(worst_inv, float(abs(iv - exact) / exact))
+        assert worst_ch < 2e-16 * max(cond, 8.0), (cond, worst_ch)
+        assert worst_inv < 2e-16 * max(cond, 8.0), (cond, worst_inv)
+        if cond < 1e4:
+            assert worst_ch < 1e-13 and worst_inv < 1e-13

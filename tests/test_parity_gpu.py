@@ -271,6 +271,84 @@ def test_multi_source_covariance_delta_kernel(oracle):
         assert np.array_equal(out["pos"], r[0]) and relerr(out["lnprob"], r[1]).max() < TOL
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_cholesky_covariance_golden(golden, mode):
+    """Cholesky-prefactored covariance (north star (3); mbb_set_data_chol replaces
+    likelihood.py:356 + :823): cfg3's golden log-likelihoods (8x8 covariance, the nodes kernel's
+    warp path) and the survey's extra vector (6 delta bands, thread kernel: lambda_peak terms)
+    within 1e-12, and within cond(C) * 1e-15 of the explicit-inverse path."""
+    from mbb_emcee_b200 import likelihood
+    g = golden.like
+    cfg, like = _make_like(golden, "cfg3", mode)
+    P, ref = g["cfg3_P"], g["cfg3_lnlike"]
+    ll_inv, _ = like.evaluate(P)
+    like.cov_solver = "cholesky"
+    ll, st = like.evaluate(P)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref)) and (st <= 1).all()
+    assert relerr(ll[fin], ref[fin]).max() < TOL
+    assert not np.array_equal(ll[fin], ll_inv[fin])          # a different arithmetic did run
+    assert relerr(ll[fin], ll_inv[fin]).max() < 1e-15 * np.linalg.cond(like.data_covmatrix)
+    like.cov_solver = "inverse"
+    assert np.array_equal(like.evaluate(P)[0][fin], ll_inv[fin])
+    if mode == 2:
+        return
+    like = likelihood(wavenorm=500.0, device=0)
+    like.math_mode = mode
+    like.cov_solver = "cholesky"
+    like.set_phot(g["extra_wave"], g["extra_flux"], g["extra_unc"])
+    like.set_cov(g["extra_cov"])
+    like.set_gaussian_prior('beta', 1.8, 0.3)
+    like.set_uplim('lambda_peak', 300.0)
+    like.set_gaussian_prior('lambda_peak', 250.0, 40.0)
+    assert relerr(like(g["extra_P"]), g["extra_lnlike"]).max() < TOL
+
+
+def test_cholesky_multi_source_delta_and_sampler(oracle):
+    """Per-source Cholesky factors through the delta kernel (forward substitution in
+    registers) and the resident sampler, against the oracle's inv(C) arithmetic; bad factors
+    are refused."""
+    from mbb_emcee_b200 import _native, synthetic, batch_fitter
+    rng = np.random.RandomState(29)
+    nsrc, nw = 7, 64
+    waves = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0]
+    flux = rng.uniform(5, 80, (nsrc, 6))
+    unc = rng.uniform(1, 6, (nsrc, 6))
+    cov = np.stack([synthetic.cfg3_covariance(flux[s], unc[s], spire_idx=(3, 4, 5)) for s in range(nsrc)])
+    low = np.array([1, 0.1, 1, 0.1, 1e-3])
+    for opthin, noalpha in ((True, True), (False, False)):
+        ctx = _native.Context(0)
+        ctx.set_model(500.0, opthin, noalpha)
+        ctx.set_bands(np.arange(7, dtype=np.int32), waves, np.ones(6))
+        ctx.set_data(flux, chol=np.linalg.cholesky(cov))
+        truth = (12.0, 1.8, 1300.0, 4.0, 30.0) if opthin else (14.0, 1.8, 400.0, 3.0, 30.0)
+        P = synthetic.walker_cloud(truth, nsrc * nw, rng, low)
+        want = np.empty(nsrc * nw)
+        for s in range(nsrc):
+            spec = oracle.LikeSpec(500.0, noalpha, opthin)
+            spec.set_phot(waves, flux[s], unc[s])
+            spec.set_cov(cov[s])
+            want[s * nw:(s + 1) * nw] = oracle.loglike_batch(spec, P[s * nw:(s + 1) * nw])
+        got, st = ctx.loglike(P, walkers_per_source=nw)
+        assert (st == 0).all() and relerr(got, want).max() < TOL
+        ctx.set_data(flux, cinv=np.linalg.inv(cov))
+        inv, _ = ctx.loglike(P, walkers_per_source=nw)
+        assert not np.array_equal(inv, got) and relerr(inv, got).max() < 1e-13
+    bad = np.linalg.cholesky(cov)
+    bad[2, 3, 3] = -1.0
+    with pytest.raises(_native.MBBNativeError):
+        ctx.set_data(flux, chol=bad)
+    # a batch fit on factored covariances reproduces the explicit-inverse fit's posterior
+    fits = []
+    for cholesky in (False, True):
+        bf = batch_fitter(nwalkers=nw, opthin=True, noalpha=True, device=0)
+        bf.set_data(waves, flux, covmatrix=cov, cholesky=cholesky)
+        p0 = bf.generate_initial_values((15.0, 1.8, 1300.0, 4.0, 30.0), (2, 0.2, 100, 0.3, 5), seed=3)
+        fits.append(bf.run(20, 60, p0, seed=11))
+    a, b = fits
+    assert np.allclose(a.mean, b.mean, rtol=1e-6) and np.allclose(a.best_lnprob, b.best_lnprob, rtol=1e-9)
+
+
 def test_small_batch_graph_replay(golden, oracle):
     """Host-buffer calls with <= 8192 parameter vectors (the 125-walker half-steps of a
     single-source fit, reference mbb_fit.py:533-542) are replayed as one CUDA graph from the

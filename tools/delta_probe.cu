@@ -93,7 +93,7 @@ static int run(int nsrc, int reps) {
   a.pars = d_P; a.out = d_out; a.status = d_st; a.n = n; a.wps = nw; a.layout = 0;
   set_wps_division(a);
   DataRef d;
-  d.flux = d_flux; d.ivar = d_ivar; d.cinv = nullptr; d.nsrc = nsrc; d.nb = NB;
+  d.flux = d_flux; d.ivar = d_ivar; d.cinv = nullptr; d.chol = 0; d.nsrc = nsrc; d.nb = NB;
 
   int dev = 0, sms = 0;
   CK(cudaGetDevice(&dev));
