@@ -193,6 +193,22 @@ int mbb_chain_flux(mbb_ctx *ctx, int64_t nwalkers, int64_t nsteps,
                    const double *chain, int band, double *out_flux,
                    int32_t *out_status, int mem);
 
+/* ---- chain statistics: what mbb_results._parcen_internal / par_lowlim /
+ * par_uplim / *_cen take from numpy.mean and numpy.percentile over the flattened
+ * chain (results.py:314-431, 946-985).  x[n][ncols] row-major (ncols <= 8: the
+ * parameter block of a chain, or one ancillary array with ncols = 1); values
+ * outside [lowlim[c], uplim[c]] are dropped (NULL = no limit).  Per column:
+ * count of kept values, their mean, and for each of the nq <= 4 quantiles q in
+ * [0, 1] the two order statistics around numpy's default ('linear') virtual
+ * index (count-1) q and its fractional part gamma, so that the caller forms
+ * lo + (hi - lo) gamma exactly as numpy does.  Order statistics are exact (radix
+ * selection); a column holding a NaN gives NaN like numpy; an empty column gives
+ * count 0 and NaN.  Outputs are host arrays; `mem` describes x. */
+int mbb_chain_stats(mbb_ctx *ctx, int64_t n, int ncols, const double *x,
+                    const double *lowlim, const double *uplim, int nq,
+                    const double *q, double *mean, int64_t *count,
+                    double *q_lo, double *q_hi, double *q_gamma, int mem);
+
 /* ---- batch fit: device-resident ensemble sampler for nsrc sources at once (SURVEY 8f
  * row 1, BASELINE configs[4]): what mbb_fitter.run asks emcee for per source
  * (mbb_fit.py:524-543: burn-in, sampler.reset(), main run -> emcee 2.2 stretch move, two

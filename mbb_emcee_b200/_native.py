@@ -83,6 +83,7 @@ def load_library():
             "mbb_chain_post": (i32, [vp, i64, i64, vp, i32, dbl, dbl, dbl, dbl, dbl, dbl,
                                      vp, vp, vp, vp, i32]),
             "mbb_chain_flux": (i32, [vp, i64, i64, vp, i32, vp, vp, i32]),
+            "mbb_chain_stats": (i32, [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32]),
             "mbb_ensemble_run": (i32, [vp, i64, i32, i64, dbl, ctypes.c_uint64, ctypes.c_uint64, vp, vp,
                                        i32, vp, vp, vp, vp, i32, i32]),
             "mbb_ensemble_fit": (i32, [vp, i64, i32, i64, i64, dbl, ctypes.c_uint64, ctypes.c_uint64, i64,
@@ -105,7 +106,7 @@ EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ct
                     "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
                     "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_lir_method", "mbb_set_bands",
                     "mbb_set_data", "mbb_set_data_chol", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
-                    "mbb_chain_post", "mbb_chain_flux", "mbb_ensemble_run", "mbb_ensemble_fit", "mbb_host_alloc", "mbb_host_free", "mbb_host_register",
+                    "mbb_chain_post", "mbb_chain_flux", "mbb_chain_stats", "mbb_ensemble_run", "mbb_ensemble_fit", "mbb_host_alloc", "mbb_host_free", "mbb_host_register",
                     "mbb_host_unregister", "mbb_fp64_peak"]
 
 # layout of one row of mbb_ensemble_fit's per-source summary (include/mbb_b200.h MBB_FS_*)
@@ -354,6 +355,46 @@ class Context(object):
         st = np.empty((nw, ns), dtype=np.int32)
         self._ck(self._lib.mbb_chain_flux(self._h, nw, ns, _ptr(chain), int(band), _ptr(out), _ptr(st), HOST))
         return out, st
+
+    def chain_stats(self, x, percentiles=(), lowlim=None, uplim=None, where=HOST, nrows=None, ncols=None):
+        """Mean and percentiles of the columns of x[n][ncols] (or x[n]) on the device
+        (mbb_chain_stats), clipped to [lowlim, uplim] per column.  Returns (mean[ncols],
+        count[ncols], perc[ncols][len(percentiles)]) with the percentiles formed from the two
+        bracketing order statistics exactly as numpy.percentile's default method does
+        (numpy/lib/_function_base_impl.py _lerp), so they equal numpy's bit for bit.
+        ``where=DEVICE``: x is a device pointer (int) and nrows / ncols give its shape."""
+        if where == HOST:
+            x = _f64(x)
+            if x.ndim == 1:
+                x = x.reshape(-1, 1)
+            n, nc = x.shape
+            xp = _ptr(x)
+        else:
+            n, nc, xp = int(nrows), int(ncols), ctypes.c_void_p(int(x))
+        q = np.true_divide(_f64(np.atleast_1d(percentiles)), 100)
+        nq = int(q.size)
+
+        def lim(v, fill):
+            if v is None:
+                return None
+            a = np.full(nc, fill, dtype=np.float64)
+            vv = np.atleast_1d(v)
+            for i in range(nc):
+                if vv[min(i, vv.size - 1)] is not None:
+                    a[i] = float(vv[min(i, vv.size - 1)])
+            return a
+        lo, hi = lim(lowlim, -np.inf), lim(uplim, np.inf)
+        mean = np.empty(nc)
+        count = np.empty(nc, dtype=np.int64)
+        qlo, qhi, gam = (np.empty((nc, nq)) for _ in range(3))
+        self._ck(self._lib.mbb_chain_stats(self._h, n, nc, xp, _ptr(lo), _ptr(hi), nq, _ptr(q), _ptr(mean),
+                                           _ptr(count), _ptr(qlo), _ptr(qhi), _ptr(gam), where))
+        # numpy's _lerp: a + (b - a) t, and b - (b - a)(1 - t) where t >= 0.5
+        diff = qhi - qlo
+        perc = qlo + diff * gam
+        with np.errstate(invalid="ignore"):
+            perc = np.where(gam >= 0.5, qhi - diff * (1 - gam), perc)
+        return mean, count, perc
 
     def ensemble_run(self, pos, nsteps, seed=0, step0=0, a=2.0, lnprob=None):
         """Device-resident stretch-move sampler (host arrays in/out).

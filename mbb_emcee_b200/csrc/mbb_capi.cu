@@ -13,6 +13,7 @@
 #include "mbb_gaussrule.h"
 #include "mbb_gausskernel.cuh"
 #include "mbb_kernels.cuh"
+#include "mbb_chainstats.cuh"
 
 using namespace mbb;
 
@@ -143,6 +144,9 @@ struct mbb_ctx {
   DevBuf<double> d_in, d_out, d_aux0, d_aux1;
   DevBuf<int> d_st, d_src, d_owner, d_work;
   DevBuf<unsigned> d_count;
+  DevBuf<unsigned long long> d_stat_cnt;     // mbb_chain_stats: counts, NaN counts
+  DevBuf<double> d_stat_part;
+  DevBuf<unsigned> d_stat_hist;
   // ensemble sampler scratch
   // per-stream scratch of the split warp path (main stream + 3 pipeline slots)
   struct Scratch {
@@ -1349,6 +1353,125 @@ int mbb_chain_flux(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
       CK(cudaMemcpyAsync(out_status, dst, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
+  return 0;
+}
+
+int mbb_chain_stats(mbb_ctx* c, int64_t n, int ncols, const double* x, const double* lowlim,
+                    const double* uplim, int nq, const double* q, double* mean, int64_t* count,
+                    double* q_lo, double* q_hi, double* q_gamma, int mem) {
+  if (!c) return fail("null context");
+  if (n <= 0 || ncols <= 0 || ncols > kStatMaxCols) return fail("n must be positive and 1 <= ncols <= 8");
+  if (nq < 0 || 2 * nq > kStatMaxSel) return fail("at most 4 quantiles per call");
+  if (!x || !mean || !count || (nq > 0 && (!q || !q_lo || !q_hi || !q_gamma))) return fail("null pointer");
+  if (n >= (int64_t)1 << 32) return fail("more than 2^32 rows; shard the chain");
+  for (int i = 0; i < nq; ++i)
+    if (!(q[i] >= 0.0 && q[i] <= 1.0)) return fail("quantiles must lie in [0, 1]");
+  Use u(c);
+  const long long total = (long long)n * ncols;
+  const double* dx = x;
+  if (mem != MBB_DEVICE) {
+    CK(c->d_in.reserve((size_t)total));
+    CK(cudaMemcpyAsync(c->d_in.p, x, (size_t)total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dx = c->d_in.p;
+  }
+  StatCols sc;
+  sc.ncols = ncols;
+  for (int k = 0; k < kStatMaxCols; ++k) {
+    sc.lo[k] = (lowlim && k < ncols) ? lowlim[k] : -kInf;
+    sc.hi[k] = (uplim && k < ncols) ? uplim[k] : kInf;
+  }
+  const long long want = (n + 255) / 256, cap = (long long)c->sm_count * 8;
+  const unsigned gx = (unsigned)(want < cap ? want : cap);
+  const dim3 grid(gx, (unsigned)ncols);
+  CK(c->d_stat_cnt.reserve(2 * kStatMaxCols));
+  CK(c->d_stat_part.reserve((size_t)ncols * gx));
+  CK(c->d_stat_hist.reserve((size_t)kStatMaxCols * kStatMaxSel * 256));
+  CK(cudaMemsetAsync(c->d_stat_cnt.p, 0, 2 * kStatMaxCols * sizeof(unsigned long long), c->stream));
+  begin_timing(c);
+  chain_moments_kernel<<<grid, 256, 0, c->stream>>>(dx, total, sc, c->d_stat_cnt.p, c->d_stat_cnt.p + kStatMaxCols,
+                                                    c->d_stat_part.p);
+  c->launches += 1;
+  unsigned long long h_cnt[2 * kStatMaxCols];
+  std::vector<double> h_part((size_t)ncols * gx);
+  CK(cudaMemcpyAsync(h_cnt, c->d_stat_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(h_part.data(), c->d_stat_part.p, h_part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const double nan = kInf - kInf;
+  // wanted ranks: numpy's default 'linear' quantile -- virtual index (count - 1) q formed as
+  // count q + (1 + q (-1)) - 1, neighbours floor and floor + 1, clipped to the ends
+  struct Sel { unsigned long long rank, prefix, rem; };
+  Sel sel[kStatMaxCols][kStatMaxSel];
+  int nsel[kStatMaxCols];
+  for (int col = 0; col < ncols; ++col) {
+    const unsigned long long cnt = h_cnt[col], bad = h_cnt[kStatMaxCols + col];
+    count[col] = (int64_t)cnt;
+    long double acc = 0.0L;
+    for (unsigned b = 0; b < gx; ++b) acc += (long double)h_part[(size_t)col * gx + b];
+    mean[col] = (cnt && !bad) ? (double)(acc / (long double)cnt) : nan;
+    nsel[col] = 0;
+    for (int i = 0; i < nq; ++i) {
+      q_lo[col * nq + i] = q_hi[col * nq + i] = q_gamma[col * nq + i] = nan;
+      if (!cnt || bad) continue;                      // numpy: NaN in -> NaN out; empty -> caller's error
+      const double vi = (double)cnt * q[i] + (1.0 + q[i] * (-1.0)) - 1.0;
+      double prev = floor(vi);
+      q_gamma[col * nq + i] = vi - prev;
+      double next = prev + 1.0;
+      if (vi >= (double)(cnt - 1)) prev = next = (double)(cnt - 1);
+      if (vi < 0.0) prev = next = 0.0;
+      sel[col][nsel[col]++] = Sel{(unsigned long long)prev, 0ull, (unsigned long long)prev};
+      sel[col][nsel[col]++] = Sel{(unsigned long long)next, 0ull, (unsigned long long)next};
+    }
+  }
+  std::vector<unsigned> h_hist((size_t)kStatMaxCols * kStatMaxSel * 256);
+  for (int shift = 56; shift >= 0 && nq > 0; shift -= 8) {
+    StatPass ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.shift = shift;
+    int group_of[kStatMaxCols][kStatMaxSel];
+    bool any = false;
+    for (int col = 0; col < ncols; ++col) {
+      int ng = 0;
+      for (int s = 0; s < nsel[col]; ++s) {
+        int g = -1;
+        for (int k = 0; k < ng; ++k)
+          if (ps.prefix[col][k] == sel[col][s].prefix) g = k;
+        if (g < 0) {
+          g = ng++;
+          ps.prefix[col][g] = sel[col][s].prefix;
+        }
+        group_of[col][s] = g;
+      }
+      ps.ngroups[col] = ng;
+      any = any || ng > 0;
+    }
+    if (!any) break;
+    CK(cudaMemsetAsync(c->d_stat_hist.p, 0, h_hist.size() * sizeof(unsigned), c->stream));
+    chain_select_hist_kernel<<<grid, 256, 0, c->stream>>>(dx, total, sc, ps, c->d_stat_hist.p);
+    c->launches += 1;
+    CK(cudaMemcpyAsync(h_hist.data(), c->d_stat_hist.p, h_hist.size() * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int col = 0; col < ncols; ++col)
+      for (int s = 0; s < nsel[col]; ++s) {
+        const unsigned* h = h_hist.data() + ((size_t)col * kStatMaxSel + group_of[col][s]) * 256;
+        unsigned long long rem = sel[col][s].rem;
+        int b = 0;
+        for (; b < 255; ++b) {
+          if (rem < h[b]) break;
+          rem -= h[b];
+        }
+        if (rem >= h[b]) return fail("mbb_chain_stats: rank outside the histogram (internal error)");
+        sel[col][s].rem = rem;
+        sel[col][s].prefix = (sel[col][s].prefix << 8) | (unsigned long long)b;
+      }
+  }
+  end_timing(c);
+  CK(cudaGetLastError());
+  for (int col = 0; col < ncols; ++col)
+    for (int s = 0; s < nsel[col]; ++s) {
+      const double v = stat_unkey(sel[col][s].prefix);
+      (s & 1 ? q_hi : q_lo)[col * nq + s / 2] = v;
+    }
   return 0;
 }
 

@@ -89,6 +89,12 @@ _ALMA_IF_BOTTOM = (4.0, 4.0, 6.0, 4.0, 4.0)
 _ALMA_SIDEBAND = 3.75
 
 
+def _as_str(v):
+    if isinstance(v, bytes):
+        return v.decode()
+    return str(v)
+
+
 class response(object):
     """Response of one instrument passband to an SED."""
 
@@ -362,6 +368,71 @@ class response(object):
         x = self._freq if freq else self._wave
         return (fnufunc(x) * self._sedmult).sum() * self._normfac
 
+    # ---------------------------------------------------------- serialisation
+    _ATTRS = (("Name", "_name"), ("IsDelta", "_isdelta"), ("NormWave", "_normwave"),
+              ("NormFreq", "_normfreq"), ("NormType", "_normtype"), ("NormFac", "_normfac"),
+              ("SensEnergy", "_sens_energy"), ("EffectiveFreq", "_effective_freq"),
+              ("EffectiveWave", "_effective_wave"), ("NResp", "_nresp"))
+    _DATA = (("Wave", "_wave"), ("Freq", "_freq"), ("Response", "_resp"))
+
+    def to_tree(self):
+        """Attributes and datasets under the reference's HDF5 names (reference
+        response.py:578-606); the carrier is chosen by treeio."""
+        from .treeio import new_tree
+        if not self._data_read:
+            raise ValueError("Data must be read to write the response")
+        t = new_tree()
+        for key, attr in self._ATTRS:
+            t["attrs"][key] = getattr(self, attr)
+        t["attrs"]["WaveUnits"] = "microns"
+        t["attrs"]["FreqUnits"] = "GHz"
+        if self._normparam is not None:
+            t["attrs"]["NormParam"] = self._normparam
+        for key, attr in self._DATA:
+            t["data"][key] = numpy.asarray(getattr(self, attr))
+        if not self._isdelta:
+            t["data"]["Dnu"] = numpy.asarray(self._dnu)
+            t["data"]["Sedmult"] = numpy.asarray(self._sedmult)
+        return t
+
+    def from_tree(self, t):
+        """Inverse of to_tree (reference response.py:608-635): tables are taken
+        as stored, nothing is recomputed."""
+        a, d = t["attrs"], t["data"]
+        self._name = _as_str(a["Name"])
+        self._isdelta = bool(a["IsDelta"])
+        self._normwave = float(a["NormWave"])
+        self._normfreq = float(a["NormFreq"])
+        self._normtype = _as_str(a["NormType"])
+        self._normparam = a["NormParam"] if "NormParam" in a else None
+        if isinstance(self._normparam, numpy.generic):
+            self._normparam = self._normparam.item()
+        self._normfac = float(a["NormFac"])
+        self._sens_energy = bool(a["SensEnergy"])
+        self._effective_freq = float(a["EffectiveFreq"])
+        self._effective_wave = float(a["EffectiveWave"])
+        self._nresp = int(a["NResp"])
+        self._wave = numpy.array(d["Wave"], dtype=numpy.float64, ndmin=1)
+        self._freq = numpy.array(d["Freq"], dtype=numpy.float64, ndmin=1)
+        self._resp = numpy.array(d["Response"], dtype=numpy.float64, ndmin=1)
+        for key, attr in (("Dnu", "_dnu"), ("Sedmult", "_sedmult")):
+            if key in d:
+                setattr(self, attr, numpy.array(d[key], dtype=numpy.float64, ndmin=1))
+            elif hasattr(self, attr):
+                delattr(self, attr)
+        self._data_read = True
+        return self
+
+    def writeToHDF5(self, handle):
+        """Writes the response to an open h5py file or group (reference :578)."""
+        from .treeio import _h5_write
+        _h5_write(handle, self.to_tree())
+
+    def readFromHDF5(self, handle):
+        """Reads the response from an open h5py file or group (reference :608)."""
+        from .treeio import _h5_read
+        self.from_tree(_h5_read(handle))
+
     def __str__(self):
         return "{0:s} lambda_eff: {1:0.1f} [um]".format(self._name,
                                                        self._effective_wave)
@@ -437,6 +508,42 @@ class response_set(object):
         resp.setup(spec, xtype=xtype, xunits=xunit, senstype='energy',
                    normtype='flat', xnorm=float(nums[0]), normparam=0)
         self._responses[name] = resp
+
+    # ---------------------------------------------------------- serialisation
+    def to_tree(self):
+        """One group per response (reference response.py:782-790)."""
+        from .treeio import new_tree
+        t = new_tree()
+        for name, resp in self._responses.items():
+            t["groups"][name] = resp.to_tree()
+        return t
+
+    def from_tree(self, t):
+        """Replaces the set's contents (reference response.py:792-802)."""
+        self._responses.clear()
+        for name, sub in t["groups"].items():
+            self._responses[name] = response(name).from_tree(sub)
+        return self
+
+    def writeToHDF5(self, handle):
+        from .treeio import _h5_write
+        _h5_write(handle, self.to_tree())
+
+    def readFromHDF5(self, handle):
+        from .treeio import _h5_read
+        self.from_tree(_h5_read(handle))
+
+    def save(self, filename):
+        """The whole set to a file ('.h5' needs h5py, anything else is '.npz')."""
+        from .treeio import write_tree
+        return write_tree(filename, self.to_tree())
+
+    @classmethod
+    def load(cls, filename):
+        from .treeio import read_tree
+        self = cls.__new__(cls)          # (the constructor would read the shipped wheel first)
+        self._responses = {}
+        return self.from_tree(read_tree(filename))
 
     def __getitem__(self, name):
         return self._responses[name]

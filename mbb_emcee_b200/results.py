@@ -12,9 +12,10 @@ Reference behaviours kept on purpose:
     whatever the fit used (:575-577, :1323-1325); dust mass uses the fit's.
   * ``compute_peaklambda`` always treats the SED as optically thick with alpha
     (:574-580 never forwards opthin/noalpha).
-Not carried over: HDF5 (de)serialisation (h5py is not a dependency; use
-``save``/``load`` = ``.npz`` with the same key names) and the astropy cosmology
-lookup (pass ``lumdist`` in Mpc, or have astropy installed).
+Files: ``save``/``load`` write and read the reference's HDF5 layout (:987-1158)
+-- as a real HDF5 file when h5py is installed, else as a ``.npz`` archive with
+the same groups, attributes and datasets (treeio.py).  The astropy cosmology
+lookup needs astropy: pass ``lumdist`` in Mpc instead.
 """
 from __future__ import print_function, division
 
@@ -29,6 +30,10 @@ from .modified_blackbody import modified_blackbody
 __all__ = ["mbb_results"]
 
 _MPC_CM = 3.0856775814913673e24
+# Chain statistics (means, percentiles) of arrays with at least this many samples are formed
+# on the device (mbb_chain_stats: exact order statistics by radix selection, numpy's
+# interpolation rule); smaller ones -- a few launches' worth of work -- by numpy itself.
+DEVICE_STATS_MIN = 1 << 17
 
 
 class mbb_results(object):
@@ -40,10 +45,6 @@ class mbb_results(object):
 
     def __init__(self, fit=None, h5file=None, redshift=None, lumdist=None,
                  cosmo_type='WMAP9', device=None, devices=None):
-        if h5file is not None:
-            raise NotImplementedError("HDF5 results files are not supported "
-                                      "(h5py is not a dependency); use "
-                                      "mbb_results.load(<npz>)")
         self._fitset = False
         self._has_lir = False
         self._lir_min = None
@@ -73,6 +74,8 @@ class mbb_results(object):
         self._cosmo_type = cosmo_type
         if fit is not None:
             self.process_fit(fit)
+        elif h5file is not None:
+            self.readFromHDF5(h5file)       # .h5 (needs h5py) or the .npz carrier of the same tree
 
     # ------------------------------------------------------------------ setup
     def process_fit(self, fit):
@@ -114,7 +117,13 @@ class mbb_results(object):
         """Install a chain [nwalkers, nsteps, 5] and its log-probabilities."""
         self.chain = np.asarray(chain, dtype=np.float64)
         self.lnprobability = np.asarray(lnprobability, dtype=np.float64)
-        self.par_central_values = np.array([self.par_cen(i) for i in range(5)])
+        if self.chain.size // 5 >= DEVICE_STATS_MIN:
+            # all five parameters in one pass over the chain block (reference :314-369, 399-431)
+            pval = 0.5 * (100 - 68.3)
+            mean, _, perc = self.context.chain_stats(self.chain.reshape(-1, 5), [pval, 100 - pval])
+            self.par_central_values = np.stack([mean, perc[:, 1] - mean, mean - perc[:, 0]], axis=1)
+        else:
+            self.par_central_values = np.array([self.par_cen(i) for i in range(5)])
         flat = self.lnprobability.argmax()
         idx = np.unravel_index(flat, self.lnprobability.shape)
         self._best_fit = (self.chain[idx[0], idx[1], :],
@@ -241,6 +250,12 @@ class mbb_results(object):
             raise ValueError("Invalid percentile {:f}".format(pcnt))
         pval = 0.5 * (100 - pcnt)
         arr = array
+        if arr.size >= DEVICE_STATS_MIN:
+            mean, count, perc = self.context.chain_stats(arr.reshape(-1), [pval, 100 - pval],
+                                                         lowlim=lowlim, uplim=uplim)
+            if count[0] == 0:
+                raise Exception("No elements survive lower/upper limit clipping")
+            return np.array([mean[0], perc[0, 1] - mean[0], mean[0] - perc[0, 0]])
         if lowlim is not None or uplim is not None:
             keep = np.ones(arr.shape, dtype=bool)
             if lowlim is not None:
@@ -253,6 +268,11 @@ class mbb_results(object):
         mn = arr.mean()
         perc = np.percentile(arr, [pval, 100 - pval])
         return np.array([mn, perc[1] - mn, mn - perc[0]])
+
+    def _percentile(self, arr, p):
+        if arr.size >= DEVICE_STATS_MIN:
+            return float(self.context.chain_stats(arr.reshape(-1), [p])[2][0, 0])
+        return np.percentile(arr, p)
 
     def _paridx(self, param):
         if isinstance(param, str):
@@ -280,16 +300,14 @@ class mbb_results(object):
             return None
         if percentile <= 0 or percentile >= 100.0:
             raise ValueError("percentile needs to be between 0 and 100")
-        return np.percentile(self.parameter_chain(self._paridx(param)),
-                             100 - percentile)
+        return self._percentile(self.parameter_chain(self._paridx(param)), 100 - percentile)
 
     def par_uplim(self, param, percentile=68.3):
         if not self._fitset:
             return None
         if percentile <= 0 or percentile >= 100.0:
             raise ValueError("percentile needs to be between 0 and 100")
-        return np.percentile(self.parameter_chain(self._paridx(param)),
-                             percentile)
+        return self._percentile(self.parameter_chain(self._paridx(param)), percentile)
 
     # ------------------------------------------------------------ peak lambda
     @property
@@ -515,80 +533,159 @@ class mbb_results(object):
         return (pars,) + tuple(outs)
 
     # ------------------------------------------------------------------- I/O
-    def save(self, filename):
-        """Write the results to ``.npz`` using the reference's HDF5 key names
-        (results.py:987-1158) flattened with '/'."""
+    def _to_tree(self):
+        """The fit in the reference's HDF5 layout (results.py:987-1055): root attributes,
+        groups Responses / Data / Chain / Ancillary."""
+        from .treeio import new_tree
         if not self._fitset:
             raise Exception("Fit not processed")
-        d = {"z": np.nan if self._z is None else self._z,
-             "Noalpha": self._noalpha, "Opthin": self._opthin,
-             "Nwalkers": self._nwalkers, "Wavenorm": self._wavenorm,
-             "Lowlim": self._lowlim, "HasUplim": np.array(self._has_uplim),
-             "Uplim": self._uplim, "HasGaussianPrior": np.array(self._has_gprior),
-             "GaussianPriorMean": self._gprior_mean,
-             "GaussianPriorSigma": self._gprior_sigma,
-             "GaussianPriorIVar": self._gprior_ivar,
-             "ResponseIntegrate": self._response_integrate,
-             "Fixed": np.array(self._fixed), "Ndata": self._ndata,
-             "Chain/Chain": self.chain, "Chain/LogLike": self.lnprobability,
-             "Chain/ParamCentralValues": self.par_central_values,
-             "Chain/BestFitParams": self._best_fit[0],
-             "Chain/BestFitLogLike": self._best_fit[1],
-             "Chain/BestFitIndex": np.array(self._best_fit[2])}
-        if self._has_lumdist:
-            d["LumDist"] = self._lumdist
+        t = new_tree()
+        a = t["attrs"]
+        if self._z is not None:
+            a["z"] = self._z
+        a["Noalpha"], a["Opthin"] = bool(self._noalpha), bool(self._opthin)
+        a["Nwalkers"], a["Wavenorm"] = int(self._nwalkers), float(self._wavenorm)
+        a["Lowlim"] = np.asarray(self._lowlim, dtype=np.float64)
+        a["HasUplim"] = np.asarray(self._has_uplim, dtype=bool)
+        a["Uplim"] = np.asarray(self._uplim, dtype=np.float64)
+        a["HasGaussianPrior"] = np.asarray(self._has_gprior, dtype=bool)
+        a["GaussianPriorMean"] = np.asarray(self._gprior_mean, dtype=np.float64)
+        a["GaussianPriorSigma"] = np.asarray(self._gprior_sigma, dtype=np.float64)
+        a["GaussianPriorIVar"] = np.asarray(self._gprior_ivar, dtype=np.float64)
+        a["ResponseIntegrate"] = bool(self._response_integrate)
+        a["Fixed"] = np.asarray(self._fixed, dtype=bool)
+        a["Ndata"] = int(self._ndata)
+        if self._response_integrate:
+            t["groups"]["Responses"] = self._responsewheel.to_tree()
+        gd = t["groups"]["Data"] = new_tree()
+        gd["attrs"]["WaveUnits"], gd["attrs"]["FluxUnits"] = "microns", "mJy"
         if self._data_wave is not None:
-            d["Data/Wave"] = np.asarray(self._data_wave)
-            d["Data/FluxDensity"] = np.asarray(self._data_flux)
-            d["Data/FluxDensityUnc"] = np.asarray(self._data_flux_unc)
+            gd["data"]["Wave"] = np.asarray(self._data_wave)
+            gd["data"]["FluxDensity"] = np.asarray(self._data_flux)
+            gd["data"]["FluxDensityUnc"] = np.asarray(self._data_flux_unc)
         if self._has_covmatrix:
-            d["Data/Covmatrix"] = self._covmatrix
-            d["Data/InvCovmatrix"] = self._invcovmatrix
+            gd["data"]["Covmatrix"] = np.asarray(self._covmatrix)
+            gd["data"]["InvCovmatrix"] = np.asarray(self._invcovmatrix)
+        gc = t["groups"]["Chain"] = new_tree()
+        gc["data"]["ParamCentralValues"] = self.par_central_values
+        gc["data"]["Chain"] = self.chain
+        gc["data"]["LogLike"] = self.lnprobability
+        gc["data"]["BestFitParams"] = np.asarray(self._best_fit[0])
+        gc["data"]["BestFitLogLike"] = np.array(self._best_fit[1])
+        gc["data"]["BestFitIndex"] = np.array(self._best_fit[2])
+        ga = t["groups"]["Ancillary"] = new_tree()
+        ga["attrs"]["cosmo_type"] = str(self._cosmo_type)
+        if self._has_lumdist:
+            ga["attrs"]["lumdist"] = float(self._lumdist)      # Mpc
         if self._has_lir:
-            d["Ancillary/Lir"] = self.lir
-            d["Ancillary/LirMin"], d["Ancillary/LirMax"] = self._lir_min, self._lir_max
+            ga["attrs"]["LirMin"], ga["attrs"]["LirMax"] = self._lir_min, self._lir_max
+            ga["data"]["Lir"] = self.lir
         if self._has_dustmass:
-            d["Ancillary/Dustmass"] = self.dustmass
-            d["Ancillary/DustKappa"] = self._kappa
-            d["Ancillary/DustKappaWave"] = self._kappa_wave
+            ga["attrs"]["Kappa"], ga["attrs"]["KappaWave"] = self._kappa, self._kappa_wave
+            ga["data"]["Dustmass"] = self.dustmass
         if self._has_peaklambda:
-            d["Ancillary/PeakLambda"] = self.peaklambda
-        np.savez_compressed(filename, **d)
+            ga["data"]["PeakLambda"] = self.peaklambda
+        return t
+
+    def _from_tree(self, t):
+        """Inverse of _to_tree (reference results.py:1057-1158): every stored quantity is
+        restored as stored -- covariance, response tables, cosmology choice, ancillaries."""
+        from .response import response_set
+        a = t["attrs"]
+        self._z = float(a["z"]) if "z" in a else None
+        self._noalpha, self._opthin = bool(a["Noalpha"]), bool(a["Opthin"])
+        self._nwalkers, self._wavenorm = int(a["Nwalkers"]), float(a["Wavenorm"])
+        self._lowlim = np.array(a["Lowlim"], dtype=np.float64)
+        self._has_uplim = [bool(v) for v in a["HasUplim"]]
+        self._uplim = np.array(a["Uplim"], dtype=np.float64)
+        self._has_gprior = [bool(v) for v in a["HasGaussianPrior"]]
+        self._gprior_mean = np.array(a["GaussianPriorMean"], dtype=np.float64)
+        self._gprior_sigma = np.array(a["GaussianPriorSigma"], dtype=np.float64)
+        self._gprior_ivar = np.array(a["GaussianPriorIVar"], dtype=np.float64)
+        self._response_integrate = bool(a["ResponseIntegrate"])
+        self._fixed = [bool(v) for v in a["Fixed"]]
+        self._ndata = int(a["Ndata"])
+        if self._response_integrate:
+            if "Responses" not in t["groups"]:
+                raise ValueError("Didn't find expected responses")
+            self._responsewheel = response_set.__new__(response_set)
+            self._responsewheel._responses = {}
+            self._responsewheel.from_tree(t["groups"]["Responses"])
+        elif hasattr(self, "_responsewheel"):
+            del self._responsewheel
+        gd = t["groups"]["Data"]["data"]
+        self._data_wave = gd.get("Wave")
+        self._data_flux = gd.get("FluxDensity")
+        self._data_flux_unc = gd.get("FluxDensityUnc")
+        self._has_covmatrix = "Covmatrix" in gd
+        if self._has_covmatrix:
+            self._covmatrix = gd["Covmatrix"]
+            self._invcovmatrix = gd["InvCovmatrix"]
+        else:
+            for name in ("_covmatrix", "_invcovmatrix"):
+                if hasattr(self, name):
+                    delattr(self, name)
+        gc = t["groups"]["Chain"]["data"]
+        self.par_central_values = gc["ParamCentralValues"]
+        self.chain = np.ascontiguousarray(gc["Chain"], dtype=np.float64)
+        self.lnprobability = np.ascontiguousarray(gc["LogLike"], dtype=np.float64)
+        self._best_fit = (np.asarray(gc["BestFitParams"]), float(gc["BestFitLogLike"]),
+                          tuple(int(i) for i in np.atleast_1d(gc["BestFitIndex"])))
+        ga = t["groups"]["Ancillary"]
+        if "cosmo_type" in ga["attrs"]:
+            ct = ga["attrs"]["cosmo_type"]
+            self._cosmo_type = ct.decode() if isinstance(ct, bytes) else str(ct)
+        self._has_lumdist = "lumdist" in ga["attrs"]
+        if self._has_lumdist:
+            self._lumdist = float(ga["attrs"]["lumdist"])
+        self._has_lir = "Lir" in ga["data"]
+        if self._has_lir:
+            self.lir = ga["data"]["Lir"]
+            self._lir_min, self._lir_max = float(ga["attrs"]["LirMin"]), float(ga["attrs"]["LirMax"])
+        else:
+            self._lir_min = self._lir_max = None
+        self._has_dustmass = "Dustmass" in ga["data"]
+        if self._has_dustmass:
+            self.dustmass = ga["data"]["Dustmass"]
+            self._kappa, self._kappa_wave = float(ga["attrs"]["Kappa"]), float(ga["attrs"]["KappaWave"])
+        else:
+            self._kappa = self._kappa_wave = None
+        self._has_peaklambda = "PeakLambda" in ga["data"]
+        if self._has_peaklambda:
+            self.peaklambda = ga["data"]["PeakLambda"]
+        for name, flag in (("lir", self._has_lir), ("dustmass", self._has_dustmass),
+                           ("peaklambda", self._has_peaklambda)):
+            if not flag and hasattr(self, name):
+                delattr(self, name)
+        self._fitset = True
+        return self
+
+    def save(self, filename):
+        """Write the results: a name ending in .h5 / .hdf5 gives an HDF5 file in the reference's
+        layout (needs h5py; the reference's readFromHDF5 reads it), any other name a ``.npz``
+        archive with the same groups, attributes and datasets (the suffix is appended when
+        missing).  Returns the name of the file written."""
+        from .treeio import write_tree
+        return write_tree(filename, self._to_tree())
 
     @classmethod
-    def load(cls, filename, device=None):
-        with np.load(filename) as f:
-            z = float(f["z"])
-            self = cls.from_chain(f["Chain/Chain"], f["Chain/LogLike"],
-                                  wavenorm=float(f["Wavenorm"]),
-                                  noalpha=bool(f["Noalpha"]), opthin=bool(f["Opthin"]),
-                                  redshift=None if np.isnan(z) else z,
-                                  lumdist=float(f["LumDist"]) if "LumDist" in f else None,
-                                  device=device)
-            self._lowlim = f["Lowlim"]
-            self._has_uplim = list(f["HasUplim"])
-            self._uplim = f["Uplim"]
-            self._has_gprior = list(f["HasGaussianPrior"])
-            self._gprior_mean = f["GaussianPriorMean"]
-            self._gprior_sigma = f["GaussianPriorSigma"]
-            self._gprior_ivar = f["GaussianPriorIVar"]
-            self._fixed = list(f["Fixed"])
-            self._ndata = int(f["Ndata"])
-            if "Data/Wave" in f:
-                self._data_wave = f["Data/Wave"]
-                self._data_flux = f["Data/FluxDensity"]
-                self._data_flux_unc = f["Data/FluxDensityUnc"]
-            if "Ancillary/Lir" in f:
-                self.lir, self._has_lir = f["Ancillary/Lir"], True
-                self._lir_min = float(f["Ancillary/LirMin"])
-                self._lir_max = float(f["Ancillary/LirMax"])
-            if "Ancillary/Dustmass" in f:
-                self.dustmass, self._has_dustmass = f["Ancillary/Dustmass"], True
-                self._kappa = float(f["Ancillary/DustKappa"])
-                self._kappa_wave = float(f["Ancillary/DustKappaWave"])
-            if "Ancillary/PeakLambda" in f:
-                self.peaklambda, self._has_peaklambda = f["Ancillary/PeakLambda"], True
-        return self
+    def load(cls, filename, device=None, devices=None):
+        """Inverse of save; also reads HDF5 files written by the reference (needs h5py)."""
+        from .treeio import read_tree
+        self = cls(device=device, devices=devices)
+        return self._from_tree(read_tree(filename))
+
+    def writeToHDF5(self, filename):
+        """The reference's name for save() to an HDF5 file (results.py:987)."""
+        from .treeio import is_hdf5_name
+        if not is_hdf5_name(filename):
+            raise ValueError("writeToHDF5 needs a .h5 / .hdf5 file name; save() also writes .npz")
+        return self.save(filename)
+
+    def readFromHDF5(self, filename):
+        """Restore from a file written by save() or by the reference (results.py:1057)."""
+        from .treeio import read_tree
+        self._from_tree(read_tree(filename))
 
     def __str__(self):
         if not self._fitset:

@@ -39,7 +39,7 @@ def build_parser():
                "ghost parameter that can carry an upper limit and a prior.")
     a = p.add_argument
     a("photfile", help="text file: wavelength [um] (or passband name with --response), flux, error [mJy]")
-    a("outfile", help="file to write the results to (.npz)")
+    a("outfile", help="file to write the results to: .h5/.hdf5 (the reference's HDF5 file; needs h5py) or .npz")
     a("-b", "--burn", type=int, default=50, help="burn-in steps (def: 50)")
     a("-c", "--covfile", default=None, help="covariance matrix file [mJy^2]: FITS (needs astropy), .npy or text")
     a("-C", "--cosmotype", default="WMAP9", help="astropy.cosmology name, used only without --lumdist")
@@ -158,7 +158,9 @@ def main(argv=None):
         print("Fit results:")
         print(res)
         print("Saving results to %s" % args.outfile)
-    res.save(args.outfile)
+    written = res.save(args.outfile)
+    if args.verbose and written != args.outfile:
+        print("  (written as %s)" % written)
     return res
 
 

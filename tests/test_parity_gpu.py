@@ -881,6 +881,65 @@ def test_predict_flux_vs_oracle(oracle):
     assert cen.shape == (3,) and cen[0] > 0
 
 
+def test_chain_stats_equal_numpy(ctx):
+    """mbb_chain_stats (what mbb_results' par_cen / *_cen / par_lowlim / par_uplim take from
+    numpy.mean and numpy.percentile, reference results.py:314-431): percentiles equal numpy's bit
+    for bit (exact order statistics + numpy's interpolation), means to 1e-14, on a 5-column chain
+    block with repeats, negative values and ties, with clipping, for a device-resident block;
+    NaN and empty selections behave like numpy / the reference."""
+    import torch
+    from mbb_emcee_b200 import _native, mbb_results, results, synthetic
+    rng = np.random.RandomState(11)
+    n = 400000
+    X = np.array([14.0, 1.8, 400.0, 3.0, 30.0]) + rng.normal(size=(n, 5)) * [2, 0.2, 100, 0.3, 5]
+    X[:, 3] = np.round(X[:, 3], 2)                    # heavy ties
+    X[::7, 4] = X[3::7, 4][:X[::7, 4].size]           # exact repeats, as a chain has
+    X[:, 1] -= 1.8                                    # both signs
+    pcs = [15.85, 84.15, 50.0, 99.9]
+    mean, count, perc = ctx.chain_stats(X, pcs)
+    assert np.array_equal(count, np.full(5, n))
+    import math
+    exact = np.array([math.fsum(X[:, i]) / n for i in range(5)])
+    assert relerr(mean, exact).max() < 4e-16                     # (the second column's mean is ~1e-4 of its spread)
+    flat_means = np.array([X[:, i].copy().mean() for i in range(5)])      # the reference's flatten().mean()
+    assert np.abs(mean - flat_means).max() < 1e-13
+    assert np.array_equal(perc, np.percentile(X, pcs, axis=0).T)
+    assert np.array_equal(ctx.chain_stats(X, [0.0, 100.0])[2], np.stack([X.min(0), X.max(0)], 1))
+    # clipping per column, 1-D input
+    lo, hi = 12.5, 16.0
+    m1, c1, p1 = ctx.chain_stats(X[:, 0].copy(), [2.5, 97.5], lowlim=lo, uplim=hi)
+    kept = X[:, 0][(X[:, 0] >= lo) & (X[:, 0] <= hi)]
+    assert c1[0] == kept.size and abs(m1[0] - math.fsum(kept) / kept.size) < 4e-16 * kept.mean()
+    assert np.array_equal(p1[0], np.percentile(kept, [2.5, 97.5]))
+    # device-resident block
+    T = torch.from_numpy(X).cuda()
+    m2, c2, p2 = ctx.chain_stats(T.data_ptr(), pcs, where=_native.DEVICE, nrows=n, ncols=5)
+    assert np.array_equal(p2, perc) and np.array_equal(m2, mean)
+    # NaN in a column -> NaN out for that column only; nothing kept -> count 0
+    Y = X.copy()
+    Y[5, 2] = np.nan
+    m3, c3, p3 = ctx.chain_stats(Y, [50.0])
+    assert np.isnan(m3[2]) and np.isnan(p3[2, 0]) and np.array_equal(p3[[0, 1, 3, 4], 0], np.percentile(X, 50.0, axis=0)[[0, 1, 3, 4]])
+    assert ctx.chain_stats(X[:, 0].copy(), [50.0], lowlim=1e9)[1][0] == 0
+    # mbb_results routes big chains through it: same triples as numpy on the flattened chain
+    assert n >= results.DEVICE_STATS_MIN
+    chain = X.reshape(400, 1000, 5).copy()
+    chain[:, :, 1] += 1.8
+    res = mbb_results.from_chain(chain, device=0)
+    for i, name in enumerate(("T", "beta", "lambda0", "alpha", "fnorm")):
+        flat = chain[:, :, i].ravel()
+        mn = flat.mean()
+        pl, ph = np.percentile(flat, [15.85, 84.15])
+        got = res.par_cen(name)
+        assert abs(got[0] - mn) < 1e-14 * abs(mn)
+        assert abs((got[0] + got[1]) - ph) < 1e-13 * abs(ph) and abs((got[0] - got[2]) - pl) < 1e-13 * abs(pl)
+        assert np.allclose(res.par_central_values[i], got, rtol=0, atol=1e-12 * abs(mn))
+        assert res.par_uplim(name, 95.0) == np.percentile(flat, 95.0)
+        assert res.par_lowlim(name, 95.0) == np.percentile(flat, 5.0)
+    with pytest.raises(Exception, match="No elements survive"):
+        res.par_cen("T", lowlim=1e9)
+
+
 def test_results_shard_rows_over_devices():
     """mbb_results(devices=[...]): walker rows cut into one shard per context / host thread, the
     outputs landing in disjoint rows of one page-locked array; identical to the single-context
