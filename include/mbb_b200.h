@@ -157,10 +157,14 @@ int mbb_loglike(mbb_ctx *ctx, int64_t n, const double *pars, int layout,
 /* ---- SED evaluation: modified_blackbody.__call__ / f_nu
  * (modified_blackbody.py:441-554) for n parameter vectors on a common
  * frequency grid: out[n][nfreq] in mJy.  scalar_path selects the numpy-twin
- * rounding of x (see mbb_set_bands).  Always MBB_MATH_FAITHFUL. */
+ * rounding of x (see mbb_set_bands; MBB_MATH_FAITHFUL only).  math_mode:
+ * MBB_MATH_FAITHFUL -- the reference's formulas in the reference's order;
+ * MBB_MATH_FAST -- the per-walker setup and node arithmetic of the likelihood
+ * kernels (each frequency a single-node band of weight 1); < 0 -- the mode set
+ * by mbb_set_math_mode. */
 int mbb_fnu(mbb_ctx *ctx, int64_t n, const double *pars, int layout,
-            int nfreq, const double *freq_ghz, int scalar_path, double *out,
-            int32_t *out_status, int mem);
+            int nfreq, const double *freq_ghz, int scalar_path, int math_mode,
+            double *out, int32_t *out_status, int mem);
 
 /* ---- per-walker constants: modified_blackbody.__init__ + max_wave
  * (modified_blackbody.py:200-337, 581-637).  out_consts[n][6] =

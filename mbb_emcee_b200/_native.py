@@ -78,7 +78,7 @@ def load_library():
             "mbb_set_data_chol": (i32, [vp, i32, i32, vp, vp]),
             "mbb_set_priors": (i32, [vp, vp, vp, vp, vp, vp, vp]),
             "mbb_loglike": (i32, [vp, i64, vp, i32, vp, i64, vp, vp, i32]),
-            "mbb_fnu": (i32, [vp, i64, vp, i32, i32, vp, i32, vp, vp, i32]),
+            "mbb_fnu": (i32, [vp, i64, vp, i32, i32, vp, i32, i32, vp, vp, i32]),
             "mbb_sed_consts": (i32, [vp, i64, vp, i32, i32, vp, vp, i32]),
             "mbb_chain_post": (i32, [vp, i64, i64, vp, i32, dbl, dbl, dbl, dbl, dbl, dbl,
                                      vp, vp, vp, vp, i32]),
@@ -296,13 +296,15 @@ class Context(object):
                                        max(wps, 1), ctypes.c_void_p(out_ptr),
                                        ctypes.c_void_p(status_ptr) if status_ptr else None, DEVICE))
 
-    def fnu(self, pars, freq_ghz, scalar_path=False):
+    def fnu(self, pars, freq_ghz, scalar_path=False, math_mode=MATH_FAITHFUL):
+        """f_nu[n][nfreq]; math_mode MATH_FAITHFUL (default: the reference's formulas in the
+        reference's order) or MATH_FAST (the likelihood kernels' arithmetic)."""
         P = _f64(pars).reshape(-1, 5)
         f = _f64(freq_ghz).ravel()
         out = np.empty((P.shape[0], f.size), dtype=np.float64)
         st = np.empty(P.shape[0], dtype=np.int32)
         self._ck(self._lib.mbb_fnu(self._h, P.shape[0], _ptr(P), AOS, f.size, _ptr(f),
-                                   int(bool(scalar_path)), _ptr(out), _ptr(st), HOST))
+                                   int(bool(scalar_path)), int(math_mode), _ptr(out), _ptr(st), HOST))
         return out, st
 
     def sed_consts(self, pars, want_peak=False):

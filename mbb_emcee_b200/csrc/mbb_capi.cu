@@ -559,6 +559,16 @@ struct LaunchFnu {
 };
 
 template <bool THIN, bool ALPHA, bool UNUSED>
+struct LaunchFnuFast {
+  static void run(mbb_ctx* c, const EvalArgs& a, const double* freq, const double* weff, const double* lp,
+                  int nfreq) {
+    dim3 grid((unsigned)((nfreq + 255) / 256), (unsigned)a.n);
+    const ModelP m = model_of(c);
+    fnu_fast_kernel<THIN, ALPHA><<<grid, 256, 0, c->stream>>>(a, m, freq, weff, lp, nfreq);
+  }
+};
+
+template <bool THIN, bool ALPHA, bool UNUSED>
 struct LaunchConsts {
   static void run(mbb_ctx* c, const EvalArgs& a, int want_peak) {
     const unsigned grid = (unsigned)((a.n + 127) / 128);
@@ -1116,13 +1126,40 @@ int mbb_loglike(mbb_ctx* c, int64_t n, const double* pars, int layout, const int
 }
 
 int mbb_fnu(mbb_ctx* c, int64_t n, const double* pars, int layout, int nfreq, const double* freq_ghz,
-            int scalar_path, double* out, int32_t* out_status, int mem) {
+            int scalar_path, int math_mode, double* out, int32_t* out_status, int mem) {
   if (!c) return fail("null context");
   if (n <= 0 || nfreq <= 0) return fail("n and nfreq must be positive");
   if (n > 65535) return fail("mbb_fnu: at most 65535 parameter vectors per call");
   if (!pars || !freq_ghz || !out) return fail("null pointer");
   if (layout != MBB_AOS && layout != MBB_SOA) return fail("bad layout");
+  if (math_mode < 0) math_mode = c->math_mode;
+  if (math_mode != MBB_MATH_FAITHFUL && math_mode != MBB_MATH_FAST && math_mode != MBB_MATH_FAST_GAUSS)
+    return fail("bad math mode");
+  const bool fast = math_mode != MBB_MATH_FAITHFUL;
   Use u(c);
+  // FAST: node records of the frequency grid, built as mbb_set_bands builds a delta band's
+  if (fast) {
+    std::vector<double> hf((size_t)nfreq);
+    if (mem == MBB_DEVICE) {
+      CK(cudaMemcpyAsync(hf.data(), freq_ghz, (size_t)nfreq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    } else {
+      memcpy(hf.data(), freq_ghz, (size_t)nfreq * sizeof(double));
+    }
+    std::vector<double> rec((size_t)nfreq * 2);
+    double numax = 0.0, lmax = 0.0;
+    for (int i = 0; i < nfreq; ++i) {
+      if (!(hf[i] > 0.0) || !std::isfinite(hf[i])) return fail("mbb_fnu: frequencies must be positive and finite");
+      const FastNode nd = fast_node(kUmToGHz / hf[i], 1.0, c->wavenorm, c->opthin != 0);
+      rec[i] = nd.weff;
+      rec[(size_t)nfreq + i] = nd.lp;
+      if (hf[i] > numax) numax = hf[i];
+      if (nd.labs > lmax) lmax = nd.labs;
+    }
+    CK(c->d_aux0.reserve(rec.size()));
+    CK(cudaMemcpyAsync(c->d_aux0.p, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));      // rec goes out of scope
+  }
   EvalArgs a{};
   a.n = n;
   a.wps = 1;
@@ -1151,7 +1188,11 @@ int mbb_fnu(mbb_ctx* c, int64_t n, const double* pars, int layout, int nfreq, co
     a.status = c->d_st.p;
   }
   begin_timing(c);
-  dispatch3<LaunchFnu>(c->opthin != 0, c->noalpha == 0, false, c, a, dfreq, nfreq, scalar_path);
+  if (fast)
+    dispatch3<LaunchFnuFast>(c->opthin != 0, c->noalpha == 0, false, c, a, dfreq, (const double*)c->d_aux0.p,
+                             (const double*)(c->d_aux0.p + nfreq), nfreq);
+  else
+    dispatch3<LaunchFnu>(c->opthin != 0, c->noalpha == 0, false, c, a, dfreq, nfreq, scalar_path);
   end_timing(c);
   c->launches += 1;
   CK(cudaGetLastError());

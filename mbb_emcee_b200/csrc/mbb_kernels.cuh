@@ -840,6 +840,31 @@ fnu_kernel(const EvalArgs a, const ModelP m, const double* __restrict__ freq, in
   a.out[e * nfreq + i] = v;
 }
 
+// The same grid through the FAST arithmetic: the per-walker setup and the node code of the
+// likelihood kernels (saturating instantiations), on node records {freq, weff, L'} built by the
+// host exactly as mbb_set_bands builds a delta band's (fast_node) -- f_nu = the band flux of a
+// single node of weight 1.
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(256)
+fnu_fast_kernel(const EvalArgs a, const ModelP m, const double* __restrict__ freq,
+                const double* __restrict__ weff, const double* __restrict__ lp, int nfreq) {
+  __shared__ FastSed s;
+  const long long e = blockIdx.y;
+  if (threadIdx.x == 0) {
+    double p[5];
+    load_pars(a, e, p);
+    fast_setup<THIN, ALPHA>(s, p[0], p[1], p[2], p[3], p[4], m);
+    if (a.status && blockIdx.x == 0) a.status[e] = s.status;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nfreq) return;
+  double v = qnan();
+  if (s.status == ST_OK)
+    v = node_acc<THIN, ALPHA, true, 0>(s, __ldg(freq + i), __ldg(lp + i), __ldg(weff + i), 0.0, exp2_tab_default());
+  a.out[e * nfreq + i] = v;
+}
+
 // per-walker constants (+ optional peak wavelength): out[n][6]
 template <bool THIN, bool ALPHA>
 __global__ void __launch_bounds__(128)

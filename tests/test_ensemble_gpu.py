@@ -60,6 +60,11 @@ def test_device_sampler_replays_on_host(oracle, response, nsrc, nw, nsteps):
     assert np.array_equal(nacc, rnacc)
     assert relerr(lnp, rlnp).max() < TOL
     assert 0 < nacc.sum() < nsrc * nw * nsteps
+    # emcee 2.2's ORIGINAL acceptance test, lnpdiff > log(u) (the device uses the log-free
+    # form u < z^4 exp(dlnp)): the same chain
+    lpos, llnp, lnacc = philox_np.replay(lambda s, Q: oracle.loglike_batch(specs[s], Q), p0, nsteps,
+                                         0x1234ABCD5678, log_form=True)
+    assert np.array_equal(pos, lpos) and np.array_equal(nacc, lnacc)
     # continuing a run (burn-in then main chain) == one long run
     p1, l1, n1, _ = ctx.ensemble_run(p0, nsteps - 3, seed=0x1234ABCD5678)
     p2, l2, n2, _ = ctx.ensemble_run(p1, 3, seed=0x1234ABCD5678, step0=nsteps - 3, lnprob=l1)
@@ -287,3 +292,32 @@ def test_sampler_kernels_agree_bitwise(monkeypatch, opthin, noalpha, nsrc, nw):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert 0 < a[2].sum() < nsrc * nw * 5
+
+
+def test_with_installed_emcee(oracle):
+    """When emcee itself is importable (it is not in the build image): its EnsembleSampler,
+    handed the product's likelihood and the same RandomState, walks the chain of the product's
+    own emcee-2.2 restatement (mbb_emcee_b200/ensemble.py) -- bit for bit under emcee 2.x, and
+    statistically (posterior mean within 5 MC sigma) under emcee 3.x, whose move scheduling
+    draws differently."""
+    emcee = pytest.importorskip("emcee")
+    from mbb_emcee_b200 import likelihood, synthetic
+    from mbb_emcee_b200.ensemble import EnsembleSampler
+    cfg = synthetic.CONFIGS["cfg1"]
+    like = likelihood(wavenorm=cfg["wavenorm"], noalpha=cfg["noalpha"], opthin=cfg["opthin"], device=0)
+    _, flux, unc, _, P = synthetic.sample_problem("cfg1", 64)
+    like.set_phot(cfg["bands"], flux, unc)
+    ours = EnsembleSampler(64, 5, like)
+    ours.random_state = np.random.RandomState(7).get_state()
+    ours.run_mcmc(P, 60)
+    major = int(emcee.__version__.split(".")[0])
+    if major < 3:
+        theirs = emcee.EnsembleSampler(64, 5, like)
+        theirs.random_state = np.random.RandomState(7).get_state()
+        theirs.run_mcmc(P, 60)
+        assert np.array_equal(theirs.chain, ours.chain)
+    else:
+        theirs = emcee.EnsembleSampler(64, 5, like, vectorize=True)
+        theirs.run_mcmc(P, 400, progress=False)
+        a, b = theirs.get_chain()[200:, :, 0].ravel(), ours.chain[:, 30:, 0].ravel()
+        assert abs(a.mean() - b.mean()) < 5 * np.hypot(a.std() / np.sqrt(64), b.std() / np.sqrt(64))

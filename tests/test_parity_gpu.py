@@ -38,6 +38,13 @@ def test_fnu_and_constants_golden(ctx, golden, name, opthin, noalpha, wavenorm):
     assert relerr(arr, g[tag + "_fnu_array"]).max() < TOL
     sc, st = ctx.fnu(P, freq, scalar_path=True)
     assert relerr(sc, g[tag + "_fnu_scalar"]).max() < TOL
+    # the FAST arithmetic of the likelihood kernels (per-walker setup incl. the merge-point
+    # solve, lean exp family, node formulas) on the same grid
+    from mbb_emcee_b200 import _native
+    fast, st = ctx.fnu(P, freq, math_mode=_native.MATH_FAST)
+    assert (st == 0).all()
+    assert relerr(fast, g[tag + "_fnu_array"]).max() < TOL
+    assert not np.array_equal(fast, arr)
     c, st = ctx.sed_consts(P, want_peak=True)
     assert (st == 0).all()
     assert relerr(c[:, 0], g[tag + "_normfac"]).max() < TOL
@@ -799,7 +806,7 @@ def test_cli_end_to_end(tmp_path):
 
 
 @pytest.mark.parametrize("name,opthin,noalpha", VARIANTS)
-def test_chain_post_golden(golden, name, opthin, noalpha):
+def test_chain_post_golden(golden, observed, name, opthin, noalpha):
     from mbb_emcee_b200 import mbb_results, synthetic
     cfg = synthetic.CONFIGS["cfg4"]
     g = golden.results
@@ -815,11 +822,14 @@ def test_chain_post_golden(golden, name, opthin, noalpha):
     # chaotic at the ulp level, though: where a termination / ordering test of
     # QUADPACK is decided by the last bit of an integrand value (libdevice pow
     # vs glibc pow), the two runs subdivide differently and differ by the
-    # quadrature's own error (<= ~3e-8).  Require the first for the bulk.
+    # quadrature's own error.  Bar: >= 99 % of the samples within 1e-12, the rest
+    # within 5e-9 (observed on B200: 719 of 720 <= 7e-16, one at 5e-10).
     res.compute_lir(wavemin=cfg["lir"][0], wavemax=cfg["lir"][1])
     dev = relerr(res.lir, g[name + "_lir"])
-    assert dev.max() < 1e-7
-    assert np.mean(dev < TOL) >= 0.9, np.mean(dev < TOL)
+    observed.record("L_IR quadpack replay vs golden, max [%s]" % name, dev.max())
+    observed.record("L_IR quadpack replay vs golden, fraction within 1e-12 [%s]" % name, np.mean(dev < TOL))
+    assert dev.max() < 5e-9
+    assert np.mean(dev < TOL) >= 0.99, np.mean(dev < TOL)
     lir_q = res.lir.copy()
     # L_IR, fixed-rule quadrature: the true integral (1e-13 vs 40-digit mpmath in
     # test_device_logic_cpu.py::test_freq_integrate); the reference's own quad error
@@ -851,12 +861,12 @@ def test_freq_integrate_golden(golden, oracle, name, opthin, noalpha):
                                noalpha=noalpha, opthin=opthin)
         got = m.freq_integrate(24.0, 3000.0)                          # QUADPACK replay
         nclose += abs(got - ref[i]) <= TOL * abs(ref[i])
-        assert abs(got - ref[i]) <= 1e-7 * abs(ref[i])
+        assert abs(got - ref[i]) <= 5e-9 * abs(ref[i])
         got = m.freq_integrate(24.0, 3000.0, method="gauss")
         assert abs(got - ref[i]) <= 1e-7 * abs(ref[i])
         assert abs(got - want[i]) <= 1e-13 * abs(want[i])
         assert abs(m.max_wave() - g[tag + "_maxwave"][i]) <= TOL * g[tag + "_maxwave"][i]
-    assert nclose >= len(P) - 2        # see test_chain_post_golden on the rare subdivision flips
+    assert nclose >= len(P) - 1        # see test_chain_post_golden on the rare subdivision flips
 
 
 def test_predict_flux_vs_oracle(oracle):
@@ -988,7 +998,7 @@ def test_chain_post_full_size_properties(oracle):
     for flat in np.argsort(dev, axis=None)[-4:]:
         w, t = np.unravel_index(flat, dev.shape)
         ref = pref0 * oracle.lir_step(chain[w, t], cfg["z"], 8.0, 1000.0, False, False)
-        assert abs(res.lir[w, t] - ref) <= 1e-7 * ref, (dev[w, t], res.lir[w, t], ref)
+        assert abs(res.lir[w, t] - ref) <= 5e-9 * ref, (dev[w, t], res.lir[w, t], ref)
     for arr in (res.peaklambda, res.dustmass, res.lir):
         assert arr.shape == (nw, ns) and np.isfinite(arr).all() and (arr > 0).all()
     # (1) idempotence of the dedupe: exact repeats carry their predecessor's value
@@ -1028,5 +1038,5 @@ def test_chain_post_full_size_properties(oracle):
         lir_ref = pref * oracle.lir_step(st, cfg["z"], 8.0, 1000.0, False, False)
         nchk += 1
         nclose += abs(res.lir[w, t] - lir_ref) <= TOL * lir_ref
-        assert abs(res.lir[w, t] - lir_ref) <= 1e-7 * lir_ref
-    assert nclose >= 0.9 * nchk, (nclose, nchk)
+        assert abs(res.lir[w, t] - lir_ref) <= 5e-9 * lir_ref
+    assert nclose >= nchk - 1, (nclose, nchk)
