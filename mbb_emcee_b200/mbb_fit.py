@@ -1,12 +1,15 @@
 """Fit driver: owns the GPU likelihood and the ensemble sampler.
 
-Host-side mirror of the reference's ``mbb_fitter`` (reference
-mbb_emcee/mbb_fit.py:13-563): same constructor, pass-through setters,
-``generate_initial_values`` and ``run``.  The one structural change is that the
-sampler receives a *block* log-probability: every half-ensemble proposal is
-one CUDA launch instead of ``nwalkers/2`` Python calls.  ``nthreads`` is
-accepted for API compatibility but a CUDA context cannot be forked into a
-multiprocessing pool, so values other than 1 are refused.
+Drop-in for the reference's ``mbb_fitter`` (mbb_emcee/mbb_fit.py:13-563): same
+constructor arguments, the same limit / prior / fixing calls,
+``generate_initial_values`` and ``run``.  Everything about limits and priors
+lives in the likelihood object; the calls of that name here are installed as
+delegates (the loop at the end of this module) rather than written out one by one.  The one
+structural change against the reference is that the sampler receives a *block*
+log-probability: every half-ensemble proposal is one CUDA launch instead of
+``nwalkers/2`` Python calls.  ``nthreads`` is accepted for API compatibility,
+but a CUDA context cannot be forked into a multiprocessing pool, so values
+other than 1 are refused.
 """
 from __future__ import print_function
 
@@ -19,8 +22,13 @@ from .likelihood import likelihood
 
 __all__ = ["mbb_fitter"]
 
+_NPAR = 5
+_MAX_REDRAWS = 100
+
 
 def _make_sampler(nwalkers, like):
+    """The package's emcee-2.2 restatement by default; MBB_B200_USE_EMCEE=1 asks for an
+    installed emcee instead (block log-probability either way)."""
     if os.environ.get("MBB_B200_USE_EMCEE", "0") == "1":
         try:
             import emcee
@@ -29,77 +37,59 @@ def _make_sampler(nwalkers, like):
         if emcee is not None:
             major = int(str(getattr(emcee, "__version__", "2")).split(".")[0])
             if major >= 3:
-                return emcee.EnsembleSampler(nwalkers, 5, like, vectorize=True)
-            return emcee.EnsembleSampler(nwalkers, 5, like, pool=like.as_pool())
-    return EnsembleSampler(nwalkers, 5, like, vectorize=True)
+                return emcee.EnsembleSampler(nwalkers, _NPAR, like, vectorize=True)
+            return emcee.EnsembleSampler(nwalkers, _NPAR, like, pool=like.as_pool())
+    return EnsembleSampler(nwalkers, _NPAR, like, vectorize=True)
+
+
+def _delegate(name):
+    def call(self, *args):
+        return getattr(self.like, name)(*args)
+    call.__name__ = name
+    call.__doc__ = "likelihood.%s (reference mbb_fit.py:176-360 forwards the same way)." % name
+    return call
 
 
 class mbb_fitter(object):
-    """ Does fit"""
+    """Fits a modified blackbody to photometry with an affine-invariant ensemble sampler."""
 
     _param_order = {'t': 0, 't/(1+z)': 0, 'beta': 1, 'lambda0': 2,
                     'lambda0*(1+z)': 2, 'lambda_0': 2, 'lambda_0*(1+z)': 2,
                     'alpha': 3, 'fnorm': 4, 'f500': 4, 'lambda_peak': 5,
                     'peaklam': 5}
-
-    _parnames = np.array(['T/(1+z)', 'Beta', 'Lambda0*(1+z)',
-                          'Alpha', 'Fnorm'])
+    _parnames = np.array(['T/(1+z)', 'Beta', 'Lambda0*(1+z)', 'Alpha', 'Fnorm'])
 
     def __init__(self, nwalkers=250, photfile=None, covfile=None,
                  covextn=0, response=False, responsefile=None,
                  responsedir=None, wavenorm=500.0, noalpha=False,
                  opthin=False, nthreads=1, device=None):
-        """Same parameters as reference mbb_fit.py:26-67 (+ ``device``)."""
-        self._noalpha = noalpha
-        self._opthin = opthin
-        self._wavenorm = float(wavenorm)
-        self._nwalkers = int(nwalkers)
-        self._nthreads = int(nthreads)
-        if self._nthreads != 1:
+        """Arguments of reference mbb_fit.py:26-67, plus ``device`` (CUDA ordinal)."""
+        if int(nthreads) != 1:
             raise ValueError("nthreads != 1 is not supported: the whole "
                              "ensemble is evaluated by one GPU launch and a "
                              "CUDA context cannot be shared with forked workers")
-        self.like = likelihood(photfile=photfile, covfile=covfile,
-                               covextn=covextn, wavenorm=wavenorm,
-                               noalpha=noalpha, opthin=opthin,
+        self._settings = dict(noalpha=noalpha, opthin=opthin, wavenorm=float(wavenorm),
+                              nwalkers=int(nwalkers), nthreads=1)
+        self.like = likelihood(photfile=photfile, covfile=covfile, covextn=covextn,
+                               wavenorm=wavenorm, noalpha=noalpha, opthin=opthin,
                                response=response, responsefile=responsefile,
                                responsedir=responsedir, device=device)
-        self.sampler = _make_sampler(self._nwalkers, self.like)
+        self.sampler = _make_sampler(self.nwalkers, self.like)
         self._sampled = False
-        # order: T, beta, lambda0, alpha, fnorm
-        self._fixed = [False, False, False, False, False]
+        self._fixed = [False] * _NPAR          # T, beta, lambda0, alpha, fnorm
 
-    @property
-    def noalpha(self):
-        return self._noalpha
-
-    @property
-    def opthin(self):
-        return self._opthin
-
-    @property
-    def wavenorm(self):
-        return self._wavenorm
-
-    @property
-    def nwalkers(self):
-        return self._nwalkers
-
-    @property
-    def nthreads(self):
-        return self._nthreads
-
-    @property
-    def sampled(self):
-        return self._sampled
-
-    @property
-    def fixed(self):
-        return self._fixed
-
-    @property
-    def response_integrate(self):
-        return self.like.response_integrate
+    # settings are read-only, as in the reference
+    noalpha = property(lambda self: self._settings["noalpha"])
+    opthin = property(lambda self: self._settings["opthin"])
+    wavenorm = property(lambda self: self._settings["wavenorm"])
+    nwalkers = property(lambda self: self._settings["nwalkers"])
+    nthreads = property(lambda self: self._settings["nthreads"])
+    sampled = property(lambda self: self._sampled)
+    fixed = property(lambda self: self._fixed)
+    response_integrate = property(lambda self: self.like.response_integrate)
+    # (kept for code that reached into the reference's private names)
+    _noalpha, _opthin = noalpha, opthin
+    _wavenorm, _nwalkers, _nthreads = wavenorm, nwalkers, nthreads
 
     # ------------------------------------------------------------------ data
     def read_data(self, photfile, covfile=None, covextn=0,
@@ -119,8 +109,7 @@ class mbb_fitter(object):
 
     # ------------------------------------------------- fixing, limits, priors
     def _pidx(self, param):
-        return self._param_order[param.lower()] if isinstance(param, str) \
-            else int(param)
+        return self._param_order[param.lower()] if isinstance(param, str) else int(param)
 
     def fix_param(self, param):
         self._fixed[self._pidx(param)] = True
@@ -128,115 +117,74 @@ class mbb_fitter(object):
     def unfix_param(self, param):
         self._fixed[self._pidx(param)] = False
 
-    def set_lowlim(self, param, val):
-        self.like.set_lowlim(param, val)
-
-    def lowlim(self, param):
-        return self.like.lowlim(param)
-
-    def set_uplim(self, param, val):
-        self.like.set_uplim(param, val)
-
-    def has_uplim(self, param):
-        return self.like.has_uplim(param)
-
-    def uplim(self, param):
-        return self.like.uplim(param)
-
-    def set_gaussian_prior(self, param, mean, sigma):
-        self.like.set_gaussian_prior(param, mean, sigma)
-
-    def has_gaussian_prior(self, param):
-        return self.like.has_gaussian_prior(param)
-
-    def get_gaussian_prior(self, param):
-        return self.like.get_gaussian_prior(param)
-
     # ---------------------------------------------------------- initial ball
+    def _ball_centres(self, initvals, initsigma):
+        """Centre of each parameter's starting ball: the requested value when it obeys the
+        limits, else 2 sigma inside the violated limit (the middle of a range narrower than
+        4 sigma); reference mbb_fit.py:398-443."""
+        lo = np.array([self.lowlim(i) for i in range(_NPAR)], dtype=np.float64)
+        bounded = np.array([bool(self.has_uplim(i)) for i in range(_NPAR)])
+        hi = np.array([self.uplim(i) if bounded[i] else np.inf for i in range(_NPAR)], dtype=np.float64)
+        want = np.asarray(initvals, dtype=np.float64)
+        sig = np.asarray(initsigma, dtype=np.float64)
+        below, above = want < lo, bounded & (want > hi)
+        stuck = np.asarray(self._fixed) & (below | above)
+        if stuck.any():
+            raise ValueError("Some fixed parameters outside limits: "
+                             "{:s}".format(', '.join(self._parnames[stuck.nonzero()[0]])))
+        centre = want.copy()
+        for i in np.nonzero(below | above)[0]:
+            if not bounded[i]:
+                centre[i] = lo[i] + 2 * sig[i]
+                continue
+            span = hi[i] - lo[i]
+            if span <= 0:
+                raise ValueError("Limits on parameter {:d} cross".format(int(i)))
+            if 2.0 * sig[i] >= span:
+                centre[i] = lo[i] + 0.5 * span
+            else:
+                centre[i] = lo[i] + 2 * sig[i] if below[i] else hi[i] - 2 * sig[i]
+        return centre, lo, hi
+
     def generate_initial_values(self, initvals, initsigma):
         """nwalkers x 5 starting positions obeying the limits (reference
-        mbb_fit.py:362-479): Gaussian ball, out-of-range draws redrawn;
-        centres outside the limits are moved 2 sigma inside (or to the middle
-        of a narrow range); fixed parameters get one identical value.  Uses
-        the global ``np.random`` stream like the reference (:449, :461)."""
-        if len(initvals) != 5:
+        mbb_fit.py:362-479): per free parameter a Gaussian ball around its centre
+        (``_ball_centres``) whose out-of-range members are redrawn until none is left; a fixed
+        parameter gets its one value.  Draws come from the global ``np.random`` stream in the
+        reference's order -- ``randn(nwalkers)`` per free parameter, then ``randn(#rejected)``
+        per redraw round (:449, :461) -- so a seeded run starts from the reference's ensemble."""
+        if len(initvals) != _NPAR:
             raise ValueError("Initial values not expected length")
-        if len(initsigma) != 5:
+        if len(initsigma) != _NPAR:
             raise ValueError("Initial sigma values not expected length")
-
-        outside = [False] * 5
-        for i, val in enumerate(initvals):
-            if val < self.lowlim(i):
-                outside[i] = True
-            elif self.has_uplim(i) and val > self.uplim(i):
-                outside[i] = True
-
-        fixed_and_outside = np.logical_and(self._fixed, outside)
-        if fixed_and_outside.any():
-            bad = ', '.join(self._parnames[fixed_and_outside.nonzero()[0]])
-            raise ValueError("Some fixed parameters outside limits: "
-                             "{:s}".format(bad))
-
-        centre = np.zeros(5)
-        for i in range(5):
-            if not outside[i]:
-                centre[i] = initvals[i]
-            elif self.has_uplim(i):
-                span = self.uplim(i) - self.lowlim(i)
-                if span <= 0:
-                    raise ValueError("Limits on parameter {:d} cross".format(i))
-                if 2.0 * initsigma[i] >= span:
-                    centre[i] = self.lowlim(i) + 0.5 * span
-                elif initvals[i] < self.lowlim(i):
-                    centre[i] = self.lowlim(i) + 2 * initsigma[i]
-                else:
-                    centre[i] = self.uplim(i) - 2 * initsigma[i]
-            else:
-                centre[i] = self.lowlim(i) + 2 * initsigma[i]
-
-        p0 = np.zeros((self._nwalkers, 5))
-        maxiters = 100
-        for i in range(5):
+        centre, lo, hi = self._ball_centres(initvals, initsigma)
+        nw = self.nwalkers
+        p0 = np.empty((nw, _NPAR))
+        for i in range(_NPAR):
             if self._fixed[i]:
-                p0[:, i] = centre[i] * np.ones(self._nwalkers)
+                p0[:, i] = centre[i]
                 continue
-            lo = self.lowlim(i)
-            has_hi = self.has_uplim(i)
-            hi = self.uplim(i)
-
-            def outliers(v):
-                if has_hi:
-                    return np.logical_or(v > hi, v < lo).nonzero()[0]
-                return np.nonzero(v < lo)[0]
-
-            pvec = initsigma[i] * np.random.randn(self._nwalkers) + centre[i]
-            bad = outliers(pvec)
-            iters = 0
-            while len(bad) > 0:
-                pvec[bad] = initsigma[i] * np.random.randn(len(bad)) + centre[i]
-                iters += 1
-                bad = outliers(pvec)
-                if iters > maxiters:
-                    raise Exception("Too many iterations initializing param "
-                                    "{:d}".format(i))
-            p0[:, i] = pvec
+            col = initsigma[i] * np.random.randn(nw) + centre[i]
+            for _ in range(_MAX_REDRAWS + 1):
+                reject = np.nonzero((col > hi[i]) | (col < lo[i]))[0]
+                if reject.size == 0:
+                    break
+                col[reject] = initsigma[i] * np.random.randn(reject.size) + centre[i]
+            else:
+                if np.any((col > hi[i]) | (col < lo[i])):
+                    raise Exception("Too many iterations initializing param {:d}".format(i))
+            p0[:, i] = col
         return p0
 
     # -------------------------------------------------------------------- run
-    def run(self, nburn, nsteps, p0, verbose=False):
-        """Burn in, reset, main chain (reference mbb_fit.py:481-563)."""
-        if not self.like.data_read:
-            raise Exception("Data not read, needed to do fit")
-        if verbose:
-            print("Starting fit")
-            if self.response_integrate:
-                print("  Using response integration")
+    def _used_params(self):
+        """Indices whose start values are checked: lambda0 / alpha only when the model uses
+        them (reference mbb_fit.py:497-513)."""
+        skip = ({2} if self.opthin else set()) | ({3} if self.noalpha else set())
+        return [i for i in range(_NPAR) if i not in skip]
 
-        for i in range(5):
-            if i == 2 and self._opthin:
-                continue
-            if i == 3 and self._noalpha:
-                continue
+    def _check_start(self, p0):
+        for i in self._used_params():
             if self.has_uplim(i) and p0[:, i].max() > self.uplim(i):
                 raise ValueError("Upper limit initial value violation for "
                                  "{:s}".format(self._parnames[i]))
@@ -244,40 +192,43 @@ class mbb_fitter(object):
                 raise ValueError("Lower limit initial value violation for "
                                  "{:s}".format(self._parnames[i]))
 
-        self.sampler.reset()
+    def _report(self, nburn):
+        print("  Fit complete")
+        print("   Mean acceptance fraction:", np.mean(self.sampler.acceptance_fraction))
+        try:
+            acor = self.sampler.acor
+        except (ImportError, RuntimeError):
+            return
+        print("   Autocorrelation time: ")
+        print("    Number of burn in steps ({:d}) should be larger than these".format(nburn))
+        for i in self._used_params():
+            print("\t{:<9s} {:f}".format(("T", "beta", "lambda0", "alpha", "fnorm")[i] + ":", acor[i]))
+
+    def run(self, nburn, nsteps, p0, verbose=False):
+        """Burn in from ``p0``, forget it, then the main chain from where the burn-in ended,
+        continuing its random state -- the sequence of reference mbb_fit.py:481-563
+        (reset / run_mcmc(p0, nburn) / reset / run_mcmc(pos, nsteps, rstate0))."""
+        if not self.like.data_read:
+            raise Exception("Data not read, needed to do fit")
+        for what, n in (("burn in", nburn), ("main chain", nsteps)):
+            if n <= 0:
+                raise ValueError("Invalid (non-positive) number of {:s} steps: {:d}".format(what, n))
+        self._check_start(np.asarray(p0))
+        say = print if verbose else (lambda *a: None)
+        say("Starting fit" + ("\n  Using response integration" if self.response_integrate else ""))
         self._sampled = False
-        if nburn <= 0:
-            raise ValueError("Invalid (non-positive) number of burn in steps: "
-                             "{:d}".format(nburn))
-        if verbose:
-            print("  Doing burn in with {:d} steps".format(nburn))
-        burn = self.sampler.run_mcmc(p0, nburn)
-        pos, rstate = burn[0], burn[2]
-
         self.sampler.reset()
-        if nsteps <= 0:
-            raise ValueError("Invalid (non-positive) number of main chain "
-                             "steps: {:d}".format(nsteps))
-        if verbose:
-            print("  Doing main chain with {:d} steps".format(nsteps))
-        self.sampler.run_mcmc(pos, nsteps, rstate0=rstate)
+        say("  Doing burn in with {:d} steps".format(nburn))
+        burn = self.sampler.run_mcmc(p0, nburn)
+        self.sampler.reset()
+        say("  Doing main chain with {:d} steps".format(nsteps))
+        self.sampler.run_mcmc(burn[0], nsteps, rstate0=burn[2])
         self._sampled = True
-
         if verbose:
-            print("  Fit complete")
-            print("   Mean acceptance fraction:",
-                  np.mean(self.sampler.acceptance_fraction))
-            try:
-                acor = self.sampler.acor
-                print("   Autocorrelation time: ")
-                print("    Number of burn in steps ({:d}) should be larger "
-                      "than these".format(nburn))
-                print("\tT:        {:f}".format(acor[0]))
-                print("\tbeta:     {:f}".format(acor[1]))
-                if not self._opthin:
-                    print("\tlambda0:  {:f}".format(acor[2]))
-                if not self._noalpha:
-                    print("\talpha:    {:f}".format(acor[3]))
-                print("\tfnorm:    {:f}".format(acor[4]))
-            except (ImportError, RuntimeError):
-                pass
+            self._report(nburn)
+
+
+for _name in ("set_lowlim", "lowlim", "set_uplim", "has_uplim", "uplim", "set_gaussian_prior",
+              "has_gaussian_prior", "get_gaussian_prior"):
+    setattr(mbb_fitter, _name, _delegate(_name))
+del _name

@@ -319,7 +319,7 @@ def freq_integrate(s, minwave, maxwave):
 # ----------------------------------------------------------------------------
 # passband flux (response.py:544-576); tables come from the product's host
 # table builder, itself pinned bit-for-bit to the reference's attributes by
-# tests/test_response_tables.py
+# tests/test_host_api_cpu.py::test_response_tables_match_reference_bit_for_bit
 # ----------------------------------------------------------------------------
 Band = namedtuple("Band", "isdelta normwave wave sedmult normfac")
 

@@ -105,6 +105,35 @@ def test_generate_initial_values_obeys_limits():
         mbb_fitter(nthreads=4)
 
 
+@pytest.mark.parametrize("opthin,noalpha", [(True, True), (False, False)])
+def test_initial_ensemble_equals_the_reference(opthin, noalpha):
+    """Same np.random seed -> the starting ensemble of the executed reference's
+    mbb_fitter.generate_initial_values (mbb_fit.py:362-479), bit for bit: centres outside the
+    limits, a fixed parameter, a narrow range, redraw rounds."""
+    import sys
+    import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("/root/reference is not mounted (build container only)")
+    ref_harness.import_reference()
+    ref_fitter = sys.modules["mbb_emcee.mbb_fit"].mbb_fitter
+    waves, flux, unc = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0], np.full(6, 30.0), np.full(6, 3.0)
+    init, sig = [3.0, 1.8, 2500.0, 4.0, 30.0], [2, 0.4, 100, 0.3, 5.0]
+    out = []
+    for cls in (ref_fitter, mbb_fitter):
+        fit = cls(nwalkers=250, opthin=opthin, noalpha=noalpha)
+        fit.like.set_phot(waves, flux, unc)
+        fit.set_lowlim('T', 2.5)
+        fit.set_uplim('beta', 2.0)                # narrow-ish range: many redraws
+        fit.set_lowlim('beta', 1.5)
+        fit.set_uplim('fnorm', 31.0)
+        fit.set_lowlim('fnorm', 29.5)             # range narrower than 4 sigma -> centred
+        fit.fix_param('alpha')
+        np.random.seed(1234)
+        out.append(fit.generate_initial_values(init, sig))
+    assert np.array_equal(out[0], out[1])
+    assert (out[1][:, 3] == 4.0).all() and out[1][:, 2].max() <= 1500.0
+
+
 def test_sampler_matches_emcee2_schedule(oracle):
     """The product sampler and the oracle's restatement of the emcee 2.2
     stretch move consume the RNG identically -> identical chains."""
