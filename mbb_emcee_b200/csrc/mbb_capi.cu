@@ -421,7 +421,9 @@ struct EnsResidentLauncher {
   static void go(mbb_ctx* c, EnsFit& g, const DataRef& d, int nb, size_t smem, cudaStream_t st,
                  DevBuf<double>* scratch, cudaError_t* err) {
     if (nb == NB) {
-      auto kern = ens_resident_kernel<THIN, ALPHA, NB>;
+      // half-ensembles of exactly kEnsThreads walkers: the instantiation with compile-time indices
+      auto kern = g.h == kEnsThreads && g.G == 1 ? ens_resident_kernel<THIN, ALPHA, NB, true>
+                                                 : ens_resident_kernel<THIN, ALPHA, NB, false>;
       *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (*err != cudaSuccess) return;
       int per_sm = 1;
@@ -1604,7 +1606,7 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
         g.thin = thin;
         g.nrec = (int)nrec_total;
         g.merge = 0;
-        g.seed = seed;
+        g.keys = philox_keys(seed);
         g.step0 = step0;
         g.sc = sc;
         cudaError_t err = cudaSuccess;
@@ -1683,7 +1685,7 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
       g.thin = thin;
       g.nrec = (int)nrec;
       g.merge = main_done > 0;
-      g.seed = seed;
+      g.keys = philox_keys(seed);
       g.step0 = step0 + (uint64_t)i0;
       g.sc = sc;
       cudaError_t err = cudaSuccess;
@@ -1697,7 +1699,7 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
     EnsArgs g{};
     g.pos = dpos; g.lnp = dlnp; g.nacc = dnacc; g.status = dst;
     g.q = c->d_eq.p; g.qlnp = c->d_eqlnp.p; g.qst = c->d_eqst.p;
-    g.nsrc = nsrc; g.src0 = src0; g.nw = nwalkers; g.h = h; g.seed = seed; g.sc = sc;
+    g.nsrc = nsrc; g.src0 = src0; g.nw = nwalkers; g.h = h; g.keys = philox_keys(seed); g.sc = sc;
     const unsigned grid = (unsigned)((nh + 255) / 256);
     int64_t kept = 0;
     for (int64_t it = i0; it < i1; ++it) {

@@ -79,10 +79,10 @@ inline StretchScale stretch_scale(double a) {
   return s;
 }
 
-__device__ __forceinline__ Draw stretch_draw(unsigned long long seed, unsigned long long widx,
+__device__ __forceinline__ Draw stretch_draw(const PhiloxKeys& keys, unsigned long long widx,
                                              unsigned long long hstep, const StretchScale& sc, int ncomp) {
   const Philox r = philox4x32_10((unsigned)widx, (unsigned)(widx >> 32), (unsigned)hstep,
-                                 (unsigned)(hstep >> 32), (unsigned)seed, (unsigned)(seed >> 32));
+                                 (unsigned)(hstep >> 32), keys);
   Draw d;
   const double uz = u52w(r.c[0], r.c[1] >> 12);
   const double t = __dadd_rn(__dmul_rn(sc.am1, uz), 1.0);
@@ -104,7 +104,8 @@ struct EnsArgs {
   long long nsrc, src0;     // src0: global index of source 0 (sharded runs), enters the RNG counter
   int nw, h, half;          // h = nw/2; half 0 updates walkers [0,h) against [h,nw)
   int count;                // != 0: accepted moves are counted (main run)
-  unsigned long long seed, hstep;   // hstep = 2*iteration + half
+  unsigned long long hstep;   // hstep = 2*iteration + half
+  PhiloxKeys keys;            // philox_keys(seed)
   StretchScale sc;
 };
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) ens_propose_kernel(const EnsArgs g) {
   if (i >= g.nsrc * g.h) return;
   const long long src = i / g.h;
   const int k = (int)(i - src * g.h);
-  const Draw d = stretch_draw(g.seed, (unsigned long long)((g.src0 + src) * g.h + k), g.hstep, g.sc, g.h);
+  const Draw d = stretch_draw(g.keys, (unsigned long long)((g.src0 + src) * g.h + k), g.hstep, g.sc, g.h);
   const int own = g.half == 0 ? k : g.h + k;
   const int oth = (g.half == 0 ? g.h : 0) + d.partner;
   const double* s = g.pos + (src * g.nw + own) * 5;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
   if (i >= g.nsrc * g.h) return;
   const long long src = i / g.h;
   const int k = (int)(i - src * g.h);
-  const Draw d = stretch_draw(g.seed, (unsigned long long)((g.src0 + src) * g.h + k), g.hstep, g.sc, g.h);
+  const Draw d = stretch_draw(g.keys, (unsigned long long)((g.src0 + src) * g.h + k), g.hstep, g.sc, g.h);
   const int own = g.half == 0 ? k : g.h + k;
   const long long w = src * g.nw + own;
   const double newlnp = g.qlnp[i];
@@ -333,7 +334,8 @@ struct EnsFit {
   int thin;
   int nrec;                 // recorded iterations in this launch
   int merge;                // the stats rows already hold earlier segments of this main run
-  unsigned long long seed, step0;   // step0: global iteration index of this launch's iteration 0
+  unsigned long long step0;   // step0: global iteration index of this launch's iteration 0
+  PhiloxKeys keys;            // philox_keys(seed)
   StretchScale sc;
 };
 
@@ -355,12 +357,16 @@ __host__ __device__ inline size_t ens_resident_smem(int G, int nw, int nb, bool 
   return d * 8 + (size_t)G * nw * 4;
 }
 
-template <bool THIN, bool ALPHA, int NB>
+// HT: the half-ensemble has exactly kEnsThreads walkers (BASELINE cfg5: 512 walkers) -- one
+// source per CTA, one walker per thread and half-step; every index of the loop below is then a
+// compile-time function of threadIdx.x (the generic form re-derives them from the launch
+// arguments under register pressure: 140 of its 830 instructions per proposal).
+template <bool THIN, bool ALPHA, int NB, bool HT>
 __global__ void __launch_bounds__(kEnsThreads, MBB_ENS_MINB)
 ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataRef d, const SmallTab t,
                     const ColdArgs* __restrict__ cold) {
   extern __shared__ __align__(16) double smem[];
-  const int nw = g.nw, h = g.h, G = g.G;
+  const int nw = HT ? 2 * kEnsThreads : g.nw, h = HT ? kEnsThreads : g.h, G = HT ? 1 : g.G;
   const bool stats = g.stats != nullptr;
   double* const s_tab = smem;
   double* const s_pos = s_tab + kTabRepDoubles;
@@ -374,20 +380,21 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
   stage_exp_table(s_tab);
   const double* tab = lane_exp_table(s_tab);
   // thread -> (source of the group, first walker of the half, stride)
-  const int sg = h <= kEnsThreads ? tid / h : 0;
-  const int kfirst = h <= kEnsThreads ? tid - sg * h : tid;
-  const int kstride = h <= kEnsThreads ? h : kEnsThreads;
+  const int sg = HT ? 0 : (h <= kEnsThreads ? tid / h : 0);
+  const int kfirst = HT ? tid : (h <= kEnsThreads ? tid - sg * h : tid);
+  const int kstride = HT ? kEnsThreads : (h <= kEnsThreads ? h : kEnsThreads);
   // summaries: thread r of the hs threads serving a source owns component r % 5, walkers r / 5 + i * nslots
   const int hs = h <= kEnsThreads ? h : kEnsThreads;
   const int nslots = hs / 5, cj = kfirst % 5, slot = kfirst / 5;
   const long long ngroups = (g.nsrc + G - 1) / G;
   double* const bp = g.scratch + (size_t)blockIdx.x * 5 * kEnsThreads;
   const bool use_cinv = d.cinv != nullptr;
+  const int thin = g.thin;
 
   for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const long long s_first = grp * G;
-    const int ga = (int)((g.nsrc - s_first) < G ? (g.nsrc - s_first) : G);
-    const bool active = sg < ga;
+    const int ga = HT ? 1 : (int)((g.nsrc - s_first) < G ? (g.nsrc - s_first) : G);
+    const bool active = HT || sg < ga;
     const long long src = s_first + sg;                  // this thread's source (index within the call)
     __syncthreads();      // the previous group's epilogue is done with the shared arrays (first pass: table staged)
     {
@@ -413,19 +420,30 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
     }
     __syncthreads();
 
+    // the next iteration of this launch that ends on a record (main iteration j records when
+    // (main_done + j + 1) % thin == 0), and its record index: counters instead of a 64-bit
+    // remainder per iteration
+    int next_rec = g.main_from + (int)((thin - 1) - g.main_done % thin);
+    int rec = 0;
+    unsigned long long hstep = 2ull * g.step0;
+    const unsigned long long wbase = (unsigned long long)((g.src0 + src) * h);
+
+    // (Measured and rejected: a split barrier -- mbarrier arrive, the Philox draw of the next
+    // half-step, then the wait -- so that an early warp has 11 % of its next proposal to do
+    // before it waits: 0.3365 against 0.3337 ms per iteration of 2e4 sources, same chains.)
     for (int it = 0; it < g.niter; ++it) {
       const bool is_main = it >= g.main_from;
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        const unsigned long long hstep = 2ull * (g.step0 + (unsigned long long)it) + (unsigned long long)half;
+      for (int half = 0; half < 2; ++half, ++hstep) {
         if (active) {
+          const int own0 = sg * nw + (half == 0 ? 0 : h);      // first walker of the updating half
+          const int oth0 = sg * nw + (half == 0 ? h : 0);
 #pragma unroll 1
           for (int k = kfirst; k < h; k += kstride) {
-            const Draw dr = stretch_draw(g.seed, (unsigned long long)((g.src0 + src) * h + k), hstep, g.sc, h);
-            const int own = sg * nw + (half == 0 ? k : h + k);
-            const int oth = sg * nw + (half == 0 ? h : 0) + dr.partner;
-            const double* sj = s_pos + (size_t)own * 5;
-            const double* cj5 = s_pos + (size_t)oth * 5;
+            const Draw dr = stretch_draw(g.keys, wbase + (unsigned)k, hstep, g.sc, h);
+            const int own = own0 + k;
+            double* const sj = s_pos + own * 5;
+            const double* const cj5 = s_pos + (oth0 + dr.partner) * 5;
             double q[5];
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
@@ -442,20 +460,19 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
               int* gs = g.status + (s_first * nw + own);
               if (*gs <= ST_BELOW_LOWLIM) *gs = st;
             } else if (stretch_accept(dr.z, dr.u, newlnp, s_lnp[own])) {
-              double* p = s_pos + (size_t)own * 5;
 #pragma unroll
-              for (int j = 0; j < 5; ++j) p[j] = q[j];
+              for (int j = 0; j < 5; ++j) sj[j] = q[j];
               s_lnp[own] = newlnp;
               if (is_main) s_nacc[own] += 1;
             }
+            if (HT) break;
           }
         }
         __syncthreads();
       }
-      if (is_main) {
-        const long long jm = g.main_done + (it - g.main_from);       // index within the main run
-        if ((jm + 1) % g.thin == 0) {
-          const long long rec = (jm + 1) / g.thin - 1 - g.main_done / g.thin;       // record index within the launch
+      if (it == next_rec) {
+        next_rec += thin;
+        {
           if (stats && active) {
             const double* P = s_pos + (size_t)sg * nw * 5;
             if (slot < nslots) {
@@ -501,6 +518,7 @@ ens_resident_kernel(const EnsFit g, const ModelP m, const Priors pr, const DataR
               for (int i = tid; i < ga * nw / 2; i += kEnsThreads) dst[i] = sl2[i];
             }
           }
+          ++rec;
           // a record reads rows that other threads own: they must not move before everyone has read
           if (stats || g.chain || g.chain_lnp) __syncthreads();
         }

@@ -250,7 +250,22 @@ MBB_HD Red red_sum_prod(double a_hi, double a_lo, double b, double c) {
 template <int TS, bool CLAMP>
 MBB_HD double scaled_T(const double* tab, int k) {
   using C = TabCfg<TS>;
+#if defined(__CUDA_ARCH__) && !defined(MBB_NO_ASM_LOOKUP)
+  double tb;
+  if constexpr (C::stride != 0) {
+    // the replicated shared-memory copy: mask, one scaled add, LDS.64 -- written out because
+    // ptxas otherwise re-derives the lane's copy offset for every lookup (shift, mask, or, LEA)
+    unsigned addr;
+    asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, %2;\n\tmad.lo.u32 %0, t, %3, %4;\n\t}"
+        : "=r"(addr)
+        : "r"(k), "n"(C::mask), "n"(8 << C::stride), "r"((unsigned)__cvta_generic_to_shared(tab)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tb) : "r"(addr));
+  } else {
+    tb = tab[k & C::mask];
+  }
+#else
   const double tb = tab[(k & C::mask) << C::stride];
+#endif
   if (!CLAMP) return from_hilo(hi32_of(tb) + (int)((unsigned)k << C::hishift), lo32_of(tb));
   const int j = (k + C::half) & C::mask;
   int m = (k + C::half) >> C::bits;

@@ -433,9 +433,18 @@ void emu_qags_test(int kind, double a, double b, double epsabs, double epsrel, d
 }
 
 void emu_philox(const unsigned* ctr, const unsigned* key, unsigned* out, double* u) {
-  const Philox r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
-  for (int i = 0; i < 4; ++i) out[i] = r.c[i];
+  // the shipped form (round keys formed beforehand) and the textbook one must agree
+  const Philox r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3],
+                                 philox_keys(((unsigned long long)key[1] << 32) | key[0]));
+  const Philox r2 = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = r.c[i] == r2.c[i] ? r.c[i] : ~r2.c[i];
   *u = u53(r.c[0], r.c[1]);
+}
+
+// the two uniforms the sampler cuts out of one block (bit-assembled on the device)
+void emu_philox_uniforms(unsigned w0, unsigned w1, unsigned w3, double* uz, double* ua) {
+  *uz = u52w(w0, w1 >> 12);
+  *ua = u43(w3, w1 & 0x7ffu);
 }
 
 void emu_fnu(int thin, int alpha, long long n, const double* pars, double wavenorm, int nfreq,

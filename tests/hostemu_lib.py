@@ -180,6 +180,14 @@ def philox(ctr, key):
     return out, u.value
 
 
+def philox_uniforms(w0, w1, w3):
+    """(stretch uniform, acceptance uniform) the sampler cuts out of one Philox block."""
+    uz, ua = ctypes.c_double(), ctypes.c_double()
+    lib().emu_philox_uniforms(ctypes.c_uint(int(w0)), ctypes.c_uint(int(w1)), ctypes.c_uint(int(w3)),
+                              ctypes.byref(uz), ctypes.byref(ua))
+    return uz.value, ua.value
+
+
 def qags(opthin, noalpha, pars, wavenorm, minwave, maxwave, prefac=1.0):
     """freq_integrate by the QUADPACK replay (csrc/mbb_quadpack.cuh)."""
     P = _c(pars).reshape(-1, 5)

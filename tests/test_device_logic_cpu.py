@@ -415,6 +415,15 @@ def test_philox_known_answers():
         got = philox_np.philox4x32_10(*[np.array([c], dtype=np.uint64) for c in ctr], key[0], key[1])
         assert tuple(int(g[0]) for g in got) == want
         assert u == philox_np.u53(got[0], got[1])[0] and 0.0 < u < 1.0
+    # the bit-assembled uniforms of the device equal the (m + 0.5) 2^-k form of the numpy twin
+    rng = np.random.default_rng(5)
+    words = rng.integers(0, 2**32, size=(2000, 3), dtype=np.uint64)
+    words[:4] = [[0, 0, 0], [2**32 - 1] * 3, [1, 0xFFF, 1], [2**32 - 1, 0, 0]]
+    for w0, w1, w3 in words:
+        uz, ua = emu.philox_uniforms(w0, w1, w3)
+        assert uz == philox_np.u52w(np.uint64(w0), np.uint64(w1) >> np.uint64(12))
+        assert ua == philox_np.u43(np.uint64(w3), np.uint64(w1) & np.uint64(0x7FF))
+        assert 0.0 < uz < 1.0 and 0.0 < ua < 1.0
 
 
 def test_qags_matches_scipy(golden):

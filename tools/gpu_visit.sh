@@ -42,6 +42,15 @@ probe_ncu)   # PROBE_V="0 1": per-source-line executed instruction counts of one
   ncu -i $O/r02_probe_$T.ncu-rep --page source --csv > $O/r02_probe_src_sass_$T.csv 2>> $O/r02_probe_ncu_$T.log
   python tools/ncu_summary.py full $O/r02_probe_$T.ncu-rep > $O/r02_probe_full_$T.md 2>> $O/r02_probe_ncu_$T.log
   rm -f $O/r02_probe_$T.ncu-rep; tail -3 $O/r02_probe_ncu_$T.log ;;
+ens_probe)    # ENS_ARGS="1 0 20000 20 1"
+  for a in "1 0 20000 20 1" "1 0 20000 20 0" "0 1 20000 20 1"; do timeout 120 tools/_build/ens_probe $a 2>&1 | tee -a $O/r02_ens_probe.jsonl; done ;;
+ens_probe_ncu)
+  V=${PROBE_V:-1 0}; T=$(echo $V | tr -d ' ')
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:ens_resident -s 1 -c 1 \
+      -o $O/r02_ensp_$T -f tools/_build/ens_probe $V 4000 10 1 > $O/r02_ensp_ncu_$T.log 2>&1
+  ncu -i $O/r02_ensp_$T.ncu-rep --page source --csv > $O/r02_ensp_src_sass_$T.csv 2>> $O/r02_ensp_ncu_$T.log
+  python tools/ncu_summary.py full $O/r02_ensp_$T.ncu-rep > $O/r02_ensp_full_$T.md 2>> $O/r02_ensp_ncu_$T.log
+  rm -f $O/r02_ensp_$T.ncu-rep; tail -3 $O/r02_ensp_ncu_$T.log ;;
 *) echo "unknown step $step" ;;
 esac
 done

@@ -106,7 +106,7 @@ def main():
         print("| %s | %.1f | %.1f | %.1f | %.1f%% |" % (k, n * scale, n64 * scale, (n - n64) * scale, 100.0 * n / tot))
     if "--lines" in sys.argv:
         print("\n| source line | executed | FP64 |\n|---|---:|---:|")
-        for k, (n, n64) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:60]:
+        for k, (n, n64) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("NCU_LINES_TOP","60"))]:
             print("| %s | %.1f | %.1f |" % (k, n * scale, n64 * scale))
 
 
