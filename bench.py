@@ -524,6 +524,48 @@ def run_b200(args):
                        "h2d_gb_per_s_per_gpu": n * 40 / (ms_max * 1e-3) / 1e9,
                        "api": "mbb_loglike(MBB_HOST) with pinned host arrays; pipelined H2D/kernel/D2H",
                        "matches_device_path": same}
+        # the same pass with the fixed parameters declared (mbb_set_fixed_params; reference
+        # mbb_fit.fix_param, e.g. alpha under --noalpha and lambda0 for an optically thin fit:
+        # one value in every walker): SoA host block, fixed columns never cross PCIe
+        if W["cfg"]["opthin"] and W["cfg"]["noalpha"]:
+            fixed, fvals = (0, 0, 1, 1, 0), (0.0, 0.0, 1300.0, 4.0, 0.0)
+            P2 = P.clone()
+            P2[:, 2], P2[:, 3] = fvals[2], fvals[3]
+            out2 = torch.empty_like(out)
+            ctx.loglike_device(n, P2.data_ptr(), out2.data_ptr(), 0, walkers_per_source=nw)
+            ctx.sync()
+            T_host = torch.empty((5, n), dtype=torch.float64).pin_memory()
+            T_host.copy_(P2.t())
+            T_host[2].fill_(float("nan"))          # fixed columns of the host block are never read
+            T_host[3].fill_(float("nan"))
+            torch.cuda.synchronize()
+            Tn = T_host.numpy()
+            ctx.set_fixed_params(fixed, fvals)
+
+            def step_fixed():
+                rc = lib.mbb_loglike(ctx._h, n, vp(Tn.ctypes.data), 1, None, nw, vp(on.ctypes.data), None, 0)
+                if rc != 0:
+                    raise RuntimeError(lib.mbb_last_error().decode())
+
+            step_fixed()
+            barrier()
+            msf = []
+            for _ in range(k2):
+                t1 = time.perf_counter()
+                step_fixed()
+                msf.append(1e3 * (time.perf_counter() - t1))
+            barrier()
+            ctx.set_fixed_params(None)
+            same2 = bool(np.array_equal(on[:100000], out2[:100000].cpu().numpy()))
+            msf_max = allmax(float(np.mean(msf)))[0]
+            e2e_loglike["fixed_columns"] = {
+                "value": n * world / (msf_max * 1e-3), "unit": UNIT, "ms_per_step": msf_max,
+                "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": int(n * 8),
+                "h2d_gb_per_s_per_gpu": n * 24 / (msf_max * 1e-3) / 1e9,
+                "api": "mbb_set_fixed_params(lambda0, alpha) + mbb_loglike(MBB_HOST, MBB_SOA): 24 instead of 40 "
+                       "bytes per evaluation host-to-device",
+                "matches_device_path": same2}
+            del P2, out2, T_host, Tn
         del P_host, out_host, Pn, on
 
     # ---- the batch fit: device-resident sampler, resident in HBM and through host buffers --------

@@ -146,6 +146,16 @@ int mbb_set_priors(mbb_ctx *ctx, const double lowlim[5],
                    const uint8_t has_gprior[6], const double gmean[6],
                    const double givar[6]);
 
+/* ---- fixed parameters: mbb_fitter.fix_param / generate_initial_values
+ * (mbb_fit.py:183-200, 440-443: a fixed parameter holds ONE value in every walker
+ * for the whole run -- e.g. alpha under --noalpha, run_mbb_emcee.py:233).  A promise
+ * by the caller that column i of every `pars` handed to mbb_loglike equals values[i]
+ * wherever fixed[i] != 0.  The host path uses it for MBB_SOA batches: fixed columns
+ * are not copied host-to-device at all (cfg5 with lambda0 and alpha fixed: 24 instead
+ * of 40 bytes per evaluation over PCIe), they are filled on the device once.  Other
+ * paths ignore it.  fixed == NULL clears the promise. */
+int mbb_set_fixed_params(mbb_ctx *ctx, const int32_t fixed[5], const double values[5]);
+
 /* ---- THE hot entry: likelihood.__call__ for n parameter vectors
  * (likelihood.py:790-834).  Evaluation i uses source src_index[i] if
  * src_index != NULL, else i / walkers_per_source (pass n for a single

@@ -77,6 +77,7 @@ def load_library():
             "mbb_set_data": (i32, [vp, i32, i32, vp, vp, vp]),
             "mbb_set_data_chol": (i32, [vp, i32, i32, vp, vp]),
             "mbb_set_priors": (i32, [vp, vp, vp, vp, vp, vp, vp]),
+            "mbb_set_fixed_params": (i32, [vp, vp, vp]),
             "mbb_loglike": (i32, [vp, i64, vp, i32, vp, i64, vp, vp, i32]),
             "mbb_fnu": (i32, [vp, i64, vp, i32, i32, vp, i32, i32, vp, vp, i32]),
             "mbb_sed_consts": (i32, [vp, i64, vp, i32, i32, vp, vp, i32]),
@@ -105,7 +106,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["mbb_version", "mbb_last_error", "mbb_device_count", "mbb_ctx_create",
                     "mbb_ctx_destroy", "mbb_sync", "mbb_launch_count", "mbb_stream_handle",
                     "mbb_last_kernel_ms", "mbb_set_model", "mbb_set_math_mode", "mbb_set_lir_method", "mbb_set_bands",
-                    "mbb_set_data", "mbb_set_data_chol", "mbb_set_priors", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
+                    "mbb_set_data", "mbb_set_data_chol", "mbb_set_priors", "mbb_set_fixed_params", "mbb_loglike", "mbb_fnu", "mbb_sed_consts",
                     "mbb_chain_post", "mbb_chain_flux", "mbb_chain_stats", "mbb_ensemble_run", "mbb_ensemble_fit", "mbb_host_alloc", "mbb_host_free", "mbb_host_register",
                     "mbb_host_unregister", "mbb_fp64_peak"]
 
@@ -257,6 +258,19 @@ class Context(object):
             raise ValueError("limits/priors arrays have the wrong length")
         self._ck(self._lib.mbb_set_priors(self._h, _ptr(lo), _ptr(hu), _ptr(up), _ptr(hg),
                                           _ptr(gm), _ptr(gi)))
+
+    def set_fixed_params(self, fixed=None, values=None):
+        """Promise that column i of every parameter block equals values[i] where fixed[i]
+        (mbb_fitter.fix_param, reference mbb_fit.py:183-200, 440-443): the host path then skips
+        those columns of SoA batches on the way to the device.  ``fixed=None`` clears it."""
+        if fixed is None:
+            self._ck(self._lib.mbb_set_fixed_params(self._h, None, None))
+            return
+        fx = np.ascontiguousarray(fixed, dtype=np.int32)
+        va = _f64(values)
+        if fx.size != 5 or va.size != 5:
+            raise ValueError("fixed / values must have 5 entries")
+        self._ck(self._lib.mbb_set_fixed_params(self._h, _ptr(fx), _ptr(va)))
 
     # -- compute -----------------------------------------------------------
     def loglike(self, pars, src_index=None, walkers_per_source=None, layout=AOS):

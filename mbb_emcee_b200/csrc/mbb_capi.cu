@@ -131,12 +131,20 @@ struct mbb_ctx {
     DevBuf<double> din, dout;
     DevBuf<int> dst, dsrc;
     int64_t pend_e0 = -1, pend_n = 0;   // chunk whose outputs still sit in hout/hst
+    // fixed columns (mbb_set_fixed_params) this slot's din already holds: [5][fill_stride]
+    uint64_t fill_epoch = 0;
+    int64_t fill_stride = 0;
+    const double* fill_base = nullptr;
     // source chunks of mbb_ensemble_fit(MBB_HOST)
     DevBuf<double> epos, elnp, estats, escratch;
     DevBuf<int> enacc, est;
   };
   Slot slots[3];
   bool slots_ready = false;
+  // mbb_set_fixed_params: columns the caller promises to be constant
+  unsigned fixed_mask = 0;
+  double fixed_val[5] = {0, 0, 0, 0, 0};
+  uint64_t fixed_epoch = 1;
 
   // staging for the other MBB_HOST calls
   PinBuf<double> h_in, h_out;
@@ -997,6 +1005,31 @@ int loglike_small_graph(mbb_ctx* c, int64_t n, const double* pars, int layout, l
 
 }  // namespace
 
+__global__ void __launch_bounds__(256) fill_column_kernel(double* __restrict__ p, long long n, double v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+int mbb_set_fixed_params(mbb_ctx* c, const int32_t* fixed, const double* values) {
+  if (!c) return fail("null context");
+  unsigned mask = 0;
+  double val[5] = {0, 0, 0, 0, 0};
+  if (fixed) {
+    if (!values) return fail("null values");
+    for (int i = 0; i < 5; ++i)
+      if (fixed[i]) {
+        if (!std::isfinite(values[i])) return fail("fixed parameter value is not finite");
+        mask |= 1u << i;
+        val[i] = values[i];
+      }
+  }
+  Use u(c);
+  c->fixed_mask = mask;
+  for (int i = 0; i < 5; ++i) c->fixed_val[i] = val[i];
+  c->fixed_epoch += 1;
+  return 0;
+}
+
 // Host path: the batch is cut into chunks that flow through three slots, each
 // with its own stream: H2D copy, kernel and D2H copy of consecutive chunks
 // overlap (two copy engines + SMs).  Caller memory that is already pinned
@@ -1069,7 +1102,9 @@ int mbb_loglike(mbb_ctx* c, int64_t n, const double* pars, int layout, const int
     CK(sl.dst.reserve((size_t)CH));
     if (k == 0) CK(cudaStreamWaitEvent(sl.s, c->ev0, 0));
     // ---- inputs
+    int64_t col_stride = m;
     if (layout == MBB_AOS) {
+      sl.fill_epoch = 0;          // overwrites whatever fixed columns the block held
       const double* src = pars + e0 * 5;
       if (!pin_in) {
         CK(sl.hin.reserve((size_t)CH * 5));
@@ -1079,18 +1114,34 @@ int mbb_loglike(mbb_ctx* c, int64_t n, const double* pars, int layout, const int
       CK(cudaMemcpyAsync(sl.din.p, src, (size_t)m * 5 * sizeof(double), cudaMemcpyHostToDevice, sl.s));
     } else {
       if (!pin_in) CK(sl.hin.reserve((size_t)CH * 5));
+      // with fixed columns the device block keeps the stride CH for every chunk, so that a
+      // column filled once stays valid for all chunks this slot serves
+      col_stride = c->fixed_mask ? CH : m;
+      const bool filled = c->fixed_mask && sl.fill_epoch == c->fixed_epoch && sl.fill_stride == CH &&
+                          sl.fill_base == sl.din.p;
       for (int i = 0; i < 5; ++i) {
+        double* dcol = sl.din.p + (size_t)i * col_stride;
+        if ((c->fixed_mask >> i) & 1u) {
+          if (!filled) {
+            fill_column_kernel<<<(unsigned)((CH + 2047) / 2048), 256, 0, sl.s>>>(dcol, CH, c->fixed_val[i]);
+            c->launches += 1;
+          }
+          continue;
+        }
         const double* src = pars + (size_t)i * n + e0;
         if (!pin_in) {
           memcpy(sl.hin.p + (size_t)i * m, src, (size_t)m * sizeof(double));
           src = sl.hin.p + (size_t)i * m;
         }
-        CK(cudaMemcpyAsync(sl.din.p + (size_t)i * m, src, (size_t)m * sizeof(double),
-                           cudaMemcpyHostToDevice, sl.s));
+        CK(cudaMemcpyAsync(dcol, src, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, sl.s));
       }
+      sl.fill_epoch = c->fixed_mask ? c->fixed_epoch : 0;
+      sl.fill_stride = CH;
+      sl.fill_base = sl.din.p;
     }
     EvalArgs a{};
     a.n = m; a.e0 = e0; a.wps = wps; a.layout = layout;
+    a.soa_stride = layout == MBB_SOA ? col_stride : 0;
     a.pars = sl.din.p; a.src_index = nullptr; a.out = sl.dout.p; a.status = sl.dst.p;
     if (src_index) {
       CK(sl.dsrc.reserve((size_t)CH));

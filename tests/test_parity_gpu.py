@@ -521,6 +521,60 @@ def test_host_pipeline_pinned_and_pageable():
         ctx.loglike_into(P.astype(np.float32), Op.numpy())
 
 
+def test_host_pipeline_fixed_columns():
+    """mbb_set_fixed_params: SoA host batches whose fixed columns (mbb_fit.py:440-443 -- one
+    value in every walker) are not copied to the device give the bits of the plain call;
+    the caller's fixed columns are really not read (poisoned here); pageable and page-locked
+    buffers, a ragged tail, a change of the fixed values, AoS calls in between and clearing
+    the promise."""
+    import torch
+    from mbb_emcee_b200 import _native, synthetic
+    rng = np.random.RandomState(34)
+    nw = 125
+    n = (1 << 17) + 2000 - ((1 << 17) + 2000) % nw + nw
+    nsrc = n // nw
+    waves = [70.0, 100.0, 160.0, 250.0, 350.0, 500.0]
+    flux = rng.uniform(5, 80, (nsrc, 6))
+    unc = rng.uniform(1, 6, (nsrc, 6))
+    ctx = _native.Context(0)
+    ctx.set_model(500.0, False, False)          # thick + alpha: every column enters the model
+    ctx.set_bands(np.arange(7, dtype=np.int32), waves, np.ones(6))
+    ctx.set_data(flux, ivar=1.0 / unc**2)
+    low = np.array([1, 0.1, 1, 0.1, 1e-3])
+    P = synthetic.walker_cloud((14.0, 1.8, 400.0, 3.0, 30.0), n, rng, low)
+    for fixed, vals in (((0, 0, 1, 1, 0), (0, 0, 380.0, 2.5, 0)), ((0, 1, 0, 0, 0), (0, 1.7, 0, 0, 0))):
+        Q = P.copy()
+        for i in range(5):
+            if fixed[i]:
+                Q[:, i] = vals[i]
+        want, wst = ctx.loglike(Q, walkers_per_source=nw)                # AoS, no promise in effect
+        Qt = np.ascontiguousarray(Q.T)
+        for i in range(5):
+            if fixed[i]:
+                Qt[i] = np.nan                                           # must not be read
+        ctx.set_fixed_params(fixed, vals)
+        got, gst = ctx.loglike(Qt, walkers_per_source=nw, layout=_native.SOA)
+        assert np.array_equal(got, want) and np.array_equal(gst, wst)
+        l0 = ctx.launch_count()
+        got, _ = ctx.loglike(Qt, walkers_per_source=nw, layout=_native.SOA)   # columns already filled
+        assert np.array_equal(got, want)
+        l1 = ctx.launch_count()
+        chk, _ = ctx.loglike(Q, walkers_per_source=nw)                   # AoS in between reuses the slots
+        assert np.array_equal(chk, want)
+        Tp = torch.empty((5, n), dtype=torch.float64).pin_memory()
+        Op = torch.empty(n, dtype=torch.float64).pin_memory()
+        Tp.numpy()[...] = Qt
+        ctx.loglike_into(Tp.numpy(), Op.numpy(), None, walkers_per_source=nw, layout=_native.SOA)
+        assert np.array_equal(Op.numpy(), want)
+        assert l1 - l0 < ctx.launch_count() - l1                         # the refill after AoS launched fills
+    ctx.set_fixed_params(None)
+    got, _ = ctx.loglike(np.ascontiguousarray(P.T), walkers_per_source=nw, layout=_native.SOA)
+    want, _ = ctx.loglike(P, walkers_per_source=nw)
+    assert np.array_equal(got, want)
+    with pytest.raises(RuntimeError):
+        ctx.set_fixed_params((1, 0, 0, 0, 0), (np.inf, 0, 0, 0, 0))
+
+
 def test_contexts_in_concurrent_threads():
     """SURVEY 8b threading contract: a context serialises its own calls, separate contexts
     may be driven from separate threads (ctypes drops the GIL for the call).  Two
