@@ -919,6 +919,33 @@ def fits_leg(dev):
         out[name] = {"wall_s": wall, "evals": 250 * 1051, "evals_per_s": 250 * 1051 / wall,
                      "us_per_125_walker_call": call_us, "device_us_per_call": kern_us,
                      "mean_acceptance": float(np.mean(fit.sampler.acceptance_fraction))}
+        # the same fit with the stretch move inside the library (mbb_fitter(sampler="device")):
+        # burn-in and main run are two mbb_ensemble_fit(MBB_HOST) calls, the chain comes back once
+        dfit = mbb_fitter(nwalkers=250, wavenorm=cfg["wavenorm"], noalpha=cfg["noalpha"], opthin=cfg["opthin"],
+                          response=cfg["response"], device=dev.index, sampler="device", seed=cfg["seed"])
+        dfit.set_data(cfg["bands"], flux, unc, covmatrix=cov)
+        for nm, v in cfg.get("uplims", []):
+            dfit.set_uplim(nm, v)
+        for nm, m, s in cfg.get("gpriors", []):
+            dfit.set_gaussian_prior(nm, m, s)
+        dfit.run(50, 1000, p0)                             # warm-up at full size: page-locked staging, device buffers
+        dfit.sampler.random_state = cfg["seed"]
+        l0 = dfit.like.context.launch_count()
+        t0 = time.perf_counter()
+        dfit.run(50, 1000, p0)
+        dwall = time.perf_counter() - t0
+        dch = dfit.sampler.chain
+        hch = fit.sampler.chain
+        out[name]["device_sampler"] = {
+            "wall_s": dwall, "evals_per_s": 250 * 1052 / dwall,
+            "gpu_launches": int(dfit.like.context.launch_count() - l0),
+            "mean_acceptance": float(np.mean(dfit.sampler.acceptance_fraction)),
+            "chain_shape": list(dch.shape),
+            # same posterior as the host sampler's chain (different random streams): T and beta
+            "posterior_mean_T_beta": [float(dch[:, 200:, 0].mean()), float(dch[:, 200:, 1].mean())],
+            "host_sampler_mean_T_beta": [float(hch[:, 200:, 0].mean()), float(hch[:, 200:, 1].mean())],
+            "speedup_vs_host_sampler": wall / dwall}
+        del dfit
     # the same fits on the host: the CPU likelihood timed on one core (the reference's default nthreads=1),
     # times the 250 x 1051 calls emcee makes -- sampler overhead not included
     try:
@@ -933,6 +960,8 @@ def fits_leg(dev):
             out[nm]["cpu_kind"] = r[2]
             out[nm]["cpu_fit_estimate_s_one_core"] = us * 1e-6 * 250 * 1051
             out[nm]["speedup_vs_one_core"] = out[nm]["cpu_fit_estimate_s_one_core"] / out[nm]["wall_s"]
+            out[nm]["device_sampler"]["speedup_vs_one_core"] = \
+                out[nm]["cpu_fit_estimate_s_one_core"] / out[nm]["device_sampler"]["wall_s"]
     except Exception as exc:
         out["cpu_estimate_failed"] = repr(exc)
     return out

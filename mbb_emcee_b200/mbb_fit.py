@@ -26,9 +26,15 @@ _NPAR = 5
 _MAX_REDRAWS = 100
 
 
-def _make_sampler(nwalkers, like):
+def _make_sampler(nwalkers, like, where="host", seed=0):
     """The package's emcee-2.2 restatement by default; MBB_B200_USE_EMCEE=1 asks for an
-    installed emcee instead (block log-probability either way)."""
+    installed emcee instead (block log-probability either way); ``where="device"``: the
+    whole run on the GPU (device_sampler.DeviceEnsembleSampler, counter-based random numbers)."""
+    if where == "device":
+        from .device_sampler import DeviceEnsembleSampler
+        return DeviceEnsembleSampler(nwalkers, like, seed=seed)
+    if where != "host":
+        raise ValueError("sampler must be 'host' or 'device'")
     if os.environ.get("MBB_B200_USE_EMCEE", "0") == "1":
         try:
             import emcee
@@ -62,8 +68,12 @@ class mbb_fitter(object):
     def __init__(self, nwalkers=250, photfile=None, covfile=None,
                  covextn=0, response=False, responsefile=None,
                  responsedir=None, wavenorm=500.0, noalpha=False,
-                 opthin=False, nthreads=1, device=None):
-        """Arguments of reference mbb_fit.py:26-67, plus ``device`` (CUDA ordinal)."""
+                 opthin=False, nthreads=1, device=None, sampler="host", seed=0):
+        """Arguments of reference mbb_fit.py:26-67, plus ``device`` (CUDA ordinal) and
+        ``sampler``: "host" -- emcee's stretch move and random stream on the host, one device
+        call per half-ensemble (chains equal emcee's for the same state); "device" -- the whole
+        burn-in and main run inside the library (statistically equivalent chains from Philox
+        draws keyed by ``seed``; BASELINE configs[0-2] in milliseconds)."""
         if int(nthreads) != 1:
             raise ValueError("nthreads != 1 is not supported: the whole "
                              "ensemble is evaluated by one GPU launch and a "
@@ -74,7 +84,7 @@ class mbb_fitter(object):
                                wavenorm=wavenorm, noalpha=noalpha, opthin=opthin,
                                response=response, responsefile=responsefile,
                                responsedir=responsedir, device=device)
-        self.sampler = _make_sampler(self.nwalkers, self.like)
+        self.sampler = _make_sampler(self.nwalkers, self.like, sampler, seed)
         self._sampled = False
         self._fixed = [False] * _NPAR          # T, beta, lambda0, alpha, fnorm
 

@@ -73,6 +73,9 @@ def build_parser():
     a("--math", default="fast", choices=["fast", "faithful", "gauss"], help="device arithmetic mode")
     a("--covsolver", default="inverse", choices=["inverse", "cholesky"],
       help="chi-square of a covariance matrix: explicit inverse like the reference (def), or its Cholesky factor")
+    a("--sampler", default="host", choices=["host", "device"],
+      help="host: emcee's stretch move on the host, one device call per half-ensemble (def); "
+           "device: the whole burn-in and main run on the GPU")
     a("--version", action="version", version="mbb_emcee_b200 " + __import__("mbb_emcee_b200").__version__)
     a("--seed", type=int, default=None, help="seed of the initial ensemble and of the sampler")
     a("-v", "--verbose", action="store_true", help="print status messages")
@@ -126,11 +129,12 @@ def main(argv=None):
     fit = mbb_fitter(nwalkers=args.nwalkers, photfile=in_photdir(args.photfile),
                      covfile=in_photdir(args.covfile), covextn=args.covextn, wavenorm=args.wavenorm,
                      noalpha=args.noalpha, opthin=args.opthin, nthreads=args.threads,
-                     response=args.response, responsefile=args.responsefile, responsedir=args.responsedir)
+                     response=args.response, responsefile=args.responsefile, responsedir=args.responsedir,
+                     sampler=args.sampler, seed=0 if args.seed is None else args.seed + 1)
     fit.like.math_mode = {"faithful": _native.MATH_FAITHFUL, "fast": _native.MATH_FAST,
                           "gauss": _native.MATH_FAST_GAUSS}[args.math]
     fit.like.cov_solver = args.covsolver
-    if args.seed is not None and hasattr(fit.sampler, "random_state"):
+    if args.seed is not None and args.sampler == "host" and hasattr(fit.sampler, "random_state"):
         fit.sampler.random_state = np.random.RandomState(args.seed + 1).get_state()
     configure_fit(fit, args)
     p0init = np.array([getattr(args, "init" + stem) for _, stem in _PARAMS])

@@ -321,3 +321,70 @@ def test_with_installed_emcee(oracle):
         theirs.run_mcmc(P, 400, progress=False)
         a, b = theirs.get_chain()[200:, :, 0].ravel(), ours.chain[:, 30:, 0].ravel()
         assert abs(a.mean() - b.mean()) < 5 * np.hypot(a.std() / np.sqrt(64), b.std() / np.sqrt(64))
+
+
+@pytest.mark.parametrize("response", [False, True])
+def test_mbb_fitter_device_sampler(oracle, response):
+    """mbb_fitter(sampler="device"): the reference's run sequence (mbb_fit.py:524-543 -- burn in,
+    reset, main chain from where the burn-in ended) with the whole stretch move inside the
+    library.  The recorded chain is what a host replay with the same Philox draws and the CPU
+    oracle gives (positions bit for bit), and its posterior agrees with the host sampler's
+    (emcee's random stream) within Monte-Carlo error."""
+    from mbb_emcee_b200 import mbb_fitter, mbb_results
+    rng = np.random.RandomState(5)
+    if response:
+        bands = ["PACS_160um", "SPIRE_250um", "SPIRE_350um", "SPIRE_500um"]
+        kw = dict(response=True)
+        nw, nburn, nsteps = 40, 4, 12
+    else:
+        bands = [100.0, 160.0, 250.0, 350.0, 500.0, 850.0]
+        kw = dict()
+        nw, nburn, nsteps = 250, 5, 20
+    truth = np.array([14.0, 1.8, 400.0, 3.0, 30.0])
+    fits = {}
+    for where in ("device", "host"):
+        fit = mbb_fitter(nwalkers=nw, device=0, sampler=where, seed=77, **kw)
+        if not fits:
+            f0 = fit.like.get_sed(truth, np.array([100.0, 160.0, 250.0, 350.0, 500.0, 850.0]))
+            flux = (f0 if not response else f0[1:5]) * (1.0 + 0.03 * rng.standard_normal(len(bands)))
+            unc = 0.08 * flux
+        fit.set_data(bands, flux, unc)
+        fits[where] = fit
+    fit = fits["device"]
+    np.random.seed(3)
+    p0 = fit.generate_initial_values(truth, [2, 0.2, 100, 0.3, 5.0])
+    fit.run(nburn, nsteps, p0)
+    ch, lnp = fit.sampler.chain, fit.sampler.lnprobability
+    assert ch.shape == (nw, nsteps, 5) and lnp.shape == (nw, nsteps)
+    assert fit.sampler.iterations == nsteps and fit.sampler.random_state[2] == nburn + nsteps
+    # host replay: burn-in and main run are one Philox stream (iterations 0 .. nburn + nsteps)
+    sp = oracle.LikeSpec(500.0, False, False)
+    if response:
+        sp.set_phot([oracle.band_from_response(r) for r in fit.like._responses], flux, unc)
+    else:
+        sp.set_phot(bands, flux, unc)
+    sp.has_uplim = list(fit.like.has_uplims)
+    sp.uplim = np.array(fit.like.uplims)
+    r = philox_np.replay(lambda s, Q: oracle.loglike_batch(sp, Q), p0[None], nburn + nsteps, 77, chain=True)
+    assert np.array_equal(ch, np.moveaxis(r[3][nburn:, 0], 0, 1))
+    assert relerr(lnp, r[4][nburn:, 0].T).max() < TOL
+    acc = fit.sampler.acceptance_fraction
+    assert acc.shape == (nw,) and 0.05 < acc.mean() < 0.95
+    res = mbb_results(fit=fit)
+    assert np.isfinite(res.par_cen("T")).all()
+    if response:
+        return
+    # posterior against the host sampler on a longer run: means within 5 standard errors
+    # (each chain has >= 2e4 samples; integrated autocorrelation ~ 40 iterations)
+    stats = {}
+    for where in ("device", "host"):
+        f = fits[where]
+        np.random.seed(11)
+        q0 = f.generate_initial_values(truth, [2, 0.2, 100, 0.3, 5.0])
+        f.run(150, 400, q0)
+        flat = f.sampler.chain[:, ::40].reshape(-1, 5)
+        stats[where] = (flat.mean(axis=0), flat.std(axis=0), flat.shape[0])
+    (m1, s1, n1), (m2, s2, n2) = stats["device"], stats["host"]
+    for i in (0, 1, 4):
+        assert abs(m1[i] - m2[i]) < 5.0 * np.hypot(s1[i], s2[i]) / np.sqrt(n1 / 2.0)
+        assert 0.6 < s1[i] / s2[i] < 1.6
