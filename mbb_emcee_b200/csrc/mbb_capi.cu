@@ -381,7 +381,10 @@ struct DeltaLauncher {
       // photometry rows of a tile travel with it when sources are implicit (walkers_per_source)
       // and the errors are diagonal; d_flux / d_ivar are cudaMalloc'ed (256-byte aligned) and padded
       static const bool no_stage = getenv("MBB_B200_NO_STAGE_DATA") != nullptr;
-      const int stage_data = use_tma && !no_stage && !a.src_index && d.ivar && !d.cinv;
+      // (walkers_per_source below 2^31 with multiply-shift constants: the kernel finds a thread's
+      // source relative to its tile's first one in 32-bit arithmetic)
+      const int stage_data = use_tma && !no_stage && !a.src_index && d.ivar && !d.cinv && a.wps_mul != 0 &&
+                             a.wps < (1LL << 31);
       const ModelP m = model_of(c);
       // the replicated exp table is the kernel's dynamic shared memory (beside ~33 KB static)
       constexpr size_t kTabBytes = sizeof(double) * kTabRepDoubles;

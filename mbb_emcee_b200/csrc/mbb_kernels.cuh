@@ -393,8 +393,10 @@ constexpr int kDeltaStages = 3;
 constexpr int kDeltaMaxSrc = 8;
 
 struct DeltaStageHdr {
-  long long d0;       // first staged double of the flux / ivar arrays (even index)
-  int with_data;
+  long long s_first;  // source of the tile's first evaluation
+  int with_data;      // the tile's flux / inverse-variance rows were staged
+  int off0;           // index of source s_first's row in the staged arrays (0 or 1: 16-byte alignment)
+  unsigned rem0;      // position of the tile's first evaluation within source s_first
   int pad;
 };
 
@@ -421,10 +423,10 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
   auto issue = [&](unsigned tl, int stage) {
     const long long e0 = (long long)tl * kDeltaTile;
     if (!use_tma || a.n - e0 < kDeltaTile) return;
-    long long d0 = 0;
+    long long d0 = 0, s_first = 0;
     unsigned cnt = 0;
     if (stage_data) {
-      const long long s_first = source_of(a, e0);
+      s_first = source_of(a, e0);
       const long long s_end = source_of(a, e0 + kDeltaTile - 1) + 1;
       if (s_end - s_first <= kDeltaMaxSrc) {
         // doubles [d0, d0 + cnt), d0 rounded down and cnt rounded up to even (16 bytes);
@@ -433,7 +435,11 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
         cnt = (unsigned)((s_end * NB - d0 + 1) & ~1LL);
       }
     }
-    s_hdr[stage].d0 = d0;
+    // (stage_data implies implicit sources: the position of e0 within its source fits 32 bits
+    // whenever the rows are staged, because then wps >= tile / kDeltaMaxSrc and rem0 < wps)
+    s_hdr[stage].s_first = s_first;
+    s_hdr[stage].off0 = (int)(s_first * NB - d0);
+    s_hdr[stage].rem0 = (unsigned)((a.e0 + e0) - s_first * a.wps);
     s_hdr[stage].with_data = cnt != 0;
     mbar_expect_tx(&s_bar[stage], kDeltaTile * 40u + 2u * cnt * 8u);
     if (a.layout == 0) {
@@ -454,8 +460,14 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
   if (tid == 0 && tile < nt) issue(tile, 0);
   int stage = 0;            // ring position of the current tile
   unsigned par = 0;         // parity of this use of the stage's barrier
+#ifdef MBB_DELTA_ASSUME_AOS
+  constexpr int par_tid_stride = 5, par_idx_stride = 1;
+#else
   const int par_tid_stride = a.layout == 0 ? 5 : 1;
   const int par_idx_stride = a.layout == 0 ? 1 : kDeltaTile;
+#endif
+  (void)par_tid_stride;
+  (void)par_idx_stride;
   for (; tile < nt; tile += gridDim.x) {
     const long long e0 = (long long)tile * kDeltaTile, e = e0 + tid;
     const bool via_tma = use_tma && a.n - e0 >= kDeltaTile;
@@ -464,24 +476,36 @@ loglike_delta_kernel(const EvalArgs a, const ModelP m, const Priors pr, const Da
     double p[5];
     if (via_tma) {
       mbar_wait(&s_bar[stage], par);
-      const double* sp = s_par[stage] + tid * par_tid_stride;       // AoS: row tid; SoA: column tid
+      if (a.layout == 0) {                   // AoS: row tid
+        const double* sp = s_par[stage] + tid * 5;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) p[i] = sp[i * par_idx_stride];
+        for (int i = 0; i < 5; ++i) p[i] = sp[i];
+      } else {                               // SoA: column tid
+        const double* sp = s_par[stage] + tid;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) p[i] = sp[i * kDeltaTile];
+      }
     } else if (active) {
       load_pars(a, e, p);
     }
     __syncthreads();
     if (active) {
-      const long long src = source_of(a, e);
+      long long src;
       double diff[NB];
       const double* iv_smem = nullptr;
       if (via_tma && s_hdr[stage].with_data) {
         // (the slot stays valid for the whole tile: it is refilled two iterations from now)
-        const int off = (int)(src * NB - s_hdr[stage].d0);
+        // source relative to the tile's first one: a 32-bit multiply-shift division
+        const unsigned g32 = s_hdr[stage].rem0 + (unsigned)tid;
+        const unsigned tq = __umulhi(a.wps_mul, g32);
+        const int ds = (int)((tq + ((g32 - tq) >> a.wps_sh1)) >> a.wps_sh2);
+        src = s_hdr[stage].s_first + ds;
+        const int off = s_hdr[stage].off0 + ds * NB;
 #pragma unroll
         for (int b = 0; b < NB; ++b) diff[b] = s_dat[stage][0][off + b];
         iv_smem = &s_dat[stage][1][off];
       } else {
+        src = source_of(a, e);
         delta_load_data<NB>(d, src, diff);
       }
       int st;
