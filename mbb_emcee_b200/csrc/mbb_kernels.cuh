@@ -1055,7 +1055,11 @@ chain_lir_kernel(const double* __restrict__ chain, const int* __restrict__ work,
     const LirSpan sp = lir_span<ALPHA>(hk * fmin_ghz, hk * fmax_ghz, beta, c[slot][6], c[slot][2],
                                        c[slot][3]);
     double acc = 0.0;
-#pragma unroll
+#ifndef MBB_LIR_UNROLL
+#define MBB_LIR_UNROLL 1
+#endif
+    constexpr int kLirUnroll = MBB_LIR_UNROLL;
+#pragma unroll kLirUnroll
     for (int q = 0; q < kLirNodes / 32; ++q) acc += lir_node<THIN>(sp, lane + 32 * q, beta, x0);
     acc = warp_sum(acc);
     if (lane == 0) {
@@ -1071,8 +1075,11 @@ chain_lir_kernel(const double* __restrict__ chain, const int* __restrict__ work,
 // 1.49e-8, limit 50) on the reference's own integrand (modified_blackbody.py:
 // 671, numpy formulation of f_nu): one thread per unique sample.  Reproduces
 // the reference's value to ~1e-15 -- including its ~1e-8 quadrature error.
+#ifndef MBB_QAGS_MINB
+#define MBB_QAGS_MINB 1
+#endif
 template <bool THIN, bool ALPHA>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MBB_QAGS_MINB)
 chain_lir_qags_kernel(const double* __restrict__ chain, const int* __restrict__ work,
                       const unsigned* __restrict__ nwork, double wavenorm, double fmin_ghz,
                       double fmax_ghz, double prefac, double* __restrict__ out_lir,

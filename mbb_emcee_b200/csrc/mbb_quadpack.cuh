@@ -26,8 +26,26 @@ struct Gk21 {
   double result, abserr, resabs, resasc;
 };
 
+// Products and sums of the rule with separate roundings, as the Fortran original compiled
+// without fused multiply-add evaluates them (the host build of this header uses
+// -ffp-contract=off for the same reason): the result then carries dqk21's own rounding errors.
+MBB_HD double q_mul(double x, double y) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(x, y);
+#else
+  return x * y;
+#endif
+}
+MBB_HD double q_add(double x, double y) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(x, y);
+#else
+  return x + y;
+#endif
+}
+
 template <class F>
-MBB_HD Gk21 qk21(F f, double a, double b) {
+MBB_HD_NOINLINE Gk21 qk21(F f, double a, double b) {
   const double wg[5] = {0.066671344308688137593568809893332, 0.149451349150580593145776339657697,
                         0.219086362515982043995534934228163, 0.269266719309996355091226921569469,
                         0.295524224714752870173815619188769};
@@ -44,45 +62,55 @@ MBB_HD Gk21 qk21(F f, double a, double b) {
                           0.142775938577060080797094273138717, 0.147739104901338491374841515972068,
                           0.149445554002916905664936468389821};
   const double epmach = 2.220446049250313e-16, uflow = 2.2250738585072014e-308;
-  const double centr = 0.5 * (a + b);
-  const double hlgth = 0.5 * (b - a);
+  const double centr = q_mul(0.5, q_add(a, b));
+  const double hlgth = q_mul(0.5, q_add(b, -a));
   const double dhlgth = fabs(hlgth);
+  // All 21 integrand values first, through ONE call site in a rolled loop: the integrand (pow,
+  // expm1, the merge-point branch) is a few hundred instructions, and 21 inlined copies per rule
+  // times three inlined rules made a kernel that did not fit the instruction cache (ncu:
+  // `no_instruction` 6 warps per issue; 94 -> 47 ms for the 3.5e6 unique samples of cfg4).  The
+  // sums below then run in dqk21's own order.
   double fv1[10], fv2[10];
+  double fc = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < 21; ++i) {          // i = 0: centre; then node (i - 1) / 2, left for odd i, right for even
+    const int jj = i == 0 ? 10 : (i - 1) >> 1;            // xgk[10] = 0: the centre
+    const double absc = q_mul(hlgth, xgk[jj]);
+    const double v = f(q_add(centr, (i & 1) ? -absc : absc));
+    if (i == 0) fc = v;
+    else if (i & 1) fv1[jj] = v;
+    else fv2[jj] = v;
+  }
   double resg = 0.0;
-  const double fc = f(centr);
-  double resk = wgk[10] * fc;
+  double resk = q_mul(wgk[10], fc);
   double resabs = fabs(resk);
+#pragma unroll 1
   for (int j = 0; j < 5; ++j) {
     const int jtw = 2 * j + 1;
-    const double absc = hlgth * xgk[jtw];
-    const double fval1 = f(centr - absc);
-    const double fval2 = f(centr + absc);
-    fv1[jtw] = fval1;
-    fv2[jtw] = fval2;
-    const double fsum = fval1 + fval2;
-    resg = resg + wg[j] * fsum;
-    resk = resk + wgk[jtw] * fsum;
-    resabs = resabs + wgk[jtw] * (fabs(fval1) + fabs(fval2));
+    const double fval1 = fv1[jtw], fval2 = fv2[jtw];
+    const double fsum = q_add(fval1, fval2);
+    resg = q_add(resg, q_mul(wg[j], fsum));
+    resk = q_add(resk, q_mul(wgk[jtw], fsum));
+    resabs = q_add(resabs, q_mul(wgk[jtw], q_add(fabs(fval1), fabs(fval2))));
   }
+#pragma unroll 1
   for (int j = 0; j < 5; ++j) {
     const int jtwm1 = 2 * j;
-    const double absc = hlgth * xgk[jtwm1];
-    const double fval1 = f(centr - absc);
-    const double fval2 = f(centr + absc);
-    fv1[jtwm1] = fval1;
-    fv2[jtwm1] = fval2;
-    const double fsum = fval1 + fval2;
-    resk = resk + wgk[jtwm1] * fsum;
-    resabs = resabs + wgk[jtwm1] * (fabs(fval1) + fabs(fval2));
+    const double fval1 = fv1[jtwm1], fval2 = fv2[jtwm1];
+    const double fsum = q_add(fval1, fval2);
+    resk = q_add(resk, q_mul(wgk[jtwm1], fsum));
+    resabs = q_add(resabs, q_mul(wgk[jtwm1], q_add(fabs(fval1), fabs(fval2))));
   }
-  const double reskh = resk * 0.5;
-  double resasc = wgk[10] * fabs(fc - reskh);
-  for (int j = 0; j < 10; ++j) resasc = resasc + wgk[j] * (fabs(fv1[j] - reskh) + fabs(fv2[j] - reskh));
+  const double reskh = q_mul(resk, 0.5);
+  double resasc = q_mul(wgk[10], fabs(q_add(fc, -reskh)));
+#pragma unroll 1
+  for (int j = 0; j < 10; ++j)
+    resasc = q_add(resasc, q_mul(wgk[j], q_add(fabs(q_add(fv1[j], -reskh)), fabs(q_add(fv2[j], -reskh)))));
   Gk21 r;
-  r.result = resk * hlgth;
-  r.resabs = resabs * dhlgth;
-  r.resasc = resasc * dhlgth;
-  r.abserr = fabs((resk - resg) * hlgth);
+  r.result = q_mul(resk, hlgth);
+  r.resabs = q_mul(resabs, dhlgth);
+  r.resasc = q_mul(resasc, dhlgth);
+  r.abserr = fabs(q_mul(q_add(resk, -resg), hlgth));
   if (r.resasc != 0.0 && r.abserr != 0.0)
     r.abserr = r.resasc * fmin(1.0, pow(200.0 * r.abserr / r.resasc, 1.5));
   if (r.resabs > uflow / (50.0 * epmach)) r.abserr = fmax((epmach * 50.0) * r.resabs, r.abserr);
@@ -290,8 +318,11 @@ MBB_HD QagsOut qagse(F f, double a, double b, double epsabs, double epsrel) {
     const double a2 = b1;
     const double b2 = blist[maxerr];
     erlast = errmax;
-    const Gk21 g1 = qk21(f, a1, b1);
-    const Gk21 g2 = qk21(f, a2, b2);
+    // (the two halves through one call site: one copy of the rule and its integrand in the code)
+    Gk21 gh[2];
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) gh[hf] = qk21(f, hf ? a2 : a1, hf ? b2 : b1);
+    const Gk21 g1 = gh[0], g2 = gh[1];
     const double area1 = g1.result, error1 = g1.abserr, defab1 = g1.resasc;
     const double area2 = g2.result, error2 = g2.abserr, defab2 = g2.resasc;
     const double area12 = area1 + area2;

@@ -876,14 +876,17 @@ def test_chain_post_golden(golden, observed, name, opthin, noalpha):
     # chaotic at the ulp level, though: where a termination / ordering test of
     # QUADPACK is decided by the last bit of an integrand value (libdevice pow
     # vs glibc pow), the two runs subdivide differently and differ by the
-    # quadrature's own error.  Bar: >= 99 % of the samples within 1e-12, the rest
-    # within 5e-9 (observed on B200: 719 of 720 <= 7e-16, one at 5e-10).
+    # quadrature's own error.  Bar: >= 99.5 % of the samples within 1e-12, the rest
+    # within 5e-9.  Observed on B200 with the rule's products and sums rounded separately
+    # (mbb_quadpack.cuh q_mul / q_add; a contracted abscissa moved 1 sample in 100 before): all 720
+    # golden samples of each variant <= 9e-16, and 3000 of 3000 random chain samples <= 9e-16
+    # against scipy (60 % of them bit-identical).
     res.compute_lir(wavemin=cfg["lir"][0], wavemax=cfg["lir"][1])
     dev = relerr(res.lir, g[name + "_lir"])
     observed.record("L_IR quadpack replay vs golden, max [%s]" % name, dev.max())
     observed.record("L_IR quadpack replay vs golden, fraction within 1e-12 [%s]" % name, np.mean(dev < TOL))
     assert dev.max() < 5e-9
-    assert np.mean(dev < TOL) >= 0.99, np.mean(dev < TOL)
+    assert np.mean(dev < TOL) >= 0.995, np.mean(dev < TOL)
     lir_q = res.lir.copy()
     # L_IR, fixed-rule quadrature: the true integral (1e-13 vs 40-digit mpmath in
     # test_device_logic_cpu.py::test_freq_integrate); the reference's own quad error
