@@ -798,7 +798,8 @@ def chain_leg(dev, rank, world, barrier, allmax, peak_tf):
     nw, ns = 500, 20000
     chain = synthetic.random_walk_chain(cfg["truth"], nw, ns, np.random.RandomState(cfg["seed"]))
     lo, hi = shard_range(nw, rank, world)
-    mine = np.ascontiguousarray(chain[lo:hi])
+    mine = _native.pinned_empty((hi - lo, ns, 5))          # page-locked, like the other host-buffer legs
+    mine[...] = chain[lo:hi]
     uniq = 1.0 - float(np.all(chain[:, 1:] == chain[:, :-1], axis=2).mean())
     ctx = _native.Context(dev.index)
     lib = ctx._lib
@@ -843,10 +844,15 @@ def chain_leg(dev, rank, world, barrier, allmax, peak_tf):
     import torch.distributed as dist
     bar = dist.barrier if world > 1 else None
     shared = [shared_array(t, (nw, ns), rank, world, barrier=bar) for t in ("peak", "lir", "dust")]
-    stt = np.empty((hi - lo, ns), dtype=np.int32)
-    ctx.chain_post(mine[:2, :100], 7, z=cfg["z"], dl_mpc=cfg["lumdist"])      # warm-up
+    stt = _native.pinned_empty((hi - lo, ns), np.int32)
     ctx.set_model(500.0, False, False)
     ctx.set_lir_method("quadpack")
+    # warm-up at full size (device buffers of the context are allocated on first use)
+    ctx.chain_post_into(mine, 7, peak=shared[0].array[lo:hi], lir=shared[1].array[lo:hi],
+                        dustmass=shared[2].array[lo:hi], status=stt, z=cfg["z"], dl_mpc=cfg["lumdist"],
+                        kappa=cfg["kappa"], kappa_wave=cfg["kappa_wave"])
+    for sh in shared:
+        sh.array[lo:hi] = np.nan
     barrier()
     t0 = time.perf_counter()
     ctx.chain_post_into(mine, 7, peak=shared[0].array[lo:hi], lir=shared[1].array[lo:hi],
@@ -866,8 +872,8 @@ def chain_leg(dev, rank, world, barrier, allmax, peak_tf):
                   "s_local_post_processing": allmax(t_local)[0],
                   "h2d_bytes": int(mine.nbytes), "d2h_bytes": int(3 * mine.shape[0] * ns * 8 + mine.shape[0] * ns * 4),
                   "gathered_shape": list(shared[1].array.shape),
-                  "what": "mbb_chain_post(MBB_HOST): peak wavelength + L_IR (QUADPACK replay) + dust mass of this "
-                          "rank's walker rows, written by the device-to-host copies straight into this rank's rows "
+                  "what": "mbb_chain_post(MBB_HOST), page-locked chain in: peak wavelength + L_IR (QUADPACK replay) + "
+                          "dust mass of this rank's walker rows, written by the device-to-host copies straight into this rank's rows "
                           "of arrays shared by all ranks (page-locked /dev/shm mappings), then a barrier: the final "
                           "gather, inside the time, without a collective",
                   "all_finite": ok,

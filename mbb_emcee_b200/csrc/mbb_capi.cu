@@ -365,6 +365,7 @@ struct LaunchThread {
 };
 
 constexpr int kMaxDeltaNB = 8;
+constexpr long long kSmallNodesMaxN = 4096;    // up to here a CTA per evaluation beats a warp per evaluation
 
 template <bool THIN, bool ALPHA, int NB>
 struct DeltaLauncher {
@@ -524,7 +525,14 @@ struct LaunchSplit {
       const long long want = (a.n + kNodesWarps - 1) / kNodesWarps;
       const long long resident = (long long)c->sm_count * per_sm;
       const unsigned grid = (unsigned)(want < resident ? want : resident);
-      nodes<<<grid, kNodesThreads, smem, st>>>(a, c->pri.any_gprior, d, t, scratch, sst);
+      // small batches (a single source's half-ensemble): one CTA per evaluation instead of one warp
+      static const bool no_small = getenv("MBB_B200_NO_SMALL_NODES") != nullptr;
+      if (FAST && !gauss && !no_small && a.n <= kSmallNodesMaxN) {
+        loglike_nodes_small_kernel<THIN, ALPHA><<<(unsigned)a.n, kSmallNodesThreads, 0, st>>>(
+            a, c->pri.any_gprior, d, t, scratch, sst);
+      } else {
+        nodes<<<grid, kNodesThreads, smem, st>>>(a, c->pri.any_gprior, d, t, scratch, sst);
+      }
       c->launches += 1;   // the caller counts one launch per call; add the second kernel
     }
   }

@@ -835,6 +835,115 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
 }
 
 // ---------------------------------------------------------------------------
+// Small batches (the 125-walker half-ensemble of a single-source fit, reference
+// mbb_fit.py:525-542): with one warp per evaluation the launch above keeps 8 SMs
+// busy for the ~50 node iterations of an evaluation (20 us for BASELINE cfg2).
+// Here a CTA of kSmallNodesWarps warps owns ONE evaluation: the nodes of every
+// band are spread over all its threads (7 instead of 53 iterations for cfg2),
+// band sums are reduced warp-wise and then over the warps in a fixed order, and
+// warp 0 forms the chi-square.  Tables are read from global memory (L1 / L2
+// resident: 40 KB), the exp table is the plain 256-entry one.  FAST arithmetic,
+// full tables only; results equal the big kernel's to rounding (the order of
+// the node sum differs).
+// ---------------------------------------------------------------------------
+constexpr int kSmallNodesWarps = 8;
+constexpr int kSmallNodesThreads = 32 * kSmallNodesWarps;
+
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(kSmallNodesThreads)
+loglike_nodes_small_kernel(const EvalArgs a, const int any_gprior, const DataRef d, const NodeTab t,
+                           const double* __restrict__ scratch, const int* __restrict__ sst) {
+  __shared__ double s_part[kSmallNodesWarps][kMaxBands];
+  __shared__ double s_diff[kMaxBands];
+  const long long e = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = t.nb;
+  const int stw = __ldg(sst + e);
+  const int st = stw & 0xff;
+  if (st != ST_OK) {
+    if (tid == 0) {
+      a.out[e] = (st == ST_BELOW_LOWLIM) ? -kInf : qnan();
+      if (a.status) a.status[e] = st;
+    }
+    return;
+  }
+  const double2* c2 = reinterpret_cast<const double2*>(scratch + e * kScratchStride);
+  const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
+  const double2 c89 = __ldg(c2 + 4), cpg = __ldg(c2 + 7);
+  FastSed fs;
+  fs.xk_hi = c01.x; fs.xk_lo = c01.y; fs.nb = c23.x; fs.apow = c23.y;
+  fs.t0c = c45.x; fs.nu_merge = c45.y; fs.uq_hi = c67.x; fs.uq_lo = c67.y;
+  fs.amp_grey = c89.x; fs.amp_pow = c89.y;
+  const bool safe = (stw & kSafeBit) != 0;
+  const double* tab = exp2_tab256_default();
+  for (int b = 0; b < nb; ++b) {
+    const int i0 = __ldg(t.band_off + b), i1 = __ldg(t.band_off + b + 1);
+    double acc = 0.0;
+    if (safe) {
+      for (int i = i0 + tid; i < i1; i += kSmallNodesThreads) {
+        const double2 fw = __ldg(t.a + i);
+        acc = node_acc<THIN, ALPHA, false, kTab256>(fs, fw.x, __ldg(t.b + i), fw.y, acc, tab);
+      }
+    } else {
+      for (int i = i0 + tid; i < i1; i += kSmallNodesThreads) {
+        const double2 fw = __ldg(t.a + i);
+        acc = node_acc<THIN, ALPHA, true, kTab256>(fs, fw.x, __ldg(t.b + i), fw.y, acc, tab);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_part[warp][b] = acc;
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  const long long src = source_of(a, e);
+  const double* fl = d.flux + src * d.nb;
+  double chi = 0.0;
+  for (int b = lane; b < nb; b += 32) {
+    double m = 0.0;
+#pragma unroll
+    for (int w = 0; w < kSmallNodesWarps; ++w) m += s_part[w][b];
+    s_diff[b] = __ldg(fl + b) - m;
+  }
+  __syncwarp();
+  if (d.cinv) {
+    const double* ci = d.cinv + src * (long long)nb * nb;
+    double part = 0.0;
+    if (d.chol) {          // forward substitution is serial in the rows: lane 0, in place
+      if (lane == 0) {
+        for (int r = 0; r < nb; ++r) {
+          double acc = s_diff[r];
+          for (int cc = 0; cc < r; ++cc) acc = fma(-__ldg(ci + r * nb + cc), s_diff[cc], acc);
+          acc *= __ldg(ci + r * nb + r);
+          s_diff[r] = acc;
+          part = fma(acc, acc, part);
+        }
+      }
+      chi = __shfl_sync(0xffffffffu, part, 0);
+    } else {
+      for (int r = lane; r < nb; r += 32) {
+        double row = 0.0;
+        for (int cc = 0; cc < nb; ++cc) row = fma(__ldg(ci + r * nb + cc), s_diff[cc], row);
+        part = fma(s_diff[r], row, part);
+      }
+      chi = warp_sum(part);
+    }
+  } else {
+    // the big kernel accumulates the bands serially in one lane: same order here
+    if (lane == 0) {
+      const double* ivp = d.ivar + src * d.nb;
+      for (int b = 0; b < nb; ++b) chi = fma(s_diff[b] * s_diff[b], __ldg(ivp + b), chi);
+    }
+  }
+  if (lane == 0) {
+    double lnl = -0.5 * chi;
+    lnl += cpg.x;
+    if (any_gprior) lnl += cpg.y;
+    a.out[e] = lnl;
+    if (a.status) a.status[e] = (lnl != lnl) ? ST_NONFINITE : ST_OK;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // f_nu on a common frequency grid: out[n][nfreq]  (modified_blackbody.__call__)
 // grid = (ceil(nfreq/256), n); the per-walker constants are computed once per
 // block by thread 0 and broadcast through shared memory.

@@ -191,6 +191,40 @@ def test_all_variants_tabulated_vs_oracle(oracle):
             assert relerr(like(P), want).max() < TOL, (name, mode)
 
 
+def test_nodes_kernels_small_and_large_batches(oracle):
+    """Tabulated passbands, FAST: batches of <= 4096 evaluations give a CTA to every
+    evaluation (loglike_nodes_small_kernel: the half-ensemble of a single-source fit), larger
+    ones a warp (the persistent nodes kernel).  Both against the oracle, for every model
+    variant, with diagonal errors and with a full covariance (explicit inverse and Cholesky
+    factor); and the same rows through either kernel agree to rounding."""
+    from mbb_emcee_b200 import likelihood, synthetic
+    rng = np.random.RandomState(78)
+    bands = ["PACS_100um", "PACS_160um", "SPIRE_250um", "SPIRE_350um", "SPIRE_500um", "SCUBA2_850um"]
+    flux = np.array([35.0, 80.0, 70.0, 45.0, 22.0, 5.0])
+    unc = np.array([4.0, 8.0, 7.0, 5.0, 3.0, 1.0])
+    cov = synthetic.cfg3_covariance(flux, unc, spire_idx=(2, 3, 4))
+    for name, opthin, noalpha in VARIANTS:
+        for solver in (None, "inverse", "cholesky"):
+            like = likelihood(wavenorm=500.0, opthin=opthin, noalpha=noalpha, response=True, device=0)
+            like.set_phot(bands, flux, unc)
+            if solver is not None:
+                like.set_cov(cov)
+                like.cov_solver = solver
+            big = synthetic.walker_cloud((14.0, 1.8, 400.0, 3.0, 30.0), 6000, rng, like.lowlims)
+            big[::501, 0] = 0.5                       # below the lower limit: -inf through both kernels
+            got_big = like(big)                       # 6000 > 4096: warp per evaluation
+            got_small = like(big[:125])               # CTA per evaluation
+            pick = np.r_[0:125, rng.randint(125, 6000, 175)]
+            want = oracle.loglike_batch(_oracle_spec(oracle, like), big[pick])
+            fin = np.isfinite(want)
+            assert np.array_equal(np.isneginf(got_big[pick]), np.isneginf(want)) and (~fin).sum() >= 1
+            assert relerr(got_big[pick][fin], want[fin]).max() < TOL, (name, solver)
+            assert relerr(got_small[fin[:125]], want[:125][fin[:125]]).max() < TOL, (name, solver)
+            assert np.array_equal(np.isneginf(got_small), np.isneginf(got_big[:125]))
+            f2 = np.isfinite(got_small)
+            assert relerr(got_small[f2], got_big[:125][f2]).max() < 1e-13, (name, solver)
+
+
 def test_whole_wheel_global_table_path(oracle):
     """All 18 shipped filters (4677 nodes): the node table no longer fits the
     shared-memory budget, so the kernel reads it from global memory."""
