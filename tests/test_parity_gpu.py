@@ -855,7 +855,7 @@ def test_chain_bit_identity(golden, oracle, cfgname, nwalk, nsteps):
         assert (fit.sampler.chain[:, :, 3] == cfg["truth"][3]).all()     # fixed stays fixed
 
 
-def test_fitter_run_end_to_end(golden):
+def test_fitter_run_end_to_end(golden, oracle):
     """mbb_fitter.run (burn-in, reset, main chain) and mbb_results statistics."""
     from mbb_emcee_b200 import mbb_fitter, mbb_results, synthetic
     cfg = synthetic.CONFIGS["cfg1"]
@@ -867,12 +867,36 @@ def test_fitter_run_end_to_end(golden):
     p0 = fit.generate_initial_values([12.0, 1.8, 2500.0, 4.0, 30.0], [2, 0.2, 100, 0.3, 5.0])
     fit.run(30, 150, p0)
     assert fit.sampled and fit.sampler.chain.shape == (100, 150, 5)
+    ch, lnp = fit.sampler.chain, fit.sampler.lnprobability
+    # every recorded log-probability is the oracle's for the recorded position
+    spec = _oracle_spec(oracle, fit.like)
+    pick = np.random.RandomState(2).randint(0, 100 * 150, 300)
+    want = oracle.loglike_batch(spec, ch.reshape(-1, 5)[pick])
+    assert relerr(lnp.reshape(-1)[pick], want).max() < TOL
+    acc = fit.sampler.acceptance_fraction
+    assert acc.shape == (100,) and 0.15 < acc.mean() < 0.8
     res = mbb_results(fit=fit, redshift=2.0, lumdist=1.6e4)
-    cen = res.par_cen('T')
-    assert abs(cen[0] - 12.0) < 3.0
+    # statistics: the reference's formulas (results.py:314-369, 399-431) on the same chain
+    for name, col in (("T", 0), ("beta", 1), ("fnorm", 4)):
+        cen = res.par_cen(name)
+        x = ch[:, :, col].ravel()
+        lo, hi = np.percentile(x, [0.5 * (100 - 68.3), 100 - 0.5 * (100 - 68.3)])
+        assert np.allclose(cen, [x.mean(), hi - x.mean(), x.mean() - lo], rtol=1e-12, atol=0)
+    w, t = np.unravel_index(np.argmax(lnp), lnp.shape)
+    assert np.array_equal(res.best_fit[0], ch[w, t]) and res.best_fit[1] == lnp[w, t]
+    assert res.best_fit_chisq == -2.0 * lnp[w, t]
+    assert abs(res.par_cen('T')[0] - 12.0) < 3.0
     res.compute_dustmass()
     res.compute_peaklambda()
     assert np.isfinite(res.dustmass).all() and np.isfinite(res.peaklambda).all()
+    # ancillaries of individual samples against the oracle (thin, no alpha; the reference builds the
+    # peak-wavelength SED thick with alpha whatever the fit used, results.py:574-580)
+    dc = oracle.dustmass_consts(2.0, 500.0, 125.0, 1.6e4)
+    for (w, t) in ((0, 0), (17, 80), (99, 149)):
+        step = ch[w, t]
+        assert abs(res.peaklambda[w, t] - oracle.peaklambda_step(step)) <= TOL * res.peaklambda[w, t]
+        dm = oracle.dustmass_step(step, 2.64, 500.0, True, *dc)
+        assert abs(res.dustmass[w, t] - dm) <= TOL * abs(dm)
     assert "ChiSquare" in str(res)
 
 
@@ -888,6 +912,20 @@ def test_cli_end_to_end(tmp_path):
                     "--get_lir", "--get_dustmass", "--priorBeta", "1.8", "0.3"])
     assert res.chain.shape == (60, 30, 5) and np.isfinite(res.lnprobability).all()
     assert res.has_peaklambda and res.has_lir and res.has_dustmass
+    # what the command line computed is what the classes compute from the same file and settings:
+    # the recorded log-probabilities are the likelihood of the recorded positions (beta prior incl.)
+    from mbb_emcee_b200 import likelihood
+    like = likelihood(photfile=str(phot), device=0)
+    like.set_gaussian_prior("beta", 1.8, 0.3)
+    flat, fl = res.chain.reshape(-1, 5), res.lnprobability.reshape(-1)
+    pick = np.random.RandomState(1).randint(0, flat.shape[0], 200)
+    assert relerr(like(flat[pick]), fl[pick]).max() < 1e-12
+    # L_IR of a sample = the SED class's own integral (8-1000 um rest frame, z = 2)
+    from mbb_emcee_b200 import modified_blackbody
+    s0 = res.chain[3, 11]
+    m = modified_blackbody(s0[0], s0[1], s0[2], s0[3], s0[4], wavenorm=500.0)
+    lir = 3.11749657e4 * 16000.0**2 * m.freq_integrate(8.0 * 3.0, 1000.0 * 3.0)
+    assert abs(res.lir[3, 11] - lir) <= 5e-9 * lir
     back = mbb_results.load(str(out), device=0)
     assert np.array_equal(back.chain, res.chain)
     assert np.array_equal(back.lir_chain, res.lir_chain)
