@@ -538,6 +538,35 @@ struct LaunchSplit {
   }
 };
 
+// Half-step of the propose / evaluate / accept sampler over tabulated passbands for small ensembles, in
+// two launches (mbb_ensemble.cuh: ens_propose_setup_kernel, ens_nodes_accept_kernel); FAST, full tables.
+template <bool THIN, bool ALPHA, bool FAST>
+struct LaunchEnsHalfStepFused {
+  static void run(mbb_ctx* c, cudaStream_t st, const EnsArgs& g, const EvalArgs& a, const DataRef& d,
+                  cudaError_t* err) {
+    NodeTab t;
+    t.a = c->d_node_fast_a.p;
+    t.b = c->d_node_fast_b.p;
+    t.band_off = c->d_off.p;
+    t.scalar_path = c->d_scalar.p;
+    t.nb = c->nb;
+    t.nn = c->nn;
+    t.ca = c->d_comp_a.p;
+    t.cb = c->d_comp_b.p;
+    t.comp_off = c->d_comp_off.p;
+    t.nc = 0;
+    double* scratch = nullptr;
+    int* sst = nullptr;
+    *err = c->scratch_for(st, (size_t)a.n, &scratch, &sst);
+    if (*err != cudaSuccess) return;
+    const ModelP m = model_of(c);
+    ens_propose_setup_kernel<THIN, ALPHA><<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(
+        g, m, c->pri, scratch, sst, c->d_band_meta.p, 0, c->d_node_fast_a.p, c->d_off.p);
+    ens_nodes_accept_kernel<THIN, ALPHA><<<(unsigned)a.n, kSmallNodesThreads, 0, st>>>(g, a, c->pri.any_gprior, d, t,
+                                                                                      scratch, sst);
+  }
+};
+
 // MBB_MATH_FAST_GAUSS with diagonal errors: thread-per-evaluation kernel (mbb_gausskernel.cuh)
 template <bool THIN, bool ALPHA, bool UNUSED>
 struct LaunchGaussThread {
@@ -1764,16 +1793,29 @@ int mbb_ensemble_fit(mbb_ctx* c, int64_t nsrc, int nwalkers, int64_t nburn, int6
     g.nsrc = nsrc; g.src0 = src0; g.nw = nwalkers; g.h = h; g.keys = philox_keys(seed); g.sc = sc;
     const unsigned grid = (unsigned)((nh + 255) / 256);
     int64_t kept = 0;
+    // small ensembles over tabulated passbands (FAST, full tables): the half-step in two launches
+    const bool fused_half = getenv("MBB_B200_NO_FUSED_HALFSTEP") == nullptr &&
+                            getenv("MBB_B200_NO_SMALL_NODES") == nullptr && c->math_mode == MBB_MATH_FAST &&
+                            !(c->nn == c->nb && c->nb <= kMaxDeltaNB) && c->nn > kSmallMaxNodes &&
+                            nh <= kSmallNodesMaxN;
     for (int64_t it = i0; it < i1; ++it) {
       const bool is_main = it >= nburn;
       g.count = is_main ? 1 : 0;
       for (int half = 0; half < 2; ++half) {
         g.half = half;
         g.hstep = 2 * (step0 + (uint64_t)it) + (uint64_t)half;
-        ens_propose_kernel<<<grid, 256, 0, c->stream>>>(g);
         EvalArgs e{};
         e.n = nh; e.e0 = 0; e.wps = h; e.layout = MBB_AOS;
         e.pars = g.q; e.src_index = nullptr; e.out = g.qlnp; e.status = g.qst;
+        if (fused_half) {
+          set_wps_division(e);
+          cudaError_t err = cudaSuccess;
+          dispatch3<LaunchEnsHalfStepFused>(c->opthin != 0, c->noalpha == 0, true, c, c->stream, g, e, dref, &err);
+          CK(err);
+          c->launches += 2;
+          continue;
+        }
+        ens_propose_kernel<<<grid, 256, 0, c->stream>>>(g);
         if (launch_loglike(c, c->stream, e)) return 1;
         ens_accept_kernel<<<grid, 256, 0, c->stream>>>(g);
         c->launches += 2;

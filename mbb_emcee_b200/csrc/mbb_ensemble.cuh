@@ -152,6 +152,63 @@ __global__ void __launch_bounds__(256) ens_accept_kernel(const EnsArgs g) {
   }
 }
 
+// Tabulated passbands, small ensembles (a single source's 125-walker half-ensemble): the half-step
+// in TWO launches instead of four -- the proposal is formed by the thread that then does the
+// per-walker setup of the warp path, and the CTA that has summed an evaluation's nodes
+// (nodes_small_eval) accepts or rejects it on the spot.  Same draws, same arithmetic: bit-identical
+// with ens_propose_kernel / loglike_setup_kernel / loglike_nodes_small_kernel / ens_accept_kernel.
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(128)
+ens_propose_setup_kernel(const EnsArgs g, const ModelP m, const Priors pr, double* __restrict__ scratch,
+                         int* __restrict__ sst, const BandMeta* __restrict__ band_meta, const int nb_gauss,
+                         const double2* __restrict__ node_a, const int* __restrict__ band_off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nsrc * g.h) return;
+  const long long src = i / g.h;
+  const int k = (int)(i - src * g.h);
+  const Draw d = stretch_draw(g.keys, (unsigned long long)((g.src0 + src) * g.h + k), g.hstep, g.sc, g.h);
+  const int own = g.half == 0 ? k : g.h + k;
+  const int oth = (g.half == 0 ? g.h : 0) + d.partner;
+  const double* s = g.pos + (src * g.nw + own) * 5;
+  const double* c = g.pos + (src * g.nw + oth) * 5;
+  double* q = g.q + i * 5;
+  double p[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const double cj = c[j];
+    p[j] = __dsub_rn(cj, __dmul_rn(d.z, __dsub_rn(cj, s[j])));
+    q[j] = p[j];
+  }
+  setup_eval<THIN, ALPHA, true>(p, i, m, pr, scratch, sst, band_meta, nb_gauss, node_a, band_off);
+}
+
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(kSmallNodesThreads)
+ens_nodes_accept_kernel(const EnsArgs g, const EvalArgs a, const int any_gprior, const DataRef d, const NodeTab t,
+                        const double* __restrict__ scratch, const int* __restrict__ sst) {
+  const long long i = blockIdx.x;
+  double newlnp;
+  int st;
+  if (!nodes_small_eval<THIN, ALPHA>(a, i, any_gprior, d, t, scratch, sst, newlnp, st)) return;
+  const long long src = i / g.h;
+  const int k = (int)(i - src * g.h);
+  const Draw dr = stretch_draw(g.keys, (unsigned long long)((g.src0 + src) * g.h + k), g.hstep, g.sc, g.h);
+  const int own = g.half == 0 ? k : g.h + k;
+  const long long w = src * g.nw + own;
+  if (st > ST_BELOW_LOWLIM) {          // the reference would have raised here
+    if (g.status[w] <= ST_BELOW_LOWLIM) g.status[w] = st;
+    return;
+  }
+  if (stretch_accept(dr.z, dr.u, newlnp, g.lnp[w])) {
+    const double* q = g.q + i * 5;
+    double* p = g.pos + w * 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) p[j] = q[j];
+    g.lnp[w] = newlnp;
+    if (g.count) g.nacc[w] += 1;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Posterior accumulators.  The hs threads that serve one source split its 5 x nw
 // sample values by COMPONENT: thread r accumulates component j = r % 5 over the

@@ -538,15 +538,13 @@ constexpr int kScratchStride = 16;   // c[0..13], pen, gp
 constexpr int kMaxKinkBands = 4;     // split indices of the kink bands: 16 bits each in c[12]
 constexpr int kSafeBit = 0x100;
 
+// per-evaluation setup of the warp path: parameters p of evaluation e -> its scratch row
 template <bool THIN, bool ALPHA, bool FAST>
-__global__ void __launch_bounds__(128)
-loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* __restrict__ scratch,
-                     int* __restrict__ sst, const BandMeta* __restrict__ band_meta, const int nb_gauss,
-                     const double2* __restrict__ node_a, const int* __restrict__ band_off) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.n) return;
-  double p[5];
-  load_pars(a, e, p);
+__device__ __forceinline__ void setup_eval(const double p[5], long long e, const ModelP& m, const Priors& pr,
+                                           double* __restrict__ scratch, int* __restrict__ sst,
+                                           const BandMeta* __restrict__ band_meta, const int nb_gauss,
+                                           const double2* __restrict__ node_a,
+                                           const int* __restrict__ band_off) {
   int st = ST_OK, safe = 0;
   double pen = 0.0, gp = 0.0;
   double c[14];
@@ -604,6 +602,18 @@ loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* 
   for (int i = 0; i < 7; ++i) o[i] = make_double2(c[2 * i], c[2 * i + 1]);
   o[7] = make_double2(pen, gp);
   sst[e] = st | (safe ? kSafeBit : 0);
+}
+
+template <bool THIN, bool ALPHA, bool FAST>
+__global__ void __launch_bounds__(128)
+loglike_setup_kernel(const EvalArgs a, const ModelP m, const Priors pr, double* __restrict__ scratch,
+                     int* __restrict__ sst, const BandMeta* __restrict__ band_meta, const int nb_gauss,
+                     const double2* __restrict__ node_a, const int* __restrict__ band_off) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  double p[5];
+  load_pars(a, e, p);
+  setup_eval<THIN, ALPHA, FAST>(p, e, m, pr, scratch, sst, band_meta, nb_gauss, node_a, band_off);
 }
 
 #ifndef MBB_NODES_THREADS
@@ -849,23 +859,23 @@ loglike_nodes_kernel(const EvalArgs a, const int any_gprior, const DataRef d, co
 constexpr int kSmallNodesWarps = 8;
 constexpr int kSmallNodesThreads = 32 * kSmallNodesWarps;
 
+// Evaluation e by the whole CTA; the result (log-likelihood, status) is returned in thread 0
+// (return value true there, false in every other thread).
 template <bool THIN, bool ALPHA>
-__global__ void __launch_bounds__(kSmallNodesThreads)
-loglike_nodes_small_kernel(const EvalArgs a, const int any_gprior, const DataRef d, const NodeTab t,
-                           const double* __restrict__ scratch, const int* __restrict__ sst) {
+__device__ __forceinline__ bool nodes_small_eval(const EvalArgs& a, const long long e, const int any_gprior,
+                                                 const DataRef& d, const NodeTab& t,
+                                                 const double* __restrict__ scratch,
+                                                 const int* __restrict__ sst, double& lnl_out, int& st_out) {
   __shared__ double s_part[kSmallNodesWarps][kMaxBands];
   __shared__ double s_diff[kMaxBands];
-  const long long e = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = t.nb;
   const int stw = __ldg(sst + e);
   const int st = stw & 0xff;
   if (st != ST_OK) {
-    if (tid == 0) {
-      a.out[e] = (st == ST_BELOW_LOWLIM) ? -kInf : qnan();
-      if (a.status) a.status[e] = st;
-    }
-    return;
+    lnl_out = (st == ST_BELOW_LOWLIM) ? -kInf : qnan();
+    st_out = st;
+    return tid == 0;
   }
   const double2* c2 = reinterpret_cast<const double2*>(scratch + e * kScratchStride);
   const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
@@ -894,7 +904,7 @@ loglike_nodes_small_kernel(const EvalArgs a, const int any_gprior, const DataRef
     if (lane == 0) s_part[warp][b] = acc;
   }
   __syncthreads();
-  if (warp != 0) return;
+  if (warp != 0) return false;
   const long long src = source_of(a, e);
   const double* fl = d.flux + src * d.nb;
   double chi = 0.0;
@@ -934,12 +944,24 @@ loglike_nodes_small_kernel(const EvalArgs a, const int any_gprior, const DataRef
       for (int b = 0; b < nb; ++b) chi = fma(s_diff[b] * s_diff[b], __ldg(ivp + b), chi);
     }
   }
-  if (lane == 0) {
-    double lnl = -0.5 * chi;
-    lnl += cpg.x;
-    if (any_gprior) lnl += cpg.y;
+  double lnl = -0.5 * chi;
+  lnl += cpg.x;
+  if (any_gprior) lnl += cpg.y;
+  lnl_out = lnl;
+  st_out = (lnl != lnl) ? ST_NONFINITE : ST_OK;
+  return lane == 0;
+}
+
+template <bool THIN, bool ALPHA>
+__global__ void __launch_bounds__(kSmallNodesThreads)
+loglike_nodes_small_kernel(const EvalArgs a, const int any_gprior, const DataRef d, const NodeTab t,
+                           const double* __restrict__ scratch, const int* __restrict__ sst) {
+  const long long e = blockIdx.x;
+  double lnl;
+  int st;
+  if (nodes_small_eval<THIN, ALPHA>(a, e, any_gprior, d, t, scratch, sst, lnl, st)) {
     a.out[e] = lnl;
-    if (a.status) a.status[e] = (lnl != lnl) ? ST_NONFINITE : ST_OK;
+    if (a.status) a.status[e] = st;
   }
 }
 
