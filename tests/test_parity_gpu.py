@@ -920,6 +920,16 @@ def test_cli_end_to_end(tmp_path):
     flat, fl = res.chain.reshape(-1, 5), res.lnprobability.reshape(-1)
     pick = np.random.RandomState(1).randint(0, flat.shape[0], 200)
     assert relerr(like(flat[pick]), fl[pick]).max() < 1e-12
+    # the same command with the stretch move on the device: same posterior within Monte-Carlo error
+    out2 = tmp_path / "res_dev.npz"
+    res2 = cli.main([str(phot), str(out2), "-n", "60", "-N", "300", "-b", "100", "--initT", "12", "--initLambda0", "300",
+                     "--initFnorm", "30", "--seed", "3", "--sampler", "device", "--priorBeta", "1.8", "0.3"])
+    res1 = cli.main([str(phot), str(tmp_path / "res_host.npz"), "-n", "60", "-N", "300", "-b", "100", "--initT", "12",
+                     "--initLambda0", "300", "--initFnorm", "30", "--seed", "3", "--priorBeta", "1.8", "0.3"])
+    assert res2.chain.shape == (60, 300, 5)
+    for col in (0, 1, 4):
+        a, b = res1.chain[:, ::30, col].ravel(), res2.chain[:, ::30, col].ravel()
+        assert abs(a.mean() - b.mean()) < 5.0 * np.hypot(a.std(), b.std()) / np.sqrt(a.size / 2.0)
     # L_IR of a sample = the SED class's own integral (8-1000 um rest frame, z = 2)
     from mbb_emcee_b200 import modified_blackbody
     s0 = res.chain[3, 11]
