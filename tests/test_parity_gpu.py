@@ -1113,6 +1113,43 @@ def test_results_shard_rows_over_devices():
     assert np.array_equal(many.lir_cen(), many._parcen_internal(many.lir.flatten(), 68.3))
 
 
+def test_chain_post_host_path_equals_device_path():
+    """mbb_chain_post(MBB_HOST) on a chain of 10^6 samples: every output equals the device-resident
+    call bit for bit, with page-locked and pageable host arrays.  (Measured and not shipped: the
+    host path in 8 chunks of walker rows over three streams -- 56.7 -> 54.8 ms for BASELINE
+    configs[3]; the per-walker dedupe scan is latency-bound and its cost multiplies with the
+    chunks.)"""
+    import ctypes
+    import torch
+    from mbb_emcee_b200 import _native, synthetic
+    nw, ns = 19, 56000                                   # 1 064 000 samples
+    chain = synthetic.random_walk_chain((14.0, 1.8, 400.0, 3.0, 30.0), nw, ns, np.random.RandomState(9))
+    ctx = _native.Context(0)
+    ctx.set_model(500.0, False, False)
+    dev = torch.device("cuda:0")
+    ch = torch.as_tensor(chain, device=dev)
+    outs = [torch.empty((nw, ns), dtype=torch.float64, device=dev) for _ in range(3)]
+    st = torch.empty((nw, ns), dtype=torch.int32, device=dev)
+    vp = ctypes.c_void_p
+    rc = ctx._lib.mbb_chain_post(ctx._h, nw, ns, vp(ch.data_ptr()), 7, 2.0, 1.6e4, 8.0, 1000.0, 2.64, 125.0,
+                                 vp(outs[0].data_ptr()), vp(outs[1].data_ptr()), vp(outs[2].data_ptr()),
+                                 vp(st.data_ptr()), 1)
+    assert rc == 0
+    ctx.sync()
+    want = [o.cpu().numpy() for o in outs] + [st.cpu().numpy()]
+    for pinned in (False, True):
+        alloc = _native.pinned_empty if pinned else (lambda shape, dt=np.float64: np.empty(shape, dtype=dt))
+        cin = alloc((nw, ns, 5))
+        cin[...] = chain
+        got = [alloc((nw, ns)) for _ in range(3)] + [alloc((nw, ns), np.int32)]
+        for g in got:
+            g[...] = -7
+        ctx.chain_post_into(cin, 7, peak=got[0], lir=got[1], dustmass=got[2], status=got[3], z=2.0, dl_mpc=1.6e4)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+    assert np.isfinite(want[1]).all() and (want[3] == 0).all()
+
+
 def test_chain_post_full_size_properties(oracle):
     """BASELINE configs[3]: a 10^7-sample chain (500 walkers x 20000 steps, 35% of
     the steps new).  Size-independent properties + an oracle-checked sample."""
