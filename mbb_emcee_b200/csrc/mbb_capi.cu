@@ -1359,13 +1359,17 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
   if ((which & 4) && !out_dustmass) return fail("out_dustmass is NULL");
   if ((which & 2) && (!(lir_min_um > 0.0) || !(lir_max_um > 0.0))) return fail("L_IR limits must be positive");
   Use u(c);
+  const bool host = mem != MBB_DEVICE;
   const double* dchain = chain;
   double *dpk = out_peak, *ddm = out_dustmass, *dlir = out_lir;
   int* dst = out_status;
-  if (mem != MBB_DEVICE) {
+  // host chains of >= 2^20 samples go through the three slots in chunks of walker rows (the
+  // dedupe rule never crosses a walker): the copies of one chunk run behind the kernels of its
+  // neighbours
+  static const bool no_pipe = getenv("MBB_B200_NO_CHAIN_PIPELINE") != nullptr;
+  const int64_t nchunks = (host && !no_pipe && nwalkers >= 8 && ns >= ((int64_t)1 << 20)) ? 8 : 1;
+  if (host) {
     CK(c->d_in.reserve((size_t)ns * 5));
-    CK(cudaMemcpyAsync(c->d_in.p, chain, (size_t)ns * 5 * sizeof(double), cudaMemcpyHostToDevice,
-                       c->stream));
     dchain = c->d_in.p;
     if (which & 1) { CK(c->d_aux0.reserve((size_t)ns)); dpk = c->d_aux0.p; }
     if (which & 4) { CK(c->d_aux1.reserve((size_t)ns)); ddm = c->d_aux1.p; }
@@ -1375,8 +1379,8 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
   }
   CK(c->d_owner.reserve((size_t)ns));
   CK(c->d_work.reserve((size_t)ns));
-  CK(c->d_count.reserve(1));
-  CK(cudaMemsetAsync(c->d_count.p, 0, sizeof(unsigned), c->stream));
+  CK(c->d_count.reserve((size_t)nchunks));
+  CK(cudaMemsetAsync(c->d_count.p, 0, (size_t)nchunks * sizeof(unsigned), c->stream));
   // results.compute_dustmass precomputation (results.py:778-793)
   DustConsts dc;
   {
@@ -1392,48 +1396,74 @@ int mbb_chain_post(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
     dc.wavenorm = c->wavenorm;
     dc.opthin = c->opthin;
   }
-  begin_timing(c);
-  chain_dedupe_kernel<<<(unsigned)((nwalkers + 3) / 4), 128, 0, c->stream>>>(
-      dchain, nwalkers, nsteps, c->d_owner.p, c->d_work.p, c->d_count.p);
-  chain_unique_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(
-      dchain, c->d_work.p, c->d_count.p, which, dc, dpk, ddm, dst);
-  if (which & 2) {
-    // mbb_freqint (results.py:1310-1326) and freq_integrate (modified_blackbody.py:658-674)
-    double lo = lir_min_um, hi = lir_max_um;
-    if (lo > hi) { double t = lo; lo = hi; hi = t; }
-    const double opz = 1.0 + z;
-    const double fmin = kUmToGHz / (hi * opz), fmax = kUmToGHz / (lo * opz);
-    const double prefac = dl_mpc > 0.0 ? 3.11749657e4 * (dl_mpc * dl_mpc) : 1.0;
-    const unsigned grid = (unsigned)((ns + 127) / 128);
-    const bool thin = c->opthin != 0, alpha = c->noalpha == 0;
-#define LIR(K, T, A) K<T, A><<<grid, 128, 0, c->stream>>>(dchain, c->d_work.p, c->d_count.p, \
-                                   c->wavenorm, fmin, fmax, prefac, dlir, dst)
-    if (c->lir_method == MBB_LIR_GAUSS) {
-      if (thin) { if (alpha) LIR(chain_lir_kernel, true, true); else LIR(chain_lir_kernel, true, false); }
-      else { if (alpha) LIR(chain_lir_kernel, false, true); else LIR(chain_lir_kernel, false, false); }
-    } else {
-      if (thin) { if (alpha) LIR(chain_lir_qags_kernel, true, true); else LIR(chain_lir_qags_kernel, true, false); }
-      else { if (alpha) LIR(chain_lir_qags_kernel, false, true); else LIR(chain_lir_qags_kernel, false, false); }
-    }
+  // mbb_freqint (results.py:1310-1326) and freq_integrate (modified_blackbody.py:658-674)
+  double lo = lir_min_um, hi = lir_max_um;
+  if (lo > hi) { double t = lo; lo = hi; hi = t; }
+  const double fmin = kUmToGHz / (hi * (1.0 + z)), fmax = kUmToGHz / (lo * (1.0 + z));
+  const double prefac = dl_mpc > 0.0 ? 3.11749657e4 * (dl_mpc * dl_mpc) : 1.0;
+  const bool thin = c->opthin != 0, alpha = c->noalpha == 0;
+  // walker rows [r0, r1) on stream s: dedupe, unique samples, repeats filled in
+  auto rows = [&](cudaStream_t s, int64_t r0, int64_t r1, unsigned* count) {
+    const int64_t off = r0 * nsteps, m = (r1 - r0) * nsteps;
+    const double* ch = dchain + off * 5;
+    int *own = c->d_owner.p + off, *work = c->d_work.p + off, *st = dst ? dst + off : nullptr;
+    double *pk = (which & 1) ? dpk + off : nullptr, *li = (which & 2) ? dlir + off : nullptr,
+           *dm = (which & 4) ? ddm + off : nullptr;
+    chain_dedupe_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(ch, r1 - r0, nsteps, own, work, count);
+    const unsigned grid = (unsigned)((m + 127) / 128);
+    chain_unique_kernel<<<grid, 128, 0, s>>>(ch, work, count, which, dc, pk, dm, st);
+    if (which & 2) {
+#define LIR(K, T, A) K<T, A><<<grid, 128, 0, s>>>(ch, work, count, c->wavenorm, fmin, fmax, prefac, li, st)
+      if (c->lir_method == MBB_LIR_GAUSS) {
+        if (thin) { if (alpha) LIR(chain_lir_kernel, true, true); else LIR(chain_lir_kernel, true, false); }
+        else { if (alpha) LIR(chain_lir_kernel, false, true); else LIR(chain_lir_kernel, false, false); }
+      } else {
+        if (thin) { if (alpha) LIR(chain_lir_qags_kernel, true, true); else LIR(chain_lir_qags_kernel, true, false); }
+        else { if (alpha) LIR(chain_lir_qags_kernel, false, true); else LIR(chain_lir_qags_kernel, false, false); }
+      }
 #undef LIR
-    c->launches += 1;
+      c->launches += 1;
+    }
+    chain_fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(own, r1 - r0, nsteps, pk, li, dm, st);
+    c->launches += 3;
+  };
+  // host <-> device copies of rows [r0, r1) on stream s
+  auto rows_in = [&](cudaStream_t s, int64_t r0, int64_t r1) -> int {
+    const size_t off = (size_t)(r0 * nsteps), m = (size_t)((r1 - r0) * nsteps);
+    CK(cudaMemcpyAsync(c->d_in.p + off * 5, chain + off * 5, m * 5 * sizeof(double), cudaMemcpyHostToDevice, s));
+    return 0;
+  };
+  auto rows_out = [&](cudaStream_t s, int64_t r0, int64_t r1) -> int {
+    const size_t off = (size_t)(r0 * nsteps), m = (size_t)((r1 - r0) * nsteps);
+    if (which & 1) CK(cudaMemcpyAsync(out_peak + off, dpk + off, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (which & 2) CK(cudaMemcpyAsync(out_lir + off, dlir + off, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (which & 4) CK(cudaMemcpyAsync(out_dustmass + off, ddm + off, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_status) CK(cudaMemcpyAsync(out_status + off, dst + off, m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return 0;
+  };
+  if (nchunks > 1) {
+    if (ensure_slots(c)) return 1;
+    begin_timing(c);
+    for (int64_t k = 0; k < nchunks; ++k) {
+      mbb_ctx::Slot& sl = c->slots[k % 3];
+      const int64_t r0 = nwalkers * k / nchunks, r1 = nwalkers * (k + 1) / nchunks;
+      if (k < 3) CK(cudaStreamWaitEvent(sl.s, c->ev0, 0));
+      if (rows_in(sl.s, r0, r1)) return 1;
+      rows(sl.s, r0, r1, c->d_count.p + k);
+      if (rows_out(sl.s, r0, r1)) return 1;
+    }
+    CK(cudaGetLastError());
+    for (auto& sl : c->slots) CK(cudaStreamSynchronize(sl.s));
+    end_timing(c);
+    return 0;
   }
-  chain_fill_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(
-      c->d_owner.p, nwalkers, nsteps, (which & 1) ? dpk : nullptr, (which & 2) ? dlir : nullptr,
-      (which & 4) ? ddm : nullptr, dst);
+  if (host && rows_in(c->stream, 0, nwalkers)) return 1;
+  begin_timing(c);
+  rows(c->stream, 0, nwalkers, c->d_count.p);
   end_timing(c);
-  c->launches += 3;
   CK(cudaGetLastError());
-  if (mem != MBB_DEVICE) {
-    if (which & 1)
-      CK(cudaMemcpyAsync(out_peak, dpk, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (which & 2)
-      CK(cudaMemcpyAsync(out_lir, dlir, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (which & 4)
-      CK(cudaMemcpyAsync(out_dustmass, ddm, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost,
-                         c->stream));
-    if (out_status)
-      CK(cudaMemcpyAsync(out_status, dst, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (host) {
+    if (rows_out(c->stream, 0, nwalkers)) return 1;
     CK(cudaStreamSynchronize(c->stream));
   }
   return 0;
@@ -1466,7 +1496,7 @@ int mbb_chain_flux(mbb_ctx* c, int64_t nwalkers, int64_t nsteps, const double* c
   CK(c->d_count.reserve(1));
   CK(cudaMemsetAsync(c->d_count.p, 0, sizeof(unsigned), c->stream));
   begin_timing(c);
-  chain_dedupe_kernel<<<(unsigned)((nwalkers + 3) / 4), 128, 0, c->stream>>>(
+  chain_dedupe_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(
       dchain, nwalkers, nsteps, c->d_owner.p, c->d_work.p, c->d_count.p);
   const unsigned grid = (unsigned)((ns + 127) / 128);
   const int i0 = c->h_off[band], i1 = c->h_off[band + 1], sp = c->h_scalar[band];

@@ -1113,6 +1113,66 @@ def test_results_shard_rows_over_devices():
     assert np.array_equal(many.lir_cen(), many._parcen_internal(many.lir.flatten(), 68.3))
 
 
+def test_chain_dedupe_rule_on_adversarial_chains(oracle):
+    """The allclose-dedupe of results._map_chain (results.py:553-566) is sequential -- a step is
+    compared with the last KEPT step -- while the device cuts every walker into segments at steps
+    that are certainly new.  Chains built to stress the difference: slow drifts (every step within
+    the tolerance of its predecessor, but not of the kept one), jumps between one and two
+    tolerances (new, yet not a certain segment start), runs of more than 6 such steps, exact
+    repeats, constants.  Every output must be the value computed for the owner that a numpy replay
+    of the sequential rule assigns."""
+    from mbb_emcee_b200 import mbb_results
+    rng = np.random.RandomState(12)
+    nw, ns = 7, 700
+    base = np.array([14.0, 1.8, 400.0, 3.0, 30.0])
+    chain = np.empty((nw, ns, 5))
+    for w in range(nw):
+        cur = base * (1.0 + 0.05 * rng.standard_normal(5))
+        for t in range(ns):
+            kind = w if w < 6 else rng.randint(0, 6)
+            if kind == 0:                                   # ordinary chain: 35 % accepted moves, else exact repeats
+                if rng.uniform() < 0.35:
+                    cur = cur + np.array([0.3, 0.03, 10.0, 0.05, 0.8]) * rng.standard_normal(5)
+            elif kind == 1:                                 # slow drift, 4e-6 per step
+                cur = cur * (1.0 + 4e-6)
+            elif kind == 2:                                 # jumps of 1.5 tolerances, alternating sign
+                cur = cur * (1.0 + (1.5e-5 if t % 2 else -1.5e-5))
+            elif kind == 3:                                 # constant
+                pass
+            elif kind == 4:                                 # a run of steps each 1.2 tolerances from the previous one
+                cur = cur * (1.0 + 1.2e-5)
+            else:                                           # one component moves at a time, just above / below tol
+                k = t % 5
+                cur = cur.copy()
+                cur[k] *= 1.0 + (1.02e-5 if (t // 5) % 2 else 0.98e-5)
+            chain[w, t] = np.maximum(cur, [3.0, 0.3, 30.0, 0.6, 1.0])
+    owner = np.empty((nw, ns), dtype=int)
+    for w in range(nw):
+        prev, pt = None, 0
+        for t in range(ns):
+            if prev is None or not np.allclose(prev, chain[w, t]):
+                prev, pt = chain[w, t], t
+            owner[w, t] = pt
+    frac_new = np.mean(owner == np.arange(ns)[None, :])
+    assert 0.2 < frac_new < 0.9 and (np.diff(owner[1]) == 0).any() and (owner[1] > 0).any()
+    res = mbb_results.from_chain(chain, wavenorm=500.0, noalpha=False, opthin=False, redshift=2.0,
+                                 lumdist=1.6e4, device=0)
+    res.compute_dustmass()
+    res.compute_peaklambda()
+    dc = oracle.dustmass_consts(2.0, 500.0, 125.0, 1.6e4)
+    uniq = {}
+    for w in range(nw):
+        for t in range(ns):
+            o = owner[w, t]
+            if (w, o) not in uniq:
+                uniq[(w, o)] = oracle.dustmass_step(chain[w, o], 2.64, 500.0, False, *dc)
+            want = uniq[(w, o)]
+            assert abs(res.dustmass[w, t] - want) <= 1e-13 * want, (w, t, o)
+            assert res.peaklambda[w, t] == res.peaklambda[w, o]
+    # a relative change of 4e-6 in T moves the dust mass by far more than 1e-13: a wrong owner shows
+    assert abs(uniq[(1, 0)] / uniq[(1, owner[1, -1])] - 1.0) > 1e-9
+
+
 def test_chain_post_host_path_equals_device_path():
     """mbb_chain_post(MBB_HOST) on a chain of 10^6 samples: every output equals the device-resident
     call bit for bit, with page-locked and pageable host arrays.  (Measured and not shipped: the
