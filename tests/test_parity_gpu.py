@@ -1174,11 +1174,10 @@ def test_chain_dedupe_rule_on_adversarial_chains(oracle):
 
 
 def test_chain_post_host_path_equals_device_path():
-    """mbb_chain_post(MBB_HOST) on a chain of 10^6 samples: every output equals the device-resident
-    call bit for bit, with page-locked and pageable host arrays.  (Measured and not shipped: the
-    host path in 8 chunks of walker rows over three streams -- 56.7 -> 54.8 ms for BASELINE
-    configs[3]; the per-walker dedupe scan is latency-bound and its cost multiplies with the
-    chunks.)"""
+    """mbb_chain_post(MBB_HOST) on a chain of >= 2^20 samples works through 8 chunks of walker rows
+    on three streams (copies of one chunk behind the kernels of its neighbours); every output equals
+    the single-launch device-resident call bit for bit, with page-locked and pageable host arrays
+    and a walker count that the chunks do not divide."""
     import ctypes
     import torch
     from mbb_emcee_b200 import _native, synthetic
