@@ -489,3 +489,69 @@ def test_cholesky_quadratic_form_vs_exact():
         assert worst_inv < 2e-16 * max(cond, 8.0), (cond, worst_inv)
         if cond < 1e4:
             assert worst_ch < 1e-13 and worst_inv < 1e-13
+
+
+def test_segmented_dedupe_equals_the_sequential_rule():
+    """csrc/mbb_kernels.cuh chain_dedupe_kernel cuts the sequential np.allclose rule of
+    results._map_chain (reference results.py:553-566) into independent segments at steps that
+    differ from their predecessor by more than both tolerances.  The same algorithm in numpy,
+    against the sequential rule, on walks built around the tolerance (steps of 0 - 3 tolerances,
+    single components, drifts, repeats, sign changes, values near zero where the absolute term
+    of the tolerance dominates)."""
+    rng = np.random.RandomState(77)
+
+    def tol(x):
+        return 1e-8 + 1e-5 * np.abs(x)
+
+    def sequential(ch):
+        owner = np.empty(len(ch), dtype=int)
+        prev, pt = None, 0
+        for t, c in enumerate(ch):
+            if prev is None or not np.all(np.abs(prev - c) <= tol(c)):
+                prev, pt = c, t
+            owner[t] = pt
+        return owner
+
+    def segmented(ch):
+        n = len(ch)
+        hard = np.ones(n, dtype=bool)
+        d = np.abs(ch[:-1] - ch[1:])
+        hard[1:] = np.any(d > 1.001 * (tol(ch[1:]) + tol(ch[:-1])), axis=1)
+        owner = np.full(n, -1)
+        for t in np.nonzero(hard)[0]:                  # every segment start independently
+            prev, pt = ch[t], t
+            owner[t] = t
+            j = t + 1
+            while j < n and not hard[j]:
+                if not np.all(np.abs(prev - ch[j]) <= tol(ch[j])):
+                    prev, pt = ch[j], j
+                owner[j] = pt
+                j += 1
+        return owner
+
+    nbad = 0
+    for trial in range(60):
+        n = 400
+        scale = rng.choice([1e-9, 1e-6, 1e-3, 1.0, 30.0, 1e4], size=5)      # incl. |x| << atol / rtol
+        cur = scale * (1.0 + rng.uniform(-0.5, 0.5, 5))
+        ch = np.empty((n, 5))
+        for t in range(n):
+            kind = rng.randint(0, 7)
+            step = np.zeros(5)
+            if kind == 1:
+                step = tol(cur) * rng.uniform(0, 3, 5) * rng.choice([-1, 1], 5)
+            elif kind == 2:
+                k = rng.randint(0, 5)
+                step[k] = tol(cur)[k] * rng.choice([0.98, 0.999, 1.001, 1.02, 1.98, 2.0, 2.02])
+            elif kind == 3:
+                step = cur * 4e-6
+            elif kind == 4:
+                step = scale * rng.standard_normal(5) * 0.1
+            elif kind == 5:
+                step = -2.0 * cur * (rng.uniform(size=5) < 0.3)               # sign flips
+            cur = cur + step
+            ch[t] = cur
+        a, b = sequential(ch), segmented(ch)
+        nbad += int(not np.array_equal(a, b))
+        assert (b >= 0).all()
+    assert nbad == 0
