@@ -1,5 +1,6 @@
 #!/bin/bash
-# One GPU box visit: parity suite, smoke, the bench lines and the ncu evidence that profiles/ summarises.
+# One GPU box visit (round-1 form; round 2 uses tools/gpu_visit.sh, tools/ncu_capture.py and tools/gpu_scaling.sh):
+# parity suite, smoke, the bench lines and the ncu evidence that profiles/ summarises.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- tools/gpu_round.sh r01
 # Everything lands in gpurun_out/<tag>_*; tools/ncu_summary.py turns it into profiles/ here.
 T=${1:-r01}
@@ -34,7 +35,7 @@ full cfg5 loglike_delta $B --workload cfg5
 full cfg2 loglike_nodes $B --workload cfg2
 full cfg2_gauss loglike_gauss_thread $B --workload cfg2 --math gauss
 full cfg5p_gauss loglike_gauss_thread $B --workload cfg5p --math gauss
-full ens_delta ens_delta python tools/sampler_probe.py 4
+full ens ens_resident python tools/sampler_probe.py 4 20000
 python tools/sampler_probe.py 10 > $O/${T}_sampler.json 2> $O/${T}_sampler.err
 head -c 600 $O/${T}_bench_cfg5.json; echo
 echo DONE
